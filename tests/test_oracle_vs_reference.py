@@ -1,0 +1,108 @@
+"""Pin the oracle against the live reference (build container only).
+
+Compares oracle/nvit_oracle.py with /root/reference/nvit/model.py on identical weights and
+inputs: logits, aux losses and every parameter gradient, in fp64 so that any mismatch is a
+formula mismatch and not rounding.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nvit_oracle as O
+
+
+def _ref_model(ref, cfg: O.OracleConfig, sd):
+    m = ref.ViT(ref.ViTConfig(**cfg.as_dict()))
+    if not cfg.use_nvit:
+        # use_nvit=False crashes unless RMSNorms are attached from outside
+        for blk in m.transformer.h:
+            blk.rmsnorm_att = ref.RMSNorm(cfg.n_embd)
+            blk.rmsnorm_mlp = ref.RMSNorm(cfg.n_embd)
+    m = m.double()
+    missing, unexpected = m.load_state_dict({k: v.double() for k, v in sd.items()}, strict=True)
+    assert not missing and not unexpected
+    # the init_value/init_scaling scalars are fp32 attributes, keep their fp32 values (as the model does)
+    return m
+
+
+CASES = [
+    ("micro", dict()),
+    ("micro", dict(bias=True)),
+    ("mini", dict(base_scale=1.0 / 32.0)),
+    ("micro", dict(use_nvit=False)),
+]
+
+
+@pytest.mark.parametrize("name,over", CASES)
+def test_oracle_matches_reference(reference_model_module, name, over):
+    ref = reference_model_module
+    cfg = O.named_config(name, **over)
+    sd = O.init_state_dict(cfg, seed=3)
+    # move scalars/vectors off their init so every term is exercised
+    g = torch.Generator().manual_seed(11)
+    for k, v in sd.items():
+        if v.dim() <= 1 or "pos_embed" in k:
+            v.add_(torch.randn(v.shape, generator=g) * (0.3 * v.abs().mean().clamp_min(0.02)))
+    assert set(sd) == set(O.param_shapes(cfg))
+    m = _ref_model(ref, cfg, sd)
+    m.train()
+    B = 3
+    X = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g, dtype=torch.float64)
+    y = torch.randint(0, cfg.num_classes, (B,), generator=g)
+
+    logits_r, aux_r = m(X)
+    loss_r = F.cross_entropy(logits_r, y) + 0.1 * aux_r["reconstruction"]
+    loss_r.backward()
+
+    osd = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    logits_o, aux_o = O.vit_forward(osd, cfg, X)
+    loss_o = F.cross_entropy(logits_o, y) + 0.1 * aux_o["reconstruction"]
+    loss_o.backward()
+
+    # the reference multiplies by fp32 scalar attributes (e.g. 0.05/base_scale in fp32): allow 1e-6
+    torch.testing.assert_close(logits_o, logits_r, rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(aux_o["reconstruction"], aux_r["reconstruction"], rtol=1e-6, atol=1e-6)
+    ref_params = dict(m.named_parameters())
+    for k, p in osd.items():
+        gr = ref_params[k].grad
+        if gr is None:
+            assert p.grad is None or p.grad.abs().max() == 0, k
+            continue
+        assert p.grad is not None, k
+        scale = gr.abs().max().clamp_min(1e-12)
+        assert (p.grad - gr).abs().max() <= 5e-6 * scale + 1e-12, (k, float((p.grad - gr).abs().max()), float(scale))
+
+
+def test_oracle_step_matches_reference(reference_model_module):
+    """Three restated training steps == three reference steps (train.py:898-946, 461-480) in fp32."""
+    ref = reference_model_module
+    cfg = O.named_config("micro")
+    sd = O.init_state_dict(cfg, seed=5)
+    m = ref.ViT(ref.ViTConfig(**cfg.as_dict()))
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    opt = m.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu")
+    tr = O.OracleTrainer(sd, cfg, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0)
+    g = torch.Generator().manual_seed(7)
+    for _ in range(3):
+        X = torch.randn(4, 3, cfg.image_size, cfg.image_size, generator=g)
+        y = torch.randint(0, cfg.num_classes, (4,), generator=g)
+        logits, _ = m(X)
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            for blk in m.transformer.h:      # normalize_matrices, train.py:474-480
+                for name, dim in O.NORMALIZED:
+                    w = getattr(blk, name).weight
+                    w.copy_(w / w.norm(p=2, dim=dim, keepdim=True))
+        loss_o, _, _ = tr.step(X, y)
+        assert abs(float(loss_o) - float(loss)) < 2e-5
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(tr.sd[k].detach(), p.detach(), rtol=2e-4, atol=2e-5, msg=k)
+    for i in range(cfg.n_layer):
+        for name, dim in O.NORMALIZED:
+            w = tr.sd[f"transformer.h.{i}.{name}.weight"].detach()
+            assert (w.norm(dim=dim) - 1).abs().max() < 1e-5
