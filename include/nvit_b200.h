@@ -1,0 +1,132 @@
+/* nvit_b200 C ABI — the drop-in boundary of the B200-native nViT training hot path.
+ *
+ * The reference (slobodaapl/nvit) is pure PyTorch and has no FFI of its own; every entry point below replaces a
+ * group of eager PyTorch ops at the cited lines of /root/reference/nvit/{model,train}.py.  A maintainer binds them
+ * with ctypes; nvit_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All pointers are DEVICE pointers owned by the caller (PyTorch); kernels never
+ *    allocate, free or retain them.  `stream` is a cudaStream_t passed as void*.
+ *  - "bf16" buffers are raw uint16 bfloat16; "f32" are float.  Matrices are row-major with explicit leading dims
+ *    (in elements) where given, dense otherwise.
+ *  - Return 0 on success, negative on error (never throws, never exits); nvit_last_error() gives the message of the
+ *    last failure on the calling thread.
+ *  - Entry points are re-entrant and stream-ordered.
+ */
+#ifndef NVIT_B200_H_
+#define NVIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+const char* nvit_last_error(void);
+int nvit_version(void);
+int nvit_sm_count(void);
+
+/* ---- GEMM: nn.Linear / nn.Conv2d-as-GEMM forward, dgrad and wgrad (model.py:99-101,130,148,155,226-228,259,262,
+ *      286-304,329-332,341-344 and their autograd backward) ------------------------------------------------------
+ *   C[M,N] (+)= A · B^T, bf16 operands, fp32 accumulation in tensor memory (tcgen05).
+ *   a_mn_major = 0: A stored [M,K] (lda = row pitch); 1: A stored [K,M] (M contiguous).  Likewise B ([N,K] / [K,N]).
+ *   out_f32: C is float (else bf16).  C2_bf16 (optional, only with out_f32): second bf16 copy of the result.
+ *   accumulate: C += result (fp32 only).  splits > 1: split the K range across CTAs, partial sums added atomically.
+ *   Epilogue, in this order: + bias[N]; * colscale[N]*colscale_mul; + rowadd[row % rowadd_period, N]  (any may be NULL).
+ *   swiglu_half F > 0: B holds [2F, K] (u rows then v rows, torch.chunk order of model.py:153); N must equal F.  The
+ *     kernel computes both halves of a column pair in one CTA and writes C[M,F] = (u*cs_u) * silu(v*cs_v) as bf16
+ *     (colscale has 2F entries or is NULL), and, if C2_bf16 != NULL, the raw bf16 product [M,2F] (ldc2) for backward.
+ */
+int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
+                   int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major, int out_f32, int accumulate,
+                   int splits, const float* bias, const float* colscale, float colscale_mul, const float* rowadd,
+                   int64_t rowadd_period, int64_t swiglu_half, void* stream);
+
+/* ---- casts / reductions ------------------------------------------------------------------------------------- */
+/* autocast's weight/activation casts (torch.autocast around model.py:905 of train.py) */
+int nvit_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* out[0] += sum(x^2): global gradient norm of clip_grad_norm_ (train.py:938) */
+int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream);
+/* out[N] += column sums of a bf16 [M,N] matrix (bias gradients of nn.Linear when config.bias) */
+int nvit_colsum_bf16(const void* x_bf16, int64_t M, int64_t N, int64_t ldx, float* out_accum, void* stream);
+/* dpos[T,C] = sum_b dx[b,t,c]; dbias[C] += sum_{b,t} dx  (autograd of `+ pos_embed` and conv bias, model.py:407-415) */
+int nvit_pos_bias_grad(const float* dx, int64_t B, int64_t T, int64_t C, float* dpos, float* dbias_accum, void* stream);
+
+/* ---- normalized residual update (model.py:134-142, 159-167, 265-273; norm_skip model.py:84-87, 450-452) -------
+ *   lr  = |alpha * alpha_mul|            (alpha_mul = 0.05 / base_scale)
+ *   o   = N( N(h) + lr * (N(x) - N(h)) )                     N(v) = v / ||v||_2 over C, no epsilon
+ *   out = h0 ? N( o * skip[0] + h0 ) : o
+ *   fwd writes out as fp32 and/or bf16 (either may be NULL).
+ *   bwd recomputes the forward from (h, x, h0) and, given g = dL/dout, writes dx (bf16), dh (fp32, += if
+ *   dh_accumulate), dh0 (fp32, written), and accumulates dalpha[C] (w.r.t. the STORED alpha) and dskip[1].
+ */
+int nvit_residual_fwd(const float* h, const void* x_bf16, const float* alpha, float alpha_mul, const float* h0,
+                      const float* skip, float* out_f32, void* out_bf16, int64_t M, int64_t C, void* stream);
+int nvit_residual_bwd(const float* g, const float* h, const void* x_bf16, const float* alpha, float alpha_mul,
+                      const float* h0, const float* skip, float* dh, int dh_accumulate, void* dx_bf16, float* dh0,
+                      float* dalpha_accum, float* dskip_accum, int64_t M, int64_t C, void* stream);
+
+/* ---- suv-scaled SiLU gate, unfused form (model.py:150-154, 259-261).  uv [M,2F] bf16: u = cols [0,F), v = [F,2F).
+ *   x = (u*su) * silu(v*sv),  s = suv * suv_mul (suv NULL -> 1).  bwd: duv bf16 [M,2F], dsuv[2F] += (w.r.t. stored suv).
+ */
+int nvit_swiglu_fwd(const void* uv_bf16, const float* suv, float suv_mul, void* x_bf16, int64_t M, int64_t F, void* stream);
+int nvit_swiglu_bwd(const void* dx_bf16, const void* uv_bf16, const float* suv, float suv_mul, void* duv_bf16,
+                    float* dsuv_accum, int64_t M, int64_t F, void* stream);
+
+/* ---- unit-norm QK attention (model.py:104-127, 231-258) ------------------------------------------------------
+ *   q,k,v: bf16, token-major [B*T, ld*] with head h at columns [h*D, (h+1)*D).   D must be 64.
+ *   qh = s * N_D(q), kh = s * N_D(k) with s = sqk * sqk_mul ([H*D]; sqk NULL -> no normalization, s = 1),
+ *   out[B*T, H*D] = softmax(scale * qh kh^T) v  (non-causal).  lse [B,H,T] (fp32) is saved for backward.
+ *   bwd: dq, dk, dv (bf16, same layouts) and dsqk[H*D] += (w.r.t. stored sqk).
+ */
+int nvit_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                       const float* sqk, float sqk_mul, float scale, void* out, int64_t ldo, float* lse, int64_t B,
+                       int64_t H, int64_t T, int64_t D, void* stream);
+int nvit_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                       const float* sqk, float sqk_mul, float scale, const void* out, const void* dout, int64_t ldo,
+                       const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
+                       float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, void* stream);
+
+/* ---- patch embedding operand (model.py:286-304, 407-408; reconstruction target model.py:460-463) --------------
+ *   out[(b,i,j), (c,kh,kw)] = reflect_pad(img, pad)[b, c, i*stride + kh, j*stride + kw]   as bf16, [B*g*g, ch*ksize^2]
+ */
+int nvit_im2col_bf16(const float* img, void* out_bf16, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
+                     int64_t pad, void* stream);
+
+/* ---- classifier head (model.py:455-456, 466-468): mean over T -> LayerNorm(eps) -> (GEMM) ------------------- */
+int nvit_pool_ln_fwd(const float* h, const float* gamma, const float* beta, float eps, void* y_bf16, float* xhat,
+                     float* rstd, int64_t B, int64_t T, int64_t C, void* stream);
+/* dy bf16 [B,C] (grad wrt LayerNorm output) -> dh[B,T,C] (fp32, written), dgamma/dbeta += */
+int nvit_pool_ln_bwd(const void* dy_bf16, const float* gamma, const float* xhat, const float* rstd, float* dh,
+                     float* dgamma_accum, float* dbeta_accum, int64_t B, int64_t T, int64_t C, void* stream);
+/* logits = raw * sz_eff (model.py:466-468);  bwd: draw_bf16 = dlogits * sz_eff, dsz[N] += sum_b dlogits*raw*sz_mul */
+int nvit_head_scale_bwd(const float* dlogits, const float* raw, const float* sz, float sz_mul, void* draw_bf16,
+                        float* dsz_accum, int64_t B, int64_t N, int64_t ld_draw, void* stream);
+/* softmax cross-entropy, mean over batch (train.py:906): loss[0] = mean CE; dlogits = (softmax - onehot)*gscale/B */
+int nvit_cross_entropy(const float* logits, const int64_t* target, float* loss, float* dlogits, float gscale,
+                       int64_t B, int64_t N, void* stream);
+/* reconstruction loss (model.py:459-464): out[0] += sum (tanh(pred) - target)^2 * inv_count */
+int nvit_tanh_mse(const void* pred_bf16, const void* target_bf16, int64_t n, float inv_count, float* out_accum,
+                  void* stream);
+
+/* ---- optimizer tail ------------------------------------------------------------------------------------------
+ * AdamW over one flat fp32 buffer (torch.optim.AdamW semantics, model.py:369-385; clip train.py:935-938).
+ * Elements [0,n_decay) get weight decay.  gnorm_sq (device scalar, may be NULL) holds sum(g^2); the clip coefficient
+ * min(1, max_norm / (sqrt(gnorm_sq) + 1e-6)) is applied to g on the fly.  step is the 1-based step count.
+ */
+int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int64_t step, const float* gnorm_sq, float max_norm,
+                    void* stream);
+/* Trainer.normalize_matrices (train.py:461-480) as ONE launch over a device table of n_tensors entries, each
+ * 6 x int64: {w_f32 ptr, w_bf16 ptr or 0, rows, cols, axis, first_unit}.  axis = 1 normalizes every row over cols,
+ * axis = 0 every column over rows (the reference's norm dims).  Units: 8 rows (axis 1) or 32 columns (axis 0) each;
+ * first_unit is the running sum of units before the tensor; total_units the grand total.  The optional bf16 pointer
+ * receives the GEMM operand copy in the same pass.
+ */
+int nvit_weight_norm_multi(const int64_t* table_dev, int64_t n_tensors, int64_t total_units, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVIT_B200_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of libnvit_b200.so — the C ABI declared in include/nvit_b200.h.
+
+This is the binding a maintainer of the reference would add.  There is NO fallback: if the shared
+library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnvit_b200.so")
+
+P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
+
+# name -> argument types (all return int except the three library calls)
+SIGNATURES = {
+    "nvit_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, I32, I32, I32, I32, P, P, F32, P, I64, I64, P],
+    "nvit_cast_f32_to_bf16": [P, P, I64, P],
+    "nvit_sumsq_f32": [P, I64, P, P],
+    "nvit_colsum_bf16": [P, I64, I64, I64, P, P],
+    "nvit_pos_bias_grad": [P, I64, I64, I64, P, P, P],
+    "nvit_residual_fwd": [P, P, P, F32, P, P, P, P, I64, I64, P],
+    "nvit_residual_bwd": [P, P, P, P, F32, P, P, P, I32, P, P, P, P, I64, I64, P],
+    "nvit_swiglu_fwd": [P, P, F32, P, I64, I64, P],
+    "nvit_swiglu_bwd": [P, P, P, F32, P, P, I64, I64, P],
+    "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],
+    "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P],
+    "nvit_im2col_bf16": [P, P, I64, I64, I64, I64, I64, I64, P],
+    "nvit_pool_ln_fwd": [P, P, P, F32, P, P, P, I64, I64, I64, P],
+    "nvit_pool_ln_bwd": [P, P, P, P, P, P, P, I64, I64, I64, P],
+    "nvit_head_scale_bwd": [P, P, P, F32, P, P, I64, I64, I64, P],
+    "nvit_cross_entropy": [P, P, P, P, F32, I64, I64, P],
+    "nvit_tanh_mse": [P, P, I64, F32, P, P],
+    "nvit_adamw_flat": [P, P, P, P, I64, I64, F32, F32, F32, F32, F32, I64, P, F32, P],
+    "nvit_weight_norm_multi": [P, I64, I64, P],
+}
+LIBRARY_CALLS = {"nvit_last_error": ([], c_char_p), "nvit_version": ([], c_int), "nvit_sm_count": ([], c_int)}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built: there is no CPU or PyTorch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m nvit_b200.build` (nvit_b200 has no fallback path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    for name, (argtypes, restype) in LIBRARY_CALLS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().nvit_last_error()
+    return msg.decode() if msg else ""
+
+
+def call(name: str, *args) -> None:
+    """Call an entry point; a non-zero status becomes a RuntimeError carrying nvit_last_error()."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")

@@ -1,0 +1,450 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma -> TMEM -> epilogue.
+//
+//   C[M,N] (+)= A[M,K] * B[N,K]^T        fp32 accumulate in tensor memory
+//
+// Operand storage (both bf16, row-major in global memory):
+//   a_mn = 0 : A is stored [M, K]  (K contiguous, "K-major")        -> forward / dgrad
+//   a_mn = 1 : A is stored [K, M]  (M contiguous, "MN-major")       -> wgrad (dW = dY^T X reads dY and X as they lie)
+//   b_mn likewise for B ([N, K] or [K, N]).
+// This replaces what the reference gets from nn.Linear/nn.Conv2d -> cuBLAS/cuDNN (nvit/model.py:99-101,130,148,155,
+// 226-228,259,262,286-304,329-332,341-344) and their autograd backward.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue.
+// Tile 128 x BN x 64, BN in {128, 256}; 4 (BN=256) or 6 (BN=128) smem stages; two TMEM accumulator stages so
+// the epilogue of tile i overlaps the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule
+// with n fastest so CTAs running together share the same A row-panel in L2.  Optional split along K (wgrad: K = B*T)
+// with fp32 red.add into the output.
+//
+// SWIGLU variant (model.py:148-154): B is the c_fc weight [2F, K]; each CTA tile takes 128 "u" rows j..j+127 and the
+// matching 128 "v" rows F+j.., so the accumulator holds u in TMEM columns [0,128) and v in [128,256) and the epilogue
+// emits x = (u*su) * silu(v*sv) directly (plus, optionally, the raw bf16 u|v for the backward pass).
+#include "common.cuh"
+#include <string.h>
+
+namespace nvit {
+
+struct alignas(64) GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  void* C;
+  __nv_bfloat16* C2;
+  const float* bias;      // [N] or null
+  const float* colscale;  // [N] ([2F] for swiglu) or null
+  const float* rowadd;    // [rowadd_period, N] or null
+  long long ldc, ldc2;
+  int M, N, K;
+  int out_f32, accumulate, atomic;
+  int rowadd_period;
+  int swiglu_half;
+  float colscale_mul;
+  int tiles_m, tiles_n, splits, kb_total, kb_per_split;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+struct GemmTraits {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int UMMA_K = 16;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // K-major SW128: 8 rows x 128 B per swizzle atom, atoms stacked along M/N every 1024 B.
+  // MN-major SW128: 64 elements (128 B) along M/N x 8 k-rows per atom; next 8 k-rows +1024 B; next 64 M/N elements
+  // is a separate TMA box of BK rows -> +BK*128 B.
+  static constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16;
+  static constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16;
+  static constexpr uint32_t SBO = 1024;
+  static constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K step
+  static constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+};
+
+__device__ __forceinline__ float silu_mul(float u, float v) { return u * v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v, int valid, bool vec) {
+  if (valid >= 32 && vec) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 o = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
+                           pack_bf16(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(dst + i) = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < valid) dst[i] = __float2bfloat16(v[i]);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU>
+__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using T = GemmTraits<BN, A_MN, B_MN>;
+  static_assert(!SWIGLU || (BN == 256 && !A_MN && !B_MN), "swiglu epilogue: 128x256 K-major tiles only");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + T::STAGES;
+  uint64_t* tmem_full = empty_bar + T::STAGES;
+  uint64_t* tmem_empty = tmem_full + T::ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + T::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = p.tiles_m * p.tiles_n * p.splits;
+  constexpr int TILE_N = SWIGLU ? 128 : BN;  // output columns covered by one tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    for (int i = 0; i < T::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < T::ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, T::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u % p.splits;
+        const int t = u / p.splits;
+        const int n_blk = t % p.tiles_n;
+        const int m_blk = t / p.tiles_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * T::STAGE_BYTES;
+          uint8_t* sB = sA + T::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(&p.tma_a, &full_bar[stage], sA, kb * T::BK, m_blk * T::BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < T::BM / 64; ++j)
+              tma_load_2d(&p.tma_a, &full_bar[stage], sA + j * (T::BK * 128), m_blk * T::BM + j * 64, kb * T::BK);
+          }
+          if constexpr (SWIGLU) {
+            tma_load_2d(&p.tma_b, &full_bar[stage], sB, kb * T::BK, n_blk * 128);
+            tma_load_2d(&p.tma_b, &full_bar[stage], sB + 128 * 128, kb * T::BK, p.swiglu_half + n_blk * 128);
+          } else if constexpr (!B_MN) {
+            tma_load_2d(&p.tma_b, &full_bar[stage], sB, kb * T::BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&p.tma_b, &full_bar[stage], sB + j * (T::BK * 128), n_blk * BN + j * 64, kb * T::BK);
+          }
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(T::BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int split = u % p.splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * T::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + T::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < T::BK / T::UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * T::A_KSTEP, T::A_LBO, T::SBO);
+            const uint64_t db = umma_smem_desc(b_addr + k * T::B_KSTEP, T::B_LBO, T::SBO);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
+    const bool vec2_ok = (p.C2 == nullptr) || ((p.ldc2 & 7) == 0);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int t = u / p.splits;
+      const int n_blk = t % p.tiles_n;
+      const int m_blk = t / p.tiles_n;
+      const int row = m_blk * T::BM + q * 32 + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      constexpr int NCHUNK = TILE_N / 32;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t r[32];
+        uint32_t r2[SWIGLU ? 32 : 1];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        if constexpr (SWIGLU) tmem_ld_32x32b_x32(taddr + 128 + c * 32, r2);
+        tmem_wait_ld();
+        if (c == NCHUNK - 1) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int n0 = n_blk * TILE_N + c * 32;
+        if (n0 < p.N && row < p.M) {
+          const int valid = min(32, p.N - n0);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if constexpr (SWIGLU) {
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = round_bf16(v[i]);  // the reference's c_fc output is bf16 under autocast
+              w[i] = round_bf16(__uint_as_float(r2[i]));
+            }
+            if (p.C2) {
+              store_bf16x32(p.C2 + static_cast<long long>(row) * p.ldc2 + n0, v, valid, vec2_ok);
+              store_bf16x32(p.C2 + static_cast<long long>(row) * p.ldc2 + p.swiglu_half + n0, w, valid, vec2_ok);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float su = 1.f, sv = 1.f;
+              if (p.colscale && i < valid) {
+                su = __ldg(p.colscale + n0 + i) * p.colscale_mul;
+                sv = __ldg(p.colscale + p.swiglu_half + n0 + i) * p.colscale_mul;
+              }
+              v[i] = silu_mul(v[i] * su, w[i] * sv);
+            }
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0, v, valid, vec_ok);
+          } else {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < valid) v[i] += __ldg(p.bias + n0 + i);
+            }
+            if (p.colscale) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < valid) v[i] *= __ldg(p.colscale + n0 + i) * p.colscale_mul;
+            }
+            if (p.rowadd) {
+              const float* ra = p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N + n0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < valid) v[i] += __ldg(ra + i);
+            }
+            if (p.out_f32) {
+              float* dst = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + n0;
+              if (p.atomic) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < valid) atomicAdd(dst + i, v[i]);
+              } else if (valid == 32 && vec_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                  if (p.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + i);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + i) = o;
+                }
+              } else {
+                for (int i = 0; i < valid; ++i) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
+              }
+              if (p.C2) store_bf16x32(p.C2 + static_cast<long long>(row) * p.ldc2 + n0, v, valid, vec2_ok);
+            } else {
+              store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + n0, v, valid, vec_ok);
+            }
+          }
+        }  // in bounds
+        __syncwarp();  // re-converge before the next warp-aligned tcgen05.ld
+      }
+      if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, T::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+// bf16 tensor map of rank 2 or 3 (dims innermost first, strides in elements for dims 1..rank-1), 128B swizzle.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    nvit_set_error("cuTensorMapEncodeTiled entry point not available");
+    return NVIT_ERR_DRIVER;
+  }
+  cuuint64_t d[3], s[2];
+  cuuint32_t b[3], e[3] = {1, 1, 1};
+  if (reinterpret_cast<uintptr_t>(base) & 15) {
+    nvit_set_error("TMA operand base %p must be 16-byte aligned", base);
+    return NVIT_ERR_ARG;
+  }
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    s[i] = strides_elems[i] * 2;
+    if (s[i] & 15) {
+      nvit_set_error("TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)strides_elems[i]);
+      return NVIT_ERR_ARG;
+    }
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nvit_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return NVIT_ERR_DRIVER;
+  }
+  return NVIT_OK;
+}
+
+static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                             uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t strides[1] = {pitch_elems};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU>
+static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
+  using T = GemmTraits<BN, A_MN, B_MN>;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&p.tma_a, A, p.K, p.M, lda, T::BK, T::BM);
+  else       rc = make_tmap_bf16_2d(&p.tma_a, A, p.M, p.K, lda, 64, T::BK);
+  if (rc) return rc;
+  if (SWIGLU)     rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, 2ull * p.swiglu_half, ldb, T::BK, 128);
+  else if (!B_MN) rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, p.N, ldb, T::BK, BN);
+  else            rc = make_tmap_bf16_2d(&p.tma_b, B, p.N, p.K, ldb, 64, T::BK);
+  if (rc) return rc;
+  constexpr int TILE_N = SWIGLU ? 128 : BN;
+  p.tiles_m = (p.M + T::BM - 1) / T::BM;
+  p.tiles_n = (p.N + TILE_N - 1) / TILE_N;
+  p.kb_total = (p.K + T::BK - 1) / T::BK;
+  int splits = p.splits < 1 ? 1 : p.splits;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.splits > 1) {
+    p.atomic = 1;
+    if (!p.accumulate)  // partial sums are red.add'ed into C: start from zero
+      NVIT_CUDA_CHECK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, p.N * sizeof(float), p.M, stream));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         T::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long units = 1ll * p.tiles_m * p.tiles_n * p.splits;
+  const int grid = (int)(units < nvit_num_sms() ? units : nvit_num_sms());
+  gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU><<<grid, 192, T::SMEM_BYTES, stream>>>(p);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+}  // namespace nvit
+
+using namespace nvit;
+
+extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
+                              int64_t lda, int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major,
+                              int out_f32, int accumulate, int splits, const float* bias, const float* colscale,
+                              float colscale_mul, const float* rowadd, int64_t rowadd_period, int64_t swiglu_half,
+                              void* stream) {
+  NVIT_REQUIRE(A && B && C, "nvit_gemm_bf16: null operand");
+  NVIT_REQUIRE(M > 0 && N > 0 && K > 0, "nvit_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  NVIT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "nvit_gemm_bf16: dimension overflow");
+  NVIT_REQUIRE(!(splits > 1) || out_f32, "nvit_gemm_bf16: split-K needs an fp32 output");
+  NVIT_REQUIRE(!accumulate || out_f32, "nvit_gemm_bf16: accumulate needs an fp32 output");
+  NVIT_REQUIRE(!C2_bf16 || out_f32 || swiglu_half > 0, "nvit_gemm_bf16: the bf16 side output goes with an fp32 or swiglu output");
+  NVIT_REQUIRE(!(splits > 1) || (!bias && !colscale && !rowadd && !C2_bf16), "nvit_gemm_bf16: split-K supports no epilogue");
+  NVIT_REQUIRE(!rowadd || rowadd_period > 0, "nvit_gemm_bf16: rowadd needs a positive period");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C;
+  p.C2 = reinterpret_cast<__nv_bfloat16*>(C2_bf16);
+  p.bias = bias;
+  p.colscale = colscale;
+  p.colscale_mul = colscale_mul;
+  p.rowadd = rowadd;
+  p.ldc = ldc;
+  p.ldc2 = ldc2;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.out_f32 = out_f32;
+  p.accumulate = accumulate;
+  p.atomic = 0;
+  p.rowadd_period = (int)(rowadd ? rowadd_period : 1);
+  p.splits = splits;
+  p.swiglu_half = (int)swiglu_half;
+  if (swiglu_half > 0) {
+    NVIT_REQUIRE(N == swiglu_half, "nvit_gemm_bf16: swiglu needs N == F");
+    NVIT_REQUIRE(!a_mn_major && !b_mn_major && !out_f32 && !accumulate && splits <= 1 && !bias && !rowadd,
+                 "nvit_gemm_bf16: swiglu supports K-major operands, bf16 output and the colscale epilogue only");
+    return launch_gemm<256, false, false, true>(p, A, B, lda, ldb, st);
+  }
+  // BN = 256 unless the problem is narrow enough that a 256-wide tile would be mostly padding.
+  const bool wide = (N > 128) && ((N % 256 == 0) || (N % 256 > 128) || N >= 1024);
+  const int sel = (wide ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_gemm<128, false, false, false>(p, A, B, lda, ldb, st);
+    case 1: return launch_gemm<128, false, true, false>(p, A, B, lda, ldb, st);
+    case 2: return launch_gemm<128, true, false, false>(p, A, B, lda, ldb, st);
+    case 3: return launch_gemm<128, true, true, false>(p, A, B, lda, ldb, st);
+    case 4: return launch_gemm<256, false, false, false>(p, A, B, lda, ldb, st);
+    case 5: return launch_gemm<256, false, true, false>(p, A, B, lda, ldb, st);
+    case 6: return launch_gemm<256, true, false, false>(p, A, B, lda, ldb, st);
+    default: return launch_gemm<256, true, true, false>(p, A, B, lda, ldb, st);
+  }
+}

@@ -1,0 +1,608 @@
+// HBM-streaming helper kernels of the nViT training step: casts, reductions, the unfused SiLU gate, im2col,
+// the pooled LayerNorm head, cross-entropy, the reconstruction loss, flat AdamW and the multi-tensor weight
+// normalization.  Each replaces a run of eager PyTorch ops at the reference lines cited in include/nvit_b200.h.
+#include "common.cuh"
+
+namespace nvit {
+
+static inline int stream_grid(long long work_items, int threads, int per_sm = 8) {
+  long long want = (work_items + threads - 1) / threads;
+  long long cap = 1ll * nvit_num_sms() * per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (w == 0) r = warp_max(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  return red[0];
+}
+
+// ------------------------------------------------------------------------------------------------ cast
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = 1ll * gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    for (; i < n8; i += stride) {
+      const float4 a = ldg_f4_stream(src + i * 8), b = ldg_f4_stream(src + i * 8 + 4);
+      uint4 o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      *reinterpret_cast<uint4*>(dst + i * 8) = o;
+    }
+    for (long long t = n8 * 8 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) dst[t] = __float2bfloat16(src[t]);
+  } else {
+    for (; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sum of squares
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  const long long stride = 1ll * gridDim.x * blockDim.x;
+  float acc = 0.f;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    const long long n4 = n >> 2;
+    for (; i < n4; i += stride) {
+      const float4 a = ldg_f4_stream(x + i * 4);
+      acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    for (long long t = n4 * 4 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc += x[t] * x[t];
+  } else {
+    for (; i < n; i += stride) acc += x[i] * x[i];
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, tot);
+}
+
+// ------------------------------------------------------------------------------------------------ column sums (bias grads)
+// grid.x over 256-column chunks (thread = column), grid.y over row slabs.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ldx,
+                                                          float* __restrict__ out, int rows_per_slab) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(M, r0 + rows_per_slab);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __bfloat162float(x[1ll * r * ldx + c]);
+  atomicAdd(out + c, acc);
+}
+
+// dpos[t,c] = sum_b dx[b,t,c]; dbias[c] += sum_t dpos[t,c].   grid (T, ceil(C/256)).
+__global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restrict__ dx, int B, int T, int C,
+                                                            float* __restrict__ dpos, float* __restrict__ dbias) {
+  const int t = blockIdx.x;
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += dx[(1ll * b * T + t) * C + c];
+  dpos[1ll * t * C + c] = acc;
+  if (dbias) atomicAdd(dbias + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ SiLU gate (unfused form)
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+// thread = 8 consecutive columns of F; grid.y = row slabs
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ uv, const float* __restrict__ suv,
+                                                         float suv_mul, __nv_bfloat16* __restrict__ xo, int M, int F,
+                                                         int rows_per_slab) {
+  const int c8 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c8 >= F) return;
+  float su[8], sv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    su[e] = suv ? suv[c8 + e] * suv_mul : 1.f;
+    sv[e] = suv ? suv[F + c8 + e] * suv_mul : 1.f;
+  }
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
+  for (int r = r0; r < r1; ++r) {
+    const __nv_bfloat16* row = uv + 2ll * r * F;
+    const uint4 uu = ldg_u4_stream(row + c8), vv = ldg_u4_stream(row + F + c8);
+    const uint32_t ua[4] = {uu.x, uu.y, uu.z, uu.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float u0 = bf16lo(ua[e]) * su[2 * e], u1 = bf16hi(ua[e]) * su[2 * e + 1];
+      const float v0 = bf16lo(va[e]) * sv[2 * e], v1 = bf16hi(va[e]) * sv[2 * e + 1];
+      o[e] = pack_bf16(u0 * v0 * sigmoidf_(v0), u1 * v1 * sigmoidf_(v1));
+    }
+    *reinterpret_cast<uint4*>(xo + 1ll * r * F + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ uv,
+                                                         const float* __restrict__ suv, float suv_mul,
+                                                         __nv_bfloat16* __restrict__ duv, float* __restrict__ dsuv, int M, int F,
+                                                         int rows_per_slab) {
+  const int c8 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c8 >= F) return;
+  float su[8], sv[8], gsu[8], gsv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    su[e] = suv ? suv[c8 + e] * suv_mul : 1.f;
+    sv[e] = suv ? suv[F + c8 + e] * suv_mul : 1.f;
+    gsu[e] = 0.f;
+    gsv[e] = 0.f;
+  }
+  const int r0 = blockIdx.y * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
+  for (int r = r0; r < r1; ++r) {
+    const __nv_bfloat16* row = uv + 2ll * r * F;
+    const uint4 uu = ldg_u4_stream(row + c8), vv = ldg_u4_stream(row + F + c8), dd = ldg_u4_stream(dx + 1ll * r * F + c8);
+    const uint32_t ua[4] = {uu.x, uu.y, uu.z, uu.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, da[4] = {dd.x, dd.y, dd.z, dd.w};
+    uint32_t ou[4], ov[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float du_[2], dv_[2];
+#pragma unroll
+      for (int hgh = 0; hgh < 2; ++hgh) {
+        const int k = 2 * e + hgh;
+        const float ur = hgh ? bf16hi(ua[e]) : bf16lo(ua[e]);
+        const float vr = hgh ? bf16hi(va[e]) : bf16lo(va[e]);
+        const float g = hgh ? bf16hi(da[e]) : bf16lo(da[e]);
+        const float u = ur * su[k], v = vr * sv[k];
+        const float sg = sigmoidf_(v);
+        const float gu = g * v * sg;                           // dL/d(u scaled)
+        const float gv = g * u * sg * (1.f + v * (1.f - sg));  // dL/d(v scaled)
+        gsu[k] += gu * ur;
+        gsv[k] += gv * vr;
+        du_[hgh] = gu * su[k];
+        dv_[hgh] = gv * sv[k];
+      }
+      ou[e] = pack_bf16(du_[0], du_[1]);
+      ov[e] = pack_bf16(dv_[0], dv_[1]);
+    }
+    __nv_bfloat16* drow = duv + 2ll * r * F;
+    *reinterpret_cast<uint4*>(drow + c8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    *reinterpret_cast<uint4*>(drow + F + c8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  }
+  if (dsuv) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(dsuv + c8 + e, gsu[e] * suv_mul);
+      atomicAdd(dsuv + F + c8 + e, gsv[e] * suv_mul);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+__device__ __forceinline__ int reflect_idx(int i, int S) {
+  if (i < 0) i = -i;
+  if (i >= S) i = 2 * (S - 1) - i;
+  return i;
+}
+// One thread per output element pair (kw even): out[(b,i,j), (c,kh,kw)] = img[b,c,refl(i*st+kh-pad),refl(j*st+kw-pad)]
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int ch,
+                                                     int S, int ks, int st, int pad, int g, long long total_pairs) {
+  const int K = ch * ks * ks;
+  const int halfK = K >> 1;
+  for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += 1ll * gridDim.x * blockDim.x) {
+    const long long m = idx / halfK;
+    const int k = (int)(idx - m * halfK) * 2;
+    const int c = k / (ks * ks);
+    const int rem = k - c * ks * ks;
+    const int kh = rem / ks, kw = rem - kh * ks;
+    const int b = (int)(m / (g * g));
+    const int ij = (int)(m - 1ll * b * g * g);
+    const int i = ij / g, j = ij - i * g;
+    const int y = reflect_idx(i * st + kh - pad, S);
+    const int x0 = reflect_idx(j * st + kw - pad, S), x1 = reflect_idx(j * st + kw + 1 - pad, S);
+    const float* src = img + ((1ll * b * ch + c) * S + y) * S;
+    *reinterpret_cast<uint32_t*>(out + m * K + k) = pack_bf16(__ldg(src + x0), __ldg(src + x1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooled LayerNorm head
+// One CTA per image: mean over T (coalesced over C), LayerNorm over C; saves xhat and rstd for backward.
+__global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
+                                                          float* __restrict__ xhat, float* __restrict__ rstd, int T, int C) {
+  extern __shared__ float s_pool[];  // [C]
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float invT = 1.f / (float)T;
+  float lsum = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    const float* p = h + (1ll * b * T) * C + c;
+    for (int t = 0; t < T; ++t) acc += p[1ll * t * C];
+    acc *= invT;
+    s_pool[c] = acc;
+    lsum += acc;
+  }
+  const float mean = block_sum(lsum, red) / (float)C;
+  float lvar = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float d = s_pool[c] - mean;
+    lvar += d * d;
+  }
+  const float var = block_sum(lvar, red) / (float)C;
+  const float rs = rsqrtf(var + eps);
+  if (threadIdx.x == 0) rstd[b] = rs;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float xh = (s_pool[c] - mean) * rs;
+    xhat[1ll * b * C + c] = xh;
+    y[1ll * b * C + c] = __float2bfloat16(xh * gamma[c] + beta[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ gamma,
+                                                          const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                          float* __restrict__ dh, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int T, int C) {
+  extern __shared__ float s_dp[];  // [C]
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = __bfloat162float(dy[1ll * b * C + c]);
+    const float xh = xhat[1ll * b * C + c];
+    const float gx = g * gamma[c];
+    s1 += gx;
+    s2 += gx * xh;
+    atomicAdd(dgamma + c, g * xh);
+    atomicAdd(dbeta + c, g);
+  }
+  const float m1 = block_sum(s1, red) / (float)C;
+  const float m2 = block_sum(s2, red) / (float)C;
+  const float rs = rstd[b];
+  const float invT = 1.f / (float)T;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = __bfloat162float(dy[1ll * b * C + c]);
+    const float xh = xhat[1ll * b * C + c];
+    s_dp[c] = (g * gamma[c] - m1 - xh * m2) * rs * invT;
+  }
+  __syncthreads();
+  const int C4 = C >> 2;  // C % 4 == 0 checked on the host
+  float4* out = reinterpret_cast<float4*>(dh + 1ll * b * T * C);
+  const float4* sp = reinterpret_cast<const float4*>(s_dp);
+  for (int i = threadIdx.x; i < T * C4; i += blockDim.x) out[i] = sp[i % C4];
+}
+
+// logits = raw * sz_eff backward
+__global__ void __launch_bounds__(256) head_scale_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ raw,
+                                                             const float* __restrict__ sz, float sz_mul,
+                                                             __nv_bfloat16* __restrict__ draw, float* __restrict__ dsz, int B, int N,
+                                                             long long ld) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float s = sz ? sz[n] * sz_mul : 1.f;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float g = dlogits[1ll * b * N + n];
+    acc += g * raw[1ll * b * N + n];
+    draw[1ll * b * ld + n] = __float2bfloat16(g * s);
+  }
+  if (dsz) atomicAdd(dsz + n, acc * sz_mul);
+}
+
+// softmax cross-entropy, one CTA per sample
+__global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                            float* __restrict__ loss, float* __restrict__ dlogits, float gscale, int B,
+                                                            int N) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* row = logits + 1ll * b * N;
+  float mx = -INFINITY;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, row[n]);
+  mx = block_max(mx, red);
+  float se = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) se += __expf(row[n] - mx);
+  se = block_sum(se, red);
+  const float lse = mx + __logf(se);
+  const int t = (int)target[b];
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, (lse - row[t]) / (float)B);
+  if (dlogits) {
+    const float k = gscale / (float)B;
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+      dlogits[1ll * b * N + n] = (__expf(row[n] - lse) - (n == t ? 1.f : 0.f)) * k;
+  }
+}
+
+__global__ void __launch_bounds__(256) tanh_mse_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
+                                                       long long n, float inv_count, float* __restrict__ out) {
+  __shared__ float red[32];
+  const long long n8 = n >> 3;
+  const long long stride = 1ll * gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 p = ldg_u4_stream(pred + i * 8), t = ldg_u4_stream(tgt + i * 8);
+    const uint32_t pa[4] = {p.x, p.y, p.z, p.w}, ta[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = tanhf(bf16lo(pa[e])) - bf16lo(ta[e]);
+      const float d1 = tanhf(bf16hi(pa[e])) - bf16hi(ta[e]);
+      acc += d0 * d0 + d1 * d1;
+    }
+  }
+  for (long long i = n8 * 8 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = tanhf(__bfloat162float(pred[i])) - __bfloat162float(tgt[i]);
+    acc += d * d;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, tot * inv_count);
+}
+
+// ------------------------------------------------------------------------------------------------ AdamW (flat)
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n, long long n_decay, float lr, float b1,
+                                                         float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                         const float* __restrict__ gnorm_sq, float max_norm) {
+  float clip = 1.f;
+  if (gnorm_sq) {
+    const float tot = sqrtf(gnorm_sq[0]);
+    clip = fminf(1.f, max_norm / (tot + 1e-6f));
+  }
+  const float step_size = lr / bc1;
+  const float decay = 1.f - lr * wd;
+  const long long n4 = n >> 2;
+  const long long stride = 1ll * gridDim.x * blockDim.x;
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = *reinterpret_cast<const float4*>(p + i * 4);
+    const float4 gg = ldg_f4_stream(g + i * 4);
+    float4 mm = *reinterpret_cast<const float4*>(m + i * 4);
+    float4 vv = *reinterpret_cast<const float4*>(v + i * 4);
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = ga[e] * clip;
+      if (i * 4 + e < n_decay) pa[e] *= decay;
+      ma[e] = b1 * ma[e] + (1.f - b1) * gr;
+      va[e] = b2 * va[e] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[e]) / bc2_sqrt + eps;
+      pa[e] -= step_size * (ma[e] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i * 4) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    *reinterpret_cast<float4*>(m + i * 4) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    *reinterpret_cast<float4*>(v + i * 4) = make_float4(va[0], va[1], va[2], va[3]);
+  }
+  for (long long i = n4 * 4 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gr = g[i] * clip;
+    float pe = p[i];
+    if (i < n_decay) pe *= decay;
+    const float me = b1 * m[i] + (1.f - b1) * gr;
+    const float ve = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = me;
+    v[i] = ve;
+    p[i] = pe - step_size * (me / (sqrtf(ve) / bc2_sqrt + eps));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight normalization
+// table entry: {w ptr, w16 ptr, rows, cols, axis, first_unit}.  256 threads per CTA, one unit per CTA iteration.
+//   axis 1: unit = 8 rows, one warp per row (cols contiguous).
+//   axis 0: unit = 32 columns; thread (tx = threadIdx%32 -> column, ty = threadIdx/32 -> row phase); two passes, the
+//           second re-reads the slab from L2.
+__global__ void __launch_bounds__(256) weight_norm_multi_kernel(const long long* __restrict__ table, int n_tensors,
+                                                                long long total_units) {
+  __shared__ float s_part[8][33];
+  __shared__ float s_inv[32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  for (long long unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    int lo = 0, hi = n_tensors - 1;  // last tensor with first_unit <= unit
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid * 6 + 5] <= unit) lo = mid; else hi = mid - 1;
+    }
+    const long long* e = table + lo * 6;
+    float* w = reinterpret_cast<float*>(e[0]);
+    __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(e[1]);
+    const int rows = (int)e[2], cols = (int)e[3], axis = (int)e[4];
+    const int u = (int)(unit - e[5]);
+    if (axis == 1) {
+      const int r = u * 8 + wy;
+      if (r < rows) {
+        float* row = w + 1ll * r * cols;
+        float ss = 0.f;
+        for (int c = lane; c < cols; c += 32) { const float x = row[c]; ss += x * x; }
+        ss = warp_sum(ss);
+        const float inv = 1.f / sqrtf(ss);
+        for (int c = lane; c < cols; c += 32) {
+          const float x = row[c] * inv;
+          row[c] = x;
+          if (w16) w16[1ll * r * cols + c] = __float2bfloat16(x);
+        }
+      }
+    } else {
+      const int c = u * 32 + lane;
+      float ss = 0.f;
+      if (c < cols)
+        for (int r = wy; r < rows; r += 8) { const float x = w[1ll * r * cols + c]; ss += x * x; }
+      s_part[wy][lane] = ss;
+      __syncthreads();
+      if (wy == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
+        s_inv[lane] = 1.f / sqrtf(t);
+      }
+      __syncthreads();
+      if (c < cols) {
+        const float inv = s_inv[lane];
+        for (int r = wy; r < rows; r += 8) {
+          const float x = w[1ll * r * cols + c] * inv;
+          w[1ll * r * cols + c] = x;
+          if (w16) w16[1ll * r * cols + c] = __float2bfloat16(x);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace nvit
+
+using namespace nvit;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int nvit_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  NVIT_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "nvit_cast_f32_to_bf16: bad arguments");
+  if (n == 0) return NVIT_OK;
+  cast_f32_bf16_kernel<<<stream_grid(n / 8 + 1, 256), 256, 0, ST(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream) {
+  NVIT_REQUIRE(n >= 0 && out_accum && (n == 0 || x), "nvit_sumsq_f32: bad arguments");
+  if (n == 0) return NVIT_OK;
+  sumsq_kernel<<<stream_grid(n / 4 + 1, 256, 4), 256, 0, ST(stream)>>>(x, n, out_accum);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ldx, float* out_accum, void* stream) {
+  NVIT_REQUIRE(x && out_accum && M >= 0 && N > 0 && ldx >= N, "nvit_colsum_bf16: bad arguments");
+  if (M == 0) return NVIT_OK;
+  const int gx = (int)((N + 255) / 256);
+  int slabs = (nvit_num_sms() * 4 + gx - 1) / gx;
+  if (slabs > M) slabs = (int)M;
+  const int rps = (int)((M + slabs - 1) / slabs);
+  dim3 grid(gx, (unsigned)((M + rps - 1) / rps));
+  colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), (int)M, (int)N, ldx, out_accum, rps);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_pos_bias_grad(const float* dx, int64_t B, int64_t T, int64_t C, float* dpos, float* dbias_accum, void* stream) {
+  NVIT_REQUIRE(dx && dpos && B > 0 && T > 0 && C > 0, "nvit_pos_bias_grad: bad arguments");
+  dim3 grid((unsigned)T, (unsigned)((C + 255) / 256));
+  pos_bias_grad_kernel<<<grid, 256, 0, ST(stream)>>>(dx, (int)B, (int)T, (int)C, dpos, dbias_accum);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+static void slab_grid(int64_t M, int64_t F, dim3* grid, int* rps) {
+  const int gx = (int)((F / 8 + 255) / 256);
+  int slabs = (nvit_num_sms() * 8 + gx - 1) / gx;
+  if (slabs > M) slabs = (int)M;
+  if (slabs < 1) slabs = 1;
+  *rps = (int)((M + slabs - 1) / slabs);
+  *grid = dim3(gx, (unsigned)((M + *rps - 1) / *rps));
+}
+
+extern "C" int nvit_swiglu_fwd(const void* uv, const float* suv, float suv_mul, void* x, int64_t M, int64_t F, void* stream) {
+  NVIT_REQUIRE(uv && x && M >= 0 && F > 0 && (F % 8) == 0, "nvit_swiglu_fwd: F=%lld must be a positive multiple of 8", (long long)F);
+  if (M == 0) return NVIT_OK;
+  dim3 grid; int rps;
+  slab_grid(M, F, &grid, &rps);
+  swiglu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(uv), suv, suv_mul, static_cast<__nv_bfloat16*>(x), (int)M, (int)F, rps);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_swiglu_bwd(const void* dx, const void* uv, const float* suv, float suv_mul, void* duv, float* dsuv_accum,
+                               int64_t M, int64_t F, void* stream) {
+  NVIT_REQUIRE(dx && uv && duv && M >= 0 && F > 0 && (F % 8) == 0, "nvit_swiglu_bwd: bad arguments (F=%lld)", (long long)F);
+  NVIT_REQUIRE((suv == nullptr) == (dsuv_accum == nullptr), "nvit_swiglu_bwd: suv and dsuv go together");
+  if (M == 0) return NVIT_OK;
+  dim3 grid; int rps;
+  slab_grid(M, F, &grid, &rps);
+  swiglu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
+                                                  static_cast<__nv_bfloat16*>(duv), dsuv_accum, (int)M, (int)F, rps);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_im2col_bf16(const float* img, void* out, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
+                                int64_t pad, void* stream) {
+  NVIT_REQUIRE(img && out && B > 0 && ch > 0 && S > 0 && ksize > 0 && stride > 0 && pad >= 0, "nvit_im2col_bf16: bad arguments");
+  NVIT_REQUIRE((ksize % 2) == 0, "nvit_im2col_bf16: kernel size must be even");
+  NVIT_REQUIRE(pad < S, "nvit_im2col_bf16: reflect padding must be smaller than the image");
+  NVIT_REQUIRE((S + 2 * pad - ksize) % stride == 0, "nvit_im2col_bf16: (S + 2 pad - k) must be a multiple of the stride");
+  const int g = (int)((S + 2 * pad - ksize) / stride + 1);
+  const long long total_pairs = 1ll * B * g * g * ch * ksize * ksize / 2;
+  im2col_kernel<<<stream_grid(total_pairs, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
+                                                                          (int)ksize, (int)stride, (int)pad, g, total_pairs);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_pool_ln_fwd(const float* h, const float* gamma, const float* beta, float eps, void* y, float* xhat, float* rstd,
+                                int64_t B, int64_t T, int64_t C, void* stream) {
+  NVIT_REQUIRE(h && gamma && beta && y && xhat && rstd && B > 0 && T > 0 && C > 0, "nvit_pool_ln_fwd: bad arguments");
+  NVIT_REQUIRE(C * sizeof(float) <= 48 * 1024, "nvit_pool_ln_fwd: C too large");
+  pool_ln_fwd_kernel<<<(unsigned)B, 256, C * sizeof(float), ST(stream)>>>(h, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), xhat, rstd, (int)T, (int)C);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_pool_ln_bwd(const void* dy, const float* gamma, const float* xhat, const float* rstd, float* dh, float* dgamma,
+                                float* dbeta, int64_t B, int64_t T, int64_t C, void* stream) {
+  NVIT_REQUIRE(dy && gamma && xhat && rstd && dh && dgamma && dbeta && B > 0 && T > 0 && C > 0, "nvit_pool_ln_bwd: bad arguments");
+  NVIT_REQUIRE((C % 4) == 0 && C * sizeof(float) <= 48 * 1024, "nvit_pool_ln_bwd: C must be a multiple of 4 and fit shared memory");
+  pool_ln_bwd_kernel<<<(unsigned)B, 256, C * sizeof(float), ST(stream)>>>(static_cast<const __nv_bfloat16*>(dy), gamma, xhat, rstd, dh, dgamma, dbeta, (int)T, (int)C);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_head_scale_bwd(const float* dlogits, const float* raw, const float* sz, float sz_mul, void* draw, float* dsz,
+                                   int64_t B, int64_t N, int64_t ld_draw, void* stream) {
+  NVIT_REQUIRE(dlogits && raw && draw && B > 0 && N > 0 && ld_draw >= N, "nvit_head_scale_bwd: bad arguments");
+  head_scale_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ST(stream)>>>(dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_cross_entropy(const float* logits, const int64_t* target, float* loss, float* dlogits, float gscale, int64_t B,
+                                  int64_t N, void* stream) {
+  NVIT_REQUIRE(logits && target && B > 0 && N > 0 && (loss || dlogits), "nvit_cross_entropy: bad arguments");
+  cross_entropy_kernel<<<(unsigned)B, 256, 0, ST(stream)>>>(logits, reinterpret_cast<const long long*>(target), loss, dlogits, gscale, (int)B, (int)N);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_tanh_mse(const void* pred, const void* target, int64_t n, float inv_count, float* out_accum, void* stream) {
+  NVIT_REQUIRE(pred && target && out_accum && n >= 0, "nvit_tanh_mse: bad arguments");
+  if (n == 0) return NVIT_OK;
+  tanh_mse_kernel<<<stream_grid(n / 8 + 1, 256, 4), 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(target), n, inv_count, out_accum);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, int64_t step, const float* gnorm_sq, float max_norm,
+                               void* stream) {
+  NVIT_REQUIRE(p && g && m && v && n >= 0 && n_decay >= 0 && n_decay <= n && step >= 1, "nvit_adamw_flat: bad arguments");
+  NVIT_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+               "nvit_adamw_flat: buffers must be 16-byte aligned");
+  if (n == 0) return NVIT_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adamw_flat_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, n_decay, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                                       (float)sqrt(bc2), gnorm_sq, max_norm);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_weight_norm_multi(const int64_t* table_dev, int64_t n_tensors, int64_t total_units, void* stream) {
+  NVIT_REQUIRE(table_dev && n_tensors > 0 && total_units > 0, "nvit_weight_norm_multi: bad arguments");
+  const long long cap = 1ll * nvit_num_sms() * 8;
+  const int grid = (int)(total_units < cap ? total_units : cap);
+  weight_norm_multi_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table_dev), (int)n_tensors, total_units);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}

@@ -1,0 +1,337 @@
+// Normalized residual update of nViT, forward and backward, as ONE HBM-streaming kernel each.
+//
+//   lr  = |alpha * alpha_mul|
+//   o   = N( N(h) + lr * (N(x) - N(h)) )          (nvit/model.py:134-142, 159-167, 265-273)
+//   out = N( o * skip + h0 )   when h0 != NULL    (Block.norm_skip, nvit/model.py:84-87, applied at 450-452)
+//
+// The reference runs ~11 (+3) eager kernels with fp32 [M,C] temporaries for this; here one warp owns one row, holds it
+// in registers (C/128 float4 per lane), reduces with warp shuffles and touches HBM exactly once per operand:
+//   fwd : read h (fp32) + x (bf16) [+ h0 (fp32)], write out (fp32 + bf16)
+//   bwd : read g, h, x [, h0], write dh, dx [, dh0]; per-channel dalpha and scalar dskip reduced in-CTA then atomically.
+// No epsilon anywhere, as in the reference (a zero row gives NaN there too).
+#include "common.cuh"
+
+namespace nvit {
+
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_bf4(__nv_bfloat16* p, const float* v) {
+  uint2 o = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+  *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ void ld_bf4(const __nv_bfloat16* p, float* v) {
+  const uint2 u = ldg_u2_stream(p);
+  v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+}
+__device__ __forceinline__ void ld_f4(const float* p, float* v) {
+  const float4 f = ldg_f4_stream(p);
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+
+template <int NV, bool SKIP>
+__global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ alpha, float alpha_mul,
+                                                           const float* __restrict__ h0, const float* __restrict__ skip,
+                                                           float* __restrict__ out32, __nv_bfloat16* __restrict__ out16,
+                                                           int M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float lr[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lr[j][e] = (c < C) ? fabsf(alpha[c + e] * alpha_mul) : 0.f;
+  }
+  const float s = SKIP ? skip[0] : 0.f;
+  for (int row = warp; row < M; row += nwarps) {
+    const size_t base = static_cast<size_t>(row) * C;
+    float hv[NV][4], xv[NV][4], h0v[NV][4];
+    float ssh = 0.f, ssx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        ld_f4(h + base + c, hv[j]);
+        ld_bf4(x + base + c, xv[j]);
+        if (SKIP) ld_f4(h0 + base + c, h0v[j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { hv[j][e] = 0.f; xv[j][e] = 0.f; h0v[j][e] = 0.f; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ssh += hv[j][e] * hv[j][e]; ssx += xv[j][e] * xv[j][e]; }
+    }
+    ssh = warp_sum(ssh);
+    ssx = warp_sum(ssx);
+    const float invh = 1.f / sqrtf(ssh), invx = 1.f / sqrtf(ssx);
+    float ssz = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = hv[j][e] * invh, b = xv[j][e] * invx;
+        const float z = a + lr[j][e] * (b - a);
+        hv[j][e] = z;
+        ssz += z * z;
+      }
+    ssz = warp_sum(ssz);
+    float inv = 1.f / sqrtf(ssz);
+    if (SKIP) {
+      float ssy = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = hv[j][e] * inv * s + h0v[j][e];
+          hv[j][e] = y;
+          ssy += y * y;
+        }
+      ssy = warp_sum(ssy);
+      inv = 1.f / sqrtf(ssy);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = hv[j][e] * inv;
+        if (out32) st_f4(out32 + base + c, make_float4(o[0], o[1], o[2], o[3]));
+        if (out16) st_bf4(out16 + base + c, o);
+      }
+    }
+  }
+}
+
+template <int NV, bool SKIP>
+__global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h,
+                                                           const __nv_bfloat16* __restrict__ x, const float* __restrict__ alpha,
+                                                           float alpha_mul, const float* __restrict__ h0,
+                                                           const float* __restrict__ skip, float* __restrict__ dh,
+                                                           int dh_accumulate, __nv_bfloat16* __restrict__ dx,
+                                                           float* __restrict__ dh0, float* __restrict__ dalpha,
+                                                           float* __restrict__ dskip, int M, int C) {
+  extern __shared__ float s_dlr[];  // [C] per-CTA reduction of d lr
+  __shared__ float s_dskip;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_dlr[c] = 0.f;
+  if (threadIdx.x == 0) s_dskip = 0.f;
+  __syncthreads();
+
+  float lr[NV][4], dlr[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      lr[j][e] = (c < C) ? fabsf(alpha[c + e] * alpha_mul) : 0.f;
+      dlr[j][e] = 0.f;
+    }
+  }
+  const float s = SKIP ? skip[0] : 0.f;
+  float ds_acc = 0.f;
+
+  for (int row = warp; row < M; row += nwarps) {
+    const size_t base = static_cast<size_t>(row) * C;
+    float av[NV][4], bv[NV][4], gv[NV][4], ov[NV][4];
+    float ssh = 0.f, ssx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        ld_f4(h + base + c, av[j]);
+        ld_bf4(x + base + c, bv[j]);
+        ld_f4(g + base + c, gv[j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { av[j][e] = 0.f; bv[j][e] = 0.f; gv[j][e] = 0.f; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ssh += av[j][e] * av[j][e]; ssx += bv[j][e] * bv[j][e]; }
+    }
+    ssh = warp_sum(ssh);
+    ssx = warp_sum(ssx);
+    const float invh = 1.f / sqrtf(ssh), invx = 1.f / sqrtf(ssx);
+    float ssz = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        av[j][e] *= invh;
+        bv[j][e] *= invx;
+        const float z = av[j][e] + lr[j][e] * (bv[j][e] - av[j][e]);
+        ov[j][e] = z;
+        ssz += z * z;
+      }
+    ssz = warp_sum(ssz);
+    const float invz = 1.f / sqrtf(ssz);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ov[j][e] *= invz;
+
+    if (SKIP) {
+      // y = o*s + h0 ; out = y/|y| ; g is dL/dout
+      float ssy = 0.f, gy = 0.f;
+      float yv[NV][4];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        float h0v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < C) ld_f4(h0 + base + c, h0v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = ov[j][e] * s + h0v[e];
+          yv[j][e] = y;
+          ssy += y * y;
+          gy += gv[j][e] * y;
+        }
+      }
+      ssy = warp_sum(ssy);
+      gy = warp_sum(gy);
+      const float invy = 1.f / sqrtf(ssy);
+      const float gdot = gy * invy;  // g . out
+      float dso = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        float dy[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dy[e] = (gv[j][e] - yv[j][e] * invy * gdot) * invy;
+          dso += dy[e] * ov[j][e];
+          gv[j][e] = dy[e] * s;  // dL/do
+        }
+        if (c < C) st_f4(dh0 + base + c, make_float4(dy[0], dy[1], dy[2], dy[3]));
+      }
+      ds_acc += dso;  // lane-partial; reduced at the end
+    }
+
+    float odot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) odot += gv[j][e] * ov[j][e];
+    odot = warp_sum(odot);
+    float adot = 0.f, bdot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float dz = (gv[j][e] - ov[j][e] * odot) * invz;
+        dlr[j][e] += dz * (bv[j][e] - av[j][e]);
+        const float da = dz * (1.f - lr[j][e]);
+        const float db = dz * lr[j][e];
+        adot += da * av[j][e];
+        bdot += db * bv[j][e];
+        gv[j][e] = da;
+        ov[j][e] = db;
+      }
+    adot = warp_sum(adot);
+    bdot = warp_sum(bdot);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (j * 32 + lane) * 4;
+      if (c < C) {
+        float o[4], d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          d[e] = (gv[j][e] - av[j][e] * adot) * invh;
+          o[e] = (ov[j][e] - bv[j][e] * bdot) * invx;
+        }
+        if (dh_accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(dh + base + c);
+          d[0] += old.x; d[1] += old.y; d[2] += old.z; d[3] += old.w;
+        }
+        st_f4(dh + base + c, make_float4(d[0], d[1], d[2], d[3]));
+        st_bf4(dx + base + c, o);
+      }
+    }
+  }
+
+  // CTA-level reduction of the per-channel / scalar parameter gradients, then one atomic per channel per CTA.
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&s_dlr[c + e], dlr[j][e]);
+    }
+  }
+  if (SKIP) {
+    ds_acc = warp_sum(ds_acc);
+    if (lane == 0) atomicAdd(&s_dskip, ds_acc);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float am = alpha[c] * alpha_mul;
+    const float sgn = (am > 0.f) ? 1.f : ((am < 0.f) ? -1.f : 0.f);  // d|u|/du, torch.abs backward convention
+    atomicAdd(dalpha + c, s_dlr[c] * sgn * alpha_mul);
+  }
+  if (SKIP && threadIdx.x == 0) atomicAdd(dskip, s_dskip);
+}
+
+static int residual_grid(int M) {
+  const int rows_per_cta = 8;
+  const int want = (M + rows_per_cta - 1) / rows_per_cta;
+  const int cap = nvit_num_sms() * 4;
+  return want < cap ? want : cap;
+}
+
+}  // namespace nvit
+
+using namespace nvit;
+
+#define NVIT_DISPATCH_NV(C, ...)                                  \
+  do {                                                            \
+    if (C <= 128) { constexpr int NV = 1; __VA_ARGS__ }           \
+    else if (C <= 256) { constexpr int NV = 2; __VA_ARGS__ }      \
+    else if (C <= 512) { constexpr int NV = 4; __VA_ARGS__ }      \
+    else if (C <= 768) { constexpr int NV = 6; __VA_ARGS__ }      \
+    else { constexpr int NV = 8; __VA_ARGS__ }                    \
+  } while (0)
+
+extern "C" int nvit_residual_fwd(const float* h, const void* x_bf16, const float* alpha, float alpha_mul, const float* h0,
+                                 const float* skip, float* out_f32, void* out_bf16, int64_t M, int64_t C, void* stream) {
+  NVIT_REQUIRE(h && x_bf16 && alpha, "nvit_residual_fwd: null input");
+  NVIT_REQUIRE(out_f32 || out_bf16, "nvit_residual_fwd: no output requested");
+  NVIT_REQUIRE((h0 == nullptr) == (skip == nullptr), "nvit_residual_fwd: h0 and skip go together");
+  NVIT_REQUIRE(M >= 0 && M < (1ll << 31), "nvit_residual_fwd: bad M");
+  NVIT_REQUIRE(C > 0 && C <= 1024 && (C % 4) == 0, "nvit_residual_fwd: C=%lld must be a multiple of 4, at most 1024", (long long)C);
+  if (M == 0) return NVIT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = residual_grid((int)M);
+  auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  auto ob = static_cast<__nv_bfloat16*>(out_bf16);
+  NVIT_DISPATCH_NV(C, {
+    if (h0) residual_fwd_kernel<NV, true><<<grid, 256, 0, st>>>(h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
+    else    residual_fwd_kernel<NV, false><<<grid, 256, 0, st>>>(h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
+  });
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_bf16, const float* alpha, float alpha_mul,
+                                 const float* h0, const float* skip, float* dh, int dh_accumulate, void* dx_bf16, float* dh0,
+                                 float* dalpha_accum, float* dskip_accum, int64_t M, int64_t C, void* stream) {
+  NVIT_REQUIRE(g && h && x_bf16 && alpha && dh && dx_bf16 && dalpha_accum, "nvit_residual_bwd: null argument");
+  NVIT_REQUIRE((h0 == nullptr) == (skip == nullptr), "nvit_residual_bwd: h0 and skip go together");
+  NVIT_REQUIRE(!h0 || (dh0 && dskip_accum), "nvit_residual_bwd: skip form needs dh0 and dskip");
+  NVIT_REQUIRE(M >= 0 && M < (1ll << 31), "nvit_residual_bwd: bad M");
+  NVIT_REQUIRE(C > 0 && C <= 1024 && (C % 4) == 0, "nvit_residual_bwd: C=%lld must be a multiple of 4, at most 1024", (long long)C);
+  if (M == 0) return NVIT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = residual_grid((int)M);
+  const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  auto dxb = static_cast<__nv_bfloat16*>(dx_bf16);
+  NVIT_DISPATCH_NV(C, {
+    if (h0) residual_bwd_kernel<NV, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dh_accumulate, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else    residual_bwd_kernel<NV, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dh_accumulate, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+  });
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}

@@ -1,0 +1,151 @@
+"""Thin tensor-level wrappers over the C ABI (include/nvit_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes CUDA tensors, passes their raw
+pointers plus the current CUDA stream to libnvit_b200.so and returns nothing (outputs are caller-allocated).
+No function has a PyTorch/CPU fallback; non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _p(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("nvit_b200 ops need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+
+
+def gemm(a, b, c, *, M, N, K, lda, ldb, ldc, a_mn=False, b_mn=False, accumulate=False, splits=1, bias=None,
+         colscale=None, colscale_mul=1.0, rowadd=None, rowadd_period=0, c2=None, ldc2=0, swiglu_half=0):
+    """c[M,N] (+)= a @ b^T on tcgen05 (see nvit_gemm_bf16).  c.dtype selects fp32 or bf16 output."""
+    out_f32 = 1 if c.dtype == F32 else 0
+    _lib.call("nvit_gemm_bf16", _p(a), _p(b), _p(c), _p(c2), M, N, K, lda, ldb, ldc, ldc2, int(a_mn), int(b_mn), out_f32,
+              int(accumulate), splits, _p(bias), _p(colscale), float(colscale_mul), _p(rowadd), rowadd_period, swiglu_half,
+              _stream())
+
+
+def linear_fwd(x, w, out, *, bias=None, colscale=None, colscale_mul=1.0, rowadd=None, rowadd_period=0, c2=None):
+    """out[M,N] = x[M,K] @ w[N,K]^T (+ epilogue).  x, w bf16 row-major (views with a row pitch are fine)."""
+    M, K = x.shape
+    N = w.shape[0]
+    gemm(x, w, out, M=M, N=N, K=K, lda=x.stride(0), ldb=w.stride(0), ldc=out.stride(0), bias=bias, colscale=colscale,
+         colscale_mul=colscale_mul, rowadd=rowadd, rowadd_period=rowadd_period, c2=c2, ldc2=(c2.stride(0) if c2 is not None else 0))
+
+
+def linear_dgrad(dy, w, dx, *, accumulate=False):
+    """dx[M,K] (+)= dy[M,N] @ w[N,K]  — B operand is w as it lies (MN-major)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    gemm(dy, w, dx, M=M, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), b_mn=True, accumulate=accumulate)
+
+
+def linear_wgrad(dy, x, dw, *, splits=1, accumulate=False):
+    """dw[N,K] (+)= dy[M,N]^T @ x[M,K] — both operands read as they lie (MN-major), fp32 output."""
+    M, N = dy.shape
+    K = x.shape[1]
+    gemm(dy, x, dw, M=N, N=K, K=M, lda=dy.stride(0), ldb=x.stride(0), ldc=dw.stride(0), a_mn=True, b_mn=True, splits=splits,
+         accumulate=accumulate)
+
+
+def cast_bf16(src, dst):
+    _lib.call("nvit_cast_f32_to_bf16", _p(src), _p(dst), src.numel(), _stream())
+
+
+def sumsq(x, out):
+    _lib.call("nvit_sumsq_f32", _p(x), x.numel(), _p(out), _stream())
+
+
+def colsum(x, out):
+    _lib.call("nvit_colsum_bf16", _p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream())
+
+
+def pos_bias_grad(dx, B, T, C, dpos, dbias):
+    _lib.call("nvit_pos_bias_grad", _p(dx), B, T, C, _p(dpos), _p(dbias), _stream())
+
+
+def residual_fwd(h, x, alpha, alpha_mul, out32, out16, h0=None, skip=None):
+    M, C = h.shape
+    _lib.call("nvit_residual_fwd", _p(h), _p(x), _p(alpha), float(alpha_mul), _p(h0), _p(skip), _p(out32), _p(out16), M, C, _stream())
+
+
+def residual_bwd(g, h, x, alpha, alpha_mul, dh, dx, dalpha, *, dh_accumulate=False, h0=None, skip=None, dh0=None, dskip=None):
+    M, C = h.shape
+    _lib.call("nvit_residual_bwd", _p(g), _p(h), _p(x), _p(alpha), float(alpha_mul), _p(h0), _p(skip), _p(dh), int(dh_accumulate),
+              _p(dx), _p(dh0), _p(dalpha), _p(dskip), M, C, _stream())
+
+
+def swiglu_fwd(uv, suv, suv_mul, x):
+    M, F2 = uv.shape
+    _lib.call("nvit_swiglu_fwd", _p(uv), _p(suv), float(suv_mul), _p(x), M, F2 // 2, _stream())
+
+
+def swiglu_bwd(dx, uv, suv, suv_mul, duv, dsuv):
+    M, F2 = uv.shape
+    _lib.call("nvit_swiglu_bwd", _p(dx), _p(uv), _p(suv), float(suv_mul), _p(duv), _p(dsuv), M, F2 // 2, _stream())
+
+
+def attention_fwd(q, k, v, sqk, sqk_mul, scale, out, lse, B, H, T, D=64):
+    _lib.call("nvit_attention_fwd", _p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(sqk), float(sqk_mul), float(scale),
+              _p(out), out.stride(0), _p(lse), B, H, T, D, _stream())
+
+
+def attention_bwd(q, k, v, sqk, sqk_mul, scale, out, dout, lse, dq, dk, dv, dsqk, B, H, T, D=64):
+    assert out.stride(0) == dout.stride(0)
+    _lib.call("nvit_attention_bwd", _p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(sqk), float(sqk_mul), float(scale),
+              _p(out), _p(dout), out.stride(0), _p(lse), _p(dq), _p(dk), _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _p(dsqk),
+              B, H, T, D, _stream())
+
+
+def im2col(img, out, ksize, stride, pad):
+    B, ch, S, _ = img.shape
+    _lib.call("nvit_im2col_bf16", _p(img), _p(out), B, ch, S, ksize, stride, pad, _stream())
+
+
+def pool_ln_fwd(h, gamma, beta, eps, y, xhat, rstd, B, T, C):
+    _lib.call("nvit_pool_ln_fwd", _p(h), _p(gamma), _p(beta), float(eps), _p(y), _p(xhat), _p(rstd), B, T, C, _stream())
+
+
+def pool_ln_bwd(dy, gamma, xhat, rstd, dh, dgamma, dbeta, B, T, C):
+    _lib.call("nvit_pool_ln_bwd", _p(dy), _p(gamma), _p(xhat), _p(rstd), _p(dh), _p(dgamma), _p(dbeta), B, T, C, _stream())
+
+
+def head_scale_bwd(dlogits, raw, sz, sz_mul, draw, dsz):
+    B, N = dlogits.shape
+    _lib.call("nvit_head_scale_bwd", _p(dlogits), _p(raw), _p(sz), float(sz_mul), _p(draw), _p(dsz), B, N, draw.stride(0), _stream())
+
+
+def cross_entropy(logits, target, loss, dlogits, gscale=1.0):
+    B, N = logits.shape
+    _lib.call("nvit_cross_entropy", _p(logits), _p(target), _p(loss), _p(dlogits), float(gscale), B, N, _stream())
+
+
+def tanh_mse(pred, target, out):
+    n = pred.numel()
+    _lib.call("nvit_tanh_mse", _p(pred), _p(target), n, 1.0 / n, _p(out), _stream())
+
+
+def adamw_flat(p, g, m, v, n_decay, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0):
+    _lib.call("nvit_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), n_decay, float(lr), float(beta1), float(beta2), float(eps),
+              float(weight_decay), step, _p(gnorm_sq), float(max_norm), _stream())
+
+
+def weight_norm_multi(table, n_tensors, total_units):
+    _lib.call("nvit_weight_norm_multi", _p(table), n_tensors, total_units, _stream())
