@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: nViT-B/16 224px training images/sec on N B200s (BASELINE.json metric), plus the roofline of
+the dominant kernel and the CPU baseline.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the box's host cores
+
+A "step" is one full training iteration of the step contract (train.py:885-993): forward, cross-entropy, backward,
+[gradient all-reduce], clip, AdamW, zero_grad, normalize_matrices, on a synthetic ImageNet-shaped batch of 256 images
+per GPU (weak scaling) with random-init weights.  `value` is measured with the batch resident in HBM; `e2e` goes through
+the public Trainer.step with pinned host batches copied in and the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "nViT-B/16 train images/sec"
+UNIT = "images/s"
+
+
+def flops_per_image(cfg, kohonen: bool = False) -> float:
+    """ALGORITHMIC training FLOPs per image (SURVEY.md section 8d formula)."""
+    C, L, P, G = cfg.n_embd, cfg.n_layer, cfg.local_patch_size, cfg.global_patch_size
+    T = (cfg.image_size // P) ** 2
+    Kl, Kg = 3 * P * P, 3 * G * G
+    n_ca = 1
+    fwd = 2 * T * C * (Kl + Kg + 6 * C * n_ca + 16 * C * L + Kl) + 4 * T * T * C * (L + n_ca) + 2 * C * cfg.num_classes
+    train = 3 * fwd - 2 * T * C * (Kl + Kg) - 4 * T * C * Kl
+    return float(train)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(cfg_name: str, budget_s: float = 20.0):
+    """The reference algorithm (oracle port of nvit/model.py + the train.py step) on this box's host cores."""
+    import torch
+    from oracle import nvit_oracle as O
+    cfg = O.named_config(cfg_name)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    O.time_cpu_steps(cfg, batch=4, steps=1, warmup=0, threads=cores)           # page-in / warm-up, sizes the sample
+    t4 = time.perf_counter() - t0
+    batch = int(max(4, min(32, 4 * (budget_s * 0.5) / max(t4, 1e-3))))
+    times, _ = O.time_cpu_steps(cfg, batch=batch, steps=1, warmup=0, threads=cores)
+    ips = batch / times[0]
+    return {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle (fp32 PyTorch restatement of nvit/model.py + train.py step) 1 step at batch {batch} of the same config, "
+                      f"{cores} threads"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle port) timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import nvit_oracle as O
+    cfg = O.named_config(args.config)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    O.time_cpu_steps(cfg, batch=2, steps=1, warmup=0, threads=cores)
+    t2 = time.perf_counter() - t0
+    total = args.steps + args.warmup
+    batch = int(max(1, min(32, 2 * (150.0 / total) / max(t2, 1e-3))))
+    times, _ = O.time_cpu_steps(cfg, batch=batch, steps=args.steps, warmup=args.warmup, threads=cores)
+    ms = 1000.0 * sum(times) / len(times)
+    ips = batch / (ms / 1000.0)
+    sample = f"oracle port, fp32, {cores} threads, {args.steps} steps of batch {batch} (bounded sample of the batch-256 workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"nViT-{args.config} 224px train step, CPU", "batch_per_step": batch},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="b16", choices=["b16", "l16", "tiny"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from nvit_b200 import ViT, ViTConfig, Trainer
+    from oracle import nvit_oracle as O          # config table only (shapes); nothing of the oracle runs on the GPU arm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    ocfg = O.named_config(args.config)
+    cfg = ViTConfig(**ocfg.as_dict())
+    torch.manual_seed(0)
+    model = ViT(cfg).to(dev).train()
+    trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    X_host = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g).pin_memory()
+    y_host = torch.randint(0, cfg.num_classes, (B,), generator=g).pin_memory()
+    X, y = X_host.to(dev), y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        trainer.step(X, y)
+    barrier()
+
+    # ---------------- device-resident timing (value) with the dominant-kernel probe
+    eng = model.engine
+    eng.probe = []
+    sampler = ClockSampler(local)
+    launches0 = trainer.total_launches
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    start.record()
+    for _ in range(args.steps):
+        loss = trainer.step(X, y)
+    end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = start.elapsed_time(end)
+    launches = trainer.total_launches - launches0
+    probe = eng.probe
+    eng.probe = None
+    kern_ms = sum(a.elapsed_time(b) for a, b in probe) / max(1, len(probe))
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1000.0)
+    final_loss = float(loss)
+
+    # ---------------- end-to-end through the public API: pinned host batch -> H2D -> Trainer.step -> loss D2H, every step
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [(torch.empty_like(X), torch.empty_like(y)) for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                bufs[i % 2][0].copy_(X_host, non_blocking=True)
+                bufs[i % 2][1].copy_(y_host, non_blocking=True)
+                evs[i % 2].record(copy_stream)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        prefetch(0)
+        for i in range(args.steps):
+            torch.cuda.current_stream().wait_event(evs[i % 2])
+            if i + 1 < args.steps:
+                prefetch(i + 1)
+            l = trainer.step(bufs[i % 2][0], bufs[i % 2][1])
+            _ = l.item()                                   # loss read back every step (device -> host)
+        t1.record()
+        barrier()
+        te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * args.steps / (float(te) / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": X_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4}
+
+    if rank == 0:
+        peaks, how = load_peaks()
+        M = B * (cfg.image_size // cfg.local_patch_size) ** 2
+        gemm_flops = 2.0 * M * (8 * cfg.n_embd) * cfg.n_embd
+        achieved = gemm_flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        fpi = flops_per_image(cfg)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"nViT-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
+                                   f"bf16 GEMM/attention + fp32 residual, random-init weights",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (~20 GB of activations) is far larger than the 126 MB L2, no explicit flush"},
+            "clocks": clocks,
+            "gpu_launches": launches,
+            "final_loss": final_loss,
+            "step_tensor_frac": {"flop_per_image": fpi, "achieved_tflops_per_gpu": fpi * value / world / 1e12,
+                                 "frac_of_sustained_peak": fpi * value / world / 1e12 / peak},
+            "roofline": {"kernel": "gemm_tcgen05_kernel<256,K,K,SWIGLU> (c_fc GEMM + suv*SiLU gate epilogue, forward)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
+                         "launches_timed": len(probe), "avg_launch_ms": kern_ms, "flop_per_launch": gemm_flops},
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.config)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

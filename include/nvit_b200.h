@@ -50,7 +50,7 @@ int nvit_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* str
 int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream);
 /* out[N] += column sums of a bf16 [M,N] matrix (bias gradients of nn.Linear when config.bias) */
 int nvit_colsum_bf16(const void* x_bf16, int64_t M, int64_t N, int64_t ldx, float* out_accum, void* stream);
-/* dpos[T,C] = sum_b dx[b,t,c]; dbias[C] += sum_{b,t} dx  (autograd of `+ pos_embed` and conv bias, model.py:407-415) */
+/* dpos[T,C] += sum_b dx[b,t,c]; dbias[C] += sum_{b,t} dx  (autograd of `+ pos_embed` and conv bias, model.py:407-415) */
 int nvit_pos_bias_grad(const float* dx, int64_t B, int64_t T, int64_t C, float* dpos, float* dbias_accum, void* stream);
 
 /* ---- normalized residual update (model.py:134-142, 159-167, 265-273; norm_skip model.py:84-87, 450-452) -------

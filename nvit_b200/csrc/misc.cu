@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   atomicAdd(out + c, acc);
 }
 
-// dpos[t,c] = sum_b dx[b,t,c]; dbias[c] += sum_t dpos[t,c].   grid (T, ceil(C/256)).
+// dpos[t,c] += sum_b dx[b,t,c]; dbias[c] += the same, summed over t.   grid (T, ceil(C/256)).
 __global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restrict__ dx, int B, int T, int C,
                                                             float* __restrict__ dpos, float* __restrict__ dbias) {
   const int t = blockIdx.x;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restr
   if (c >= C) return;
   float acc = 0.f;
   for (int b = 0; b < B; ++b) acc += dx[(1ll * b * T + t) * C + c];
-  dpos[1ll * t * C + c] = acc;
+  dpos[1ll * t * C + c] += acc;
   if (dbias) atomicAdd(dbias + c, acc);
 }
 

@@ -1,0 +1,487 @@
+"""Hand-scheduled forward and backward pass of the nViT training hot path over the C-ABI kernels.
+
+Restates, kernel by kernel, ``ViT.forward`` (/root/reference/nvit/model.py:403-470), ``CrossAttentionBlock.forward``
+(:219-275), ``Block.forward`` (:92-169) and ``Block.norm_skip`` (:84-87), plus the backward that autograd derives
+from them.  PyTorch provides device memory, streams and the parameter objects; all arithmetic is in
+``libnvit_b200.so``.  Precision follows the reference under ``torch.autocast(bf16)``:
+GEMM and attention operands bf16 with fp32 accumulation, norms / residual stream / parameters / gradients fp32.
+
+Memory layout (HBM):
+  * ``P32``  one flat fp32 buffer holding every parameter; ``model.parameters()`` are views into it.  Order:
+    [GEMM weights in GEMM-operand order | other weight-decayed params | no-decay params || params that never get a
+    gradient].  AdamW, the gradient norm and the data-parallel all-reduce stream over contiguous ranges of it.
+  * ``G32``  the gradients in the same layout (``p.grad`` views).
+  * ``W16``  bf16 GEMM operands, one cast launch from the head of ``P32`` (q/k/v concatenated to [3C, C], etc).
+  * per-layer activations saved for backward (bf16 GEMM operands, fp32 residual stream), allocated once per batch size.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+
+def _align(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+class _Slot:
+    __slots__ = ("name", "param", "off", "numel", "shape")
+
+    def __init__(self, name, param, off):
+        self.name, self.param, self.off = name, param, off
+        self.numel, self.shape = param.numel(), tuple(param.shape)
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        if not self.cfg.use_nvit:
+            raise NotImplementedError("use_nvit=False (BASELINE config 4) is not built yet; see DESIGN.md")
+        self.P32 = None
+        self._acts = {}
+        self._saved = None
+        self.grad_ready_hook = None     # callable(lo, hi): flat-gradient range [lo, hi) is final (data-parallel overlap)
+        self.launches = 0
+        self._p16_version = None
+        self.probe = None               # list to receive (start, end) CUDA event pairs around the c_fc GEMM (bench.py)
+
+    # ------------------------------------------------------------------------------------------ parameter layout
+    def invalidate(self):
+        self.P32 = None
+
+    def _named(self):
+        return dict(self.model.named_parameters())
+
+    def _build_layout(self):
+        m, cfg = self.model, self.cfg
+        named = self._named()
+        C, L = cfg.n_embd, cfg.n_layer
+        order: list[str] = []
+        # region A: GEMM weights, in the order/concatenation the bf16 operand buffer uses
+        order += ["local_patch_embed.weight", "global_patch_embed.1.weight"]
+        order += ["cross_attention.q_local.weight", "cross_attention.k_global.weight", "cross_attention.v_global.weight",
+                  "cross_attention.proj.weight", "cross_attention.out_proj.weight"]
+        for i in range(L):
+            b = f"transformer.h.{i}."
+            order += [b + "query.weight", b + "key.weight", b + "value.weight", b + "att_c_proj.weight", b + "c_fc.weight",
+                      b + "mlp_c_proj.weight"]
+        order += ["mlp_head.1.weight"]
+        n_gemm = len(order)
+        # region A': remaining weight-decayed parameters (dim >= 2)
+        inactive = {n for n in named if ".rmsnorm_" in n or n.startswith("reconstruction_head.")}
+        rest = [n for n in named if n not in order and n not in inactive]
+        order += [n for n in rest if named[n].dim() >= 2 and "sz" not in n]
+        n_decay_names = len(order)
+        # region B: no-decay parameters; biases of fused GEMMs kept adjacent (q,k,v) so one column-sum serves them
+        nodecay = [n for n in rest if not (named[n].dim() >= 2 and "sz" not in n)]
+
+        def key(n):
+            for i, suffix in enumerate(("query.bias", "key.bias", "value.bias")):
+                if n.endswith(suffix):
+                    return (n.rsplit(".", 2)[0], 0, i)
+            for i, suffix in enumerate(("k_global.bias", "v_global.bias")):
+                if n.endswith(suffix):
+                    return ("cross_attention", 0, i)
+            return (n, 1, 0)
+        order += sorted(nodecay, key=key)
+        n_active_names = len(order)
+        # region C: never receive a gradient: the reconstruction head first (it is a GEMM operand)
+        order += ["reconstruction_head.0.weight", "reconstruction_head.0.bias"]
+        order += sorted(n for n in inactive if not n.startswith("reconstruction_head."))
+        assert len(order) == len(named) and set(order) == set(named), "parameter layout does not cover the model"
+
+        slots, off = {}, 0
+        marks = {}
+        for idx, n in enumerate(order):
+            if idx == n_gemm:
+                marks["gemm_end"] = off
+            if idx == n_decay_names:
+                marks["decay_end"] = off
+            if idx == n_active_names:
+                marks["active_end"] = off
+            s = _Slot(n, named[n], off)
+            slots[n] = s
+            off = _align(off + s.numel, 8)
+        marks.setdefault("gemm_end", off)
+        marks.setdefault("decay_end", off)
+        marks.setdefault("active_end", off)
+        self.slots, self.order, self.n_total = slots, order, off
+        self.n_gemm, self.n_decay, self.n_active = marks["gemm_end"], marks["decay_end"], marks["active_end"]
+
+    def _materialize(self, device):
+        """(Re)build the flat buffers on `device` and alias every parameter (and its grad) into them."""
+        self._build_layout()
+        self.device = device
+        P32 = torch.zeros(self.n_total, device=device, dtype=F32)
+        self.G32 = torch.zeros(self.n_total, device=device, dtype=F32)
+        with torch.no_grad():
+            for s in self.slots.values():
+                view = P32[s.off:s.off + s.numel].view(s.shape)
+                view.copy_(s.param.data.to(device=device, dtype=F32))
+                s.param.data = view
+        self.P32 = P32
+        # bf16 GEMM operands: region A + the reconstruction weight
+        rec = self.slots["reconstruction_head.0.weight"]
+        self.W16 = torch.empty(self.n_gemm + _align(rec.numel, 8), device=device, dtype=BF16)
+        self._rec16_off = self.n_gemm
+        self._p16_version = None
+        self._acts = {}
+        self._build_norm_table()
+        self.scratch = torch.zeros(8, device=device, dtype=F32)   # [0] recon loss
+        self._ptrs = {n: s.param.data_ptr() for n, s in self.slots.items()}
+
+    def _check_alias(self, device):
+        if self.P32 is None or self.P32.device != device:
+            self._materialize(device)
+            return
+        for n, s in self.slots.items():
+            if s.param.data_ptr() != self._ptrs[n]:
+                self._materialize(device)
+                return
+
+    def param_list(self):
+        if self.P32 is None:
+            dev = next(self.model.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("nvit_b200.ViT must live on a CUDA device (model.cuda()) before forward")
+            self._materialize(dev)
+        return [self.slots[n].param for n in self.order]
+
+    def p(self, name):       # fp32 parameter view
+        s = self.slots[name]
+        return self.P32[s.off:s.off + s.numel].view(s.shape)
+
+    def g(self, name):       # fp32 gradient view
+        s = self.slots[name]
+        return self.G32[s.off:s.off + s.numel].view(s.shape)
+
+    def w16(self, name, rows=None):
+        """bf16 operand of a GEMM weight as [rows, cols]; `rows` > own rows spans the following concatenated weights."""
+        s = self.slots[name]
+        off = s.off if name != "reconstruction_head.0.weight" else self._rec16_off
+        r = s.shape[0] if rows is None else rows
+        cols = s.numel // s.shape[0]
+        return self.W16[off:off + r * cols].view(r, cols)
+
+    def g2d(self, name, rows=None):
+        s = self.slots[name]
+        r = s.shape[0] if rows is None else rows
+        cols = s.numel // s.shape[0]
+        return self.G32[s.off:s.off + r * cols].view(r, cols)
+
+    def block_grad_range(self, i):
+        b = f"transformer.h.{i}."
+        lo = self.slots[b + "query.weight"].off
+        last = self.slots[b + "mlp_c_proj.weight"]
+        return lo, last.off + last.numel
+
+    def _build_norm_table(self):
+        """Device table for nvit_weight_norm_multi (Trainer.normalize_matrices, train.py:461-480)."""
+        rows, first = [], 0
+        for i in range(self.cfg.n_layer):
+            b = f"transformer.h.{i}."
+            for nm, axis in (("query", 1), ("key", 1), ("value", 1), ("att_c_proj", 0), ("c_fc", 1), ("mlp_c_proj", 0)):
+                s = self.slots[b + nm + ".weight"]
+                r, c = s.shape
+                rows.append([self.P32.data_ptr() + 4 * s.off, 0, r, c, axis, first])
+                first += (r + 7) // 8 if axis == 1 else (c + 31) // 32
+        self.norm_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        self.norm_units = first
+
+    def normalize_matrices(self):
+        ops.weight_norm_multi(self.norm_table, self.norm_table.shape[0], self.norm_units)
+        self.launches += 1
+        self._p16_version = None
+
+    def zero_grad(self):
+        self.G32.zero_()
+
+    def refresh_operands(self, force=False):
+        """autocast's weight casts: fp32 master -> bf16 GEMM operands, one launch for region A, one for the recon head."""
+        ver = tuple(s.param._version for s in self.slots.values())
+        if not force and ver == self._p16_version:
+            return
+        ops.cast_bf16(self.P32[:self.n_gemm], self.W16[:self.n_gemm])
+        rec = self.slots["reconstruction_head.0.weight"]
+        ops.cast_bf16(self.P32[rec.off:rec.off + rec.numel], self.W16[self._rec16_off:self._rec16_off + rec.numel])
+        self.launches += 2
+        self._p16_version = ver
+
+    # ------------------------------------------------------------------------------------------ activations
+    def _buffers(self, B):
+        if B in self._acts:
+            return self._acts[B]
+        cfg, dev = self.cfg, self.device
+        C, L, P, G = cfg.n_embd, cfg.n_layer, cfg.local_patch_size, cfg.global_patch_size
+        T = (cfg.image_size // P) ** 2
+        M, H = B * T, cfg.n_head
+        Kl, Kg = cfg.channels * P * P, cfg.channels * G * G
+        ncls = cfg.num_classes
+
+        def e(*shape, dtype=BF16):
+            return torch.empty(*shape, device=dev, dtype=dtype)
+        a = {
+            "A_l": e(M, Kl), "A_g": e(M, Kg), "local32": e(M, C, dtype=F32), "local16": e(M, C), "global16": e(M, C),
+            "ca_q": e(M, C), "ca_kv": e(M, 2 * C), "ca_att": e(M, C), "ca_lse": e(B, H, T, dtype=F32), "ca_uv": e(M, 2 * C),
+            "ca_x": e(M, C), "ca_o": e(M, C),
+            "h32": [e(M, C, dtype=F32) for _ in range(L + 1)], "h16": [e(M, C) for _ in range(L + 1)],
+            "qkv": [e(M, 3 * C) for _ in range(L)], "att": [e(M, C) for _ in range(L)],
+            "lse": [e(B, H, T, dtype=F32) for _ in range(L)], "h_att": [e(M, C) for _ in range(L)],
+            "h1_32": [e(M, C, dtype=F32) for _ in range(L)], "h1_16": [e(M, C) for _ in range(L)],
+            "uv": [e(M, 8 * C) for _ in range(L)], "x": [e(M, 4 * C) for _ in range(L)], "h_mlp": [e(M, C) for _ in range(L)],
+            "y16": e(B, C), "xhat": e(B, C, dtype=F32), "rstd": e(B, dtype=F32),
+            "raw": e(B, ncls, dtype=F32), "logits": e(B, ncls, dtype=F32), "pred": e(M, Kl),
+            # backward workspace
+            "G": e(M, C, dtype=F32), "dHin": e(M, C, dtype=F32), "dH1": e(M, C, dtype=F32),
+            "d_c16": e(M, C), "d_c16b": e(M, C), "d_4c": e(M, 4 * C), "d_8c": e(M, 8 * C), "d_3c": e(M, 3 * C),
+            "draw16": torch.zeros(B, _align(ncls, 8), device=dev, dtype=BF16), "dy16": e(B, C),
+        }
+        self._acts = {B: a}      # keep one batch size resident
+        return a
+
+    def _splits(self, Mg, Ng, K):
+        """Split-K factor for a wgrad whose output grid alone cannot fill the 148 SMs."""
+        tiles = ((Mg + 127) // 128) * ((Ng + 255) // 256 if Ng > 128 else 1)
+        kb = (K + 63) // 64
+        s = max(1, min(kb, (148 + tiles - 1) // tiles))
+        return s
+
+    def _wgrad(self, dy, x, gw):
+        """gw[N,K] += dy[M,N]^T x[M,K]"""
+        s = self._splits(dy.shape[1], x.shape[1], dy.shape[0])
+        ops.linear_wgrad(dy, x, gw, splits=s, accumulate=True)
+        self.launches += 1
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, img: torch.Tensor, save: bool = True):
+        cfg = self.cfg
+        if img.dtype != F32:
+            img = img.float()
+        img = img.contiguous()
+        self._check_alias(img.device)
+        self.refresh_operands()
+        B = img.shape[0]
+        C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
+        T = (cfg.image_size // P) ** 2
+        a = self._buffers(B)
+        bias = cfg.bias
+        p, w16 = self.p, self.w16
+        amul = 0.05 / cfg.base_scale
+        smul = 1.0 / cfg.base_scale
+        att_scale = float(C // H) ** 0.5
+        n0 = self.launches
+
+        # ---- dual patch embedding as im2col + GEMM, bias and position embedding in the epilogue (model.py:407-415)
+        ops.im2col(img, a["A_l"], P, P, 0)
+        ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
+        ops.linear_fwd(a["A_l"], w16("local_patch_embed.weight"), a["local32"], bias=p("local_patch_embed.bias"),
+                       rowadd=p("local_pos_embed").view(T, C), rowadd_period=T, c2=a["local16"])
+        ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global16"], bias=p("global_patch_embed.1.bias"),
+                       rowadd=p("global_pos_embed").view(T, C), rowadd_period=T)
+        self.launches += 4
+
+        # ---- cross attention (model.py:219-275): q <- local, k,v <- global
+        ca = "cross_attention."
+        ops.linear_fwd(a["local16"], w16(ca + "q_local.weight"), a["ca_q"], bias=p(ca + "q_local.bias") if bias else None)
+        ops.linear_fwd(a["global16"], w16(ca + "k_global.weight", rows=2 * C), a["ca_kv"],
+                       bias=self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None)
+        ops.attention_fwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], p(ca + "sqk"), smul, att_scale, a["ca_att"], a["ca_lse"], B, H, T)
+        self._gated_fwd(a["ca_att"], w16(ca + "proj.weight"), p(ca + "proj.bias") if bias else None, None, 1.0, a["ca_uv"], a["ca_x"], C)
+        ops.linear_fwd(a["ca_x"], w16(ca + "out_proj.weight"), a["ca_o"], bias=p(ca + "out_proj.bias") if bias else None)
+        ops.residual_fwd(a["local32"], a["ca_o"], p(ca + "attn_alpha"), amul, a["h32"][0], a["h16"][0])
+        self.launches += 5
+
+        # ---- transformer blocks + norm_skip (model.py:92-169, 84-87, 450-452)
+        for i in range(L):
+            b = f"transformer.h.{i}."
+            ops.linear_fwd(a["h16"][i], w16(b + "query.weight", rows=3 * C), a["qkv"][i],
+                           bias=self._cat_bias(b + "query.bias", 3 * C) if bias else None)
+            qkv = a["qkv"][i]
+            ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], p(b + "sqk"), smul, att_scale, a["att"][i], a["lse"][i], B, H, T)
+            ops.linear_fwd(a["att"][i], w16(b + "att_c_proj.weight"), a["h_att"][i], bias=p(b + "att_c_proj.bias") if bias else None)
+            ops.residual_fwd(a["h32"][i], a["h_att"][i], p(b + "attn_alpha"), amul, a["h1_32"][i], a["h1_16"][i])
+            self._gated_fwd(a["h1_16"][i], w16(b + "c_fc.weight"), p(b + "c_fc.bias") if bias else None, p(b + "suv"), math.sqrt(C),
+                            a["uv"][i], a["x"][i], 4 * C)
+            ops.linear_fwd(a["x"][i], w16(b + "mlp_c_proj.weight"), a["h_mlp"][i], bias=p(b + "mlp_c_proj.bias") if bias else None)
+            ops.residual_fwd(a["h1_32"][i], a["h_mlp"][i], p(b + "mlp_alpha"), amul, a["h32"][i + 1], a["h16"][i + 1],
+                             h0=a["h32"][i], skip=p(b + "skip_param"))
+            self.launches += 6
+
+        # ---- classifier head (model.py:455-456, 466-468) and reconstruction loss (model.py:459-464)
+        ops.pool_ln_fwd(a["h32"][L], p("mlp_head.0.weight"), p("mlp_head.0.bias"), 1e-5, a["y16"], a["xhat"], a["rstd"], B, T, C)
+        ops.linear_fwd(a["y16"], w16("mlp_head.1.weight"), a["raw"], bias=p("mlp_head.1.bias"))
+        ops.linear_fwd(a["y16"], w16("mlp_head.1.weight"), a["logits"], bias=p("mlp_head.1.bias"), colscale=p("sz"),
+                       colscale_mul=cfg.sz_init_value / cfg.sz_init_scaling)
+        ops.linear_fwd(a["h16"][L], w16("reconstruction_head.0.weight"), a["pred"], bias=p("reconstruction_head.0.bias"))
+        self.scratch[0:1].zero_()
+        ops.tanh_mse(a["pred"], a["A_l"], self.scratch[0:1])
+        self.launches += 5
+        self.last_forward_launches = self.launches - n0
+        self._saved = (B, T) if save else None
+        return a["logits"].clone(), self.scratch[0].clone()
+
+    def _cat_bias(self, first_name, n):
+        s = self.slots[first_name]
+        return self.P32[s.off:s.off + n]
+
+    def _gated_fwd(self, x, w, bias, suv, mul, uv, out, Fh):
+        """uv = x W^T (+b); out = (u*su) * silu(v*sv) — fused into the GEMM epilogue unless a bias is present."""
+        M, K = x.shape
+        if bias is None:
+            probe = self.probe is not None and suv is not None
+            if probe:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            ops.gemm(x, w, out, M=M, N=Fh, K=K, lda=x.stride(0), ldb=w.stride(0), ldc=Fh, colscale=suv, colscale_mul=mul,
+                     c2=uv, ldc2=2 * Fh, swiglu_half=Fh)
+            if probe:
+                e1.record()
+                self.probe.append((e0, e1))
+            self.launches += 1
+        else:
+            ops.linear_fwd(x, w, uv, bias=bias)
+            ops.swiglu_fwd(uv, suv, mul, out)
+            self.launches += 2
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, dlogits: torch.Tensor):
+        """Accumulate dL/dparams into G32 given dL/dlogits (fp32 [B, classes]).  Forward must have run with save=True."""
+        if self._saved is None:
+            raise RuntimeError("Engine.backward called without a saved forward pass")
+        cfg = self.cfg
+        B, T = self._saved
+        C, L, H = cfg.n_embd, cfg.n_layer, cfg.n_head
+        M = B * T
+        ncls = cfg.num_classes
+        a = self._acts[B]
+        p, g, w16, g2d = self.p, self.g, self.w16, self.g2d
+        bias = cfg.bias
+        amul = 0.05 / cfg.base_scale
+        smul = 1.0 / cfg.base_scale
+        att_scale = float(C // H) ** 0.5
+        n0 = self.launches
+        dlogits = dlogits.to(F32).contiguous()
+
+        # ---- head
+        draw = a["draw16"][:, :ncls]
+        ops.head_scale_bwd(dlogits, a["raw"], p("sz"), cfg.sz_init_value / cfg.sz_init_scaling, a["draw16"], g("sz"))
+        ops.colsum(draw, g("mlp_head.1.bias"))
+        self._wgrad(draw, a["y16"], g2d("mlp_head.1.weight"))
+        ops.linear_dgrad(draw, w16("mlp_head.1.weight"), a["dy16"])
+        ops.pool_ln_bwd(a["dy16"], p("mlp_head.0.weight"), a["xhat"], a["rstd"], a["G"], g("mlp_head.0.weight"), g("mlp_head.0.bias"), B, T, C)
+        self.launches += 4
+        G, dHin, dH1 = a["G"], a["dHin"], a["dH1"]
+
+        # ---- blocks, last to first
+        for i in reversed(range(L)):
+            b = f"transformer.h.{i}."
+            dHmlp, dHatt, dAtt = a["d_c16"], a["d_c16"], a["d_c16b"]
+            ops.residual_bwd(G, a["h1_32"][i], a["h_mlp"][i], p(b + "mlp_alpha"), amul, dH1, dHmlp, g(b + "mlp_alpha"),
+                             h0=a["h32"][i], skip=p(b + "skip_param"), dh0=dHin, dskip=g(b + "skip_param"))
+            self._wgrad(dHmlp, a["x"][i], g2d(b + "mlp_c_proj.weight"))
+            if bias:
+                ops.colsum(dHmlp, g(b + "mlp_c_proj.bias"))
+            ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
+            ops.swiglu_bwd(a["d_4c"], a["uv"][i], p(b + "suv"), math.sqrt(C), a["d_8c"], g(b + "suv"))
+            self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
+            if bias:
+                ops.colsum(a["d_8c"], g(b + "c_fc.bias"))
+            ops.linear_dgrad(a["d_8c"], w16(b + "c_fc.weight"), dH1, accumulate=True)
+            ops.residual_bwd(dH1, a["h32"][i], a["h_att"][i], p(b + "attn_alpha"), amul, dHin, dHatt, g(b + "attn_alpha"),
+                             dh_accumulate=True)
+            self._wgrad(dHatt, a["att"][i], g2d(b + "att_c_proj.weight"))
+            if bias:
+                ops.colsum(dHatt, g(b + "att_c_proj.bias"))
+            ops.linear_dgrad(dHatt, w16(b + "att_c_proj.weight"), dAtt)
+            qkv, dqkv = a["qkv"][i], a["d_3c"]
+            ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], p(b + "sqk"), smul, att_scale, a["att"][i], dAtt, a["lse"][i],
+                              dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], g(b + "sqk"), B, H, T)
+            self._wgrad(dqkv, a["h16"][i], g2d(b + "query.weight", rows=3 * C))
+            if bias:
+                ops.colsum(dqkv, self._cat_grad(b + "query.bias", 3 * C))
+            ops.linear_dgrad(dqkv, w16(b + "query.weight", rows=3 * C), dHin, accumulate=True)
+            self.launches += 8 + (4 if bias else 0)
+            G, dHin = dHin, G
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(*self.block_grad_range(i))
+
+        # ---- cross attention: G = dL/d(h0)
+        ca = "cross_attention."
+        dLocal = dHin            # fp32 [M,C], written by the residual backward
+        dO, dX = a["d_c16"], a["d_c16b"]
+        ops.residual_bwd(G, a["local32"], a["ca_o"], p(ca + "attn_alpha"), amul, dLocal, dO, g(ca + "attn_alpha"))
+        self._wgrad(dO, a["ca_x"], g2d(ca + "out_proj.weight"))
+        if bias:
+            ops.colsum(dO, g(ca + "out_proj.bias"))
+        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
+        duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)     # contiguous [M, 2C] scratch
+        ops.swiglu_bwd(dX, a["ca_uv"], None, 1.0, duv, None)
+        self._wgrad(duv, a["ca_att"], g2d(ca + "proj.weight"))
+        if bias:
+            ops.colsum(duv, g(ca + "proj.bias"))
+        dAtt = a["d_c16"]
+        ops.linear_dgrad(duv, w16(ca + "proj.weight"), dAtt)
+        dq = a["d_c16b"]
+        dkv = a["d_3c"].view(-1)[:M * 2 * C].view(M, 2 * C)
+        ops.attention_bwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], p(ca + "sqk"), smul, att_scale, a["ca_att"], dAtt, a["ca_lse"],
+                          dq, dkv[:, :C], dkv[:, C:], g(ca + "sqk"), B, H, T)
+        self._wgrad(dq, a["local16"], g2d(ca + "q_local.weight"))
+        self._wgrad(dkv, a["global16"], g2d(ca + "k_global.weight", rows=2 * C))
+        if bias:
+            ops.colsum(dq, g(ca + "q_local.bias"))
+            ops.colsum(dkv, self._cat_grad(ca + "k_global.bias", 2 * C))
+            self.launches += 4
+        ops.linear_dgrad(dq, w16(ca + "q_local.weight"), dLocal, accumulate=True)
+        dGlobal = G              # fp32 scratch (G is dead now)
+        ops.linear_dgrad(dkv, w16(ca + "k_global.weight", rows=2 * C), dGlobal)
+        self.launches += 7
+
+        # ---- patch embeddings: position / bias gradients and the two conv weight gradients (no dX: images need none)
+        for dX32, A, wname, bname, pos in ((dLocal, a["A_l"], "local_patch_embed.weight", "local_patch_embed.bias", "local_pos_embed"),
+                                           (dGlobal, a["A_g"], "global_patch_embed.1.weight", "global_patch_embed.1.bias", "global_pos_embed")):
+            ops.pos_bias_grad(dX32, B, T, C, g(pos).view(T, C), g(bname))
+            ops.cast_bf16(dX32, a["d_c16"])
+            self._wgrad(a["d_c16"], A, g2d(wname))
+            self.launches += 2
+        self.last_backward_launches = self.launches - n0
+        self._saved = None
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(0, self.block_grad_range(0)[0])
+            self.grad_ready_hook(self.block_grad_range(cfg.n_layer - 1)[1], self.n_active)
+
+    def _cat_grad(self, first_name, n):
+        s = self.slots[first_name]
+        return self.G32[s.off:s.off + n]
+
+
+class NViTFunction(torch.autograd.Function):
+    """One autograd node for the whole model: forward/backward are the engine's hand-scheduled passes."""
+
+    @staticmethod
+    def forward(ctx, engine, img, *params):
+        logits, recon = engine.forward(img, save=True)
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(recon)
+        return logits, recon
+
+    @staticmethod
+    def backward(ctx, dlogits, _drecon):
+        eng = ctx.engine
+        eng.zero_grad()
+        eng.backward(dlogits)
+        grads = []
+        for n in eng.order:
+            s = eng.slots[n]
+            if s.off >= eng.n_active or not s.param.requires_grad:
+                grads.append(None)
+            else:
+                grads.append(eng.g(n).clone())
+        return (None, None, *grads)

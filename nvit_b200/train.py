@@ -1,0 +1,173 @@
+"""The reference's train-step contract (/root/reference/nvit/train.py:885-993) on the sm_100a engine.
+
+    forward (bf16 GEMMs, fp32 residual) -> cross-entropy -> backward -> [data-parallel gradient all-reduce, overlapped]
+    -> clip_grad_norm_(1.0) -> AdamW(betas 0.9/0.95, wd 0.1) -> zero_grad -> normalize_matrices
+
+``Trainer`` drives the engine directly (no autograd graph): gradients land in the engine's flat fp32 buffer, the
+gradient norm, clip, AdamW update and the weight normalisation are four launches over contiguous memory, and in
+data-parallel runs each transformer block's gradient slice is all-reduced over NCCL on a side stream as soon as that
+block's backward has been issued (train.py:434-446 intends DDP; SURVEY.md 2.3 #3 explains why the reference never
+actually reduces — the intended semantics, mean of gradients over ranks, are what is built here).
+
+Deviation kept on purpose: the reference wraps bf16 training in a GradScaler (train.py:135-136); its power-of-two
+scale/unscale is the identity for finite gradients, so it is omitted.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+
+
+class GradReducer:
+    """Bucketed all-reduce (sum) of ranges of one flat gradient buffer, issued as ranges become final.
+
+    Device-agnostic host logic (tested with gloo on CPU); on CUDA the collectives run on `comm_stream` so they overlap
+    the rest of the backward pass.  Ranges smaller than `min_bucket` elements are coalesced with their neighbours and
+    flushed at `finish()`.
+    """
+
+    def __init__(self, flat: torch.Tensor, group=None, min_bucket: int = 1 << 20):
+        import torch.distributed as dist
+        self.dist = dist
+        self.flat = flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.min_bucket = min_bucket
+        self.pending = []
+        self.small: list[tuple[int, int]] = []
+        self.comm_stream = torch.cuda.Stream() if flat.is_cuda else None
+        self.reduced_elems = 0
+
+    def _issue(self, lo: int, hi: int):
+        if hi <= lo or self.world == 1:
+            return
+        view = self.flat[lo:hi]
+        self.reduced_elems += hi - lo
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                self.pending.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.pending.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def ready(self, lo: int, hi: int):
+        if hi - lo >= self.min_bucket:
+            self._issue(lo, hi)
+        elif hi > lo:
+            self.small.append((lo, hi))
+
+    def finish(self):
+        """Flush coalesced small ranges and make the current stream wait for every collective."""
+        self.small.sort()
+        merged: list[list[int]] = []
+        for lo, hi in self.small:
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        for lo, hi in merged:
+            self._issue(lo, hi)
+        self.small = []
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+
+class Trainer:
+    """One rank of the (optionally data-parallel) nViT training loop; mirrors Trainer.train's inner step."""
+
+    def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
+                 eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None):
+        import torch.distributed as dist
+        self.model = model
+        self.engine = model.engine
+        self.lr, self.betas, self.wd, self.clip, self.eps = learning_rate, betas, weight_decay, grad_clip, eps
+        self.grad_accum = gradient_accumulation_steps
+        self.iter_num = 0
+        self.opt_step = 0
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.dp = data_parallel
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if self.dp else 1
+        self._state_for = None
+        self.reducer = None
+        self.launches = 0
+
+    # ---- optimizer state lives beside the flat parameter buffer
+    def _ensure_state(self):
+        eng = self.engine
+        eng.param_list()
+        if self._state_for is not eng.P32:
+            self.m = torch.zeros_like(eng.P32)
+            self.v = torch.zeros_like(eng.P32)
+            self.gnorm = torch.zeros(1, device=eng.P32.device, dtype=F32)
+            self.loss_buf = torch.zeros(1, device=eng.P32.device, dtype=F32)
+            self._state_for = eng.P32
+            if self.dp:
+                self.reducer = GradReducer(eng.G32, self.group)
+                self._broadcast_params()
+
+    def _broadcast_params(self):
+        import torch.distributed as dist
+        dist.broadcast(self.engine.P32, src=0, group=self.group)
+        self.engine._p16_version = None
+
+    def normalize_matrices(self):
+        """Trainer.normalize_matrices (train.py:461-480): one multi-tensor launch."""
+        if self.model.config.use_nvit:
+            self.engine.normalize_matrices()
+
+    def micro_step(self, X: torch.Tensor, y: torch.Tensor, last: bool = True):
+        """forward + loss + backward of one micro-batch; gradients accumulate in the flat buffer (train.py:898-933)."""
+        eng = self.engine
+        self._ensure_state()
+        logits, recon = eng.forward(X, save=True)
+        B, N = logits.shape
+        dlogits = eng._acts[B].setdefault("dlogits", torch.empty(B, N, device=logits.device, dtype=F32))
+        # mean CE over the batch, scaled for accumulation and for the mean over data-parallel ranks
+        ops.cross_entropy(logits, y, self.loss_buf, dlogits, 1.0 / (self.grad_accum * self.world))
+        self.launches += 1
+        eng.grad_ready_hook = self.reducer.ready if (self.dp and last) else None
+        eng.backward(dlogits)
+        self.last_recon = recon
+        return logits
+
+    def optimizer_step(self):
+        """clip -> AdamW -> zero_grad -> normalize_matrices (train.py:935-946, 989-990)."""
+        eng = self.engine
+        if self.dp:
+            self.reducer.finish()
+        self.opt_step += 1
+        na = eng.n_active
+        gn = None
+        if self.clip and self.clip > 0:
+            self.gnorm.zero_()
+            ops.sumsq(eng.G32[:na], self.gnorm)
+            gn = self.gnorm
+            self.launches += 1
+        ops.adamw_flat(eng.P32[:na], eng.G32[:na], self.m[:na], self.v[:na], eng.n_decay, self.lr, self.betas[0], self.betas[1],
+                       self.eps, self.wd, self.opt_step, gn, self.clip or 0.0)
+        self.launches += 1
+        eng._p16_version = None
+        eng.zero_grad()
+        self.normalize_matrices()
+
+    def step(self, X: torch.Tensor, y: torch.Tensor):
+        """One full training iteration on one (micro-)batch; returns the device scalar of the mean CE loss."""
+        self._ensure_state()
+        self.loss_buf.zero_()
+        for k in range(self.grad_accum):
+            self.micro_step(X, y, last=(k == self.grad_accum - 1))
+        self.optimizer_step()
+        self.iter_num += 1
+        return self.loss_buf
+
+    @property
+    def total_launches(self) -> int:
+        return self.launches + self.engine.launches

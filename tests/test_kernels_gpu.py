@@ -311,7 +311,7 @@ def test_small_reductions_and_cast():
     cs = torch.zeros(520, device=DEV)
     ops.colsum(m, cs)
     dx = randn(6, 49, 200, seed=82)
-    dpos = torch.empty(49, 200, device=DEV)
+    dpos = torch.zeros(49, 200, device=DEV)
     dbias = torch.zeros(200, device=DEV)
     ops.pos_bias_grad(dx, 6, 49, 200, dpos, dbias)
     pred = randn(4097, seed=83, dtype=torch.bfloat16)

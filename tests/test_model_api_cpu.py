@@ -1,0 +1,109 @@
+"""Drop-in API checks that need no GPU: config fields, module/attribute names, state_dict layout and initial
+distributions of nvit_b200.model against the live reference (skipped where /root/reference is absent) and against the
+oracle's parameter table; the engine's flat parameter layout; loud failure without CUDA."""
+import dataclasses
+
+import pytest
+import torch
+
+from nvit_b200 import ViT, ViTConfig, Block, CrossAttentionBlock, RMSNorm, justnorm
+from oracle import nvit_oracle as O
+
+
+def test_config_fields_match_oracle_table():
+    mine = {f.name: f.default for f in dataclasses.fields(ViTConfig)}
+    theirs = {f.name: f.default for f in dataclasses.fields(O.OracleConfig)}
+    assert mine == theirs
+
+
+def test_config_fields_match_reference(reference_model_module):
+    ref = reference_model_module
+    mine = [(f.name, f.type if isinstance(f.type, str) else f.type.__name__, f.default) for f in dataclasses.fields(ViTConfig)]
+    theirs = [(f.name, f.type if isinstance(f.type, str) else f.type.__name__, f.default) for f in dataclasses.fields(ref.ViTConfig)]
+    assert mine == theirs
+
+
+@pytest.mark.parametrize("name,over", [("micro", {}), ("micro", {"bias": True}), ("tiny", {}), ("mini", {"base_scale": 1 / 32})])
+def test_state_dict_keys_shapes_match_oracle(name, over):
+    cfg = O.named_config(name, **over)
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    sd = m.state_dict()
+    shapes = O.param_shapes(cfg)
+    assert set(sd) == set(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]) and v.dtype == torch.float32, k
+
+
+@pytest.mark.parametrize("name,over", [("micro", {}), ("tiny", {"bias": True})])
+def test_same_seed_gives_the_reference_initialisation(reference_model_module, name, over):
+    """Modules are created in the reference's order, so the RNG stream — and every initial value — is identical."""
+    ref = reference_model_module
+    cfg = O.named_config(name, **over)
+    torch.manual_seed(0)
+    theirs = ref.ViT(ref.ViTConfig(**cfg.as_dict())).state_dict()
+    torch.manual_seed(0)
+    mine = ViT(ViTConfig(**cfg.as_dict())).state_dict()
+    assert list(mine.keys()) == list(theirs.keys())
+    for k in theirs:
+        assert torch.equal(mine[k], theirs[k]), k
+
+
+def test_attribute_surface_used_by_reference_trainer():
+    cfg = O.named_config("micro")
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    blk = m.transformer.h[0]
+    assert isinstance(blk, Block) and isinstance(m.cross_attention, CrossAttentionBlock) and isinstance(blk.rmsnorm_att, RMSNorm)
+    for attr in ("sqk", "sqk_init_value", "sqk_init_scaling", "attn_alpha", "attn_alpha_init_value", "attn_alpha_init_scaling",
+                 "mlp_alpha", "suv", "suv_init_value", "suv_init_scaling", "skip_param", "query", "key", "value", "att_c_proj",
+                 "c_fc", "mlp_c_proj"):
+        assert hasattr(blk, attr), attr
+    for attr in ("sz", "step", "total_steps", "config", "local_patch_embed", "global_patch_embed", "local_pos_embed",
+                 "global_pos_embed", "reconstruction_head", "mlp_head", "configure_optimizers", "estimate_mfu", "num_params"):
+        assert hasattr(m, attr), attr
+    opt = m.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu")
+    groups = opt.param_groups
+    assert len(groups) == 3 and groups[0]["weight_decay"] == 0.1 and groups[1]["weight_decay"] == 0.0
+    assert len(groups[2]["params"]) == 1 and groups[2]["params"][0] is m.sz
+    x = torch.randn(3, 5)
+    assert torch.allclose(justnorm(x).norm(dim=-1), torch.ones(3))
+
+
+def test_engine_flat_layout_covers_every_parameter_once():
+    from nvit_b200.engine import Engine
+    cfg = O.named_config("mini", bias=True)
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    eng = Engine(m)
+    eng._build_layout()
+    named = dict(m.named_parameters())
+    assert set(eng.order) == set(named) and len(eng.order) == len(named)
+    spans = sorted((s.off, s.off + s.numel) for s in eng.slots.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert spans[-1][1] <= eng.n_total
+    assert 0 < eng.n_gemm <= eng.n_decay <= eng.n_active <= eng.n_total
+    for n, s in eng.slots.items():
+        decays = named[n].dim() >= 2 and "sz" not in n
+        inactive = ".rmsnorm_" in n or n.startswith("reconstruction_head.")
+        if inactive:
+            assert s.off >= eng.n_active, n
+        elif decays:
+            assert s.off + s.numel <= eng.n_decay, n
+        else:
+            assert eng.n_decay <= s.off and s.off + s.numel <= eng.n_active, n
+        assert s.off % 8 == 0
+    C = cfg.n_embd
+    b = "transformer.h.1."
+    assert eng.slots[b + "key.weight"].off == eng.slots[b + "query.weight"].off + C * C
+    assert eng.slots[b + "value.weight"].off == eng.slots[b + "query.weight"].off + 2 * C * C
+    assert eng.slots[b + "key.bias"].off == eng.slots[b + "query.bias"].off + C       # C % 8 == 0
+    lo, hi = eng.block_grad_range(1)
+    assert hi - lo == 16 * C * C
+
+
+def test_no_cpu_fallback():
+    cfg = O.named_config("micro")
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(ValueError, match="head_dim"):
+        ViT(ViTConfig(n_embd=96, n_head=2, use_nvit=True))

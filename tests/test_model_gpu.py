@@ -1,0 +1,195 @@
+"""Model-, step- and API-level parity on a B200 (-m gpu).
+
+The CUDA path (nvit_b200.ViT / Trainer, bf16 tensor-core GEMMs + fp32 residual stream) is compared with
+  (1) the committed golden fixtures = outputs of the REAL reference on formula weights (tests/golden/*.npz), and
+  (2) the fp32 oracle (oracle/nvit_oracle.py, pinned against the reference) run on the same device and inputs.
+Stated tolerance (north_star: "within a stated bf16 tolerance, fp32 reference"; calibrated in SURVEY.md section 4 on the
+reference's own bf16-autocast vs fp32 gap): logits rel-L2 <= 1e-2; every gradient tensor rel-L2 <= 3e-2 and cosine >=
+0.999 (tiny-magnitude tensors: abs <= 1e-3 * global gradient norm); weight rows |norm - 1| <= 1e-3 after a step.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from nvit_b200 import ViT, ViTConfig, Trainer  # noqa: E402
+from oracle import nvit_oracle as O  # noqa: E402
+
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def build(cfg: O.OracleConfig, sd):
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).train()
+
+
+def oracle_grads(cfg, sd, X, y):
+    p = {k: v.detach().to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
+    logits, aux = O.vit_forward(p, cfg, X)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    return logits.detach(), aux["reconstruction"].detach(), loss.detach(), {k: v.grad for k, v in p.items()}
+
+
+def check_grads(model, ref_grads, tol=3e-2):
+    gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values() if g is not None)))
+    worst = ("", 0.0)
+    n = 0
+    for name, p in model.named_parameters():
+        rg = ref_grads[name]
+        if rg is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{name}: reference has no gradient"
+            continue
+        assert p.grad is not None, f"{name}: missing gradient"
+        n += 1
+        err = float((p.grad.double() - rg.double()).norm())
+        if err <= 1e-3 * gnorm and float(rg.norm()) < 3e-2 * gnorm:
+            continue                       # tiny tensor: absolute criterion
+        r = rel(p.grad, rg)
+        if r > worst[1]:
+            worst = (name, r)
+        assert r <= tol, f"{name}: grad rel-L2 {r:.4f} (|g|={float(rg.norm()):.3e}, global {gnorm:.3e})"
+        assert cosine(p.grad, rg) >= 0.999, f"{name}: grad cosine {cosine(p.grad, rg):.5f}"
+    assert n > 20
+    return worst
+
+
+CASES = {
+    "micro_nvit": ("micro", dict(), 4),
+    "micro_nvit_bias": ("micro", dict(bias=True), 4),
+    "mini_nvit_bs32": ("mini", dict(base_scale=1.0 / 32.0), 3),
+}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_forward_backward_matches_reference_golden(tag):
+    """Golden vectors produced by the real reference (tests/golden/make_golden.py): loss = CE + 0.1 * recon there, so
+    only logits / CE / reconstruction are compared here; gradients are compared against the oracle below."""
+    name, over, batch = CASES[tag]
+    cfg = O.named_config(name, **over)
+    gold = dict(np.load(os.path.join(GOLDEN, tag + ".npz")))
+    model = build(cfg, O.formula_state_dict(cfg))
+    X, y = O.formula_batch(cfg, batch)
+    logits, aux = model(X.to(DEV))
+    ce = F.cross_entropy(logits, y.to(DEV))
+    assert rel(logits, torch.from_numpy(gold["logits"]).to(DEV)) <= 1e-2
+    assert abs(float(ce) - float(gold["ce"])) <= 1e-2 * abs(float(gold["ce"]))
+    assert abs(float(aux["reconstruction"]) - float(gold["reconstruction"])) <= 1e-2 * float(gold["reconstruction"])
+
+
+@pytest.mark.parametrize("name,over,batch,seed", [
+    ("micro", dict(), 4, None), ("micro", dict(bias=True), 5, None), ("mini", dict(base_scale=1.0 / 32.0), 3, None),
+    ("tiny", dict(), 16, 0), ("tiny", dict(base_scale=1.0 / 32.0), 64, 1), ("b16", dict(), 2, 0),
+])
+def test_logits_and_every_gradient_match_oracle(name, over, batch, seed):
+    cfg = O.named_config(name, **over)
+    if seed is None:
+        sd = O.formula_state_dict(cfg)
+        X, y = O.formula_batch(cfg, batch)
+    else:
+        sd = O.init_state_dict(cfg, seed)
+        g = torch.Generator().manual_seed(1234)
+        X = torch.randn(batch, cfg.channels, cfg.image_size, cfg.image_size, generator=g)
+        y = torch.randint(0, cfg.num_classes, (batch,), generator=g)
+    X, y = X.to(DEV), y.to(DEV)
+    ref_logits, ref_recon, ref_loss, ref_grads = oracle_grads(cfg, sd, X, y)
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    assert rel(logits, ref_logits) <= 1e-2, rel(logits, ref_logits)
+    assert abs(float(aux["reconstruction"]) - float(ref_recon)) <= 1e-2 * float(ref_recon)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
+    check_grads(model, ref_grads)
+    # parameters that never receive a gradient in the reference stay grad-less
+    for n, p in model.named_parameters():
+        if ".rmsnorm_" in n or n.startswith("reconstruction_head."):
+            assert p.grad is None, n
+
+
+def test_trainer_step_matches_oracle_step_and_unit_norm_rows():
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 3)
+    g = torch.Generator().manual_seed(1234)
+    X = torch.randn(32, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (32,), generator=g).to(DEV)
+    ref = O.OracleTrainer({k: v.to(DEV) for k, v in sd.items()}, cfg, lr=1e-3)
+    model = build(cfg, sd)
+    tr = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0)
+    for it in range(3):
+        ref_loss, _, _ = ref.step(X, y)
+        loss = tr.step(X, y)
+        assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss)), (it, float(loss), float(ref_loss))
+    params = dict(model.named_parameters())
+    for i in range(cfg.n_layer):
+        for nm, dim in O.NORMALIZED:
+            w = params[f"transformer.h.{i}.{nm}.weight"].detach()
+            assert float((w.norm(dim=dim) - 1).abs().max()) <= 1e-3
+            assert rel(w, ref.sd[f"transformer.h.{i}.{nm}.weight"].detach()) <= 2e-2
+    # untouched (grad-less) parameters did not move, decayed ones did
+    assert torch.equal(params["reconstruction_head.0.weight"].detach().cpu(), sd["reconstruction_head.0.weight"])
+    model.eval()
+    with torch.no_grad():
+        l1, _ = model(X)
+        l2, _ = O.vit_forward(ref.sd, cfg, X)
+    assert rel(l1, l2) <= 2e-2
+
+
+def test_trainer_path_equals_autograd_path():
+    cfg = O.named_config("mini")
+    sd = O.init_state_dict(cfg, 5)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(6, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, cfg.num_classes, (6,), generator=g).to(DEV)
+    m1, m2 = build(cfg, sd), build(cfg, sd)
+    logits, _ = m1(X)
+    F.cross_entropy(logits, y).backward()
+    tr = Trainer(m2, grad_clip=0.0)
+    tr._ensure_state()
+    tr.loss_buf.zero_()
+    m2.engine.zero_grad()
+    tr.micro_step(X, y)
+    torch.cuda.synchronize()
+    for n, p in m1.named_parameters():
+        if p.grad is not None:
+            assert rel(m2.engine.g(n), p.grad) <= 2e-3, n       # same kernels; only atomic summation order differs
+
+
+def test_state_dict_roundtrip_and_device_move():
+    cfg = O.named_config("micro")
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    keys = list(m.state_dict().keys())
+    assert set(keys) == set(O.param_shapes(cfg).keys())
+    for k, shp in O.param_shapes(cfg).items():
+        assert tuple(m.state_dict()[k].shape) == tuple(shp), k
+    m = m.to(DEV)
+    X, _ = O.formula_batch(cfg, 2)
+    m.eval()
+    with torch.no_grad():
+        a, _ = m(X.to(DEV))
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m2 = ViT(ViTConfig(**cfg.as_dict())).to(DEV).eval()
+        m2.load_state_dict(sd)
+        b, _ = m2(X.to(DEV))
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(X)                                              # CPU tensor: no fallback
