@@ -6,6 +6,13 @@ The CUDA path (nvit_b200.ViT / Trainer, bf16 tensor-core GEMMs + fp32 residual s
 Stated tolerance (north_star: "within a stated bf16 tolerance, fp32 reference"; calibrated in SURVEY.md section 4 on the
 reference's own bf16-autocast vs fp32 gap): logits rel-L2 <= 1e-2; every gradient tensor rel-L2 <= 3e-2 and cosine >=
 0.999 (tiny-magnitude tensors: abs <= 1e-3 * global gradient norm); weight rows |norm - 1| <= 1e-3 after a step.
+
+The closed-formula fixtures (micro / mini: C = 64 / 128, batch 3-5, sinusoidal weights and images) are deliberately
+ill-conditioned: per-sample gradients nearly cancel in the batch sum.  On them the REFERENCE'S OWN bf16-autocast run
+differs from its fp32 run by logits rel-L2 1.4e-2 (micro, bias) and per-tensor gradient rel-L2 of 0.3 ... 10 with an
+absolute error up to 0.43 of the global gradient norm (measured in the build container with /root/reference under
+torch.autocast("cpu", bf16)).  For those cases the stated tolerance is logits rel-L2 <= 2e-2 and, per gradient tensor,
+rel-L2 <= 3e-2 OR abs error <= 4e-3 * global gradient norm (bf16 epsilon); the random-init cases keep the strict bar.
 """
 import os
 
@@ -50,7 +57,7 @@ def oracle_grads(cfg, sd, X, y):
     return logits.detach(), aux["reconstruction"].detach(), loss.detach(), {k: v.grad for k, v in p.items()}
 
 
-def check_grads(model, ref_grads, tol=3e-2):
+def check_grads(model, ref_grads, tol=3e-2, abs_frac=1e-3):
     gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values() if g is not None)))
     worst = ("", 0.0)
     n = 0
@@ -62,8 +69,8 @@ def check_grads(model, ref_grads, tol=3e-2):
         assert p.grad is not None, f"{name}: missing gradient"
         n += 1
         err = float((p.grad.double() - rg.double()).norm())
-        if err <= 1e-3 * gnorm and float(rg.norm()) < 3e-2 * gnorm:
-            continue                       # tiny tensor: absolute criterion
+        if err <= abs_frac * gnorm and (float(rg.norm()) < 3e-2 * gnorm or abs_frac > 1e-3):
+            continue                       # tiny (or ill-conditioned fixture) tensor: absolute criterion
         r = rel(p.grad, rg)
         if r > worst[1]:
             worst = (name, r)
@@ -91,7 +98,7 @@ def test_forward_backward_matches_reference_golden(tag):
     X, y = O.formula_batch(cfg, batch)
     logits, aux = model(X.to(DEV))
     ce = F.cross_entropy(logits, y.to(DEV))
-    assert rel(logits, torch.from_numpy(gold["logits"]).to(DEV)) <= 1e-2
+    assert rel(logits.detach(), torch.from_numpy(gold["logits"]).to(DEV)) <= 2e-2
     assert abs(float(ce) - float(gold["ce"])) <= 1e-2 * abs(float(gold["ce"]))
     assert abs(float(aux["reconstruction"]) - float(gold["reconstruction"])) <= 1e-2 * float(gold["reconstruction"])
 
@@ -116,10 +123,11 @@ def test_logits_and_every_gradient_match_oracle(name, over, batch, seed):
     logits, aux = model(X)
     loss = F.cross_entropy(logits, y)
     loss.backward()
-    assert rel(logits, ref_logits) <= 1e-2, rel(logits, ref_logits)
+    formula = seed is None
+    assert rel(logits.detach(), ref_logits) <= (2e-2 if formula else 1e-2), rel(logits.detach(), ref_logits)
     assert abs(float(aux["reconstruction"]) - float(ref_recon)) <= 1e-2 * float(ref_recon)
     assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
-    check_grads(model, ref_grads)
+    check_grads(model, ref_grads, abs_frac=(4e-3 if formula else 1e-3))
     # parameters that never receive a gradient in the reference stay grad-less
     for n, p in model.named_parameters():
         if ".rmsnorm_" in n or n.startswith("reconstruction_head."):
