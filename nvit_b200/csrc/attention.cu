@@ -8,12 +8,16 @@
 // memory, the q/k row normalisation and sqk scaling run in place on those tiles (the reference spends ~8 eager kernels
 // and fp32 temporaries on it), and every matmul is a tcgen05.mma whose operands are just different descriptor views
 // (K-major or MN-major) of the same shared tiles:
-//   forward : S = Qh Kh^T (M=128 q rows, N=Tpad)  -> row softmax by the thread owning the TMEM lane -> P (bf16, smem)
+//   forward : S = Qh Kh^T (M=128 q rows, N=Tpad)  -> row softmax by the threads owning the TMEM lane -> P (bf16, smem)
 //             O = P V      (B operand = V as it lies, MN-major)
 //   backward (per 128-row kv tile j, scores kept transposed so that dV and dK complete per tile):
 //             S^T = Kh_j Qh^T ; P^T = exp(scale S^T - lse) ; dV_j = P^T dO ; dP^T = V_j dO^T ;
 //             dS^T = P^T (dP^T - delta) scale ; dK_j = dS^T Qh ; dQ += dS Kh_j (A = dS^T viewed MN-major)
 //             then the backward of the row normalisation and the sqk gradient.
+// 256 threads per CTA: two threads share a TMEM lane (score row) and split its columns, which halves the serial
+// per-thread work and doubles the warps available to hide ALU latency.  With unit-norm q/k the logits are bounded by
+// scale * max(s^2), so the forward softmax needs no running max (one pass); the general two-pass form is kept for
+// un-normalised inputs and very large learned scales.
 #include "common.cuh"
 #include <string.h>
 
@@ -22,16 +26,23 @@ namespace nvit {
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box);
 
-constexpr int ATT_ROWS = 256;                 // token capacity of a shared tile
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_ROWS = 256;                   // token capacity of a shared tile
 constexpr int ATT_TILE_BYTES = ATT_ROWS * 128;  // [256 tokens][64 bf16]
 constexpr int ATT_PB_BYTES = 128 * 256 * 2;     // [128 rows][4 k-blocks x 64 bf16]
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, int32_t c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a 128B-swizzled tile with 128-byte rows
@@ -47,22 +58,25 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // In-place q/k row normalisation on a swizzled tile: row <- s * row / ||row||.  Returns 1/||row|| (0 for a zero row).
 __device__ __forceinline__ float normalize_row(uint8_t* tile, int row, const float* s_scale) {
-  float x[64];
+  uint4 raw[8];
   float ss = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(tile + sw128(row, c));
-    unpack8(u, x + 8 * c);
-  }
+    raw[c] = *reinterpret_cast<const uint4*>(tile + sw128(row, c));
+    float x[8];
+    unpack8(raw[c], x);
 #pragma unroll
-  for (int i = 0; i < 64; ++i) ss += x[i] * x[i];
-  const float inv = ss > 0.f ? 1.f / sqrtf(ss) : 0.f;
+    for (int e = 0; e < 8; ++e) ss += x[e] * x[e];
+  }
+  const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = x[8 * c + e] * inv * s_scale[8 * c + e];
-    *reinterpret_cast<uint4*>(tile + sw128(row, c)) = pack8(y);
+    float x[8];
+    unpack8(raw[c], x);
+    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + 8 * c), s1 = *reinterpret_cast<const float4*>(s_scale + 8 * c + 4);
+    x[0] *= inv * s0.x; x[1] *= inv * s0.y; x[2] *= inv * s0.z; x[3] *= inv * s0.w;
+    x[4] *= inv * s1.x; x[5] *= inv * s1.y; x[6] *= inv * s1.z; x[7] *= inv * s1.w;
+    *reinterpret_cast<uint4*>(tile + sw128(row, c)) = pack8(x);
   }
   return inv;
 }
@@ -79,17 +93,38 @@ struct alignas(64) AttnParams {
   int B, H, T, TP, nQ, nK;
 };
 
-__host__ __device__ constexpr uint32_t IDESC_KK(int N) { return umma_idesc_bf16(128, N, 0, 0); }  // A K-major, B K-major
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
 __host__ __device__ constexpr uint32_t IDESC_MM(int N) { return umma_idesc_bf16(128, N, 1, 1); }  // A MN-major, B MN-major
-__device__ __forceinline__ uint32_t idesc_kk_n(int N) {
+__device__ __forceinline__ uint32_t idesc_kk_n(int N) {                                          // A, B K-major, runtime N
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + 512 /*scale + barriers*/;
+// common prologue pieces ------------------------------------------------------------------------------------------
+struct AttnThread {
+  int tid, warp, lane, wq, half, row, b, h;
+  int c_begin, c_end, nch;  // this thread's 16-column chunks of a score row
+};
+__device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
+  AttnThread t;
+  t.tid = threadIdx.x;
+  t.warp = t.tid >> 5;
+  t.lane = t.tid & 31;
+  t.wq = t.warp & 3;       // TMEM lane quarter this warp may access
+  t.half = t.warp >> 2;    // which half of the columns of a row
+  t.row = t.wq * 32 + t.lane;
+  t.b = blockIdx.x / p.H;
+  t.h = blockIdx.x % p.H;
+  t.nch = p.TP >> 4;
+  const int mid = (t.nch + 1) >> 1;
+  t.c_begin = t.half ? mid : 0;
+  t.c_end = t.half ? t.nch : mid;
+  return t;
+}
 
-__global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (64 + 256 + 8) * 4 + 64;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -97,15 +132,17 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
   uint8_t* sV = sK + ATT_TILE_BYTES;
   uint8_t* sP = sV + ATT_TILE_BYTES;
   float* s_scale = reinterpret_cast<float*>(sP + ATT_PB_BYTES);  // [64]
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_scale + 64);
+  float* s_part = s_scale + 64;                                  // [2][128] partial row sums / maxima
+  float* s_misc = s_part + 256;                                  // [0] = log2-domain logit bound
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const AttnThread t = attn_thread(p);
   const int T = p.T, TP = p.TP;
+  const bool has_norm = p.sqk != nullptr;
 
-  if (tid == 0) {
+  if (t.tid == 0) {
     tma_prefetch_desc(&p.tq);
     tma_prefetch_desc(&p.tk);
     tma_prefetch_desc(&p.tv);
@@ -113,40 +150,50 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (t.warp == 0) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
-  if (tid < 64) s_scale[tid] = p.sqk ? p.sqk[h * 64 + tid] * p.sqk_mul : 1.f;
+  if (t.warp == 1) {
+    // per-head scale vector and the bound  |scale * qh.kh| <= scale * max_c s_c^2
+    const float s0 = has_norm ? p.sqk[t.h * 64 + t.lane] * p.sqk_mul : 1.f;
+    const float s1 = has_norm ? p.sqk[t.h * 64 + 32 + t.lane] * p.sqk_mul : 1.f;
+    s_scale[t.lane] = s0;
+    s_scale[32 + t.lane] = s1;
+    const float mx = warp_max(fmaxf(s0 * s0, s1 * s1));
+    if (t.lane == 0) s_misc[0] = p.scale * mx;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  const float bound = s_misc[0];
+  const bool two_pass = !has_norm || !(bound <= 60.f);
 
-  if (tid == 0) {
+  if (t.tid == 0) {
     mbar_arrive_expect_tx(bar_tma, 3 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tq, bar_tma, sQ, h * 64, 0, b);
-    tma_load_3d(&p.tk, bar_tma, sK, h * 64, 0, b);
-    tma_load_3d(&p.tv, bar_tma, sV, h * 64, 0, b);
+    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
   }
   mbar_wait(bar_tma, 0);
 
-  if (p.sqk) {
-    for (int r = tid; r < T; r += 128) {
-      normalize_row(sQ, r, s_scale);
-      normalize_row(sK, r, s_scale);
+  if (has_norm) {
+    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
+      if (j < T) normalize_row(sQ, j, s_scale);
+      else normalize_row(sK, j - T, s_scale);
     }
   }
   fence_proxy_async_smem();
   __syncthreads();
 
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sP_a = smem_u32(sP);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
   const float sl2 = p.scale * LOG2E;
   uint32_t mma_phase = 0;
 
   for (int i = 0; i < p.nQ; ++i) {
-    if (tid == 0) {
+    if (t.tid == 0) {
       tc_fence_after_sync();
       const uint32_t idesc = idesc_kk_n(TP);
 #pragma unroll
@@ -159,79 +206,82 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
     mma_phase ^= 1;
     tc_fence_after_sync();
 
-    const int qtok = i * 128 + tid;
-    float mx = -INFINITY;
-    for (int c0 = 0; c0 < TP; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + c0, r);
-      tmem_wait_ld();
+    const int qtok = i * 128 + t.row;
+    float m2 = bound * LOG2E;  // log2-domain offset subtracted before exp2
+    if (two_pass) {
+      float mx = -INFINITY;
+      for (int c = t.c_begin; c < t.c_end; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, r);
+        tmem_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (c0 + e < T) mx = fmaxf(mx, __uint_as_float(r[e]));
+        for (int e = 0; e < 16; ++e)
+          if (c * 16 + e < T) mx = fmaxf(mx, __uint_as_float(r[e]));
+      }
+      s_part[t.half * 128 + t.row] = mx;
+      __syncthreads();
+      m2 = fmaxf(s_part[t.row], s_part[128 + t.row]) * sl2;
+      __syncthreads();
     }
     float sum = 0.f;
-    for (int c0 = 0; c0 < TP; c0 += 16) {
+    for (int c = t.c_begin; c < t.c_end; ++c) {
       uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + c0, r);
+      tmem_ld_32x32b_x16(t_lane + c * 16, r);
       tmem_wait_ld();
       float pv[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float v = (c0 + e < T) ? exp2f((__uint_as_float(r[e]) - mx) * sl2) : 0.f;
-        pv[e] = v;
-        sum += v;
+      for (int e = 0; e < 16; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(r[e]), sl2, -m2));
+      if (c == t.nch - 1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c * 16 + e >= T) pv[e] = 0.f;
       }
-      uint8_t* blk = sP + (c0 >> 6) * 16384;
-      const int ch = (c0 & 63) >> 3;
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch)) = pack8(pv);
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch + 1)) = pack8(pv + 8);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sum += pv[e];
+      uint8_t* blk = sP + (c >> 2) * 16384;
+      const int ch = (c & 3) * 2;
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch)) = pack8(pv);
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch + 1)) = pack8(pv + 8);
     }
+    s_part[t.half * 128 + t.row] = sum;
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
 
-    if (tid == 0) {
+    if (t.tid == 0) {
       tc_fence_after_sync();
-      constexpr uint32_t idesc = IDESC_KM(64);
       const int nks = TP >> 4;
       for (int ks = 0; ks < nks; ++ks)
         umma_bf16_ss(tmem_base + 256, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                     umma_smem_desc(sV_a + ks * 2048, 8192, 1024), idesc, ks > 0);
+                     umma_smem_desc(sV_a + ks * 2048, 8192, 1024), IDESC_KM(64), ks > 0);
       umma_commit(bar_mma);
     }
+    const float total = s_part[t.row] + s_part[128 + t.row];
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-
     {
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(t_lane + 256, r0);
-      tmem_ld_32x32b_x32(t_lane + 256 + 32, r1);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + 256 + t.half * 32, r);
       tmem_wait_ld();
       if (qtok < T) {
-        const float inv = 1.f / sum;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * T + qtok) * p.ldo + h * 64;
+        const float inv = 1.f / total;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.half * 32;
         float o[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r0[8 * c + e]) * inv;
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[8 * c + e]) * inv;
           *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(o);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r1[8 * c + e]) * inv;
-          *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = pack8(o);
-        }
-        p.lse[(static_cast<long long>(b) * p.H + h) * T + qtok] = mx * p.scale + logf(sum);
+        if (t.half == 0) p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + qtok] = (m2 + log2f(total)) * LN2;
       }
     }
     tc_fence_before_sync();
     __syncthreads();
   }
 
-  if (warp == 0) {
+  if (t.warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
@@ -240,40 +290,90 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------ backward
 constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 128) * 4 + 64;
 
-// backward of y = s * x/||x|| for one row: g = dL/dy (fp32), x raw (bf16 row in global).  Writes dx, accumulates dsqk.
-__device__ __forceinline__ void norm_bwd_row(const float* g, const __nv_bfloat16* xrow, float inv, const float* s_scale, bool has_norm,
-                                             __nv_bfloat16* dst, float* dacc) {
+// backward of y = s * x/||x|| for one row whose dL/dy sits in 64 TMEM columns at `taddr`.  Two passes over TMEM keep
+// the register footprint small.  Writes dx (bf16) and accumulates dL/ds per channel into dacc.
+__device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const __nv_bfloat16* xrow, float inv, const float* s_scale, bool has_norm,
+                                             __nv_bfloat16* dst, float (&dacc)[64], bool valid) {
   if (!has_norm) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(g + 8 * c);
-    return;
-  }
-  float n[64];
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + hh * 32, r);
+      tmem_wait_ld();
+      if (valid) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xrow + 8 * c);
-    unpack8(u, n + 8 * c);
+        for (int c = 0; c < 4; ++c) {
+          float g[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(r[8 * c + e]);
+          *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = pack8(g);
+        }
+      }
+    }
+    return;
   }
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    n[i] *= inv;
-    dacc[i] += g[i] * n[i];
-    dot += g[i] * s_scale[i] * n[i];
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + hh * 32, r);
+    tmem_wait_ld();
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float n[8];
+        unpack8(*reinterpret_cast<const uint4*>(xrow + hh * 32 + 8 * c), n);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = hh * 32 + 8 * c + e;
+          const float g = __uint_as_float(r[8 * c + e]);
+          const float nn = n[e] * inv;
+          dacc[i] += g * nn;
+          dot += g * s_scale[i] * nn;
+        }
+      }
+    }
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float d[8];
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + hh * 32, r);
+    tmem_wait_ld();
+    if (valid) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = 8 * c + e;
-      d[e] = (g[i] * s_scale[i] - n[i] * dot) * inv;
+      for (int c = 0; c < 4; ++c) {
+        float n[8], d[8];
+        unpack8(*reinterpret_cast<const uint4*>(xrow + hh * 32 + 8 * c), n);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = hh * 32 + 8 * c + e;
+          d[e] = (__uint_as_float(r[8 * c + e]) * s_scale[i] - n[e] * inv * dot) * inv;
+        }
+        *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = pack8(d);
+      }
     }
-    *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(d);
   }
 }
 
-__global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
+// Sum 64 per-lane partials over the 32 lanes of a warp by recursive halving (62 shuffles) and add them to s_out[64].
+__device__ __forceinline__ void reduce64_to_smem(float (&v)[64], float* s_out, int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int off = 16 >> step, n = 32 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const int base = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+  atomicAdd(&s_out[base], v[0]);
+  atomicAdd(&s_out[base + 1], v[1]);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -291,12 +391,11 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const AttnThread t = attn_thread(p);
   const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
 
-  if (tid == 0) {
+  if (t.tid == 0) {
     tma_prefetch_desc(&p.tq);
     tma_prefetch_desc(&p.tk);
     tma_prefetch_desc(&p.tv);
@@ -305,33 +404,34 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (t.warp == 0) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
-  if (tid < 64) {
-    s_scale[tid] = has_norm ? p.sqk[h * 64 + tid] * p.sqk_mul : 1.f;
-    s_dsqk[tid] = 0.f;
+  if (t.tid < 64) {
+    s_scale[t.tid] = has_norm ? p.sqk[t.h * 64 + t.tid] * p.sqk_mul : 1.f;
+    s_dsqk[t.tid] = 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (tid == 0) {
+  if (t.tid == 0) {
     mbar_arrive_expect_tx(bar_tma, 4 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tq, bar_tma, sQ, h * 64, 0, b);
-    tma_load_3d(&p.tk, bar_tma, sK, h * 64, 0, b);
-    tma_load_3d(&p.tv, bar_tma, sV, h * 64, 0, b);
-    tma_load_3d(&p.tdo, bar_tma, sDO, h * 64, 0, b);
+    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tdo, bar_tma, sDO, t.h * 64, 0, t.b);
   }
   // while the tiles fly: lse, delta = rowsum(dO * O), and a clean P buffer
-  for (int r = tid; r < 256; r += 128) {
+  {
+    const int r = t.tid;  // 256 threads, 256 rows
     float l = 0.f, d = 0.f;
     if (r < T) {
-      l = p.lse[(static_cast<long long>(b) * p.H + h) * T + r] * LOG2E;
-      const __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * T + r) * p.ldo + h * 64;
-      const __nv_bfloat16* grow = p.dout + (static_cast<long long>(b) * T + r) * p.ldo + h * 64;
+      l = p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E;
+      const __nv_bfloat16* orow = p.o + (static_cast<long long>(t.b) * T + r) * p.ldo + t.h * 64;
+      const __nv_bfloat16* grow = p.dout + (static_cast<long long>(t.b) * T + r) * p.ldo + t.h * 64;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float a[8], g[8];
@@ -346,21 +446,21 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
   }
-  for (int i = tid; i < ATT_PB_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = t.tid; i < ATT_PB_BYTES / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
   mbar_wait(bar_tma, 0);
   __syncthreads();
 
   if (has_norm) {
-    for (int r = tid; r < T; r += 128) {
-      s_invq[r] = normalize_row(sQ, r, s_scale);
-      s_invk[r] = normalize_row(sK, r, s_scale);
+    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
+      if (j < T) s_invq[j] = normalize_row(sQ, j, s_scale);
+      else s_invk[j - T] = normalize_row(sK, j - T, s_scale);
     }
   }
   fence_proxy_async_smem();
   __syncthreads();
 
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
   const float sl2 = p.scale * LOG2E;
   const int nks_q = TP >> 4;  // k-steps over the q axis
   uint32_t mma_phase = 0;
@@ -371,9 +471,10 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
   constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
   for (int j = 0; j < p.nK; ++j) {
-    const int kv = j * 128 + tid;
+    const int kv = j * 128 + t.row;
+    const bool kv_ok = kv < T;
     // ---- S^T_j = Kh_j Qh^T
-    if (tid == 0) {
+    if (t.tid == 0) {
       tc_fence_after_sync();
       const uint32_t idesc = idesc_kk_n(TP);
 #pragma unroll
@@ -385,27 +486,38 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    // ---- P^T = exp(scale S^T - lse)   (thread = kv row, columns = q)
-    for (int c0 = 0; c0 < TP; c0 += 16) {
+    // ---- P^T = exp(scale S^T - lse)   (two threads per kv row, columns = q)
+    for (int c = t.c_begin; c < t.c_end; ++c) {
       uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + TM_S + c0, r);
+      tmem_ld_32x32b_x16(t_lane + TM_S + c * 16, r);
       tmem_wait_ld();
       float pv[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int qi = c0 + e;
-        pv[e] = (kv < T && qi < T) ? exp2f(__uint_as_float(r[e]) * sl2 - s_lse[qi]) : 0.f;
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(s_lse + c * 16 + 4 * e4);
+        pv[4 * e4 + 0] = ex2_approx(fmaf(__uint_as_float(r[4 * e4 + 0]), sl2, -l4.x));
+        pv[4 * e4 + 1] = ex2_approx(fmaf(__uint_as_float(r[4 * e4 + 1]), sl2, -l4.y));
+        pv[4 * e4 + 2] = ex2_approx(fmaf(__uint_as_float(r[4 * e4 + 2]), sl2, -l4.z));
+        pv[4 * e4 + 3] = ex2_approx(fmaf(__uint_as_float(r[4 * e4 + 3]), sl2, -l4.w));
       }
-      uint8_t* blk = sP + (c0 >> 6) * 16384;
-      const int ch = (c0 & 63) >> 3;
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch)) = pack8(pv);
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch + 1)) = pack8(pv + 8);
+      if (!kv_ok) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+      } else if (c == t.nch - 1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c * 16 + e >= T) pv[e] = 0.f;
+      }
+      uint8_t* blk = sP + (c >> 2) * 16384;
+      const int ch = (c & 3) * 2;
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch)) = pack8(pv);
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch + 1)) = pack8(pv + 8);
     }
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
     // ---- dV_j = P^T dO ; dP^T_j = V_j dO^T
-    if (tid == 0) {
+    if (t.tid == 0) {
       tc_fence_after_sync();
       for (int ks = 0; ks < nks_q; ++ks)
         umma_bf16_ss(tmem_base + TM_DV, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
@@ -421,25 +533,31 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     mma_phase ^= 1;
     tc_fence_after_sync();
     // ---- dS^T = P^T (dP^T - delta) scale, in place over P^T
-    for (int c0 = 0; c0 < TP; c0 += 16) {
+    for (int c = t.c_begin; c < t.c_end; ++c) {
       uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + TM_S + c0, r);
+      tmem_ld_32x32b_x16(t_lane + TM_S + c * 16, r);
       tmem_wait_ld();
-      uint8_t* blk = sP + (c0 >> 6) * 16384;
-      const int ch = (c0 & 63) >> 3;
+      uint8_t* blk = sP + (c >> 2) * 16384;
+      const int ch = (c & 3) * 2;
       float pv[16];
-      unpack8(*reinterpret_cast<const uint4*>(blk + sw128(tid, ch)), pv);
-      unpack8(*reinterpret_cast<const uint4*>(blk + sw128(tid, ch + 1)), pv + 8);
+      unpack8(*reinterpret_cast<const uint4*>(blk + sw128(t.row, ch)), pv);
+      unpack8(*reinterpret_cast<const uint4*>(blk + sw128(t.row, ch + 1)), pv + 8);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pv[e] = pv[e] * (__uint_as_float(r[e]) - s_delta[c0 + e]) * p.scale;
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch)) = pack8(pv);
-      *reinterpret_cast<uint4*>(blk + sw128(tid, ch + 1)) = pack8(pv + 8);
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(s_delta + c * 16 + 4 * e4);
+        pv[4 * e4 + 0] *= (__uint_as_float(r[4 * e4 + 0]) - d4.x) * p.scale;
+        pv[4 * e4 + 1] *= (__uint_as_float(r[4 * e4 + 1]) - d4.y) * p.scale;
+        pv[4 * e4 + 2] *= (__uint_as_float(r[4 * e4 + 2]) - d4.z) * p.scale;
+        pv[4 * e4 + 3] *= (__uint_as_float(r[4 * e4 + 3]) - d4.w) * p.scale;
+      }
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch)) = pack8(pv);
+      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch + 1)) = pack8(pv + 8);
     }
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
     // ---- dK_j = dS^T Qh ; dQ_m += dS_j Kh_j
-    if (tid == 0) {
+    if (t.tid == 0) {
       tc_fence_after_sync();
       for (int ks = 0; ks < nks_q; ++ks)
         umma_bf16_ss(tmem_base + TM_DK, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
@@ -454,60 +572,46 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    // ---- write dV_j, dK_j rows
-    {
-      uint32_t r0[32], r1[32];
-      float g[64];
-      tmem_ld_32x32b_x32(t_lane + TM_DV, r0);
-      tmem_ld_32x32b_x32(t_lane + TM_DV + 32, r1);
-      tmem_wait_ld();
-      if (kv < T) {
+    // ---- write dV_j rows (column half 0 threads) and dK_j rows (half 1 threads)
+    if (t.half == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { g[i] = __uint_as_float(r0[i]); g[32 + i] = __uint_as_float(r1[i]); }
-        __nv_bfloat16* dst = p.dv + (static_cast<long long>(b) * T + kv) * p.lddv + h * 64;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + TM_DV + hh * 32, r);
+        tmem_wait_ld();
+        if (kv_ok) {
+          __nv_bfloat16* dst = p.dv + (static_cast<long long>(t.b) * T + kv) * p.lddv + t.h * 64 + hh * 32;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(g + 8 * c);
+          for (int c = 0; c < 4; ++c) {
+            float g[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(r[8 * c + e]);
+            *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(g);
+          }
+        }
       }
-      tmem_ld_32x32b_x32(t_lane + TM_DK, r0);
-      tmem_ld_32x32b_x32(t_lane + TM_DK + 32, r1);
-      tmem_wait_ld();
-      if (kv < T) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { g[i] = __uint_as_float(r0[i]); g[32 + i] = __uint_as_float(r1[i]); }
-        norm_bwd_row(g, p.k + (static_cast<long long>(b) * T + kv) * p.ldk + h * 64, s_invk[kv], s_scale, has_norm,
-                     p.dk + (static_cast<long long>(b) * T + kv) * p.lddk + h * 64, dacc);
-      }
+    } else {
+      const int kvc = kv_ok ? kv : 0;
+      norm_bwd_row(t_lane + TM_DK, p.k + (static_cast<long long>(t.b) * T + kvc) * p.ldk + t.h * 64, s_invk[kvc], s_scale, has_norm,
+                   p.dk + (static_cast<long long>(t.b) * T + kvc) * p.lddk + t.h * 64, dacc, kv_ok);
     }
     tc_fence_before_sync();
     __syncthreads();
   }
 
-  // ---- dQ rows
-  for (int m = 0; m < p.nQ; ++m) {
-    const int qi = m * 128 + tid;
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * m, r0);
-    tmem_ld_32x32b_x32(t_lane + TM_DQ + 64 * m + 32, r1);
-    tmem_wait_ld();
-    if (qi < T) {
-      float g[64];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { g[i] = __uint_as_float(r0[i]); g[32 + i] = __uint_as_float(r1[i]); }
-      norm_bwd_row(g, p.q + (static_cast<long long>(b) * T + qi) * p.ldq + h * 64, s_invq[qi], s_scale, has_norm,
-                   p.dq + (static_cast<long long>(b) * T + qi) * p.lddq + h * 64, dacc);
-    }
+  // ---- dQ rows: column-half h of the CTA takes q tile h
+  if (t.half < p.nQ) {
+    const int qi = t.half * 128 + t.row;
+    const bool ok = qi < T;
+    const int qc = ok ? qi : 0;
+    norm_bwd_row(t_lane + TM_DQ + 64 * t.half, p.q + (static_cast<long long>(t.b) * T + qc) * p.ldq + t.h * 64, s_invq[qc], s_scale, has_norm,
+                 p.dq + (static_cast<long long>(t.b) * T + qc) * p.lddq + t.h * 64, dacc, ok);
   }
-  if (has_norm) {
-#pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      const float v = warp_sum(dacc[i]);
-      if (lane == 0) atomicAdd(&s_dsqk[i], v);
-    }
-  }
+  if (has_norm) reduce64_to_smem(dacc, s_dsqk, t.lane);
   tc_fence_before_sync();
   __syncthreads();
-  if (has_norm && tid < 64) atomicAdd(p.dsqk + h * 64 + tid, s_dsqk[tid] * p.sqk_mul);
-  if (warp == 0) {
+  if (has_norm && t.tid < 64) atomicAdd(p.dsqk + t.h * 64 + t.tid, s_dsqk[t.tid] * p.sqk_mul);
+  if (t.warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
@@ -558,7 +662,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<<<(unsigned)(B * H), 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_fwd_kernel<<<(unsigned)(B * H), ATT_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -603,7 +707,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
     attr_set = true;
   }
-  attn_bwd_kernel<<<(unsigned)(B * H), 128, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_bwd_kernel<<<(unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

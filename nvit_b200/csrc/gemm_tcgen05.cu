@@ -26,8 +26,8 @@ namespace nvit {
 struct alignas(64) GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
-  CUtensorMap tma_c;   // output tile store (bf16: box 64x128 SW128; fp32: box 32x128 SW128; swiglu: box 32x128 dense)
-  CUtensorMap tma_c2;  // bf16 side copy (box 32x128 dense) / swiglu raw u
+  CUtensorMap tma_c;   // output tile store (bf16 / swiglu x: box 64x128 SW128; fp32: box 32x128 SW128)
+  CUtensorMap tma_c2;  // bf16 side copy of an fp32 output (box 32x128 dense) / swiglu raw u (box 64x128 SW128)
   CUtensorMap tma_c3;  // swiglu raw v
   int direct;          // 1: per-thread global stores (outputs that TMA cannot address), 0: smem-staged TMA stores
   void* C;
@@ -67,7 +67,7 @@ struct GemmTraits {
   static constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
 };
 
-__device__ __forceinline__ float silu_mul(float u, float v) { return u * v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_mul(float u, float v) { return __fdividef(u * v, 1.f + __expf(-v)); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v, int valid, bool vec) {
@@ -227,50 +227,65 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
       };
       if (!p.direct) {
         if constexpr (SWIGLU) {
-          // 4 chunks of 32 gate outputs; staging = x | raw u | raw v, each [128 rows][32 bf16] dense (64 B rows)
+          // two groups of 64 gate outputs; x, raw u and raw v go out as three 128B-swizzled [128 x 64] bf16 tiles that
+          // rotate through the two staging buffers
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32], r2[32];
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
-            tmem_ld_32x32b_x32(taddr + 128 + c * 32, r2);
-            tmem_wait_ld();
-            if (c == 3) release_tmem();
-            const int n0 = n_blk * 128 + c * 32;
-            if (n0 >= p.N) continue;  // uniform over the epilogue warps
-            uint32_t xo[16], uo[16], vo[16];
+          for (int g = 0; g < 2; ++g) {
+            uint32_t uo[32], vo[32], xo[32];
+            {
+              uint32_t r[32], r2[32];
+              tmem_ld_32x32b_x32(taddr + g * 64, r);
+              tmem_ld_32x32b_x32(taddr + g * 64 + 32, r2);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              uo[i >> 1] = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));   // c_fc output is bf16 under autocast
-              vo[i >> 1] = pack_bf16(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1]));
+              for (int i = 0; i < 16; ++i) {   // c_fc output is bf16 under autocast
+                uo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                uo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+              }
+              tmem_ld_32x32b_x32(taddr + 128 + g * 64, r);
+              tmem_ld_32x32b_x32(taddr + 128 + g * 64 + 32, r2);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                vo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                vo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+              }
+            }
+            if (g == 1) release_tmem();
+            const int n0 = n_blk * 128 + g * 64;
+            if (n0 >= p.N) continue;  // uniform over the epilogue warps
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
               float su0 = 1.f, su1 = 1.f, sv0 = 1.f, sv1 = 1.f;
               if (p.colscale) {
-                const int j0 = min(n0 + i, p.N - 1), j1 = min(n0 + i + 1, p.N - 1);
+                const int j0 = min(n0 + 2 * i, p.N - 1), j1 = min(n0 + 2 * i + 1, p.N - 1);
                 su0 = __ldg(p.colscale + j0) * p.colscale_mul;
                 su1 = __ldg(p.colscale + j1) * p.colscale_mul;
                 sv0 = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
                 sv1 = __ldg(p.colscale + p.swiglu_half + j1) * p.colscale_mul;
               }
-              xo[i >> 1] = pack_bf16(silu_mul(bf16lo(uo[i >> 1]) * su0, bf16lo(vo[i >> 1]) * sv0),
-                                     silu_mul(bf16hi(uo[i >> 1]) * su1, bf16hi(vo[i >> 1]) * sv1));
+              xo[i] = pack_bf16(silu_mul(bf16lo(uo[i]) * su0, bf16lo(vo[i]) * sv0), silu_mul(bf16hi(uo[i]) * su1, bf16hi(vo[i]) * sv1));
             }
-            if (issuer) bulk_wait_group_read<0>();
-            named_bar_sync(1, 128);
-            uint8_t* bx = stg + erow * 64;
+            auto stage_store = [&](const uint32_t (&src)[32], const CUtensorMap* map) {
+              uint8_t* buf = stg + (chunk_ctr & 1) * 16384;
+              ++chunk_ctr;
+              if (issuer) bulk_wait_group_read<1>();
+              named_bar_sync(1, 128);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(bx + j * 16) = make_uint4(xo[4 * j], xo[4 * j + 1], xo[4 * j + 2], xo[4 * j + 3]);
-              *reinterpret_cast<uint4*>(bx + 8192 + j * 16) = make_uint4(uo[4 * j], uo[4 * j + 1], uo[4 * j + 2], uo[4 * j + 3]);
-              *reinterpret_cast<uint4*>(bx + 16384 + j * 16) = make_uint4(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (issuer) {
-              tma_store_2d(&p.tma_c, stg, n0, m_blk * T::BM);
-              if (p.C2) {
-                tma_store_2d(&p.tma_c2, stg + 8192, n0, m_blk * T::BM);
-                tma_store_2d(&p.tma_c3, stg + 16384, n0, m_blk * T::BM);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
+                    make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+              fence_proxy_async_smem();
+              named_bar_sync(1, 128);
+              if (issuer) {
+                tma_store_2d(map, buf, n0, m_blk * T::BM);
+                bulk_commit_group();
               }
-              bulk_commit_group();
+            };
+            stage_store(xo, &p.tma_c);
+            if (p.C2) {
+              stage_store(uo, &p.tma_c2);
+              stage_store(vo, &p.tma_c3);
             }
           }
         } else if (!p.out_f32) {
@@ -547,10 +562,10 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   if (SWIGLU) {
     const bool ok = tma_addressable(p.C, p.ldc, 2) && (!p.C2 || (tma_addressable(p.C2, p.ldc2, 2) && (p.swiglu_half % 8) == 0));
     if (ok) {
-      if ((rc = make_out_tmap(&p.tma_c, p.C, false, false, p.N, p.M, p.ldc, 32))) return rc;
+      if ((rc = make_out_tmap(&p.tma_c, p.C, false, true, p.N, p.M, p.ldc, 64))) return rc;
       if (p.C2) {
-        if ((rc = make_out_tmap(&p.tma_c2, p.C2, false, false, p.N, p.M, p.ldc2, 32))) return rc;
-        if ((rc = make_out_tmap(&p.tma_c3, p.C2 + p.swiglu_half, false, false, p.N, p.M, p.ldc2, 32))) return rc;
+        if ((rc = make_out_tmap(&p.tma_c2, p.C2, false, true, p.N, p.M, p.ldc2, 64))) return rc;
+        if ((rc = make_out_tmap(&p.tma_c3, p.C2 + p.swiglu_half, false, true, p.N, p.M, p.ldc2, 64))) return rc;
       }
       p.direct = 0;
     }
