@@ -32,7 +32,8 @@ int nvit_sm_count(void);
  *   C[M,N] (+)= A · B^T, bf16 operands, fp32 accumulation in tensor memory (tcgen05).
  *   a_mn_major = 0: A stored [M,K] (lda = row pitch); 1: A stored [K,M] (M contiguous).  Likewise B ([N,K] / [K,N]).
  *   out_f32: C is float (else bf16).  C2_bf16 (optional, only with out_f32): second bf16 copy of the result.
- *   accumulate: C += result (fp32 only).  splits > 1: split the K range across CTAs, partial sums added atomically.
+ *   accumulate: C += result (fp32 only).  splits > 1: split the K range across CTAs, partial sums added with TMA
+ *   reduce-add; splits <= 0 picks the split count that fills the SMs (fp32 outputs without epilogue only).
  *   Epilogue, in this order: + bias[N]; * colscale[N]*colscale_mul; + rowadd[row % rowadd_period, N]  (any may be NULL).
  *   swiglu_half F > 0: B holds [2F, K] (u rows then v rows, torch.chunk order of model.py:153); N must equal F.  The
  *     kernel computes both halves of a column pair in one CTA and writes C[M,F] = (u*cs_u) * silu(v*cs_v) as bf16
@@ -42,6 +43,10 @@ int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t
                    int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major, int out_f32, int accumulate,
                    int splits, const float* bias, const float* colscale, float colscale_mul, const float* rowadd,
                    int64_t rowadd_period, int64_t swiglu_half, void* stream);
+
+/* Test/benchmark hook: 0 = choose automatically (default), 1 = single-CTA 128-row tiles (cta_group::1),
+ * 2 = CTA-pair 256-row tiles (cta_group::2, cluster of two SMs).  Process-wide. */
+int nvit_gemm_force_cta_group(int mode);
 
 /* ---- casts / reductions ------------------------------------------------------------------------------------- */
 /* autocast's weight/activation casts (torch.autocast around model.py:905 of train.py) */

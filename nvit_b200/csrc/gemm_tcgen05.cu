@@ -44,15 +44,16 @@ struct alignas(64) GemmParams {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CG2 = false>
 struct GemmTraits {
-  static constexpr int BM = 128;
+  static constexpr int BM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int BK = 64;
   static constexpr int UMMA_K = 16;
+  static constexpr int BN_CTA = CG2 ? BN / 2 : BN;   // B rows this CTA stages (a pair splits B between its two CTAs)
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = 196608 / STAGE_BYTES;  // 4 (48 KB stages), 6 (32 KB), 8 (24 KB)
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
   static constexpr int STAGING_BYTES = 32768;  // epilogue staging: 2 x 16 KB (or 16 + 8 / 3 x 8 KB, see the epilogue)
@@ -85,9 +86,14 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU>
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2>
 __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using T = GemmTraits<BN, A_MN, B_MN>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2>;
+  // CG2: the kernel runs as clusters of two CTAs (one SM pair); the pair computes a 256 x BN tile with
+  // tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its own 128 rows of A and half of B.
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0;
+  const int unit0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_stride = CG2 ? (int)cluster_count_x() : (int)gridDim.x;
   static_assert(!SWIGLU || (BN == 256 && !A_MN && !B_MN), "swiglu epilogue: 128x256 K-major tiles only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,16 +119,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < T::ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], CG2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, T::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG2) { tmem_alloc_cg2(tmem_ptr, T::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_ptr, T::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -131,47 +137,61 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u % p.splits;
         const int t = u / p.splits;
         const int n_blk = t % p.tiles_n;
-        const int m_blk = t / p.tiles_n;
+        const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;   // this CTA's 128-row block
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * T::STAGE_BYTES;
           uint8_t* sB = sA + T::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          // pair mode: both CTAs' bytes are counted on the rank-0 CTA's barrier, which its MMA warp waits on
+          uint32_t fb = smem_u32(&full_bar[stage]);
+          if constexpr (CG2) {
+            fb = mapa_shared(fb, 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          }
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if constexpr (CG2) tma_load_2d_cg2(m, fb, dst, c0, c1);
+            else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(&p.tma_a, &full_bar[stage], sA, kb * T::BK, m_blk * T::BM);
+            load(&p.tma_a, sA, kb * T::BK, m_blk * T::BM);
           } else {
 #pragma unroll
-            for (int j = 0; j < T::BM / 64; ++j)
-              tma_load_2d(&p.tma_a, &full_bar[stage], sA + j * (T::BK * 128), m_blk * T::BM + j * 64, kb * T::BK);
+            for (int j = 0; j < T::BM / 64; ++j) load(&p.tma_a, sA + j * (T::BK * 128), m_blk * T::BM + j * 64, kb * T::BK);
           }
           if constexpr (SWIGLU) {
-            tma_load_2d(&p.tma_b, &full_bar[stage], sB, kb * T::BK, n_blk * 128);
-            tma_load_2d(&p.tma_b, &full_bar[stage], sB + 128 * 128, kb * T::BK, p.swiglu_half + n_blk * 128);
+            if constexpr (CG2) {   // rank 0 stages the u rows, rank 1 the matching v rows
+              load(&p.tma_b, sB, kb * T::BK, (cta_rank ? p.swiglu_half : 0) + n_blk * 128);
+            } else {
+              load(&p.tma_b, sB, kb * T::BK, n_blk * 128);
+              load(&p.tma_b, sB + 128 * 128, kb * T::BK, p.swiglu_half + n_blk * 128);
+            }
           } else if constexpr (!B_MN) {
-            tma_load_2d(&p.tma_b, &full_bar[stage], sB, kb * T::BK, n_blk * BN);
+            load(&p.tma_b, sB, kb * T::BK, n_blk * BN + (int)cta_rank * T::BN_CTA);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&p.tma_b, &full_bar[stage], sB + j * (T::BK * 128), n_blk * BN + j * 64, kb * T::BK);
+            for (int j = 0; j < T::BN_CTA / 64; ++j)
+              load(&p.tma_b, sB + j * (T::BK * 128), n_blk * BN + (int)cta_rank * T::BN_CTA + j * 64, kb * T::BK);
           }
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(T::BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================== MMA issuer (rank-0 CTA of a pair issues for both) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(CG2 ? 256 : 128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units && cta_rank == 0; u += unit_stride) {
       const int split = u % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -188,10 +208,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           for (int k = 0; k < T::BK / T::UMMA_K; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * T::A_KSTEP, T::A_LBO, T::SBO);
             const uint64_t db = umma_smem_desc(b_addr + k * T::B_KSTEP, T::B_LBO, T::SBO);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG2) umma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          if constexpr (CG2) {
+            umma_commit_cg2(&empty_bar[stage]);                   // frees the slot in both CTAs
+            if (kb == kb1 - 1) umma_commit_cg2(&tmem_full[acc]);  // accumulator complete, both CTAs' epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
@@ -212,10 +238,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     uint32_t chunk_ctr = 0;
     const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec2_ok = (p.C2 == nullptr) || ((p.ldc2 & 7) == 0);
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units; u += unit_stride) {
       const int t = u / p.splits;
       const int n_blk = t % p.tiles_n;
-      const int m_blk = t / p.tiles_n;
+      const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;
       const int row = m_blk * T::BM + erow;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -223,7 +249,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
       auto release_tmem = [&]() {
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // the issuing CTA's barrier
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       };
       if (!p.direct) {
         if constexpr (SWIGLU) {
@@ -463,10 +492,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, T::TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, T::TMEM_COLS);
+    else tmem_dealloc(tmem_base, T::TMEM_COLS);
   }
 }
 
@@ -546,15 +576,15 @@ static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, u
   return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU>
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2>
 static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
-  using T = GemmTraits<BN, A_MN, B_MN>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2>;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&p.tma_a, A, p.K, p.M, lda, T::BK, T::BM);
   else       rc = make_tmap_bf16_2d(&p.tma_a, A, p.M, p.K, lda, 64, T::BK);
   if (rc) return rc;
   if (SWIGLU)     rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, 2ull * p.swiglu_half, ldb, T::BK, 128);
-  else if (!B_MN) rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, p.N, ldb, T::BK, BN);
+  else if (!B_MN) rc = make_tmap_bf16_2d(&p.tma_b, B, p.K, p.N, ldb, T::BK, T::BN_CTA);
   else            rc = make_tmap_bf16_2d(&p.tma_b, B, p.N, p.K, ldb, 64, T::BK);
   if (rc) return rc;
   // output maps for the staged epilogue (fall back to direct stores when the output is not TMA-addressable)
@@ -581,34 +611,63 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
     p.direct = 0;
   }
   constexpr int TILE_N = SWIGLU ? 128 : BN;
-  p.tiles_m = (p.M + T::BM - 1) / T::BM;
+  constexpr int TILE_M = CG2 ? 256 : 128;
+  p.tiles_m = (p.M + TILE_M - 1) / TILE_M;
   p.tiles_n = (p.N + TILE_N - 1) / TILE_N;
   p.kb_total = (p.K + T::BK - 1) / T::BK;
-  int splits = p.splits < 1 ? 1 : p.splits;
+  const int workers = CG2 ? nvit_num_sms() / 2 : nvit_num_sms();   // CTAs or CTA pairs
+  int splits = p.splits;
+  if (splits <= 0) {
+    // auto split-K (fp32 reduce-add outputs only): fewest splits that fill the machine best
+    splits = 1;
+    if (p.out_f32 && !p.bias && !p.colscale && !p.rowadd && !p.C2) {
+      const long long tiles = 1ll * p.tiles_m * p.tiles_n;
+      double best = 0.0;
+      for (int s = 1; s <= 16 && s <= p.kb_total; ++s) {
+        const long long units = tiles * s;
+        const double util = (double)units / (double)(((units + workers - 1) / workers) * workers);
+        if (util > best + 0.02) { best = util; splits = s; }
+      }
+    }
+  }
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits > 1) {
     p.atomic = 1;
-    if (!p.accumulate)  // partial sums are red.add'ed into C: start from zero
+    if (!p.accumulate)  // partial sums are added into C: start from zero
       NVIT_CUDA_CHECK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, p.N * sizeof(float), p.M, stream));
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          T::SMEM_BYTES));
     attr_set = true;
   }
   const long long units = 1ll * p.tiles_m * p.tiles_n * p.splits;
-  const int grid = (int)(units < nvit_num_sms() ? units : nvit_num_sms());
-  gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU><<<grid, 192, T::SMEM_BYTES, stream>>>(p);
-  NVIT_CUDA_CHECK(cudaGetLastError());
+  const int nwork = (int)(units < workers ? units : workers);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CG2 ? 2 * nwork : nwork);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = T::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2>, p));
   return NVIT_OK;
 }
 
 }  // namespace nvit
 
 using namespace nvit;
+
+static int g_force_cg = 0;  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
 
 extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
                               int64_t lda, int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major,
@@ -618,7 +677,7 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
   NVIT_REQUIRE(A && B && C, "nvit_gemm_bf16: null operand");
   NVIT_REQUIRE(M > 0 && N > 0 && K > 0, "nvit_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   NVIT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "nvit_gemm_bf16: dimension overflow");
-  NVIT_REQUIRE(!(splits > 1) || out_f32, "nvit_gemm_bf16: split-K needs an fp32 output");
+  NVIT_REQUIRE(!(splits > 1) || out_f32, "nvit_gemm_bf16: split-K needs an fp32 output (splits <= 0 picks automatically)");
   NVIT_REQUIRE(!accumulate || out_f32, "nvit_gemm_bf16: accumulate needs an fp32 output");
   NVIT_REQUIRE(!C2_bf16 || out_f32 || swiglu_half > 0, "nvit_gemm_bf16: the bf16 side output goes with an fp32 or swiglu output");
   NVIT_REQUIRE(!(splits > 1) || (!bias && !colscale && !rowadd && !C2_bf16), "nvit_gemm_bf16: split-K supports no epilogue");
@@ -641,23 +700,41 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
   p.rowadd_period = (int)(rowadd ? rowadd_period : 1);
   p.splits = splits;
   p.swiglu_half = (int)swiglu_half;
+  // CTA pairs (256-row tiles, cta_group::2) whenever there are at least two 128-row blocks; nvit_gemm_force_cta_group
+  // (test hook) can pin either mode.
+  const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128);
   if (swiglu_half > 0) {
     NVIT_REQUIRE(N == swiglu_half, "nvit_gemm_bf16: swiglu needs N == F");
     NVIT_REQUIRE(!a_mn_major && !b_mn_major && !out_f32 && !accumulate && splits <= 1 && !bias && !rowadd,
                  "nvit_gemm_bf16: swiglu supports K-major operands, bf16 output and the colscale epilogue only");
-    return launch_gemm<256, false, false, true>(p, A, B, lda, ldb, st);
+    if (cg2) return launch_gemm<256, false, false, true, true>(p, A, B, lda, ldb, st);
+    return launch_gemm<256, false, false, true, false>(p, A, B, lda, ldb, st);
   }
   // BN = 256 unless the problem is narrow enough that a 256-wide tile would be mostly padding.
   const bool wide = (N > 128) && ((N % 256 == 0) || (N % 256 > 128) || N >= 1024);
   const int sel = (wide ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
-  switch (sel) {
-    case 0: return launch_gemm<128, false, false, false>(p, A, B, lda, ldb, st);
-    case 1: return launch_gemm<128, false, true, false>(p, A, B, lda, ldb, st);
-    case 2: return launch_gemm<128, true, false, false>(p, A, B, lda, ldb, st);
-    case 3: return launch_gemm<128, true, true, false>(p, A, B, lda, ldb, st);
-    case 4: return launch_gemm<256, false, false, false>(p, A, B, lda, ldb, st);
-    case 5: return launch_gemm<256, false, true, false>(p, A, B, lda, ldb, st);
-    case 6: return launch_gemm<256, true, false, false>(p, A, B, lda, ldb, st);
-    default: return launch_gemm<256, true, true, false>(p, A, B, lda, ldb, st);
+  if (cg2 && wide) {
+    switch (sel & 3) {
+      case 0: return launch_gemm<256, false, false, false, true>(p, A, B, lda, ldb, st);
+      case 1: return launch_gemm<256, false, true, false, true>(p, A, B, lda, ldb, st);
+      case 2: return launch_gemm<256, true, false, false, true>(p, A, B, lda, ldb, st);
+      default: return launch_gemm<256, true, true, false, true>(p, A, B, lda, ldb, st);
+    }
   }
+  switch (sel) {
+    case 0: return launch_gemm<128, false, false, false, false>(p, A, B, lda, ldb, st);
+    case 1: return launch_gemm<128, false, true, false, false>(p, A, B, lda, ldb, st);
+    case 2: return launch_gemm<128, true, false, false, false>(p, A, B, lda, ldb, st);
+    case 3: return launch_gemm<128, true, true, false, false>(p, A, B, lda, ldb, st);
+    case 4: return launch_gemm<256, false, false, false, false>(p, A, B, lda, ldb, st);
+    case 5: return launch_gemm<256, false, true, false, false>(p, A, B, lda, ldb, st);
+    case 6: return launch_gemm<256, true, false, false, false>(p, A, B, lda, ldb, st);
+    default: return launch_gemm<256, true, true, false, false>(p, A, B, lda, ldb, st);
+  }
+}
+
+extern "C" int nvit_gemm_force_cta_group(int mode) {
+  NVIT_REQUIRE(mode == 0 || mode == 1 || mode == 2, "nvit_gemm_force_cta_group: mode must be 0 (auto), 1 or 2");
+  g_force_cg = mode;
+  return NVIT_OK;
 }

@@ -246,17 +246,9 @@ class Engine:
         self._acts = {B: a}      # keep one batch size resident
         return a
 
-    def _splits(self, Mg, Ng, K):
-        """Split-K factor for a wgrad whose output grid alone cannot fill the 148 SMs."""
-        tiles = ((Mg + 127) // 128) * ((Ng + 255) // 256 if Ng > 128 else 1)
-        kb = (K + 63) // 64
-        s = max(1, min(kb, (148 + tiles - 1) // tiles))
-        return s
-
     def _wgrad(self, dy, x, gw):
         """gw[N,K] += dy[M,N]^T x[M,K]"""
-        s = self._splits(dy.shape[1], x.shape[1], dy.shape[0])
-        ops.linear_wgrad(dy, x, gw, splits=s, accumulate=True)
+        ops.linear_wgrad(dy, x, gw, splits=0, accumulate=True)     # splits=0: the library picks the split-K factor
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------ forward

@@ -4,7 +4,7 @@
 
 The formula fixtures are ill-conditioned under bf16 (per-sample gradients cancel in the batch sum), so "matches the
 reference within bf16 tolerance" is stated per tensor relative to what the unmodified reference itself loses when run
-under torch.autocast(bf16): tests/test_model_gpu.py accepts err <= max(3e-2*|g|, 2*gap[name], 1e-3*|g|_global).
+under torch.autocast(bf16): tests/test_model_gpu.py accepts err <= max(3e-2*|g|, 3*gap[name], 1e-3*|g|_global).
 Writes tests/golden/bf16_gap.npz with keys "<case>:<param>" -> L2 norm of (grad_bf16_autocast - grad_fp32).
 """
 import os

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 if not torch.cuda.is_available():
     pytest.skip("needs a CUDA device", allow_module_level=True)
 
-from nvit_b200 import ops  # noqa: E402
+from nvit_b200 import ops, _lib  # noqa: E402
 from oracle import nvit_oracle as O  # noqa: E402
 
 DEV = "cuda"
@@ -33,6 +33,14 @@ def randn(*shape, seed=0, scale=1.0, dtype=torch.float32):
 
 
 # ---------------------------------------------------------------------------------------------- GEMM
+@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_group2"])
+def cta_group(request):
+    """Run every GEMM test with single-CTA tiles and with CTA-pair (cta_group::2) tiles."""
+    _lib.call("nvit_gemm_force_cta_group", request.param)
+    yield request.param
+    _lib.call("nvit_gemm_force_cta_group", 0)
+
+
 GEMM_SHAPES = [
     (128, 128, 64), (256, 256, 128), (384, 768, 768), (200, 192, 192), (50, 1000, 768), (1024, 3072, 768),
     (256, 768, 3072), (333, 130, 72),
@@ -41,7 +49,7 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-def test_gemm_layouts(M, N, K, a_mn, b_mn):
+def test_gemm_layouts(M, N, K, a_mn, b_mn, cta_group):
     # leading dims must be multiples of 8 elements for TMA: pad the storage, use views
     def padded(rows, cols, seed):
         ld = (cols + 7) // 8 * 8
@@ -64,7 +72,7 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     assert rel(c16[:, :N], ref) < 6e-3
 
 
-def test_gemm_epilogue_bias_scale_rowadd_and_bf16_copy():
+def test_gemm_epilogue_bias_scale_rowadd_and_bf16_copy(cta_group):
     M, N, K, T = 392, 768, 192, 196
     a = randn(M, K, seed=3, scale=0.3, dtype=torch.bfloat16)
     w = randn(N, K, seed=4, scale=0.3, dtype=torch.bfloat16)
@@ -78,8 +86,8 @@ def test_gemm_epilogue_bias_scale_rowadd_and_bf16_copy():
     assert rel(c2, ref) < 6e-3
 
 
-@pytest.mark.parametrize("splits", [1, 4, 13])
-def test_gemm_wgrad_splitk_and_accumulate(splits):
+@pytest.mark.parametrize("splits", [0, 1, 4, 13])
+def test_gemm_wgrad_splitk_and_accumulate(splits, cta_group):
     M, N, K = 6272, 768, 192   # dW[N,K] = dY[M,N]^T X[M,K]
     dy = randn(M, N, seed=8, scale=0.1, dtype=torch.bfloat16)
     x = randn(M, K, seed=9, scale=0.1, dtype=torch.bfloat16)
@@ -93,7 +101,7 @@ def test_gemm_wgrad_splitk_and_accumulate(splits):
     assert rel(dw, 2 * ref) < 2e-3
 
 
-def test_gemm_dgrad_accumulates_into_fp32():
+def test_gemm_dgrad_accumulates_into_fp32(cta_group):
     M, N, K = 520, 384, 192
     dy = randn(M, N, seed=10, scale=0.2, dtype=torch.bfloat16)
     w = randn(N, K, seed=11, scale=0.2, dtype=torch.bfloat16)
@@ -106,7 +114,7 @@ def test_gemm_dgrad_accumulates_into_fp32():
 
 @pytest.mark.parametrize("M,C", [(300, 192), (1000, 768)])
 @pytest.mark.parametrize("with_suv", [True, False])
-def test_gemm_swiglu_epilogue(M, C, with_suv):
+def test_gemm_swiglu_epilogue(M, C, with_suv, cta_group):
     Fh = 4 * C
     x = randn(M, C, seed=13, scale=1.0 / math.sqrt(C), dtype=torch.bfloat16)
     w = randn(2 * Fh, C, seed=14, scale=1.0, dtype=torch.bfloat16)
