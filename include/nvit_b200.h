@@ -125,7 +125,7 @@ int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int
                     void* stream);
 /* Trainer.normalize_matrices (train.py:461-480) as ONE launch over a device table of n_tensors entries, each
  * 6 x int64: {w_f32 ptr, w_bf16 ptr or 0, rows, cols, axis, first_unit}.  axis = 1 normalizes every row over cols,
- * axis = 0 every column over rows (the reference's norm dims).  Units: 8 rows (axis 1) or 32 columns (axis 0) each;
+ * axis = 0 every column over rows (the reference's norm dims).  Units: 8 rows (axis 1) or 128 columns (axis 0) each;
  * first_unit is the running sum of units before the tensor; total_units the grand total.  The optional bf16 pointer
  * receives the GEMM operand copy in the same pass.
  */

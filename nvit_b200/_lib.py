@@ -59,6 +59,9 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    mode = os.environ.get("NVIT_GEMM_CTA_GROUP")      # benchmarking hook: pin cta_group::1 or ::2 GEMM tiles
+    if mode in ("1", "2"):
+        lib.nvit_gemm_force_cta_group(int(mode))
     _lib = lib
     return lib
 

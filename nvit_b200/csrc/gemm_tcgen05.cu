@@ -9,7 +9,7 @@
 // This replaces what the reference gets from nn.Linear/nn.Conv2d -> cuBLAS/cuDNN (nvit/model.py:99-101,130,148,155,
 // 226-228,259,262,286-304,329-332,341-344) and their autograd backward.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue.
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-9 epilogue (two groups of four).
 // Tile 128 x BN x 64, BN in {128, 256}; 4 (BN=256) or 6 (BN=128) smem stages; two TMEM accumulator stages so
 // the epilogue of tile i overlaps the main loop of tile i+1.  One CTA per SM, static round-robin tile schedule
 // with n fastest so CTAs running together share the same A row-panel in L2.  Optional split along K (wgrad: K = B*T)
@@ -56,8 +56,9 @@ struct GemmTraits {
   static constexpr int STAGES = 196608 / STAGE_BYTES;  // 4 (48 KB stages), 6 (32 KB), 8 (24 KB)
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
-  static constexpr int STAGING_BYTES = 32768;  // epilogue staging: 2 x 16 KB (or 16 + 8 / 3 x 8 KB, see the epilogue)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 32768;  // epilogue staging: one 16 KB buffer per epilogue group
+  static constexpr int VEC_BYTES = 2048;       // per-tile scale[256] and bias[256]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256 /*barriers*/;
   // K-major SW128: 8 rows x 128 B per swizzle atom, atoms stacked along M/N every 1024 B.
   // MN-major SW128: 64 elements (128 B) along M/N x 8 k-rows per atom; next 8 k-rows +1024 B; next 64 M/N elements
   // is a separate TMA box of BK rows -> +BK*128 B.
@@ -87,7 +88,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v
 }
 
 template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2>
-__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using T = GemmTraits<BN, A_MN, B_MN, CG2>;
   // CG2: the kernel runs as clusters of two CTAs (one SM pair); the pair computes a 256 x BN tile with
   // tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its own 128 rows of A and half of B.
@@ -95,10 +96,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   const int unit0 = CG2 ? (int)cluster_id_x() : (int)blockIdx.x;
   const int unit_stride = CG2 ? (int)cluster_count_x() : (int)gridDim.x;
   static_assert(!SWIGLU || (BN == 256 && !A_MN && !B_MN), "swiglu epilogue: 128x256 K-major tiles only");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + T::STAGES * T::STAGE_BYTES;  // 1024-aligned epilogue staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + T::STAGING_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];   // the whole 227 KB is used: no slack for manual alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();         // 128B-swizzled tiles need a 1024-byte aligned base
+  uint8_t* stg = smem + T::STAGES * T::STAGE_BYTES;   // epilogue staging
+  float* s_vec = reinterpret_cast<float*>(stg + T::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + T::STAGING_BYTES + T::VEC_BYTES);
   uint64_t* empty_bar = full_bar + T::STAGES;
   uint64_t* tmem_full = empty_bar + T::STAGES;
   uint64_t* tmem_empty = tmem_full + T::ACC_STAGES;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < T::ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], CG2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tmem_empty[i], CG2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -225,24 +227,43 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
       if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two groups of four warps) =====================
     // TMEM -> registers -> (bias / scale / gate) -> 128B-swizzled shared staging -> TMA store (or TMA reduce-add for
     // accumulating / split-K fp32 outputs).  The bulk store is asynchronous and fully coalesced; rows/columns outside
-    // [M, N] are clipped by the tensor map.  `direct` keeps the per-thread global-store path for outputs whose pitch or
-    // base the TMA cannot address.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // [M, N] are clipped by the tensor map.  Group g (warps 2-5 / 6-9) takes the column chunks with index % 2 == g and
+    // owns staging buffer g, so two warps share each scheduler and the two groups overlap each other's store drains.
+    // `direct` keeps the per-thread global-store path for outputs whose pitch or base the TMA cannot address.
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int eg = (warp - 2) >> 2;  // epilogue group
     const int erow = q * 32 + lane;
-    const bool issuer = (threadIdx.x == 64);
+    const int et = threadIdx.x - 64;  // 0..255 over the epilogue threads
+    const bool issuer = (lane == 0) && (((warp - 2) & 3) == 0);
+    uint8_t* buf = stg + eg * 16384;
+    const int bar_id = 1 + eg;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
     const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec2_ok = (p.C2 == nullptr) || ((p.ldc2 & 7) == 0);
+    const bool use_vec = (p.bias != nullptr) || (p.colscale != nullptr);
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int t = u / p.splits;
       const int n_blk = t % p.tiles_n;
       const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;
       const int row = m_blk * T::BM + erow;
+      if (use_vec) {
+        // per-tile column vectors (bias, scale) staged once in shared memory instead of per-element global loads
+        named_bar_sync(3, 256);  // both groups are done with the previous tile's vectors
+        {
+          int j = n_blk * TILE_N + (SWIGLU ? (et & 127) : et);
+          j = min(j, p.N - 1);
+          if (SWIGLU) j += (et >> 7) * p.swiglu_half;   // entries 0..127: u scales, 128..255: v scales
+          if (SWIGLU || et < BN) {
+            s_vec[et] = p.colscale ? __ldg(p.colscale + j) * p.colscale_mul : 1.f;
+            s_vec[256 + et] = p.bias ? __ldg(p.bias + j) : 0.f;
+          }
+        }
+        named_bar_sync(3, 256);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -254,78 +275,76 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
           else mbar_arrive(&tmem_empty[acc]);
         }
       };
+      // write 32 packed words (a [row][64 bf16] or [row][32 fp32] line) into this group's staging buffer and store it
+      auto stage_store = [&](const uint32_t (&src)[32], const CUtensorMap* map, int n0, bool reduce) {
+        if (issuer) bulk_wait_group_read<0>();
+        named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
+              make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          if (reduce) tma_reduce_add_2d(map, buf, n0, m_blk * T::BM);
+          else tma_store_2d(map, buf, n0, m_blk * T::BM);
+          bulk_commit_group();
+        }
+      };
       if (!p.direct) {
         if constexpr (SWIGLU) {
-          // two groups of 64 gate outputs; x, raw u and raw v go out as three 128B-swizzled [128 x 64] bf16 tiles that
-          // rotate through the two staging buffers
-#pragma unroll 1
-          for (int g = 0; g < 2; ++g) {
-            uint32_t uo[32], vo[32], xo[32];
-            {
-              uint32_t r[32], r2[32];
-              tmem_ld_32x32b_x32(taddr + g * 64, r);
-              tmem_ld_32x32b_x32(taddr + g * 64 + 32, r2);
-              tmem_wait_ld();
+          // group g takes gate outputs [64g, 64g+64) of the tile: x, raw u and raw v leave as three [128 x 64] bf16 tiles
+          uint32_t uo[32], vo[32];
+          {
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32b_x32(taddr + eg * 64, r);
+            tmem_ld_32x32b_x32(taddr + eg * 64 + 32, r2);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {   // c_fc output is bf16 under autocast
-                uo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                uo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
-              }
-              tmem_ld_32x32b_x32(taddr + 128 + g * 64, r);
-              tmem_ld_32x32b_x32(taddr + 128 + g * 64 + 32, r2);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                vo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                vo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
-              }
+            for (int i = 0; i < 16; ++i) {   // c_fc output is bf16 under autocast
+              uo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+              uo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
             }
-            if (g == 1) release_tmem();
-            const int n0 = n_blk * 128 + g * 64;
-            if (n0 >= p.N) continue;  // uniform over the epilogue warps
+            tmem_ld_32x32b_x32(taddr + 128 + eg * 64, r);
+            tmem_ld_32x32b_x32(taddr + 128 + eg * 64 + 32, r2);
+            tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float su0 = 1.f, su1 = 1.f, sv0 = 1.f, sv1 = 1.f;
+            for (int i = 0; i < 16; ++i) {
+              vo[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+              vo[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+            }
+          }
+          release_tmem();
+          const int n0 = n_blk * 128 + eg * 64;
+          if (n0 < p.N) {  // uniform over the group
+            uint32_t xo[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float4 su = make_float4(1.f, 1.f, 1.f, 1.f), sv = su;
               if (p.colscale) {
-                const int j0 = min(n0 + 2 * i, p.N - 1), j1 = min(n0 + 2 * i + 1, p.N - 1);
-                su0 = __ldg(p.colscale + j0) * p.colscale_mul;
-                su1 = __ldg(p.colscale + j1) * p.colscale_mul;
-                sv0 = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
-                sv1 = __ldg(p.colscale + p.swiglu_half + j1) * p.colscale_mul;
+                su = *reinterpret_cast<const float4*>(s_vec + eg * 64 + 2 * i);
+                sv = *reinterpret_cast<const float4*>(s_vec + 128 + eg * 64 + 2 * i);
               }
-              xo[i] = pack_bf16(silu_mul(bf16lo(uo[i]) * su0, bf16lo(vo[i]) * sv0), silu_mul(bf16hi(uo[i]) * su1, bf16hi(vo[i]) * sv1));
+              xo[i] = pack_bf16(silu_mul(bf16lo(uo[i]) * su.x, bf16lo(vo[i]) * sv.x), silu_mul(bf16hi(uo[i]) * su.y, bf16hi(vo[i]) * sv.y));
+              xo[i + 1] = pack_bf16(silu_mul(bf16lo(uo[i + 1]) * su.z, bf16lo(vo[i + 1]) * sv.z),
+                                    silu_mul(bf16hi(uo[i + 1]) * su.w, bf16hi(vo[i + 1]) * sv.w));
             }
-            auto stage_store = [&](const uint32_t (&src)[32], const CUtensorMap* map) {
-              uint8_t* buf = stg + (chunk_ctr & 1) * 16384;
-              ++chunk_ctr;
-              if (issuer) bulk_wait_group_read<1>();
-              named_bar_sync(1, 128);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
-                    make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
-              fence_proxy_async_smem();
-              named_bar_sync(1, 128);
-              if (issuer) {
-                tma_store_2d(map, buf, n0, m_blk * T::BM);
-                bulk_commit_group();
-              }
-            };
-            stage_store(xo, &p.tma_c);
+            stage_store(xo, &p.tma_c, n0, false);
             if (p.C2) {
-              stage_store(uo, &p.tma_c2);
-              stage_store(vo, &p.tma_c3);
+              stage_store(uo, &p.tma_c2, n0, false);
+              stage_store(vo, &p.tma_c3, n0, false);
             }
           }
         } else if (!p.out_f32) {
-          // bf16 output: chunks of 64 columns (128 B rows, 128B swizzle), two staging buffers
+          // bf16 output: chunks of 64 columns (128 B rows, 128B swizzle)
+          constexpr int NC = BN / 64;
 #pragma unroll 1
-          for (int c = 0; c < BN / 64; ++c) {
+          for (int c = eg; c < NC; c += 2) {
             uint32_t r[32], r2[32];
             tmem_ld_32x32b_x32(taddr + c * 64, r);
             tmem_ld_32x32b_x32(taddr + c * 64 + 32, r2);
             tmem_wait_ld();
-            if (c == BN / 64 - 1) release_tmem();
+            if (c + 2 >= NC) release_tmem();
             const int n0 = n_blk * BN + c * 64;
             if (n0 >= p.N) continue;
             uint32_t o[32];
@@ -333,91 +352,97 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
             for (int i = 0; i < 64; i += 2) {
               float v0 = __uint_as_float(i < 32 ? r[i] : r2[i - 32]);
               float v1 = __uint_as_float(i < 32 ? r[i + 1] : r2[i - 31]);
-              if (p.bias || p.colscale || p.rowadd) {
+              if (use_vec) {
+                const float2 bb = *reinterpret_cast<const float2*>(s_vec + 256 + c * 64 + i);
+                const float2 cs = *reinterpret_cast<const float2*>(s_vec + c * 64 + i);
+                v0 = (v0 + bb.x) * cs.x;
+                v1 = (v1 + bb.y) * cs.y;
+              }
+              if (p.rowadd) {
                 const int j0 = min(n0 + i, p.N - 1), j1 = min(n0 + i + 1, p.N - 1);
-                if (p.bias) { v0 += __ldg(p.bias + j0); v1 += __ldg(p.bias + j1); }
-                if (p.colscale) { v0 *= __ldg(p.colscale + j0) * p.colscale_mul; v1 *= __ldg(p.colscale + j1) * p.colscale_mul; }
-                if (p.rowadd) {
-                  const float* ra = p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N;
-                  v0 += __ldg(ra + j0); v1 += __ldg(ra + j1);
-                }
+                const float* ra = p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N;
+                v0 += __ldg(ra + j0); v1 += __ldg(ra + j1);
               }
               o[i >> 1] = pack_bf16(v0, v1);
             }
-            uint8_t* buf = stg + (chunk_ctr & 1) * 16384;
-            ++chunk_ctr;
-            if (issuer) bulk_wait_group_read<1>();
-            named_bar_sync(1, 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (issuer) {
-              tma_store_2d(&p.tma_c, buf, n0, m_blk * T::BM);
-              bulk_commit_group();
-            }
+            stage_store(o, &p.tma_c, n0, false);
           }
-        } else {
-          // fp32 output: chunks of 32 columns (128 B rows, 128B swizzle).  Without a bf16 side copy two staging buffers
-          // alternate; with one, buffer 0 holds fp32 and buffer 1 the dense [128][32] bf16 copy.
-          const bool has_c2 = p.C2 != nullptr;
+        } else if (p.C2 == nullptr) {
+          // fp32 output: chunks of 32 columns (128 B rows, 128B swizzle)
+          constexpr int NC = BN / 32;
+          const bool reduce = p.accumulate || p.atomic;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
+          for (int c = eg; c < NC; c += 2) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + c * 32, r);
             tmem_wait_ld();
-            if (c == BN / 32 - 1) release_tmem();
+            if (c + 2 >= NC) release_tmem();
             const int n0 = n_blk * BN + c * 32;
             if (n0 >= p.N) continue;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.bias || p.colscale || p.rowadd) {
+            if (use_vec || p.rowadd) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int j = min(n0 + i, p.N - 1);
-                if (p.bias) v[i] += __ldg(p.bias + j);
-                if (p.colscale) v[i] *= __ldg(p.colscale + j) * p.colscale_mul;
-                if (p.rowadd) v[i] += __ldg(p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N + j);
+                float v = __uint_as_float(r[i]);
+                if (use_vec) v = (v + s_vec[256 + c * 32 + i]) * s_vec[c * 32 + i];
+                if (p.rowadd) v += __ldg(p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N + min(n0 + i, p.N - 1));
+                r[i] = __float_as_uint(v);
               }
             }
-            uint8_t* buf = has_c2 ? stg : stg + (chunk_ctr & 1) * 16384;
-            ++chunk_ctr;
-            if (issuer) {
-              if (has_c2) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
-            }
-            named_bar_sync(1, 128);
+            stage_store(r, &p.tma_c, n0, reduce);
+          }
+        } else {
+          // fp32 output with a bf16 side copy (patch embedding): group 0 alone, fp32 tile in buffer 0 and the dense
+          // [128][32] bf16 copy in buffer 1
+          constexpr int NC = BN / 32;
+          if (eg == 1) {
+            release_tmem();
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < NC; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr + c * 32, r);
+              tmem_wait_ld();
+              if (c == NC - 1) release_tmem();
+              const int n0 = n_blk * BN + c * 32;
+              if (n0 >= p.N) continue;
+              float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (has_c2) {
+              for (int i = 0; i < 32; ++i) {
+                v[i] = __uint_as_float(r[i]);
+                if (use_vec) v[i] = (v[i] + s_vec[256 + c * 32 + i]) * s_vec[c * 32 + i];
+                if (p.rowadd) v[i] += __ldg(p.rowadd + static_cast<long long>(row % p.rowadd_period) * p.N + min(n0 + i, p.N - 1));
+              }
+              if (issuer) bulk_wait_group_read<0>();
+              named_bar_sync(bar_id, 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + erow * 128 + ((j ^ (erow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(stg + 16384 + erow * 64 + j * 16) =
                     make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (issuer) {
-              if (p.accumulate || p.atomic) tma_reduce_add_2d(&p.tma_c, buf, n0, m_blk * T::BM);
-              else tma_store_2d(&p.tma_c, buf, n0, m_blk * T::BM);
-              if (has_c2) tma_store_2d(&p.tma_c2, stg + 16384, n0, m_blk * T::BM);
-              bulk_commit_group();
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, 128);
+              if (issuer) {
+                if (p.accumulate || p.atomic) tma_reduce_add_2d(&p.tma_c, stg, n0, m_blk * T::BM);
+                else tma_store_2d(&p.tma_c, stg, n0, m_blk * T::BM);
+                tma_store_2d(&p.tma_c2, stg + 16384, n0, m_blk * T::BM);
+                bulk_commit_group();
+              }
             }
           }
         }
       } else {
       constexpr int NCHUNK = TILE_N / 32;
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = eg; c < NCHUNK; c += 2) {
         uint32_t r[32];
         uint32_t r2[SWIGLU ? 32 : 1];
         tmem_ld_32x32b_x32(taddr + c * 32, r);
         if constexpr (SWIGLU) tmem_ld_32x32b_x32(taddr + 128 + c * 32, r2);
         tmem_wait_ld();
-        if (c == NCHUNK - 1) release_tmem();
+        if (c + 2 >= NCHUNK) release_tmem();
         const int n0 = n_blk * TILE_N + c * 32;
         if (n0 < p.N && row < p.M) {
           const int valid = min(32, p.N - n0);
@@ -649,7 +674,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(CG2 ? 2 * nwork : nwork);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = T::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

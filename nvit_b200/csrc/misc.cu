@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ SiLU gate (unfused form)
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 // thread = 8 consecutive columns of F; grid.y = row slabs
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ uv, const float* __restrict__ suv,
@@ -148,35 +148,49 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __
     gsv[e] = 0.f;
   }
   const int r0 = blockIdx.y * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
-  for (int r = r0; r < r1; ++r) {
-    const __nv_bfloat16* row = uv + 2ll * r * F;
-    const uint4 uu = ldg_u4_stream(row + c8), vv = ldg_u4_stream(row + F + c8), dd = ldg_u4_stream(dx + 1ll * r * F + c8);
-    const uint32_t ua[4] = {uu.x, uu.y, uu.z, uu.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, da[4] = {dd.x, dd.y, dd.z, dd.w};
-    uint32_t ou[4], ov[4];
+  constexpr int U = 4;  // rows in flight per thread: 12 independent 16-byte loads before the first use
+  for (int rb = r0; rb < r1; rb += U) {
+    uint4 uu[U], vv[U], dd[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float du_[2], dv_[2];
-#pragma unroll
-      for (int hgh = 0; hgh < 2; ++hgh) {
-        const int k = 2 * e + hgh;
-        const float ur = hgh ? bf16hi(ua[e]) : bf16lo(ua[e]);
-        const float vr = hgh ? bf16hi(va[e]) : bf16lo(va[e]);
-        const float g = hgh ? bf16hi(da[e]) : bf16lo(da[e]);
-        const float u = ur * su[k], v = vr * sv[k];
-        const float sg = sigmoidf_(v);
-        const float gu = g * v * sg;                           // dL/d(u scaled)
-        const float gv = g * u * sg * (1.f + v * (1.f - sg));  // dL/d(v scaled)
-        gsu[k] += gu * ur;
-        gsv[k] += gv * vr;
-        du_[hgh] = gu * su[k];
-        dv_[hgh] = gv * sv[k];
-      }
-      ou[e] = pack_bf16(du_[0], du_[1]);
-      ov[e] = pack_bf16(dv_[0], dv_[1]);
+    for (int k = 0; k < U; ++k) {
+      const int r = min(rb + k, r1 - 1);
+      const __nv_bfloat16* row = uv + 2ll * r * F;
+      uu[k] = ldg_u4_stream(row + c8);
+      vv[k] = ldg_u4_stream(row + F + c8);
+      dd[k] = ldg_u4_stream(dx + 1ll * r * F + c8);
     }
-    __nv_bfloat16* drow = duv + 2ll * r * F;
-    *reinterpret_cast<uint4*>(drow + c8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-    *reinterpret_cast<uint4*>(drow + F + c8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int r = rb + k;
+      if (r >= r1) break;
+      const uint32_t ua[4] = {uu[k].x, uu[k].y, uu[k].z, uu[k].w}, va[4] = {vv[k].x, vv[k].y, vv[k].z, vv[k].w},
+                     da[4] = {dd[k].x, dd[k].y, dd[k].z, dd[k].w};
+      uint32_t ou[4], ov[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float du_[2], dv_[2];
+#pragma unroll
+        for (int hgh = 0; hgh < 2; ++hgh) {
+          const int kk = 2 * e + hgh;
+          const float ur = hgh ? bf16hi(ua[e]) : bf16lo(ua[e]);
+          const float vr = hgh ? bf16hi(va[e]) : bf16lo(va[e]);
+          const float g = hgh ? bf16hi(da[e]) : bf16lo(da[e]);
+          const float u = ur * su[kk], v = vr * sv[kk];
+          const float sg = sigmoidf_(v);
+          const float gu = g * v * sg;                           // dL/d(u scaled)
+          const float gv = g * u * sg * (1.f + v * (1.f - sg));  // dL/d(v scaled)
+          gsu[kk] += gu * ur;
+          gsv[kk] += gv * vr;
+          du_[hgh] = gu * su[kk];
+          dv_[hgh] = gv * sv[kk];
+        }
+        ou[e] = pack_bf16(du_[0], du_[1]);
+        ov[e] = pack_bf16(dv_[0], dv_[1]);
+      }
+      __nv_bfloat16* drow = duv + 2ll * r * F;
+      *reinterpret_cast<uint4*>(drow + c8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      *reinterpret_cast<uint4*>(drow + F + c8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    }
   }
   if (dsuv) {
 #pragma unroll
@@ -393,13 +407,13 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
 
 // ------------------------------------------------------------------------------------------------ weight normalization
 // table entry: {w ptr, w16 ptr, rows, cols, axis, first_unit}.  256 threads per CTA, one unit per CTA iteration.
-//   axis 1: unit = 8 rows, one warp per row (cols contiguous).
-//   axis 0: unit = 32 columns; thread (tx = threadIdx%32 -> column, ty = threadIdx/32 -> row phase); two passes, the
-//           second re-reads the slab from L2.
+//   axis 1: unit = 8 rows, one warp per row held in registers (float4 per lane, cols <= 4096) -> one read, one write.
+//   axis 0: unit = 128 columns; thread (lane -> 4 columns as a float4, warp -> row phase); the second pass re-reads the
+//           slab (rows x 512 B, L2 resident) to scale it.
 __global__ void __launch_bounds__(256) weight_norm_multi_kernel(const long long* __restrict__ table, int n_tensors,
                                                                 long long total_units) {
-  __shared__ float s_part[8][33];
-  __shared__ float s_inv[32];
+  __shared__ float4 s_part[8][32];
+  __shared__ float4 s_inv[32];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   for (long long unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
     int lo = 0, hi = n_tensors - 1;  // last tensor with first_unit <= unit
@@ -412,41 +426,98 @@ __global__ void __launch_bounds__(256) weight_norm_multi_kernel(const long long*
     __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(e[1]);
     const int rows = (int)e[2], cols = (int)e[3], axis = (int)e[4];
     const int u = (int)(unit - e[5]);
+    const bool vec = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
     if (axis == 1) {
       const int r = u * 8 + wy;
       if (r < rows) {
         float* row = w + 1ll * r * cols;
-        float ss = 0.f;
-        for (int c = lane; c < cols; c += 32) { const float x = row[c]; ss += x * x; }
-        ss = warp_sum(ss);
-        const float inv = 1.f / sqrtf(ss);
-        for (int c = lane; c < cols; c += 32) {
-          const float x = row[c] * inv;
-          row[c] = x;
-          if (w16) w16[1ll * r * cols + c] = __float2bfloat16(x);
+        if (vec && cols <= 1024) {
+          float4 v[8];
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            v[j] = (c < cols) ? *reinterpret_cast<const float4*>(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+          }
+          ss = warp_sum(ss);
+          const float inv = 1.f / sqrtf(ss);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            if (c < cols) {
+              const float4 o = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+              *reinterpret_cast<float4*>(row + c) = o;
+              if (w16) *reinterpret_cast<uint2*>(w16 + 1ll * r * cols + c) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            }
+          }
+        } else {
+          float ss = 0.f;
+          for (int c = lane; c < cols; c += 32) { const float x = row[c]; ss += x * x; }
+          ss = warp_sum(ss);
+          const float inv = 1.f / sqrtf(ss);
+          for (int c = lane; c < cols; c += 32) {
+            const float x = row[c] * inv;
+            row[c] = x;
+            if (w16) w16[1ll * r * cols + c] = __float2bfloat16(x);
+          }
         }
       }
     } else {
-      const int c = u * 32 + lane;
-      float ss = 0.f;
-      if (c < cols)
-        for (int r = wy; r < rows; r += 8) { const float x = w[1ll * r * cols + c]; ss += x * x; }
+      const int c = u * 128 + lane * 4;
+      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec) {
+        if (c < cols) {
+          int r = wy;
+          for (; r + 24 < rows; r += 32) {   // four independent loads in flight
+            const float4 a0 = *reinterpret_cast<const float4*>(w + 1ll * r * cols + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(w + 1ll * (r + 8) * cols + c);
+            const float4 a2 = *reinterpret_cast<const float4*>(w + 1ll * (r + 16) * cols + c);
+            const float4 a3 = *reinterpret_cast<const float4*>(w + 1ll * (r + 24) * cols + c);
+            ss.x += a0.x * a0.x + a1.x * a1.x + a2.x * a2.x + a3.x * a3.x;
+            ss.y += a0.y * a0.y + a1.y * a1.y + a2.y * a2.y + a3.y * a3.y;
+            ss.z += a0.z * a0.z + a1.z * a1.z + a2.z * a2.z + a3.z * a3.z;
+            ss.w += a0.w * a0.w + a1.w * a1.w + a2.w * a2.w + a3.w * a3.w;
+          }
+          for (; r < rows; r += 8) {
+            const float4 a0 = *reinterpret_cast<const float4*>(w + 1ll * r * cols + c);
+            ss.x += a0.x * a0.x; ss.y += a0.y * a0.y; ss.z += a0.z * a0.z; ss.w += a0.w * a0.w;
+          }
+        }
+      } else {
+        float* sp = reinterpret_cast<float*>(&ss);
+        for (int k = 0; k < 4; ++k)
+          if (c + k < cols)
+            for (int r = wy; r < rows; r += 8) { const float x = w[1ll * r * cols + c + k]; sp[k] += x * x; }
+      }
       s_part[wy][lane] = ss;
       __syncthreads();
       if (wy == 0) {
-        float t = 0.f;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
-        s_inv[lane] = 1.f / sqrtf(t);
+        for (int k = 0; k < 8; ++k) { const float4 q = s_part[k][lane]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+        s_inv[lane] = make_float4(1.f / sqrtf(t.x), 1.f / sqrtf(t.y), 1.f / sqrtf(t.z), 1.f / sqrtf(t.w));
       }
       __syncthreads();
-      if (c < cols) {
-        const float inv = s_inv[lane];
-        for (int r = wy; r < rows; r += 8) {
-          const float x = w[1ll * r * cols + c] * inv;
-          w[1ll * r * cols + c] = x;
-          if (w16) w16[1ll * r * cols + c] = __float2bfloat16(x);
+      const float4 inv = s_inv[lane];
+      if (vec) {
+        if (c < cols) {
+          for (int r = wy; r < rows; r += 8) {
+            float4 a = *reinterpret_cast<const float4*>(w + 1ll * r * cols + c);
+            a.x *= inv.x; a.y *= inv.y; a.z *= inv.z; a.w *= inv.w;
+            *reinterpret_cast<float4*>(w + 1ll * r * cols + c) = a;
+            if (w16) *reinterpret_cast<uint2*>(w16 + 1ll * r * cols + c) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+          }
         }
+      } else {
+        const float* ip = reinterpret_cast<const float*>(&inv);
+        for (int k = 0; k < 4; ++k)
+          if (c + k < cols)
+            for (int r = wy; r < rows; r += 8) {
+              const float x = w[1ll * r * cols + c + k] * ip[k];
+              w[1ll * r * cols + c + k] = x;
+              if (w16) w16[1ll * r * cols + c + k] = __float2bfloat16(x);
+            }
       }
       __syncthreads();
     }

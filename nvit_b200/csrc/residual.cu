@@ -104,39 +104,40 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restri
   }
 }
 
-template <int NV, bool SKIP>
+template <int NV, bool SKIP, bool ACC>
 __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h,
                                                            const __nv_bfloat16* __restrict__ x, const float* __restrict__ alpha,
                                                            float alpha_mul, const float* __restrict__ h0,
-                                                           const float* __restrict__ skip, float* __restrict__ dh,
-                                                           int dh_accumulate, __nv_bfloat16* __restrict__ dx,
+                                                           const float* __restrict__ skip, float* dh,
+                                                           __nv_bfloat16* __restrict__ dx,
                                                            float* __restrict__ dh0, float* __restrict__ dalpha,
                                                            float* __restrict__ dskip, int M, int C) {
-  extern __shared__ float s_dlr[];  // [C] per-CTA reduction of d lr
+  extern __shared__ float s_dlr[];  // [C] per-CTA reduction of d lr, then [C] lr
+  float* s_lr = s_dlr + C;
   __shared__ float s_dskip;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_dlr[c] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_dlr[c] = 0.f;
+    s_lr[c] = fabsf(alpha[c] * alpha_mul);
+  }
   if (threadIdx.x == 0) s_dskip = 0.f;
   __syncthreads();
 
-  float lr[NV][4], dlr[NV][4];
+  float dlr[NV][4];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int c = (j * 32 + lane) * 4;
+  for (int j = 0; j < NV; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      lr[j][e] = (c < C) ? fabsf(alpha[c + e] * alpha_mul) : 0.f;
-      dlr[j][e] = 0.f;
-    }
-  }
+    for (int e = 0; e < 4; ++e) dlr[j][e] = 0.f;
   const float s = SKIP ? skip[0] : 0.f;
   float ds_acc = 0.f;
 
   for (int row = warp; row < M; row += nwarps) {
     const size_t base = static_cast<size_t>(row) * C;
     float av[NV][4], bv[NV][4], gv[NV][4], ov[NV][4];
+    float4 old[ACC ? NV : 1];   // dh += : the previous value is fetched with the other streams, not after the math
+    float h0r[SKIP ? NV : 1][4];
     float ssh = 0.f, ssx = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -145,7 +146,10 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
         ld_f4(h + base + c, av[j]);
         ld_bf4(x + base + c, bv[j]);
         ld_f4(g + base + c, gv[j]);
+        if (SKIP) ld_f4(h0 + base + c, h0r[j]);
+        if (ACC) old[j] = *reinterpret_cast<const float4*>(dh + base + c);
       } else {
+        if (SKIP) { h0r[j][0] = 0.f; h0r[j][1] = 0.f; h0r[j][2] = 0.f; h0r[j][3] = 0.f; }
 #pragma unroll
         for (int e = 0; e < 4; ++e) { av[j][e] = 0.f; bv[j][e] = 0.f; gv[j][e] = 0.f; }
       }
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
       for (int e = 0; e < 4; ++e) {
         av[j][e] *= invh;
         bv[j][e] *= invx;
-        const float z = av[j][e] + lr[j][e] * (bv[j][e] - av[j][e]);
+        const float z = av[j][e] + s_lr[min((j * 32 + lane) * 4 + e, C - 1)] * (bv[j][e] - av[j][e]);
         ov[j][e] = z;
         ssz += z * z;
       }
@@ -180,11 +184,9 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int c = (j * 32 + lane) * 4;
-        float h0v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c < C) ld_f4(h0 + base + c, h0v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float y = ov[j][e] * s + h0v[e];
+          const float y = ov[j][e] * s + h0r[SKIP ? j : 0][e];
           yv[j][e] = y;
           ssy += y * y;
           gy += gv[j][e] * y;
@@ -222,9 +224,10 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float dz = (gv[j][e] - ov[j][e] * odot) * invz;
+        const float lre = s_lr[min((j * 32 + lane) * 4 + e, C - 1)];
         dlr[j][e] += dz * (bv[j][e] - av[j][e]);
-        const float da = dz * (1.f - lr[j][e]);
-        const float db = dz * lr[j][e];
+        const float da = dz * (1.f - lre);
+        const float db = dz * lre;
         adot += da * av[j][e];
         bdot += db * bv[j][e];
         gv[j][e] = da;
@@ -242,10 +245,7 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
           d[e] = (gv[j][e] - av[j][e] * adot) * invh;
           o[e] = (ov[j][e] - bv[j][e] * bdot) * invx;
         }
-        if (dh_accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(dh + base + c);
-          d[0] += old.x; d[1] += old.y; d[2] += old.z; d[3] += old.w;
-        }
+        if (ACC) { d[0] += old[j].x; d[1] += old[j].y; d[2] += old[j].z; d[3] += old[j].w; }
         st_f4(dh + base + c, make_float4(d[0], d[1], d[2], d[3]));
         st_bf4(dx + base + c, o);
       }
@@ -325,12 +325,14 @@ extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_b
   if (M == 0) return NVIT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = residual_grid((int)M);
-  const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
   auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto dxb = static_cast<__nv_bfloat16*>(dx_bf16);
   NVIT_DISPATCH_NV(C, {
-    if (h0) residual_bwd_kernel<NV, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dh_accumulate, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
-    else    residual_bwd_kernel<NV, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dh_accumulate, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    if (h0 && dh_accumulate)       residual_bwd_kernel<NV, true, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else if (h0)                   residual_bwd_kernel<NV, true, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else if (dh_accumulate)        residual_bwd_kernel<NV, false, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else                           residual_bwd_kernel<NV, false, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;

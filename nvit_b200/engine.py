@@ -191,7 +191,7 @@ class Engine:
                 s = self.slots[b + nm + ".weight"]
                 r, c = s.shape
                 rows.append([self.P32.data_ptr() + 4 * s.off, 0, r, c, axis, first])
-                first += (r + 7) // 8 if axis == 1 else (c + 31) // 32
+                first += (r + 7) // 8 if axis == 1 else (c + 127) // 128
         self.norm_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
         self.norm_units = first
 

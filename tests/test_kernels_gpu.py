@@ -356,13 +356,14 @@ def test_adamw_flat_matches_torch_with_clip():
 
 
 def test_weight_norm_multi_rows_and_columns():
-    shapes = [(768, 768, 1), (768, 768, 0), (6144, 768, 1), (768, 3072, 0), (100, 36, 1), (36, 100, 0)]
+    shapes = [(768, 768, 1), (768, 768, 0), (6144, 768, 1), (768, 3072, 0), (100, 36, 1), (36, 100, 0), (50, 37, 1), (37, 50, 0),
+              (64, 2048, 1), (1024, 4096, 0)]
     ws = [randn(r, c, seed=100 + i) for i, (r, c, _) in enumerate(shapes)]
     w16 = [torch.empty(r, c, device=DEV, dtype=torch.bfloat16) for (r, c, _) in shapes]
     rows, first = [], 0
     for w, h16, (r, c, axis) in zip(ws, w16, shapes):
         rows.append([w.data_ptr(), h16.data_ptr(), r, c, axis, first])
-        first += (r + 7) // 8 if axis == 1 else (c + 31) // 32
+        first += (r + 7) // 8 if axis == 1 else (c + 127) // 128
     table = torch.tensor(rows, dtype=torch.int64, device=DEV)
     refs = [w / w.norm(p=2, dim=axis, keepdim=True) for w, (_, _, axis) in zip(ws, shapes)]
     ops.weight_norm_multi(table, len(shapes), first)
