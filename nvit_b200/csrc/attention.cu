@@ -82,7 +82,7 @@ __device__ __forceinline__ float normalize_row(uint8_t* tile, int row, const flo
 }
 
 struct alignas(64) AttnParams {
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, to;
   const __nv_bfloat16 *q, *k, *o, *dout;  // raw rows for the normalisation backward / delta
   __nv_bfloat16 *out, *dq, *dk, *dv;
   const float* sqk;
@@ -119,6 +119,34 @@ __device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
   t.c_begin = t.half ? mid : 0;
   t.c_end = t.half ? t.nch : mid;
   return t;
+}
+
+
+// ---- MMA issue helpers.  Called by ALL lanes of one warp so that descriptors stay in uniform registers; only the
+//      tcgen05 instruction itself is predicated on an elected lane (see gemm_tcgen05.cu).
+// D (+)= A * B over `nks` k-steps; A advances a_step (in 16-byte units) per k-step, B advances b_step.
+__device__ __forceinline__ void mma_seq(uint32_t tmem_d, uint64_t da, uint32_t a_step, uint64_t db, uint32_t b_step, uint32_t idesc,
+                                        int nks, bool accumulate_first) {
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ++ks) {
+    const uint32_t acc = (accumulate_first || ks > 0) ? 1u : 0u;
+    if (elect_one()) umma_bf16_ss(tmem_d, da, db, idesc, acc);
+    da += a_step;
+    db += b_step;
+  }
+}
+// Same with A = the [128 x Tpad] P / dS buffer read K-major: k-step ks sits in 16 KB k-block ks/4 at byte (ks%4)*32.
+__device__ __forceinline__ void mma_seq_pk(uint32_t tmem_d, uint64_t dp, uint64_t db, uint32_t b_step, uint32_t idesc, int nks) {
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ++ks) {
+    const uint64_t da = dp + static_cast<uint64_t>((ks >> 2) * 1024 + (ks & 3) * 2);
+    if (elect_one()) umma_bf16_ss(tmem_d, da, db, idesc, ks > 0 ? 1u : 0u);
+    db += b_step;
+  }
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -193,14 +221,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   uint32_t mma_phase = 0;
 
   for (int i = 0; i < p.nQ; ++i) {
-    if (t.tid == 0) {
+    if (t.warp == 0) {
       tc_fence_after_sync();
-      const uint32_t idesc = idesc_kk_n(TP);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16_ss(tmem_base, umma_smem_desc(sQ_a + i * 16384 + ks * 32, 16, 1024), umma_smem_desc(sK_a + ks * 32, 16, 1024),
-                     idesc, ks > 0);
-      umma_commit(bar_mma);
+      mma_seq(tmem_base, umma_smem_desc(sQ_a + i * 16384, 16, 1024), 2, umma_smem_desc(sK_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
+      mma_commit(bar_mma);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -248,13 +272,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     fence_proxy_async_smem();
     __syncthreads();
 
-    if (t.tid == 0) {
+    if (t.warp == 0) {
       tc_fence_after_sync();
-      const int nks = TP >> 4;
-      for (int ks = 0; ks < nks; ++ks)
-        umma_bf16_ss(tmem_base + 256, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                     umma_smem_desc(sV_a + ks * 2048, 8192, 1024), IDESC_KM(64), ks > 0);
-      umma_commit(bar_mma);
+      mma_seq_pk(tmem_base + 256, umma_smem_desc(sP_a, 16, 1024), umma_smem_desc(sV_a, 8192, 1024), 128, IDESC_KM(64), TP >> 4);
+      mma_commit(bar_mma);
     }
     const float total = s_part[t.row] + s_part[128 + t.row];
     mbar_wait(bar_mma, mma_phase);
@@ -288,12 +309,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 128) * 4 + 64;
+constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 192) * 4 + 64;
 
-// backward of y = s * x/||x|| for one row whose dL/dy sits in 64 TMEM columns at `taddr`.  Two passes over TMEM keep
-// the register footprint small.  Writes dx (bf16) and accumulates dL/ds per channel into dacc.
-__device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const __nv_bfloat16* xrow, float inv, const float* s_scale, bool has_norm,
-                                             __nv_bfloat16* dst, float (&dacc)[64], bool valid) {
+// backward of y = s * x/||x|| for one row whose dL/dy sits in 64 TMEM columns at `taddr`.  The unit vector n = x/||x||
+// is recovered from the normalised bf16 row still resident in the swizzled shared tile (n_c = y_c / s_c), so the
+// epilogue touches no global memory except its store.  Two passes over TMEM keep the register footprint small.
+// Writes dx (bf16) and accumulates dL/ds per channel into dacc.
+__device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const uint8_t* tile, int trow, float inv, const float* s_scale,
+                                             const float* s_rscale, bool has_norm, __nv_bfloat16* dst, float (&dacc)[64], bool valid) {
   if (!has_norm) {
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -318,19 +341,17 @@ __device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const __nv_bfloat16
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + hh * 32, r);
     tmem_wait_ld();
-    if (valid) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float n[8];
-        unpack8(*reinterpret_cast<const uint4*>(xrow + hh * 32 + 8 * c), n);
+    for (int c = 0; c < 4; ++c) {
+      float n[8];
+      unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, hh * 4 + c)), n);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = hh * 32 + 8 * c + e;
-          const float g = __uint_as_float(r[8 * c + e]);
-          const float nn = n[e] * inv;
-          dacc[i] += g * nn;
-          dot += g * s_scale[i] * nn;
-        }
+      for (int e = 0; e < 8; ++e) {
+        const int i = hh * 32 + 8 * c + e;
+        const float g = __uint_as_float(r[8 * c + e]);
+        const float nn = n[e] * s_rscale[i];
+        dacc[i] += valid ? g * nn : 0.f;
+        dot += g * s_scale[i] * nn;
       }
     }
   }
@@ -343,11 +364,11 @@ __device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const __nv_bfloat16
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float n[8], d[8];
-        unpack8(*reinterpret_cast<const uint4*>(xrow + hh * 32 + 8 * c), n);
+        unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, hh * 4 + c)), n);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int i = hh * 32 + 8 * c + e;
-          d[e] = (__uint_as_float(r[8 * c + e]) * s_scale[i] - n[e] * inv * dot) * inv;
+          d[e] = (__uint_as_float(r[8 * c + e]) * s_scale[i] - n[e] * s_rscale[i] * dot) * inv;
         }
         *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = pack8(d);
       }
@@ -387,7 +408,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   float* s_invk = s_invq + 256;                                // [256]
   float* s_scale = s_invk + 256;                               // [64]
   float* s_dsqk = s_scale + 64;                                // [64]
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dsqk + 64);
+  float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_rscale + 64);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -400,6 +422,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     tma_prefetch_desc(&p.tk);
     tma_prefetch_desc(&p.tv);
     tma_prefetch_desc(&p.tdo);
+    tma_prefetch_desc(&p.to);
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
@@ -409,7 +432,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     tmem_relinquish();
   }
   if (t.tid < 64) {
-    s_scale[t.tid] = has_norm ? p.sqk[t.h * 64 + t.tid] * p.sqk_mul : 1.f;
+    const float sc = has_norm ? p.sqk[t.h * 64 + t.tid] * p.sqk_mul : 1.f;
+    s_scale[t.tid] = sc;
+    s_rscale[t.tid] = sc != 0.f ? 1.f / sc : 0.f;
     s_dsqk[t.tid] = 0.f;
   }
   tc_fence_before_sync();
@@ -418,37 +443,36 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (t.tid == 0) {
-    mbar_arrive_expect_tx(bar_tma, 4 * ATT_TILE_BYTES);
+    mbar_arrive_expect_tx(bar_tma, 5 * ATT_TILE_BYTES);
     tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
     tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
     tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
     tma_load_3d(&p.tdo, bar_tma, sDO, t.h * 64, 0, t.b);
+    tma_load_3d(&p.to, bar_tma, sP, t.h * 64, 0, t.b);   // O parks in the (not yet used) P buffer for the delta pass
   }
-  // while the tiles fly: lse, delta = rowsum(dO * O), and a clean P buffer
+  // while the tiles fly: lse; then delta = rowsum(dO * O) from the shared tiles, and a clean P buffer
   {
     const int r = t.tid;  // 256 threads, 256 rows
-    float l = 0.f, d = 0.f;
-    if (r < T) {
-      l = p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E;
-      const __nv_bfloat16* orow = p.o + (static_cast<long long>(t.b) * T + r) * p.ldo + t.h * 64;
-      const __nv_bfloat16* grow = p.dout + (static_cast<long long>(t.b) * T + r) * p.ldo + t.h * 64;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float a[8], g[8];
-        unpack8(*reinterpret_cast<const uint4*>(orow + 8 * c), a);
-        unpack8(*reinterpret_cast<const uint4*>(grow + 8 * c), g);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d += a[e] * g[e];
-      }
-    }
-    s_lse[r] = l;
-    s_delta[r] = d;
+    s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E : 0.f;
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
   }
-  for (int i = t.tid; i < ATT_PB_BYTES / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
   mbar_wait(bar_tma, 0);
+  {
+    const int r = t.tid;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a[8], g[8];
+      unpack8(*reinterpret_cast<const uint4*>(sP + sw128(r, c)), a);    // rows >= T are zero-filled by the TMA
+      unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, c)), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d += a[e] * g[e];
+    }
+    s_delta[r] = d;
+  }
   __syncthreads();
+  for (int i = t.tid; i < ATT_PB_BYTES / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
 
   if (has_norm) {
     for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
@@ -474,14 +498,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     const int kv = j * 128 + t.row;
     const bool kv_ok = kv < T;
     // ---- S^T_j = Kh_j Qh^T
-    if (t.tid == 0) {
+    if (t.warp == 0) {
       tc_fence_after_sync();
-      const uint32_t idesc = idesc_kk_n(TP);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16_ss(tmem_base + TM_S, umma_smem_desc(sK_a + j * 16384 + ks * 32, 16, 1024),
-                     umma_smem_desc(sQ_a + ks * 32, 16, 1024), idesc, ks > 0);
-      umma_commit(bar_mma);
+      mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + j * 16384, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
+      mma_commit(bar_mma);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -517,17 +537,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     fence_proxy_async_smem();
     __syncthreads();
     // ---- dV_j = P^T dO ; dP^T_j = V_j dO^T
-    if (t.tid == 0) {
+    if (t.warp == 0) {
       tc_fence_after_sync();
-      for (int ks = 0; ks < nks_q; ++ks)
-        umma_bf16_ss(tmem_base + TM_DV, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                     umma_smem_desc(sDO_a + ks * 2048, 8192, 1024), IDESC_KM(64), ks > 0);
-      const uint32_t idesc = idesc_kk_n(TP);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16_ss(tmem_base + TM_S, umma_smem_desc(sV_a + j * 16384 + ks * 32, 16, 1024),
-                     umma_smem_desc(sDO_a + ks * 32, 16, 1024), idesc, ks > 0);
-      umma_commit(bar_mma);
+      mma_seq_pk(tmem_base + TM_DV, umma_smem_desc(sP_a, 16, 1024), umma_smem_desc(sDO_a, 8192, 1024), 128, IDESC_KM(64), nks_q);
+      mma_seq(tmem_base + TM_S, umma_smem_desc(sV_a + j * 16384, 16, 1024), 2, umma_smem_desc(sDO_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
+      mma_commit(bar_mma);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -557,17 +571,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     fence_proxy_async_smem();
     __syncthreads();
     // ---- dK_j = dS^T Qh ; dQ_m += dS_j Kh_j
-    if (t.tid == 0) {
+    if (t.warp == 0) {
       tc_fence_after_sync();
-      for (int ks = 0; ks < nks_q; ++ks)
-        umma_bf16_ss(tmem_base + TM_DK, umma_smem_desc(sP_a + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                     umma_smem_desc(sQ_a + ks * 2048, 8192, 1024), IDESC_KM(64), ks > 0);
+      mma_seq_pk(tmem_base + TM_DK, umma_smem_desc(sP_a, 16, 1024), umma_smem_desc(sQ_a, 8192, 1024), 128, IDESC_KM(64), nks_q);
       const int kv_steps = min(8, (TP - j * 128) >> 4);
       for (int m = 0; m < p.nQ; ++m)
-        for (int ks = 0; ks < kv_steps; ++ks)
-          umma_bf16_ss(tmem_base + TM_DQ + 64 * m, umma_smem_desc(sP_a + 2 * m * 16384 + ks * 2048, 16384, 1024),
-                       umma_smem_desc(sK_a + j * 16384 + ks * 2048, 8192, 1024), IDESC_MM(64), (j > 0 || ks > 0));
-      umma_commit(bar_mma);
+        mma_seq(tmem_base + TM_DQ + 64 * m, umma_smem_desc(sP_a + 2 * m * 16384, 16384, 1024), 128,
+                umma_smem_desc(sK_a + j * 16384, 8192, 1024), 128, IDESC_MM(64), kv_steps, j > 0);
+      mma_commit(bar_mma);
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
       }
     } else {
       const int kvc = kv_ok ? kv : 0;
-      norm_bwd_row(t_lane + TM_DK, p.k + (static_cast<long long>(t.b) * T + kvc) * p.ldk + t.h * 64, s_invk[kvc], s_scale, has_norm,
+      norm_bwd_row(t_lane + TM_DK, sK, kvc, s_invk[kvc], s_scale, s_rscale, has_norm,
                    p.dk + (static_cast<long long>(t.b) * T + kvc) * p.lddk + t.h * 64, dacc, kv_ok);
     }
     tc_fence_before_sync();
@@ -604,7 +615,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     const int qi = t.half * 128 + t.row;
     const bool ok = qi < T;
     const int qc = ok ? qi : 0;
-    norm_bwd_row(t_lane + TM_DQ + 64 * t.half, p.q + (static_cast<long long>(t.b) * T + qc) * p.ldq + t.h * 64, s_invq[qc], s_scale, has_norm,
+    norm_bwd_row(t_lane + TM_DQ + 64 * t.half, sQ, qc, s_invq[qc], s_scale, s_rscale, has_norm,
                  p.dq + (static_cast<long long>(t.b) * T + qc) * p.lddq + t.h * 64, dacc, ok);
   }
   if (has_norm) reduce64_to_smem(dacc, s_dsqk, t.lane);
@@ -685,6 +696,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tdo, dout, ldo, (int)B, (int)H, (int)T))) return rc;
+  if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T))) return rc;
   p.q = static_cast<const __nv_bfloat16*>(q);
   p.k = static_cast<const __nv_bfloat16*>(k);
   p.o = static_cast<const __nv_bfloat16*>(out);

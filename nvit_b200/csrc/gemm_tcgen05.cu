@@ -188,43 +188,57 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (rank-0 CTA of a pair issues for both) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(CG2 ? 256 : 128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int u = unit0; u < total_units && cta_rank == 0; u += unit_stride) {
-      const int split = u % p.splits;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after_sync();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // The whole warp runs the loop so that barrier addresses and descriptors live in uniform registers; only the
+    // tcgen05 instructions themselves are predicated on one elected lane.  Descriptors are base + constant offsets:
+    // the tensor pipe drains a 128x256x16 step in 128 cycles, so the issue path between two MMAs must stay short.
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CG2 ? 256 : 128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t smem_a0 = smem_u32(smem);
+      const uint64_t da_base = umma_smem_desc(smem_a0, T::A_LBO, T::SBO);
+      const uint64_t db_base = umma_smem_desc(smem_a0 + T::A_BYTES, T::B_LBO, T::SBO);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = unit0; u < total_units; u += unit_stride) {
+        const int split = u % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after_sync();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + stage * T::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + T::A_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_a(full0 + stage * 8, phase);
+          tc_fence_after_sync();
+          const uint64_t da = da_base + static_cast<uint64_t>((stage * T::STAGE_BYTES) >> 4);
+          const uint64_t db = db_base + static_cast<uint64_t>((stage * T::STAGE_BYTES) >> 4);
+          const uint32_t first = kb > kb0 ? 1u : 0u;
+          const uint32_t ebar = empty0 + stage * 8, fbar = tfull0 + acc * 8;
+          const bool last = (kb == kb1 - 1);
+          if (elect_one()) {
+            if constexpr (CG2) {
+              umma_bf16_ss_cg2(tmem_d, da, db, idesc, first);
 #pragma unroll
-          for (int k = 0; k < T::BK / T::UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(a_addr + k * T::A_KSTEP, T::A_LBO, T::SBO);
-            const uint64_t db = umma_smem_desc(b_addr + k * T::B_KSTEP, T::B_LBO, T::SBO);
-            if constexpr (CG2) umma_bf16_ss_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 1; k < T::BK / T::UMMA_K; ++k)
+                umma_bf16_ss_cg2_acc(tmem_d, da + k * (T::A_KSTEP >> 4), db + k * (T::B_KSTEP >> 4), idesc);
+              umma_commit_cg2_a(ebar);            // frees the slot in both CTAs
+              if (last) umma_commit_cg2_a(fbar);  // accumulator complete, both CTAs' epilogues
+            } else {
+              umma_bf16_ss(tmem_d, da, db, idesc, first);
+#pragma unroll
+              for (int k = 1; k < T::BK / T::UMMA_K; ++k)
+                umma_bf16_ss_acc(tmem_d, da + k * (T::A_KSTEP >> 4), db + k * (T::B_KSTEP >> 4), idesc);
+              umma_commit_a(ebar);            // smem slot free once these MMAs retire
+              if (last) umma_commit_a(fbar);  // accumulator complete
+            }
           }
-          if constexpr (CG2) {
-            umma_commit_cg2(&empty_bar[stage]);                   // frees the slot in both CTAs
-            if (kb == kb1 - 1) umma_commit_cg2(&tmem_full[acc]);  // accumulator complete, both CTAs' epilogues
-          } else {
-            umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-            if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
-          }
+          __syncwarp();
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9: two groups of four warps) =====================
