@@ -119,10 +119,12 @@ int nvit_tanh_mse(const void* pred_bf16, const void* target_bf16, int64_t n, flo
  * AdamW over one flat fp32 buffer (torch.optim.AdamW semantics, model.py:369-385; clip train.py:935-938).
  * Elements [0,n_decay) get weight decay.  gnorm_sq (device scalar, may be NULL) holds sum(g^2); the clip coefficient
  * min(1, max_norm / (sqrt(gnorm_sq) + 1e-6)) is applied to g on the fly.  step is the 1-based step count.
+ * dev_lr_step (optional device float[2] = {learning rate, step count}) overrides lr/step so that a captured CUDA graph
+ * of the training step can be replayed while the schedule advances.
  */
 int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, const float* gnorm_sq, float max_norm,
-                    void* stream);
+                    const float* dev_lr_step, void* stream);
 /* Trainer.normalize_matrices (train.py:461-480) as ONE launch over a device table of n_tensors entries, each
  * 6 x int64: {w_f32 ptr, w_bf16 ptr or 0, rows, cols, axis, first_unit}.  axis = 1 normalizes every row over cols,
  * axis = 0 every column over rows (the reference's norm dims).  Units: 8 rows (axis 1) or 128 columns (axis 0) each;

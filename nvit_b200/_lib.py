@@ -34,7 +34,7 @@ SIGNATURES = {
     "nvit_head_scale_bwd": [P, P, P, F32, P, P, I64, I64, I64, P],
     "nvit_cross_entropy": [P, P, P, P, F32, I64, I64, P],
     "nvit_tanh_mse": [P, P, I64, F32, P, P],
-    "nvit_adamw_flat": [P, P, P, P, I64, I64, F32, F32, F32, F32, F32, I64, P, F32, P],
+    "nvit_adamw_flat": [P, P, P, P, I64, I64, F32, F32, F32, F32, F32, I64, P, F32, P, P],
     "nvit_weight_norm_multi": [P, I64, I64, P],
 }
 LIBRARY_CALLS = {"nvit_last_error": ([], c_char_p), "nvit_version": ([], c_int), "nvit_sm_count": ([], c_int)}

@@ -363,7 +363,14 @@ __global__ void __launch_bounds__(256) tanh_mse_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, long long n, long long n_decay, float lr, float b1,
                                                          float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                         const float* __restrict__ gnorm_sq, float max_norm) {
+                                                         const float* __restrict__ gnorm_sq, float max_norm,
+                                                         const float* __restrict__ dev_lr_step) {
+  if (dev_lr_step) {   // CUDA-graph friendly: learning rate and 1-based step count live in device memory
+    lr = dev_lr_step[0];
+    const float t = dev_lr_step[1];
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   float clip = 1.f;
   if (gnorm_sq) {
     const float tot = sqrtf(gnorm_sq[0]);
@@ -656,15 +663,16 @@ extern "C" int nvit_tanh_mse(const void* pred, const void* target, int64_t n, fl
 
 extern "C" int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, float lr, float beta1,
                                float beta2, float eps, float weight_decay, int64_t step, const float* gnorm_sq, float max_norm,
-                               void* stream) {
-  NVIT_REQUIRE(p && g && m && v && n >= 0 && n_decay >= 0 && n_decay <= n && step >= 1, "nvit_adamw_flat: bad arguments");
+                               const float* dev_lr_step, void* stream) {
+  NVIT_REQUIRE(p && g && m && v && n >= 0 && n_decay >= 0 && n_decay <= n && (step >= 1 || dev_lr_step), "nvit_adamw_flat: bad arguments");
+  if (step < 1) step = 1;
   NVIT_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                "nvit_adamw_flat: buffers must be 16-byte aligned");
   if (n == 0) return NVIT_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adamw_flat_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, n_decay, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                                       (float)sqrt(bc2), gnorm_sq, max_norm);
+                                                                       (float)sqrt(bc2), gnorm_sq, max_norm, dev_lr_step);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

@@ -142,9 +142,9 @@ def tanh_mse(pred, target, out):
     _lib.call("nvit_tanh_mse", _p(pred), _p(target), n, 1.0 / n, _p(out), _stream())
 
 
-def adamw_flat(p, g, m, v, n_decay, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0):
+def adamw_flat(p, g, m, v, n_decay, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, dev_lr_step=None):
     _lib.call("nvit_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), n_decay, float(lr), float(beta1), float(beta2), float(eps),
-              float(weight_decay), step, _p(gnorm_sq), float(max_norm), _stream())
+              float(weight_decay), step, _p(gnorm_sq), float(max_norm), _p(dev_lr_step), _stream())
 
 
 def weight_norm_multi(table, n_tensors, total_units):

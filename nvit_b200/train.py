@@ -82,7 +82,8 @@ class Trainer:
     """One rank of the (optionally data-parallel) nViT training loop; mirrors Trainer.train's inner step."""
 
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
-                 eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None):
+                 eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
+                 cuda_graph: bool = False, graph_warmup_steps: int = 2):
         import torch.distributed as dist
         self.model = model
         self.engine = model.engine
@@ -98,6 +99,14 @@ class Trainer:
         self._state_for = None
         self.reducer = None
         self.launches = 0
+        # CUDA-graph replay of the whole step (single rank): the ~275 launches, their tensor-map encodes and the Python
+        # between them are captured once; learning rate and step count then live in device memory (self.hyper)
+        self.use_graph = bool(cuda_graph) and not self.dp
+        self.graph_warmup_steps = max(1, graph_warmup_steps)
+        self._graph = None
+        self._graph_inputs = None
+        self._graph_launches = 0
+        self.replays = 0
 
     # ---- optimizer state lives beside the flat parameter buffer
     def _ensure_state(self):
@@ -108,7 +117,9 @@ class Trainer:
             self.v = torch.zeros_like(eng.P32)
             self.gnorm = torch.zeros(1, device=eng.P32.device, dtype=F32)
             self.loss_buf = torch.zeros(1, device=eng.P32.device, dtype=F32)
+            self.hyper = torch.tensor([self.lr, float(self.opt_step)], device=eng.P32.device, dtype=F32)   # {lr, step}
             self._state_for = eng.P32
+            self._graph = None
             if self.dp:
                 self.reducer = GradReducer(eng.G32, self.group)
                 self._broadcast_params()
@@ -144,6 +155,7 @@ class Trainer:
         if self.dp:
             self.reducer.finish()
         self.opt_step += 1
+        self.hyper[1:2].add_(1.0)          # device-side step count (what a replayed graph advances)
         na = eng.n_active
         gn = None
         if self.clip and self.clip > 0:
@@ -152,20 +164,58 @@ class Trainer:
             gn = self.gnorm
             self.launches += 1
         ops.adamw_flat(eng.P32[:na], eng.G32[:na], self.m[:na], self.v[:na], eng.n_decay, self.lr, self.betas[0], self.betas[1],
-                       self.eps, self.wd, self.opt_step, gn, self.clip or 0.0)
+                       self.eps, self.wd, self.opt_step, gn, self.clip or 0.0, dev_lr_step=self.hyper)
         self.launches += 1
         eng._p16_version = None
         eng.zero_grad()
         self.normalize_matrices()
 
-    def step(self, X: torch.Tensor, y: torch.Tensor):
-        """One full training iteration on one (micro-)batch; returns the device scalar of the mean CE loss."""
-        self._ensure_state()
+    def set_lr(self, lr: float):
+        """Learning-rate schedule hook (train.py:874-876 sets it per epoch); safe with a captured graph."""
+        self.lr = lr
+        if self._state_for is not None:
+            self.hyper[0:1].fill_(lr)
+
+    def _step_eager(self, X, y):
         self.loss_buf.zero_()
         for k in range(self.grad_accum):
             self.micro_step(X, y, last=(k == self.grad_accum - 1))
         self.optimizer_step()
+        return self.loss_buf
+
+    def input_buffers(self, like_X: torch.Tensor, like_y: torch.Tensor):
+        """Static device buffers the captured graph reads; fill them in place (e.g. H2D copies) to avoid a staging copy."""
+        if self._graph_inputs is None or self._graph_inputs[0].shape != like_X.shape:
+            self._graph_inputs = (torch.empty_like(like_X, device=self.engine.P32.device),
+                                  torch.empty_like(like_y, device=self.engine.P32.device))
+            self._graph = None
+        return self._graph_inputs
+
+    def step(self, X: torch.Tensor, y: torch.Tensor):
+        """One full training iteration on one (micro-)batch; returns the device scalar of the mean CE loss."""
+        self._ensure_state()
         self.iter_num += 1
+        if not self.use_graph or self.iter_num <= self.graph_warmup_steps:
+            return self._step_eager(X, y)
+        Xs, ys = self.input_buffers(X, y)
+        if X.data_ptr() != Xs.data_ptr():
+            Xs.copy_(X, non_blocking=True)
+            ys.copy_(y, non_blocking=True)
+        if self._graph is None:
+            before = self.total_launches
+            host_step = self.opt_step
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager(Xs, ys)
+            self.opt_step = host_step           # capture does not execute; the replay below is the real step
+            self.hyper[1:2].fill_(float(host_step))
+            self._graph_launches = self.total_launches - before
+            self.launches -= self._graph_launches   # count launches when they run, i.e. per replay
+            self._graph = g
+        self._graph.replay()
+        self.opt_step += 1
+        self.replays += 1
+        self.launches += self._graph_launches
         return self.loss_buf
 
     @property
