@@ -583,8 +583,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    // ---- write dV_j rows (column half 0 threads) and dK_j rows (half 1 threads)
-    if (t.half == 0) {
+    // ---- write dV_j rows and dK_j rows: the two column-half groups swap roles every tile so that the expensive
+    //      normalisation backward (dK) is shared evenly between them
+    if (t.half == (j & 1)) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[32];
