@@ -136,9 +136,15 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // MEASURED (B200, nViT-B/16 step): an extra cursor issuing cp.async.bulk.prefetch.tensor (L2 prefetch) six k-blocks
+    // ahead of the loads dropped every GEMM variant from 65-90 % to ~43 % tensor-pipe activity - the main loop is bound
+    // by L2 request throughput, not latency, and the prefetch doubles the requests.  Likewise anything but a handful of
+    // integer instructions per k-block in this single thread shows up directly as lost tensor time, so all tile
+    // arithmetic is hoisted out of the k loop.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full0 = smem_u32(full_bar);
       for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u % p.splits;
         const int t = u / p.splits;
@@ -146,12 +152,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
         const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;   // this CTA's 128-row block
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int a_row = m_blk * T::BM;
+        const int b_row = SWIGLU ? ((CG2 && cta_rank) ? p.swiglu_half : 0) + n_blk * 128 : n_blk * BN + (int)cta_rank * T::BN_CTA;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * T::STAGE_BYTES;
           uint8_t* sB = sA + T::A_BYTES;
           // pair mode: both CTAs' bytes are counted on the rank-0 CTA's barrier, which its MMA warp waits on
-          uint32_t fb = smem_u32(&full_bar[stage]);
+          uint32_t fb = full0 + stage * 8;
           if constexpr (CG2) {
             fb = mapa_shared(fb, 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);
@@ -162,25 +170,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             if constexpr (CG2) tma_load_2d_cg2(m, fb, dst, c0, c1);
             else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
           };
+          const int k0 = kb * T::BK;
           if constexpr (!A_MN) {
-            load(&p.tma_a, sA, kb * T::BK, m_blk * T::BM);
+            load(&p.tma_a, sA, k0, a_row);
           } else {
 #pragma unroll
-            for (int j = 0; j < T::BM / 64; ++j) load(&p.tma_a, sA + j * (T::BK * 128), m_blk * T::BM + j * 64, kb * T::BK);
+            for (int j = 0; j < T::BM / 64; ++j) load(&p.tma_a, sA + j * (T::BK * 128), a_row + j * 64, k0);
           }
           if constexpr (SWIGLU) {
-            if constexpr (CG2) {   // rank 0 stages the u rows, rank 1 the matching v rows
-              load(&p.tma_b, sB, kb * T::BK, (cta_rank ? p.swiglu_half : 0) + n_blk * 128);
-            } else {
-              load(&p.tma_b, sB, kb * T::BK, n_blk * 128);
-              load(&p.tma_b, sB + 128 * 128, kb * T::BK, p.swiglu_half + n_blk * 128);
-            }
+            load(&p.tma_b, sB, k0, b_row);
+            if constexpr (!CG2) load(&p.tma_b, sB + 128 * 128, k0, p.swiglu_half + b_row);
           } else if constexpr (!B_MN) {
-            load(&p.tma_b, sB, kb * T::BK, n_blk * BN + (int)cta_rank * T::BN_CTA);
+            load(&p.tma_b, sB, k0, b_row);
           } else {
 #pragma unroll
-            for (int j = 0; j < T::BN_CTA / 64; ++j)
-              load(&p.tma_b, sB + j * (T::BK * 128), n_blk * BN + (int)cta_rank * T::BN_CTA + j * 64, kb * T::BK);
+            for (int j = 0; j < T::BN_CTA / 64; ++j) load(&p.tma_b, sB + j * (T::BK * 128), b_row + j * 64, k0);
           }
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -350,7 +354,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             }
           }
         } else if (!p.out_f32) {
-          // bf16 output: chunks of 64 columns (128 B rows, 128B swizzle)
+          // bf16 output: chunks of 64 columns (128 B rows, 128B swizzle).  (Pulling all of a group's chunks out of TMEM
+          // first, to hand the accumulator back earlier, was measured slower: 65 -> 54 % tensor activity.)
           constexpr int NC = BN / 64;
 #pragma unroll 1
           for (int c = eg; c < NC; c += 2) {
