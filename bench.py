@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--sm-budget", type=int, default=0, help="data parallel: SMs the persistent kernels may use (0 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -188,7 +190,8 @@ def main():
     cfg = ViTConfig(**ocfg.as_dict())
     torch.manual_seed(0)
     model = ViT(cfg).to(dev).train()
-    trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph)
+    trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
+                      overlap_allreduce=not args.no_overlap, sm_budget=args.sm_budget)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     X_host = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g).pin_memory()
@@ -302,8 +305,10 @@ def main():
                                  "frac_of_sustained_peak": fpi * value / world / 1e12 / peak},
             "roofline": {"kernel": "gemm_tcgen05_kernel<256,K,K,SWIGLU> (c_fc GEMM + suv*SiLU gate epilogue, forward)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
+                         "traffic": (955.66e6 if (args.config == "b16" and B == 256) else None), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
                          "launches_timed": len(probe), "avg_launch_ms": kern_ms, "flop_per_launch": gemm_flops,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
+                                           "profiles/r01_ncu_full_cfc_swiglu_gemm_raw.csv (bytes; algorithmic 1011e6)",
                          "probe": f"CUDA events around each c_fc launch over {probe_steps} eager steps of the same workload"
                                   + (" (the timed region replays a CUDA graph, where events cannot be timed)" if trainer.use_graph else "")},
         }

@@ -26,6 +26,8 @@ extern "C" {
 const char* nvit_last_error(void);
 int nvit_version(void);
 int nvit_sm_count(void);
+/* Size persistent grids for at most n SMs (0 = all): leaves SMs free for concurrent NCCL kernels in data-parallel runs. */
+int nvit_set_sm_budget(int n);
 
 /* ---- GEMM: nn.Linear / nn.Conv2d-as-GEMM forward, dgrad and wgrad (model.py:99-101,130,148,155,226-228,259,262,
  *      286-304,329-332,341-344 and their autograd backward) ------------------------------------------------------

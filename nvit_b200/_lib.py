@@ -18,6 +18,7 @@ P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 SIGNATURES = {
     "nvit_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, I32, I32, I32, I32, P, P, F32, P, I64, I64, P],
     "nvit_gemm_force_cta_group": [I32],
+    "nvit_set_sm_budget": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
     "nvit_colsum_bf16": [P, I64, I64, I64, P, P],

@@ -12,6 +12,10 @@ void nvit_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_sm_budget = 0;  // 0 = all SMs
+
+// Number of SMs the persistent kernels size their grids for: the device's SM count, or the budget set through
+// nvit_set_sm_budget (data-parallel runs leave a few SMs to the NCCL kernels that overlap the backward pass).
 int nvit_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -19,9 +23,17 @@ int nvit_num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return n;
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
 }
 
 extern "C" const char* nvit_last_error(void) { return g_err; }
 extern "C" int nvit_version(void) { return 100; }
 extern "C" int nvit_sm_count(void) { return nvit_num_sms(); }
+extern "C" int nvit_set_sm_budget(int n) {
+  if (n < 0) {
+    nvit_set_error("nvit_set_sm_budget: negative budget");
+    return NVIT_ERR_ARG;
+  }
+  g_sm_budget = n & ~1;  // CTA pairs: keep it even
+  return NVIT_OK;
+}

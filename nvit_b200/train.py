@@ -83,7 +83,7 @@ class Trainer:
 
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
                  eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
-                 cuda_graph: bool = False, graph_warmup_steps: int = 2):
+                 cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = True, sm_budget: int = 0):
         import torch.distributed as dist
         self.model = model
         self.engine = model.engine
@@ -99,6 +99,10 @@ class Trainer:
         self._state_for = None
         self.reducer = None
         self.launches = 0
+        self.overlap = overlap_allreduce      # bucketed all-reduce behind the backward pass vs one all-reduce after it
+        if self.dp and sm_budget:
+            from . import _lib
+            _lib.call("nvit_set_sm_budget", int(sm_budget))
         # CUDA-graph replay of the whole step (single rank): the ~275 launches, their tensor-map encodes and the Python
         # between them are captured once; learning rate and step count then live in device memory (self.hyper)
         self.use_graph = bool(cuda_graph) and not self.dp
@@ -144,7 +148,7 @@ class Trainer:
         # mean CE over the batch, scaled for accumulation and for the mean over data-parallel ranks
         ops.cross_entropy(logits, y, self.loss_buf, dlogits, 1.0 / (self.grad_accum * self.world))
         self.launches += 1
-        eng.grad_ready_hook = self.reducer.ready if (self.dp and last) else None
+        eng.grad_ready_hook = self.reducer.ready if (self.dp and last and self.overlap) else None
         eng.backward(dlogits)
         self.last_recon = recon
         return logits
@@ -153,6 +157,8 @@ class Trainer:
         """clip -> AdamW -> zero_grad -> normalize_matrices (train.py:935-946, 989-990)."""
         eng = self.engine
         if self.dp:
+            if not self.overlap:
+                self.reducer.ready(0, eng.n_active)
             self.reducer.finish()
         self.opt_step += 1
         self.hyper[1:2].add_(1.0)          # device-side step count (what a replayed graph advances)
