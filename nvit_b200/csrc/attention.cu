@@ -14,8 +14,8 @@
 //             S^T = Kh_j Qh^T ; P^T = exp(scale S^T - lse) ; dV_j = P^T dO ; dP^T = V_j dO^T ;
 //             dS^T = P^T (dP^T - delta) scale ; dK_j = dS^T Qh ; dQ += dS Kh_j (A = dS^T viewed MN-major)
 //             then the backward of the row normalisation and the sqk gradient.
-// 256 threads per CTA: two threads share a TMEM lane (score row) and split its columns, which halves the serial
-// per-thread work and doubles the warps available to hide ALU latency.  With unit-norm q/k the logits are bounded by
+// 512 threads per CTA: four threads share a TMEM lane (score row) and split its columns (and, in the epilogues, its 64
+// channels), which quarters the serial per-thread work and gives every scheduler four warps to hide ALU latency.  With unit-norm q/k the logits are bounded by
 // scale * max(s^2), so the forward softmax needs no running max (one pass); the general two-pass form is kept for
 // un-normalised inputs and very large learned scales.
 #include "common.cuh"
@@ -26,7 +26,8 @@ namespace nvit {
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box);
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 512;   // 16 warps: four threads share a TMEM lane (a score row)
+constexpr int ATT_PARTS = 4;       // ... and split its columns / channels four ways
 constexpr int ATT_ROWS = 256;                   // token capacity of a shared tile
 constexpr int ATT_TILE_BYTES = ATT_ROWS * 128;  // [256 tokens][64 bf16]
 constexpr int ATT_PB_BYTES = 128 * 256 * 2;     // [128 rows][4 k-blocks x 64 bf16]
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t idesc_kk_n(int N) {                         
 
 // common prologue pieces ------------------------------------------------------------------------------------------
 struct AttnThread {
-  int tid, warp, lane, wq, half, row, b, h;
+  int tid, warp, lane, wq, part, row, b, h;
   int c_begin, c_end, nch;  // this thread's 16-column chunks of a score row
 };
 __device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
@@ -110,14 +111,13 @@ __device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
   t.warp = t.tid >> 5;
   t.lane = t.tid & 31;
   t.wq = t.warp & 3;       // TMEM lane quarter this warp may access
-  t.half = t.warp >> 2;    // which half of the columns of a row
+  t.part = t.warp >> 2;    // which quarter of the columns / channels of a row
   t.row = t.wq * 32 + t.lane;
   t.b = blockIdx.x / p.H;
   t.h = blockIdx.x % p.H;
   t.nch = p.TP >> 4;
-  const int mid = (t.nch + 1) >> 1;
-  t.c_begin = t.half ? mid : 0;
-  t.c_end = t.half ? t.nch : mid;
+  t.c_begin = (t.part * t.nch) / ATT_PARTS;
+  t.c_end = ((t.part + 1) * t.nch) / ATT_PARTS;
   return t;
 }
 
@@ -150,7 +150,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (64 + 256 + 8) * 4 + 64;
+constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (64 + 512 + 8) * 4 + 64;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   uint8_t* sV = sK + ATT_TILE_BYTES;
   uint8_t* sP = sV + ATT_TILE_BYTES;
   float* s_scale = reinterpret_cast<float*>(sP + ATT_PB_BYTES);  // [64]
-  float* s_part = s_scale + 64;                                  // [2][128] partial row sums / maxima
-  float* s_misc = s_part + 256;                                  // [0] = log2-domain logit bound
+  float* s_part = s_scale + 64;                                  // [4][128] partial row sums / maxima
+  float* s_misc = s_part + 512;                                  // [0] = log2-domain logit bound
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         for (int e = 0; e < 16; ++e)
           if (c * 16 + e < T) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
-      s_part[t.half * 128 + t.row] = mx;
+      s_part[t.part * 128 + t.row] = mx;
       __syncthreads();
-      m2 = fmaxf(s_part[t.row], s_part[128 + t.row]) * sl2;
+      m2 = fmaxf(fmaxf(s_part[t.row], s_part[128 + t.row]), fmaxf(s_part[256 + t.row], s_part[384 + t.row])) * sl2;
       __syncthreads();
     }
     float sum = 0.f;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       *reinterpret_cast<uint4*>(blk + sw128(t.row, ch)) = pack8(pv);
       *reinterpret_cast<uint4*>(blk + sw128(t.row, ch + 1)) = pack8(pv + 8);
     }
-    s_part[t.half * 128 + t.row] = sum;
+    s_part[t.part * 128 + t.row] = sum;
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
@@ -277,25 +277,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       mma_seq_pk(tmem_base + 256, umma_smem_desc(sP_a, 16, 1024), umma_smem_desc(sV_a, 8192, 1024), 128, IDESC_KM(64), TP >> 4);
       mma_commit(bar_mma);
     }
-    const float total = s_part[t.row] + s_part[128 + t.row];
+    const float total = (s_part[t.row] + s_part[128 + t.row]) + (s_part[256 + t.row] + s_part[384 + t.row]);
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
     {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_lane + 256 + t.half * 32, r);
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_lane + 256 + t.part * 16, r);
       tmem_wait_ld();
       if (qtok < T) {
         const float inv = 1.f / total;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.half * 32;
-        float o[8];
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.part * 16;
+        float o[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[8 * c + e]) * inv;
-          *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(o);
-        }
-        if (t.half == 0) p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + qtok] = (m2 + log2f(total)) * LN2;
+        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]) * inv;
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
+        *reinterpret_cast<uint4*>(dst + 8) = pack8(o + 8);
+        if (t.part == 0) p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + qtok] = (m2 + log2f(total)) * LN2;
       }
     }
     tc_fence_before_sync();
@@ -309,78 +307,58 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 192) * 4 + 64;
+constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 192 + 512) * 4 + 64;
 
-// backward of y = s * x/||x|| for one row whose dL/dy sits in 64 TMEM columns at `taddr`.  The unit vector n = x/||x||
-// is recovered from the normalised bf16 row still resident in the swizzled shared tile (n_c = y_c / s_c), so the
-// epilogue touches no global memory except its store.  Two passes over TMEM keep the register footprint small.
-// Writes dx (bf16) and accumulates dL/ds per channel into dacc.
-__device__ __forceinline__ void norm_bwd_row(uint32_t taddr, const uint8_t* tile, int trow, float inv, const float* s_scale,
-                                             const float* s_rscale, bool has_norm, __nv_bfloat16* dst, float (&dacc)[64], bool valid) {
-  if (!has_norm) {
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + hh * 32, r);
-      tmem_wait_ld();
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float g[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(r[8 * c + e]);
-          *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = pack8(g);
-        }
-      }
-    }
-    return;
-  }
+// Backward of y = s * x/||x|| for one row, four threads per row, each owning 16 of the 64 channels.  dL/dy sits in TMEM
+// (16 columns at `taddr` for this thread); the unit vector n = x/||x|| is recovered from the normalised bf16 row still
+// resident in the swizzled shared tile (n_c = y_c / s_c), so the epilogue touches no global memory except its store.
+//   phase A (norm_bwd_load): g <- TMEM, n <- smem, partial dot = sum_c g_c s_c n_c, dacc += g*n
+//   (the four partial dots of a row are exchanged through shared memory by the caller)
+//   phase B (norm_bwd_store): dx_c = (g_c s_c - n_c dot) / ||x||
+__device__ __forceinline__ float norm_bwd_load(uint32_t taddr, const uint8_t* tile, int trow, int part, const float* s_scale,
+                                               const float* s_rscale, float (&g)[16], float (&n)[16], float (&dacc)[16], bool valid) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_wait_ld();
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part)), n);
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part + 1)), n + 8);
   float dot = 0.f;
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(taddr + hh * 32, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float n[8];
-      unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, hh * 4 + c)), n);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = hh * 32 + 8 * c + e;
-        const float g = __uint_as_float(r[8 * c + e]);
-        const float nn = n[e] * s_rscale[i];
-        dacc[i] += valid ? g * nn : 0.f;
-        dot += g * s_scale[i] * nn;
-      }
-    }
+  for (int e = 0; e < 16; ++e) {
+    const int i = part * 16 + e;
+    g[e] = __uint_as_float(r[e]);
+    n[e] *= s_rscale[i];
+    dacc[e] += valid ? g[e] * n[e] : 0.f;
+    g[e] *= s_scale[i];
+    dot += g[e] * n[e];
   }
+  return dot;
+}
+__device__ __forceinline__ void norm_bwd_store(const float (&g)[16], const float (&n)[16], float dot, float inv, __nv_bfloat16* dst) {
+  float d[16];
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(taddr + hh * 32, r);
-    tmem_wait_ld();
-    if (valid) {
+  for (int e = 0; e < 16; ++e) d[e] = (g[e] - n[e] * dot) * inv;
+  *reinterpret_cast<uint4*>(dst) = pack8(d);
+  *reinterpret_cast<uint4*>(dst + 8) = pack8(d + 8);
+}
+__device__ __forceinline__ void tmem_row16_to_bf16(uint32_t taddr, __nv_bfloat16* dst, bool valid) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_wait_ld();
+  if (valid) {
+    float g[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float n[8], d[8];
-        unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, hh * 4 + c)), n);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = hh * 32 + 8 * c + e;
-          d[e] = (__uint_as_float(r[8 * c + e]) * s_scale[i] - n[e] * s_rscale[i] * dot) * inv;
-        }
-        *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = pack8(d);
-      }
-    }
+    for (int e = 0; e < 16; ++e) g[e] = __uint_as_float(r[e]);
+    *reinterpret_cast<uint4*>(dst) = pack8(g);
+    *reinterpret_cast<uint4*>(dst + 8) = pack8(g + 8);
   }
 }
 
-// Sum 64 per-lane partials over the 32 lanes of a warp by recursive halving (62 shuffles) and add them to s_out[64].
-__device__ __forceinline__ void reduce64_to_smem(float (&v)[64], float* s_out, int lane) {
+// Sum 16 per-lane partials over the 32 lanes of a warp by recursive halving and add them to s_out[16].
+__device__ __forceinline__ void reduce16_to_smem(float (&v)[16], float* s_out, int lane) {
 #pragma unroll
-  for (int step = 0; step < 5; ++step) {
-    const int off = 16 >> step, n = 32 >> step;
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step, n = 8 >> step;
     const bool up = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
@@ -389,9 +367,9 @@ __device__ __forceinline__ void reduce64_to_smem(float (&v)[64], float* s_out, i
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
-  const int base = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
-  atomicAdd(&s_out[base], v[0]);
-  atomicAdd(&s_out[base + 1], v[1]);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if ((lane & 1) == 0) atomicAdd(&s_out[ch], v[0]);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
@@ -409,7 +387,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   float* s_scale = s_invk + 256;                               // [64]
   float* s_dsqk = s_scale + 64;                                // [64]
   float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_rscale + 64);
+  float* s_dot = s_rscale + 64;                                // [4][128] partial row dots of the normalisation backward
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dot + 512);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -451,14 +430,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     tma_load_3d(&p.to, bar_tma, sP, t.h * 64, 0, t.b);   // O parks in the (not yet used) P buffer for the delta pass
   }
   // while the tiles fly: lse; then delta = rowsum(dO * O) from the shared tiles, and a clean P buffer
-  {
-    const int r = t.tid;  // 256 threads, 256 rows
+  if (t.tid < 256) {
+    const int r = t.tid;  // one thread per (padded) token row
     s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E : 0.f;
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
   }
   mbar_wait(bar_tma, 0);
-  {
+  if (t.tid < 256) {
     const int r = t.tid;
     float d = 0.f;
 #pragma unroll
@@ -488,9 +467,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   const float sl2 = p.scale * LOG2E;
   const int nks_q = TP >> 4;  // k-steps over the q axis
   uint32_t mma_phase = 0;
-  float dacc[64];
+  float dacc[16];   // dL/d(sqk) partials for this thread's 16 channels
 #pragma unroll
-  for (int i = 0; i < 64; ++i) dacc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
 
   constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
@@ -583,43 +562,43 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    // ---- write dV_j rows and dK_j rows: the two column-half groups swap roles every tile so that the expensive
-    //      normalisation backward (dK) is shared evenly between them
-    if (t.half == (j & 1)) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_lane + TM_DV + hh * 32, r);
-        tmem_wait_ld();
-        if (kv_ok) {
-          __nv_bfloat16* dst = p.dv + (static_cast<long long>(t.b) * T + kv) * p.lddv + t.h * 64 + hh * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float g[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(r[8 * c + e]);
-            *reinterpret_cast<uint4*>(dst + 8 * c) = pack8(g);
-          }
-        }
-      }
-    } else {
+    // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both
+    {
       const int kvc = kv_ok ? kv : 0;
-      norm_bwd_row(t_lane + TM_DK, sK, kvc, s_invk[kvc], s_scale, s_rscale, has_norm,
-                   p.dk + (static_cast<long long>(t.b) * T + kvc) * p.lddk + t.h * 64, dacc, kv_ok);
+      const long long grow = static_cast<long long>(t.b) * T + kvc;
+      tmem_row16_to_bf16(t_lane + TM_DV + t.part * 16, p.dv + grow * p.lddv + t.h * 64 + t.part * 16, kv_ok);
+      if (has_norm) {
+        float g[16], n[16];
+        s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DK + t.part * 16, sK, kvc, t.part, s_scale, s_rscale, g, n, dacc, kv_ok);
+        __syncthreads();
+        const float dot = (s_dot[t.row] + s_dot[128 + t.row]) + (s_dot[256 + t.row] + s_dot[384 + t.row]);
+        if (kv_ok) norm_bwd_store(g, n, dot, s_invk[kvc], p.dk + grow * p.lddk + t.h * 64 + t.part * 16);
+      } else {
+        tmem_row16_to_bf16(t_lane + TM_DK + t.part * 16, p.dk + grow * p.lddk + t.h * 64 + t.part * 16, kv_ok);
+      }
     }
     tc_fence_before_sync();
     __syncthreads();
   }
 
-  // ---- dQ rows: column-half h of the CTA takes q tile h
-  if (t.half < p.nQ) {
-    const int qi = t.half * 128 + t.row;
+  // ---- dQ rows, one 128-row q tile at a time, 16 channels per thread
+  for (int m = 0; m < p.nQ; ++m) {
+    const int qi = m * 128 + t.row;
     const bool ok = qi < T;
     const int qc = ok ? qi : 0;
-    norm_bwd_row(t_lane + TM_DQ + 64 * t.half, sQ, qc, s_invq[qc], s_scale, s_rscale, has_norm,
-                 p.dq + (static_cast<long long>(t.b) * T + qc) * p.lddq + t.h * 64, dacc, ok);
+    const long long grow = static_cast<long long>(t.b) * T + qc;
+    if (has_norm) {
+      float g[16], n[16];
+      s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DQ + 64 * m + t.part * 16, sQ, qc, t.part, s_scale, s_rscale, g, n, dacc, ok);
+      __syncthreads();
+      const float dot = (s_dot[t.row] + s_dot[128 + t.row]) + (s_dot[256 + t.row] + s_dot[384 + t.row]);
+      if (ok) norm_bwd_store(g, n, dot, s_invq[qc], p.dq + grow * p.lddq + t.h * 64 + t.part * 16);
+      __syncthreads();
+    } else {
+      tmem_row16_to_bf16(t_lane + TM_DQ + 64 * m + t.part * 16, p.dq + grow * p.lddq + t.h * 64 + t.part * 16, ok);
+    }
   }
-  if (has_norm) reduce64_to_smem(dacc, s_dsqk, t.lane);
+  if (has_norm) reduce16_to_smem(dacc, s_dsqk + t.part * 16, t.lane);
   tc_fence_before_sync();
   __syncthreads();
   if (has_norm && t.tid < 64) atomicAdd(p.dsqk + t.h * 64 + t.tid, s_dsqk[t.tid] * p.sqk_mul);
