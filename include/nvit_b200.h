@@ -74,6 +74,22 @@ int nvit_residual_bwd(const float* g, const float* h, const void* x_bf16, const 
                       const float* h0, const float* skip, float* dh, int dh_accumulate, void* dx_bf16, float* dh0,
                       float* dalpha_accum, float* dskip_accum, int64_t M, int64_t C, void* stream);
 
+/* ---- original-ViT branch (config.use_nvit = False; BASELINE config 4) -------------------------------------------------
+ *   add_rmsnorm : t = h (+ x_bf16, may be NULL);  y = t * rsqrt(mean(t^2) + eps) * w      (RMSNorm, model.py:172-184, applied
+ *                 to the plain residual sum, model.py:95-96, 132-133, 145-146; cross-attention norms :221-223)
+ *                 bwd: dh (+)= dt, dx = dt (bf16), dw[C] +=          (recomputes t from h and x)
+ *   add_skipnorm: out = N((h + x) * skip[0] + h0)      (second residual add model.py:157-158 + norm_skip :84-87, 450-452)
+ *                 bwd: dh (written, fp32) = dx (bf16) = d(h+x), dh0 (written), dskip[1] +=
+ */
+int nvit_add_rmsnorm_fwd(const float* h, const void* x_bf16, const float* w, float eps, float* y_f32, void* y_bf16,
+                         int64_t M, int64_t C, void* stream);
+int nvit_add_rmsnorm_bwd(const float* dy, const float* h, const void* x_bf16, const float* w, float eps, float* dh,
+                         int dh_accumulate, void* dx_bf16, float* dw_accum, int64_t M, int64_t C, void* stream);
+int nvit_add_skipnorm_fwd(const float* h, const void* x_bf16, const float* h0, const float* skip, float* out_f32,
+                          void* out_bf16, int64_t M, int64_t C, void* stream);
+int nvit_add_skipnorm_bwd(const float* g, const float* h, const void* x_bf16, const float* h0, const float* skip, float* dh,
+                          void* dx_bf16, float* dh0, float* dskip_accum, int64_t M, int64_t C, void* stream);
+
 /* ---- suv-scaled SiLU gate, unfused form (model.py:150-154, 259-261).  uv [M,2F] bf16: u = cols [0,F), v = [F,2F).
  *   x = (u*su) * silu(v*sv),  s = suv * suv_mul (suv NULL -> 1).  bwd: duv bf16 [M,2F], dsuv[2F] += (w.r.t. stored suv).
  */

@@ -25,6 +25,10 @@ SIGNATURES = {
     "nvit_pos_bias_grad": [P, I64, I64, I64, P, P, P],
     "nvit_residual_fwd": [P, P, P, F32, P, P, P, P, I64, I64, P],
     "nvit_residual_bwd": [P, P, P, P, F32, P, P, P, I32, P, P, P, P, I64, I64, P],
+    "nvit_add_rmsnorm_fwd": [P, P, P, F32, P, P, I64, I64, P],
+    "nvit_add_rmsnorm_bwd": [P, P, P, P, F32, P, I32, P, P, I64, I64, P],
+    "nvit_add_skipnorm_fwd": [P, P, P, P, P, P, I64, I64, P],
+    "nvit_add_skipnorm_bwd": [P, P, P, P, P, P, P, P, P, I64, I64, P],
     "nvit_swiglu_fwd": [P, P, F32, P, I64, I64, P],
     "nvit_swiglu_bwd": [P, P, P, F32, P, P, I64, I64, P],
     "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],

@@ -42,8 +42,6 @@ class Engine:
     def __init__(self, model):
         self.model = model
         self.cfg = model.config
-        if not self.cfg.use_nvit:
-            raise NotImplementedError("use_nvit=False (BASELINE config 4) is not built yet; see DESIGN.md")
         self.P32 = None
         self._acts = {}
         self._saved = None
@@ -75,7 +73,7 @@ class Engine:
         order += ["mlp_head.1.weight"]
         n_gemm = len(order)
         # region A': remaining weight-decayed parameters (dim >= 2)
-        inactive = {n for n in named if ".rmsnorm_" in n or n.startswith("reconstruction_head.")}
+        inactive = {n for n in named if (cfg.use_nvit and ".rmsnorm_" in n) or n.startswith("reconstruction_head.")}
         rest = [n for n in named if n not in order and n not in inactive]
         order += [n for n in rest if named[n].dim() >= 2 and "sz" not in n]
         n_decay_names = len(order)
@@ -185,17 +183,19 @@ class Engine:
     def _build_norm_table(self):
         """Device table for nvit_weight_norm_multi (Trainer.normalize_matrices, train.py:461-480)."""
         rows, first = [], 0
-        for i in range(self.cfg.n_layer):
+        for i in range(self.cfg.n_layer if self.cfg.use_nvit else 0):
             b = f"transformer.h.{i}."
             for nm, axis in (("query", 1), ("key", 1), ("value", 1), ("att_c_proj", 0), ("c_fc", 1), ("mlp_c_proj", 0)):
                 s = self.slots[b + nm + ".weight"]
                 r, c = s.shape
                 rows.append([self.P32.data_ptr() + 4 * s.off, 0, r, c, axis, first])
                 first += (r + 7) // 8 if axis == 1 else (c + 127) // 128
-        self.norm_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        self.norm_table = torch.tensor(rows if rows else [[0] * 6], dtype=torch.int64, device=self.device)
         self.norm_units = first
 
     def normalize_matrices(self):
+        if not self.cfg.use_nvit:        # train.py:463-464: only in nViT mode
+            return
         ops.weight_norm_multi(self.norm_table, self.norm_table.shape[0], self.norm_units)
         self.launches += 1
         self._p16_version = None
@@ -243,6 +243,9 @@ class Engine:
             "d_c16": e(M, C), "d_c16b": e(M, C), "d_4c": e(M, 4 * C), "d_8c": e(M, 8 * C), "d_3c": e(M, 3 * C),
             "draw16": torch.zeros(B, _align(ncls, 8), device=dev, dtype=BF16), "dy16": e(B, C),
         }
+        if not cfg.use_nvit:
+            a.update({"global32": e(M, C, dtype=F32), "y1_32": [e(M, C, dtype=F32) for _ in range(L)],
+                      "y1_16": [e(M, C) for _ in range(L)], "dY1": e(M, C, dtype=F32)})
         self._acts = {B: a}      # keep one batch size resident
         return a
 
@@ -260,6 +263,8 @@ class Engine:
         self._check_alias(img.device)
         self.refresh_operands()
         B = img.shape[0]
+        if not cfg.use_nvit:
+            return self._forward_orig(img, save)
         C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
         T = (cfg.image_size // P) ** 2
         a = self._buffers(B)
@@ -348,6 +353,8 @@ class Engine:
         if self._saved is None:
             raise RuntimeError("Engine.backward called without a saved forward pass")
         cfg = self.cfg
+        if not cfg.use_nvit:
+            return self._backward_orig(dlogits)
         B, T = self._saved
         C, L, H = cfg.n_embd, cfg.n_layer, cfg.n_head
         M = B * T
@@ -436,6 +443,156 @@ class Engine:
         self.launches += 7
 
         # ---- patch embeddings: position / bias gradients and the two conv weight gradients (no dX: images need none)
+        for dX32, A, wname, bname, pos in ((dLocal, a["A_l"], "local_patch_embed.weight", "local_patch_embed.bias", "local_pos_embed"),
+                                           (dGlobal, a["A_g"], "global_patch_embed.1.weight", "global_patch_embed.1.bias", "global_pos_embed")):
+            ops.pos_bias_grad(dX32, B, T, C, g(pos).view(T, C), g(bname))
+            ops.cast_bf16(dX32, a["d_c16"])
+            self._wgrad(a["d_c16"], A, g2d(wname))
+            self.launches += 2
+        self.last_backward_launches = self.launches - n0
+        self._saved = None
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(0, self.block_grad_range(0)[0])
+            self.grad_ready_hook(self.block_grad_range(cfg.n_layer - 1)[1], self.n_active)
+
+
+    # ------------------------------------------------------------------------------------------ original-ViT branch
+    # config.use_nvit = False (BASELINE config 4): RMSNorm pre-norm that OVERWRITES h, plain residual adds, 1/sqrt(D)
+    # attention without q/k normalisation, no suv / sz, cross-attention without residual - and norm_skip still applied
+    # (model.py:95-96, 132-133, 145-146, 157-158, 221-223, 450-452; SURVEY.md appendix B "original ViT branch as written").
+    def _forward_orig(self, img, save=True):
+        cfg = self.cfg
+        B = img.shape[0]
+        C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
+        T = (cfg.image_size // P) ** 2
+        a = self._buffers(B)
+        bias = cfg.bias
+        p, w16 = self.p, self.w16
+        att_scale = 1.0 / float(C // H) ** 0.5
+        eps = 1e-6
+        n0 = self.launches
+        ops.im2col(img, a["A_l"], P, P, 0)
+        ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
+        ops.linear_fwd(a["A_l"], w16("local_patch_embed.weight"), a["local32"], bias=p("local_patch_embed.bias"),
+                       rowadd=p("local_pos_embed").view(T, C), rowadd_period=T)
+        ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global32"], bias=p("global_patch_embed.1.bias"),
+                       rowadd=p("global_pos_embed").view(T, C), rowadd_period=T)
+        ca = "cross_attention."
+        ops.add_rmsnorm_fwd(a["local32"], None, p(ca + "local_norm.weight"), eps, None, a["local16"])
+        ops.add_rmsnorm_fwd(a["global32"], None, p(ca + "global_norm.weight"), eps, None, a["global16"])
+        ops.linear_fwd(a["local16"], w16(ca + "q_local.weight"), a["ca_q"], bias=p(ca + "q_local.bias") if bias else None)
+        ops.linear_fwd(a["global16"], w16(ca + "k_global.weight", rows=2 * C), a["ca_kv"],
+                       bias=self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None)
+        ops.attention_fwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], None, 1.0, att_scale, a["ca_att"], a["ca_lse"], B, H, T)
+        self._gated_fwd(a["ca_att"], w16(ca + "proj.weight"), p(ca + "proj.bias") if bias else None, None, 1.0, a["ca_uv"], a["ca_x"], C)
+        ops.linear_fwd(a["ca_x"], w16(ca + "out_proj.weight"), a["h32"][0], bias=p(ca + "out_proj.bias") if bias else None, c2=a["h16"][0])
+        self.launches += 11
+        for i in range(L):
+            b = f"transformer.h.{i}."
+            ops.add_rmsnorm_fwd(a["h32"][i], None, p(b + "rmsnorm_att.weight"), eps, a["y1_32"][i], a["y1_16"][i])
+            ops.linear_fwd(a["y1_16"][i], w16(b + "query.weight", rows=3 * C), a["qkv"][i],
+                           bias=self._cat_bias(b + "query.bias", 3 * C) if bias else None)
+            qkv = a["qkv"][i]
+            ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], None, 1.0, att_scale, a["att"][i], a["lse"][i], B, H, T)
+            ops.linear_fwd(a["att"][i], w16(b + "att_c_proj.weight"), a["h_att"][i], bias=p(b + "att_c_proj.bias") if bias else None)
+            ops.add_rmsnorm_fwd(a["y1_32"][i], a["h_att"][i], p(b + "rmsnorm_mlp.weight"), eps, a["h1_32"][i], a["h1_16"][i])
+            self._gated_fwd(a["h1_16"][i], w16(b + "c_fc.weight"), p(b + "c_fc.bias") if bias else None, None, 1.0, a["uv"][i], a["x"][i], 4 * C)
+            ops.linear_fwd(a["x"][i], w16(b + "mlp_c_proj.weight"), a["h_mlp"][i], bias=p(b + "mlp_c_proj.bias") if bias else None)
+            ops.add_skipnorm_fwd(a["h1_32"][i], a["h_mlp"][i], a["h32"][i], p(b + "skip_param"), a["h32"][i + 1], a["h16"][i + 1])
+            self.launches += 7
+        ops.pool_ln_fwd(a["h32"][L], p("mlp_head.0.weight"), p("mlp_head.0.bias"), 1e-5, a["y16"], a["xhat"], a["rstd"], B, T, C)
+        ops.linear_fwd(a["y16"], w16("mlp_head.1.weight"), a["logits"], bias=p("mlp_head.1.bias"))
+        ops.linear_fwd(a["h16"][L], w16("reconstruction_head.0.weight"), a["pred"], bias=p("reconstruction_head.0.bias"))
+        self.scratch[0:1].zero_()
+        ops.tanh_mse(a["pred"], a["A_l"], self.scratch[0:1])
+        self.launches += 4
+        self.last_forward_launches = self.launches - n0
+        self._saved = (B, T) if save else None
+        return a["logits"].clone(), self.scratch[0].clone()
+
+    def _backward_orig(self, dlogits):
+        cfg = self.cfg
+        B, T = self._saved
+        C, L, H = cfg.n_embd, cfg.n_layer, cfg.n_head
+        M = B * T
+        ncls = cfg.num_classes
+        a = self._acts[B]
+        p, g, w16, g2d = self.p, self.g, self.w16, self.g2d
+        bias = cfg.bias
+        att_scale = 1.0 / float(C // H) ** 0.5
+        eps = 1e-6
+        n0 = self.launches
+        dlogits = dlogits.to(F32).contiguous()
+        draw = a["draw16"][:, :ncls]
+        ops.head_scale_bwd(dlogits, a["logits"], None, 1.0, a["draw16"], None)     # no sz: draw = bf16(dlogits)
+        ops.colsum(draw, g("mlp_head.1.bias"))
+        self._wgrad(draw, a["y16"], g2d("mlp_head.1.weight"))
+        ops.linear_dgrad(draw, w16("mlp_head.1.weight"), a["dy16"])
+        ops.pool_ln_bwd(a["dy16"], p("mlp_head.0.weight"), a["xhat"], a["rstd"], a["G"], g("mlp_head.0.weight"), g("mlp_head.0.bias"), B, T, C)
+        self.launches += 4
+        G, dHin, dY2, dY1 = a["G"], a["dHin"], a["dH1"], a["dY1"]
+        for i in reversed(range(L)):
+            b = f"transformer.h.{i}."
+            dHmlp, dHatt, dAtt = a["d_c16"], a["d_c16"], a["d_c16b"]
+            ops.add_skipnorm_bwd(G, a["h1_32"][i], a["h_mlp"][i], a["h32"][i], p(b + "skip_param"), dY2, dHmlp, dHin, g(b + "skip_param"))
+            self._wgrad(dHmlp, a["x"][i], g2d(b + "mlp_c_proj.weight"))
+            if bias:
+                ops.colsum(dHmlp, g(b + "mlp_c_proj.bias"))
+            ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
+            ops.swiglu_bwd(a["d_4c"], a["uv"][i], None, 1.0, a["d_8c"], None)
+            self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
+            if bias:
+                ops.colsum(a["d_8c"], g(b + "c_fc.bias"))
+            ops.linear_dgrad(a["d_8c"], w16(b + "c_fc.weight"), dY2, accumulate=True)
+            ops.add_rmsnorm_bwd(dY2, a["y1_32"][i], a["h_att"][i], p(b + "rmsnorm_mlp.weight"), eps, dY1, dHatt, g(b + "rmsnorm_mlp.weight"))
+            self._wgrad(dHatt, a["att"][i], g2d(b + "att_c_proj.weight"))
+            if bias:
+                ops.colsum(dHatt, g(b + "att_c_proj.bias"))
+            ops.linear_dgrad(dHatt, w16(b + "att_c_proj.weight"), dAtt)
+            qkv, dqkv = a["qkv"][i], a["d_3c"]
+            ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], None, 1.0, att_scale, a["att"][i], dAtt, a["lse"][i],
+                              dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], None, B, H, T)
+            self._wgrad(dqkv, a["y1_16"][i], g2d(b + "query.weight", rows=3 * C))
+            if bias:
+                ops.colsum(dqkv, self._cat_grad(b + "query.bias", 3 * C))
+            ops.linear_dgrad(dqkv, w16(b + "query.weight", rows=3 * C), dY1, accumulate=True)
+            ops.add_rmsnorm_bwd(dY1, a["h32"][i], None, p(b + "rmsnorm_att.weight"), eps, dHin, None, g(b + "rmsnorm_att.weight"),
+                                dh_accumulate=True)
+            self.launches += 9 + (4 if bias else 0)
+            G, dHin = dHin, G
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(*self.block_grad_range(i))
+        # cross attention (no residual in this mode): G = dL/d(out_proj output)
+        ca = "cross_attention."
+        dO, dX = a["d_c16"], a["d_c16b"]
+        ops.cast_bf16(G, dO)
+        self._wgrad(dO, a["ca_x"], g2d(ca + "out_proj.weight"))
+        if bias:
+            ops.colsum(dO, g(ca + "out_proj.bias"))
+        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
+        duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)
+        ops.swiglu_bwd(dX, a["ca_uv"], None, 1.0, duv, None)
+        self._wgrad(duv, a["ca_att"], g2d(ca + "proj.weight"))
+        if bias:
+            ops.colsum(duv, g(ca + "proj.bias"))
+        dAtt = a["d_c16"]
+        ops.linear_dgrad(duv, w16(ca + "proj.weight"), dAtt)
+        dq = a["d_c16b"]
+        dkv = a["d_3c"].view(-1)[:M * 2 * C].view(M, 2 * C)
+        ops.attention_bwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], None, 1.0, att_scale, a["ca_att"], dAtt, a["ca_lse"],
+                          dq, dkv[:, :C], dkv[:, C:], None, B, H, T)
+        self._wgrad(dq, a["local16"], g2d(ca + "q_local.weight"))
+        self._wgrad(dkv, a["global16"], g2d(ca + "k_global.weight", rows=2 * C))
+        if bias:
+            ops.colsum(dq, g(ca + "q_local.bias"))
+            ops.colsum(dkv, self._cat_grad(ca + "k_global.bias", 2 * C))
+        dLn, dGn = dY2, dY1
+        ops.linear_dgrad(dq, w16(ca + "q_local.weight"), dLn)
+        ops.linear_dgrad(dkv, w16(ca + "k_global.weight", rows=2 * C), dGn)
+        dLocal, dGlobal = dHin, G
+        ops.add_rmsnorm_bwd(dLn, a["local32"], None, p(ca + "local_norm.weight"), eps, dLocal, None, g(ca + "local_norm.weight"))
+        ops.add_rmsnorm_bwd(dGn, a["global32"], None, p(ca + "global_norm.weight"), eps, dGlobal, None, g(ca + "global_norm.weight"))
+        self.launches += 12
         for dX32, A, wname, bname, pos in ((dLocal, a["A_l"], "local_patch_embed.weight", "local_patch_embed.bias", "local_pos_embed"),
                                            (dGlobal, a["A_g"], "global_patch_embed.1.weight", "global_patch_embed.1.bias", "global_pos_embed")):
             ops.pos_bias_grad(dX32, B, T, C, g(pos).view(T, C), g(bname))

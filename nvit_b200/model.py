@@ -80,10 +80,12 @@ class Block(nn.Module):
         self.c_fc = nn.Linear(C, 2 * 4 * C, bias=config.bias)
         self.silu = nn.SiLU()
         self.mlp_c_proj = nn.Linear(4 * C, C, bias=config.bias)
+        # The reference creates these only when use_nvit (model.py:63-65) but uses them only when NOT use_nvit
+        # (model.py:95-96, 145-146), so its original-ViT mode crashes.  Here they exist in both
+        # modes: unused (and grad-less) under nViT exactly as in the reference, functional in the original-ViT mode.
+        self.rmsnorm_att = RMSNorm(C)
+        self.rmsnorm_mlp = RMSNorm(C)
         if config.use_nvit:
-            # created but never used in nViT mode, exactly as in the reference (model.py:63-65)
-            self.rmsnorm_att = RMSNorm(C)
-            self.rmsnorm_mlp = RMSNorm(C)
             f32 = torch.float32
             self.attn_alpha_init_value = torch.scalar_tensor(0.05, dtype=f32)
             self.attn_alpha_init_scaling = torch.scalar_tensor(config.base_scale, dtype=f32)

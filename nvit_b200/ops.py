@@ -92,6 +92,26 @@ def residual_bwd(g, h, x, alpha, alpha_mul, dh, dx, dalpha, *, dh_accumulate=Fal
               _p(dx), _p(dh0), _p(dalpha), _p(dskip), M, C, _stream())
 
 
+def add_rmsnorm_fwd(h, x, w, eps, y32, y16):
+    M, C = h.shape
+    _lib.call("nvit_add_rmsnorm_fwd", _p(h), _p(x), _p(w), float(eps), _p(y32), _p(y16), M, C, _stream())
+
+
+def add_rmsnorm_bwd(dy, h, x, w, eps, dh, dx, dw, *, dh_accumulate=False):
+    M, C = h.shape
+    _lib.call("nvit_add_rmsnorm_bwd", _p(dy), _p(h), _p(x), _p(w), float(eps), _p(dh), int(dh_accumulate), _p(dx), _p(dw), M, C, _stream())
+
+
+def add_skipnorm_fwd(h, x, h0, skip, out32, out16):
+    M, C = h.shape
+    _lib.call("nvit_add_skipnorm_fwd", _p(h), _p(x), _p(h0), _p(skip), _p(out32), _p(out16), M, C, _stream())
+
+
+def add_skipnorm_bwd(g, h, x, h0, skip, dh, dx, dh0, dskip):
+    M, C = h.shape
+    _lib.call("nvit_add_skipnorm_bwd", _p(g), _p(h), _p(x), _p(h0), _p(skip), _p(dh), _p(dx), _p(dh0), _p(dskip), M, C, _stream())
+
+
 def swiglu_fwd(uv, suv, suv_mul, x):
     M, F2 = uv.shape
     _lib.call("nvit_swiglu_fwd", _p(uv), _p(suv), float(suv_mul), _p(x), M, F2 // 2, _stream())

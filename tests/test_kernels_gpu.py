@@ -174,6 +174,56 @@ def test_residual_fwd_bwd(M, C, skip):
         assert rel(dskip, sk.grad) < 1e-3
 
 
+# ---------------------------------------------------------------------------------------------- original-ViT row kernels
+@pytest.mark.parametrize("M,C", [(65, 64), (500, 192), (1024, 768), (300, 1024)])
+@pytest.mark.parametrize("with_x", [True, False])
+def test_add_rmsnorm_fwd_bwd(M, C, with_x):
+    h = randn(M, C, seed=25).requires_grad_(True)
+    xb = randn(M, C, seed=26, scale=0.5, dtype=torch.bfloat16) if with_x else None
+    x = xb.float().requires_grad_(True) if with_x else None
+    w = (1 + 0.2 * randn(C, seed=27)).requires_grad_(True)
+    t = h + x if with_x else h
+    ref = O.rmsnorm(t, w)
+    gy = randn(M, C, seed=28)
+    ref.backward(gy)
+    y32 = torch.empty(M, C, device=DEV)
+    y16 = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    ops.add_rmsnorm_fwd(h.detach(), xb, w.detach(), 1e-6, y32, y16)
+    dh = torch.full((M, C), 0.5, device=DEV)
+    dx = torch.empty(M, C, device=DEV, dtype=torch.bfloat16) if with_x else None
+    dw = torch.zeros(C, device=DEV)
+    ops.add_rmsnorm_bwd(gy, h.detach(), xb, w.detach(), 1e-6, dh, dx, dw, dh_accumulate=True)
+    torch.cuda.synchronize()
+    assert rel(y32, ref) < 1e-5 and rel(y16, ref) < 4e-3
+    assert rel(dh - 0.5, h.grad) < 1e-4
+    assert rel(dw, w.grad) < 1e-3
+    if with_x:
+        assert rel(dx, x.grad) < 6e-3
+
+
+@pytest.mark.parametrize("M,C", [(65, 64), (500, 192), (1024, 768)])
+def test_add_skipnorm_fwd_bwd(M, C):
+    h = randn(M, C, seed=35).requires_grad_(True)
+    xb = randn(M, C, seed=36, scale=0.5, dtype=torch.bfloat16)
+    x = xb.float().requires_grad_(True)
+    h0 = randn(M, C, seed=37).requires_grad_(True)
+    sk = torch.tensor([0.8], device=DEV, requires_grad=True)
+    ref = O.justnorm((h + x) * sk + h0)
+    g = randn(M, C, seed=38)
+    ref.backward(g)
+    o32 = torch.empty(M, C, device=DEV)
+    o16 = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    ops.add_skipnorm_fwd(h.detach(), xb, h0.detach(), sk.detach(), o32, o16)
+    dh, dh0 = torch.empty(M, C, device=DEV), torch.empty(M, C, device=DEV)
+    dx = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    dsk = torch.zeros(1, device=DEV)
+    ops.add_skipnorm_bwd(g, h.detach(), xb, h0.detach(), sk.detach(), dh, dx, dh0, dsk)
+    torch.cuda.synchronize()
+    assert rel(o32, ref) < 1e-5 and rel(o16, ref) < 4e-3
+    assert rel(dh, h.grad) < 1e-4 and rel(dh0, h0.grad) < 1e-4 and rel(dx, x.grad) < 6e-3
+    assert rel(dsk, sk.grad) < 1e-3
+
+
 # ---------------------------------------------------------------------------------------------- swiglu (unfused)
 @pytest.mark.parametrize("with_suv", [True, False])
 def test_swiglu_fwd_bwd(with_suv):

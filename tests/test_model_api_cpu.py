@@ -23,7 +23,8 @@ def test_config_fields_match_reference(reference_model_module):
     assert mine == theirs
 
 
-@pytest.mark.parametrize("name,over", [("micro", {}), ("micro", {"bias": True}), ("tiny", {}), ("mini", {"base_scale": 1 / 32})])
+@pytest.mark.parametrize("name,over", [("micro", {}), ("micro", {"bias": True}), ("tiny", {}), ("mini", {"base_scale": 1 / 32}),
+                                       ("micro", {"use_nvit": False}), ("tiny", {"use_nvit": False, "bias": True})])
 def test_state_dict_keys_shapes_match_oracle(name, over):
     cfg = O.named_config(name, **over)
     m = ViT(ViTConfig(**cfg.as_dict()))
