@@ -84,11 +84,11 @@ def check_grads(model, ref_grads, tol=3e-2, abs_frac=1e-3, gap=None):
     return worst
 
 
-CASES = {
-    "micro_nvit": ("micro", dict(), 4),
-    "micro_nvit_bias": ("micro", dict(bias=True), 4),
-    "mini_nvit_bs32": ("mini", dict(base_scale=1.0 / 32.0), 3),
-    "micro_orig": ("micro", dict(use_nvit=False), 4),      # BASELINE config 4 branch (reference + attached RMSNorms)
+CASES = {      # tag -> (config, overrides, batch, key in bf16_gap.npz)
+    "micro_nvit": ("micro", dict(), 4, "micro"),
+    "micro_nvit_bias": ("micro", dict(bias=True), 4, "micro_bias4"),
+    "mini_nvit_bs32": ("mini", dict(base_scale=1.0 / 32.0), 3, "mini_bs32"),
+    "micro_orig": ("micro", dict(use_nvit=False), 4, "micro_orig"),      # BASELINE config 4 branch (reference + attached RMSNorms)
 }
 
 
@@ -96,16 +96,19 @@ CASES = {
 def test_forward_backward_matches_reference_golden(tag):
     """Golden vectors produced by the real reference (tests/golden/make_golden.py): loss = CE + 0.1 * recon there, so
     only logits / CE / reconstruction are compared here; gradients are compared against the oracle below."""
-    name, over, batch = CASES[tag]
+    name, over, batch, gap_key = CASES[tag]
     cfg = O.named_config(name, **over)
     gold = dict(np.load(os.path.join(GOLDEN, tag + ".npz")))
+    # logits tolerance: 2e-2, or 1.5 x what the reference itself loses on this ill-conditioned fixture under bf16 autocast
+    ref_gap = float(np.load(os.path.join(GOLDEN, "bf16_gap.npz"))[gap_key + ":__logits_rel__"])
+    tol = max(2e-2, 1.5 * ref_gap)
     model = build(cfg, O.formula_state_dict(cfg))
     X, y = O.formula_batch(cfg, batch)
     logits, aux = model(X.to(DEV))
     ce = F.cross_entropy(logits, y.to(DEV))
-    assert rel(logits.detach(), torch.from_numpy(gold["logits"]).to(DEV)) <= 2e-2
-    assert abs(float(ce) - float(gold["ce"])) <= 1e-2 * abs(float(gold["ce"]))
-    assert abs(float(aux["reconstruction"]) - float(gold["reconstruction"])) <= 1e-2 * float(gold["reconstruction"])
+    assert rel(logits.detach(), torch.from_numpy(gold["logits"]).to(DEV)) <= tol
+    assert abs(float(ce.detach()) - float(gold["ce"])) <= max(1e-2, ref_gap) * abs(float(gold["ce"]))
+    assert abs(float(aux["reconstruction"]) - float(gold["reconstruction"])) <= max(1e-2, ref_gap) * float(gold["reconstruction"])
 
 
 @pytest.mark.parametrize("name,over,batch,seed", [
