@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="b16", choices=["b16", "l16", "tiny"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--variant", default="nvit", choices=["nvit", "orig"],
+                    help="nvit = normalized ViT (headline); orig = the reference's use_nvit=False branch (BASELINE config 4 A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
@@ -186,7 +188,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    ocfg = O.named_config(args.config)
+    ocfg = O.named_config(args.config, use_nvit=(args.variant == "nvit"))
     cfg = ViTConfig(**ocfg.as_dict())
     torch.manual_seed(0)
     model = ViT(cfg).to(dev).train()
@@ -290,10 +292,12 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         fpi = flops_per_image(cfg)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if (args.config == "b16" and args.variant == "nvit") else
+                      f"{'nViT' if args.variant == 'nvit' else 'ViT(original branch)'}-{args.config.upper()} train images/sec",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"nViT-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
+            "config": {"workload": f"{'nViT' if args.variant == 'nvit' else 'original-ViT-branch'}-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
                                    f"bf16 GEMM/attention + fp32 residual, random-init weights",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~20 GB of activations) is far larger than the 126 MB L2, no explicit flush",

@@ -332,7 +332,7 @@ class Engine:
         """uv = x W^T (+b); out = (u*su) * silu(v*sv) — fused into the GEMM epilogue unless a bias is present."""
         M, K = x.shape
         if bias is None:
-            probe = self.probe is not None and suv is not None
+            probe = self.probe is not None and Fh > K          # the block MLP (Fh = 4C), not the cross-attention gate
             if probe:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
