@@ -49,6 +49,9 @@ int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t
 /* Test/benchmark hook: 0 = choose automatically (default), 1 = single-CTA 128-row tiles (cta_group::1),
  * 2 = CTA-pair 256-row tiles (cta_group::2, cluster of two SMs).  Process-wide. */
 int nvit_gemm_force_cta_group(int mode);
+/* Measurement aid for scripts/gemm_bench.py (outputs are WRONG when non-zero): 1 = the epilogue returns the accumulator
+ * without reading it (main-loop-only time), 2 = it reads and converts but neither stages nor stores. */
+int nvit_gemm_debug(int mode);
 
 /* ---- casts / reductions ------------------------------------------------------------------------------------- */
 /* autocast's weight/activation casts (torch.autocast around model.py:905 of train.py) */

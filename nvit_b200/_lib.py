@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnvit_b200.so")
+LIB_PATH = os.environ.get("NVIT_LIB_PATH") or os.path.join(_HERE, "libnvit_b200.so")
 
 P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 
@@ -19,6 +19,7 @@ SIGNATURES = {
     "nvit_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, I32, I32, I32, I32, P, P, F32, P, I64, I64, P],
     "nvit_gemm_force_cta_group": [I32],
     "nvit_set_sm_budget": [I32],
+    "nvit_gemm_debug": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
     "nvit_colsum_bf16": [P, I64, I64, I64, P, P],

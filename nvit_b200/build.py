@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("NVIT_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -30,6 +30,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tma_c2;  // bf16 side copy of an fp32 output (box 32x128 dense) / swiglu raw u (box 64x128 SW128)
   CUtensorMap tma_c3;  // swiglu raw v
   int direct;          // 1: per-thread global stores (outputs that TMA cannot address), 0: smem-staged TMA stores
+  int dbg;             // benchmarking only (nvit_gemm_debug): 1 = epilogue releases TMEM without reading it, 2 = reads but does not store
   void* C;
   __nv_bfloat16* C2;
   const float* bias;      // [N] or null
@@ -53,10 +54,15 @@ struct GemmTraits {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 196608 / STAGE_BYTES;  // 4 (48 KB stages), 6 (32 KB), 8 (24 KB)
+#ifndef NVIT_GEMM_NBUF
+#define NVIT_GEMM_NBUF 1
+#endif
+  // epilogue staging: NBUF 16 KB buffers per epilogue group (two groups); what is left of the 224 KB goes to the TMA ring
+  static constexpr int NBUF = (CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1;
+  static constexpr int STAGING_BYTES = 2 * NBUF * 16384;
+  static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
-  static constexpr int STAGING_BYTES = 32768;  // epilogue staging: one 16 KB buffer per epilogue group
   static constexpr int VEC_BYTES = 2048;       // per-tile scale[256] and bias[256]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256 /*barriers*/;
   // K-major SW128: 8 rows x 128 B per swizzle atom, atoms stacked along M/N every 1024 B.
@@ -256,7 +262,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     const int erow = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255 over the epilogue threads
     const bool issuer = (lane == 0) && (((warp - 2) & 3) == 0);
-    uint8_t* buf = stg + eg * 16384;
+    uint8_t* const gbuf = stg + eg * (T::NBUF * 16384);   // this group's staging buffers
+    uint32_t store_ctr = 0;
     const int bar_id = 1 + eg;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -295,21 +302,33 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
       };
       // write 32 packed words (a [row][64 bf16] or [row][32 fp32] line) into this group's staging buffer and store it
       auto stage_store = [&](const uint32_t (&src)[32], const CUtensorMap* map, int n0, bool reduce) {
-        if (issuer) bulk_wait_group_read<0>();
+        if (p.dbg == 2) return;                // measurement aid: TMEM reads + math, no staging / stores
+        uint8_t* buf = gbuf + (store_ctr % T::NBUF) * 16384;
+        ++store_ctr;
+        if (issuer) bulk_wait_group_read<T::NBUF - 1>();   // the store that last used this buffer has drained it
         named_bar_sync(bar_id, 128);
+        if (p.dbg != 4) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
-              make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
+                make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+        }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (issuer) {
+        if (issuer && p.dbg != 3) {
           if (reduce) tma_reduce_add_2d(map, buf, n0, m_blk * T::BM);
           else tma_store_2d(map, buf, n0, m_blk * T::BM);
           bulk_commit_group();
         }
       };
-      if (!p.direct) {
+      // MEASURED (scripts/gemm_bench.py, nvit_gemm_debug): main loop alone 1555-1700 TFLOP/s; + TMEM reads and conversion
+      // -7 %; + staging and barriers -6 %; + the TMA stores themselves -13 % (plain bf16) to -25 % (gate, three outputs).
+      // Sending the staged tile out through coalesced LSU stores instead was slower still (qkv 1151 -> 941 TFLOP/s), and
+      // two or three staging buffers per group (at the price of ring stages) changed nothing: the cost follows the
+      // output bytes, not the mechanism.
+      if (p.dbg == 1) {                      // measurement aid: main loop only
+        release_tmem();
+      } else if (!p.direct) {
         if constexpr (SWIGLU) {
           // group g takes gate outputs [64g, 64g+64) of the tile: x, raw u and raw v leave as three [128 x 64] bf16 tiles
           uint32_t uo[32], vo[32];
@@ -712,6 +731,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
 using namespace nvit;
 
 static int g_force_cg = 0;  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
+static int g_dbg = 0;       // see GemmParams::dbg
 
 extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
                               int64_t lda, int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major,
@@ -744,6 +764,7 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
   p.rowadd_period = (int)(rowadd ? rowadd_period : 1);
   p.splits = splits;
   p.swiglu_half = (int)swiglu_half;
+  p.dbg = g_dbg;
   // CTA pairs (256-row tiles, cta_group::2) whenever there are at least two 128-row blocks; nvit_gemm_force_cta_group
   // (test hook) can pin either mode.
   const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128);
@@ -775,6 +796,11 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
     case 6: return launch_gemm<256, true, false, false, false>(p, A, B, lda, ldb, st);
     default: return launch_gemm<256, true, true, false, false>(p, A, B, lda, ldb, st);
   }
+}
+
+extern "C" int nvit_gemm_debug(int mode) {   // measurement aid, results are WRONG when non-zero
+  g_dbg = mode;
+  return NVIT_OK;
 }
 
 extern "C" int nvit_gemm_force_cta_group(int mode) {
