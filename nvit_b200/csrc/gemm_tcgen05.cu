@@ -765,9 +765,10 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
   p.splits = splits;
   p.swiglu_half = (int)swiglu_half;
   p.dbg = g_dbg;
-  // CTA pairs (256-row tiles, cta_group::2) whenever there are at least two 128-row blocks; nvit_gemm_force_cta_group
-  // (test hook) can pin either mode.
-  const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128);
+  // CTA pairs (256-row tiles, cta_group::2) pay off for long reductions and fp32 outputs (wgrad, accumulating dgrad);
+  // MEASURED on the nViT-B/16 shapes, single-CTA 128-row tiles are a few percent faster for bf16 outputs with
+  // K < 2048 (qkv / att_c_proj forward, the gate GEMM, mlp_c_proj dgrad).  nvit_gemm_force_cta_group pins either mode.
+  const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128 && (out_f32 || K >= 2048));
   if (swiglu_half > 0) {
     NVIT_REQUIRE(N == swiglu_half, "nvit_gemm_bf16: swiglu needs N == F");
     NVIT_REQUIRE(!a_mn_major && !b_mn_major && !out_f32 && !accumulate && splits <= 1 && !bias && !rowadd,
