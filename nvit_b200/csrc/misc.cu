@@ -103,13 +103,18 @@ __global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ SiLU gate (unfused form)
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+// sigmoid(v) = 0.5 + 0.5 tanh(v/2): one MUFU instead of EX2 + RCP
+__device__ __forceinline__ float sigmoidf_(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 // thread = 8 consecutive columns of F; grid.y = row slabs
-__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ uv, const float* __restrict__ suv,
+__global__ void __launch_bounds__(128) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ uv, const float* __restrict__ suv,
                                                          float suv_mul, __nv_bfloat16* __restrict__ xo, int M, int F,
                                                          int rows_per_slab) {
-  const int c8 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const int c8 = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (c8 >= F) return;
   float su[8], sv[8];
 #pragma unroll
@@ -133,11 +138,11 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ uv,
+__global__ void __launch_bounds__(128) swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ uv,
                                                          const float* __restrict__ suv, float suv_mul,
                                                          __nv_bfloat16* __restrict__ duv, float* __restrict__ dsuv, int M, int F,
                                                          int rows_per_slab) {
-  const int c8 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  const int c8 = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (c8 >= F) return;
   float su[8], sv[8], gsu[8], gsv[8];
 #pragma unroll
@@ -207,14 +212,16 @@ __device__ __forceinline__ int reflect_idx(int i, int S) {
   if (i >= S) i = 2 * (S - 1) - i;
   return i;
 }
-// One thread per output element pair (kw even): out[(b,i,j), (c,kh,kw)] = img[b,c,refl(i*st+kh-pad),refl(j*st+kw-pad)]
+// One thread per 8 consecutive kw (one 16-byte store) when ks % 8 == 0, else per pair (kw even):
+//   out[(b,i,j), (c,kh,kw)] = img[b, c, refl(i*st + kh - pad), refl(j*st + kw - pad)]
+template <int V>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int ch,
-                                                     int S, int ks, int st, int pad, int g, long long total_pairs) {
+                                                     int S, int ks, int st, int pad, int g, long long total_vec) {
   const int K = ch * ks * ks;
-  const int halfK = K >> 1;
-  for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += 1ll * gridDim.x * blockDim.x) {
-    const long long m = idx / halfK;
-    const int k = (int)(idx - m * halfK) * 2;
+  const int vecK = K / V;
+  for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec; idx += 1ll * gridDim.x * blockDim.x) {
+    const long long m = idx / vecK;
+    const int k = (int)(idx - m * vecK) * V;
     const int c = k / (ks * ks);
     const int rem = k - c * ks * ks;
     const int kh = rem / ks, kw = rem - kh * ks;
@@ -222,9 +229,23 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
     const int ij = (int)(m - 1ll * b * g * g);
     const int i = ij / g, j = ij - i * g;
     const int y = reflect_idx(i * st + kh - pad, S);
-    const int x0 = reflect_idx(j * st + kw - pad, S), x1 = reflect_idx(j * st + kw + 1 - pad, S);
+    const int x0 = j * st + kw - pad;
     const float* src = img + ((1ll * b * ch + c) * S + y) * S;
-    *reinterpret_cast<uint32_t*>(out + m * K + k) = pack_bf16(__ldg(src + x0), __ldg(src + x1));
+    float v[V];
+    if (V == 8 && x0 >= 0 && x0 + 8 <= S && ((x0 & 3) == 0) && ((S & 3) == 0)) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + x0)), a1 = __ldg(reinterpret_cast<const float4*>(src + x0 + 4));
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+      if (V == 8) { v[V - 4] = a1.x; v[V - 3] = a1.y; v[V - 2] = a1.z; v[V - 1] = a1.w; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = __ldg(src + reflect_idx(x0 + e, S));
+    }
+    if (V == 8) {
+      *reinterpret_cast<uint4*>(out + m * K + k) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[V - 4], v[V - 3]), pack_bf16(v[V - 2], v[V - 1]));
+    } else {
+      *reinterpret_cast<uint32_t*>(out + m * K + k) = pack_bf16(v[0], v[1]);
+    }
   }
 }
 
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(256) head_scale_bwd_kernel(const float* __rest
   if (n >= N) return;
   const float s = sz ? sz[n] * sz_mul : 1.f;
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const float g = dlogits[1ll * b * N + n];
     acc += g * raw[1ll * b * N + n];
     draw[1ll * b * ld + n] = __float2bfloat16(g * s);
@@ -574,8 +595,8 @@ extern "C" int nvit_pos_bias_grad(const float* dx, int64_t B, int64_t T, int64_t
 }
 
 static void slab_grid(int64_t M, int64_t F, dim3* grid, int* rps) {
-  const int gx = (int)((F / 8 + 255) / 256);
-  int slabs = (nvit_num_sms() * 8 + gx - 1) / gx;
+  const int gx = (int)((F / 8 + 127) / 128);
+  int slabs = (nvit_num_sms() * 16 + gx - 1) / gx;
   if (slabs > M) slabs = (int)M;
   if (slabs < 1) slabs = 1;
   *rps = (int)((M + slabs - 1) / slabs);
@@ -587,7 +608,7 @@ extern "C" int nvit_swiglu_fwd(const void* uv, const float* suv, float suv_mul, 
   if (M == 0) return NVIT_OK;
   dim3 grid; int rps;
   slab_grid(M, F, &grid, &rps);
-  swiglu_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(uv), suv, suv_mul, static_cast<__nv_bfloat16*>(x), (int)M, (int)F, rps);
+  swiglu_fwd_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(uv), suv, suv_mul, static_cast<__nv_bfloat16*>(x), (int)M, (int)F, rps);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -599,7 +620,7 @@ extern "C" int nvit_swiglu_bwd(const void* dx, const void* uv, const float* suv,
   if (M == 0) return NVIT_OK;
   dim3 grid; int rps;
   slab_grid(M, F, &grid, &rps);
-  swiglu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
+  swiglu_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
                                                   static_cast<__nv_bfloat16*>(duv), dsuv_accum, (int)M, (int)F, rps);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -612,9 +633,13 @@ extern "C" int nvit_im2col_bf16(const float* img, void* out, int64_t B, int64_t 
   NVIT_REQUIRE(pad < S, "nvit_im2col_bf16: reflect padding must be smaller than the image");
   NVIT_REQUIRE((S + 2 * pad - ksize) % stride == 0, "nvit_im2col_bf16: (S + 2 pad - k) must be a multiple of the stride");
   const int g = (int)((S + 2 * pad - ksize) / stride + 1);
-  const long long total_pairs = 1ll * B * g * g * ch * ksize * ksize / 2;
-  im2col_kernel<<<stream_grid(total_pairs, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
-                                                                          (int)ksize, (int)stride, (int)pad, g, total_pairs);
+  const long long total = 1ll * B * g * g * ch * ksize * ksize;
+  if ((ksize % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    im2col_kernel<8><<<stream_grid(total / 8, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
+                                                                             (int)ksize, (int)stride, (int)pad, g, total / 8);
+  else
+    im2col_kernel<2><<<stream_grid(total / 2, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
+                                                                             (int)ksize, (int)stride, (int)pad, g, total / 2);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -640,7 +665,7 @@ extern "C" int nvit_pool_ln_bwd(const void* dy, const float* gamma, const float*
 extern "C" int nvit_head_scale_bwd(const float* dlogits, const float* raw, const float* sz, float sz_mul, void* draw, float* dsz,
                                    int64_t B, int64_t N, int64_t ld_draw, void* stream) {
   NVIT_REQUIRE(dlogits && raw && draw && B > 0 && N > 0 && ld_draw >= N, "nvit_head_scale_bwd: bad arguments");
-  head_scale_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ST(stream)>>>(dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
+  head_scale_bwd_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)(B < 32 ? B : 32)), 256, 0, ST(stream)>>>(dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
