@@ -114,6 +114,10 @@ int nvit_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq,
                        const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
                        float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, void* stream);
 
+/* Measurement aid: device buffer of 256 int64 receiving clock64() phase marks of the first 8 CTAs of the next attention
+ * launches (NULL switches it off). */
+int nvit_attention_debug(void* dev_buf_256_int64);
+
 /* ---- patch embedding operand (model.py:286-304, 407-408; reconstruction target model.py:460-463) --------------
  *   out[(b,i,j), (c,kh,kw)] = reflect_pad(img, pad)[b, c, i*stride + kh, j*stride + kw]   as bf16, [B*g*g, ch*ksize^2]
  */

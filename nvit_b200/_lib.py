@@ -34,6 +34,7 @@ SIGNATURES = {
     "nvit_swiglu_bwd": [P, P, P, F32, P, P, I64, I64, P],
     "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],
     "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P],
+    "nvit_attention_debug": [P],
     "nvit_im2col_bf16": [P, P, I64, I64, I64, I64, I64, I64, P],
     "nvit_pool_ln_fwd": [P, P, P, F32, P, P, P, I64, I64, I64, P],
     "nvit_pool_ln_bwd": [P, P, P, P, P, P, P, I64, I64, I64, P],

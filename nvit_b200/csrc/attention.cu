@@ -92,7 +92,10 @@ struct alignas(64) AttnParams {
   long long ldq, ldk, ldo, lddq, lddk, lddv;
   float sqk_mul, scale;
   int B, H, T, TP, nQ, nK;
+  long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
 };
+
+#define ATT_MARK(i) do { if (p.dbg && blockIdx.x < 8 && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + (i)] = clock64(); } while (0)
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
 __host__ __device__ constexpr uint32_t IDESC_MM(int N) { return umma_idesc_bf16(128, N, 1, 1); }  // A MN-major, B MN-major
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   const AttnThread t = attn_thread(p);
   const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
+  ATT_MARK(0);
 
   if (t.tid == 0) {
     tma_prefetch_desc(&p.tq);
@@ -204,7 +208,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
     tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
   }
+  ATT_MARK(1);
   mbar_wait(bar_tma, 0);
+  ATT_MARK(2);
 
   if (has_norm) {
     for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   }
   fence_proxy_async_smem();
   __syncthreads();
+  ATT_MARK(3);
 
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sP_a = smem_u32(sP);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
+    ATT_MARK(4 + 4 * i);
 
     const int qtok = i * 128 + t.row;
     float m2 = bound * LOG2E;  // log2-domain offset subtracted before exp2
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
+    ATT_MARK(5 + 4 * i);
 
     if (t.warp == 0) {
       tc_fence_after_sync();
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
+    ATT_MARK(6 + 4 * i);
     {
       uint32_t r[16];
       tmem_ld_32x32b_x16(t_lane + 256 + t.part * 16, r);
@@ -298,6 +308,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     }
     tc_fence_before_sync();
     __syncthreads();
+    ATT_MARK(7 + 4 * i);
   }
 
   if (t.warp == 0) {
@@ -395,6 +406,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   const AttnThread t = attn_thread(p);
   const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
+  ATT_MARK(0);
 
   if (t.tid == 0) {
     tma_prefetch_desc(&p.tq);
@@ -436,7 +448,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
   }
+  ATT_MARK(1);
   mbar_wait(bar_tma, 0);
+  ATT_MARK(2);
   if (t.tid < 256) {
     const int r = t.tid;
     float d = 0.f;
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
   fence_proxy_async_smem();
   __syncthreads();
+  ATT_MARK(3);
 
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
@@ -485,7 +500,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    // ---- P^T = exp(scale S^T - lse)   (two threads per kv row, columns = q)
+    ATT_MARK(4 + 8 * j);
+    // ---- P^T = exp(scale S^T - lse)   (four threads per kv row, columns = q)
     for (int c = t.c_begin; c < t.c_end; ++c) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(t_lane + TM_S + c * 16, r);
@@ -515,6 +531,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
+    ATT_MARK(5 + 8 * j);
     // ---- dV_j = P^T dO ; dP^T_j = V_j dO^T
     if (t.warp == 0) {
       tc_fence_after_sync();
@@ -525,6 +542,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
+    ATT_MARK(6 + 8 * j);
     // ---- dS^T = P^T (dP^T - delta) scale, in place over P^T
     for (int c = t.c_begin; c < t.c_end; ++c) {
       uint32_t r[16];
@@ -549,6 +567,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     tc_fence_before_sync();
     fence_proxy_async_smem();
     __syncthreads();
+    ATT_MARK(7 + 8 * j);
     // ---- dK_j = dS^T Qh ; dQ_m += dS_j Kh_j
     if (t.warp == 0) {
       tc_fence_after_sync();
@@ -562,6 +581,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
+    ATT_MARK(8 + 8 * j);
     // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both
     {
       const int kvc = kv_ok ? kv : 0;
@@ -579,6 +599,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     }
     tc_fence_before_sync();
     __syncthreads();
+    ATT_MARK(9 + 8 * j);
   }
 
   // ---- dQ rows, one 128-row q tile at a time, 16 channels per thread
@@ -598,10 +619,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
       tmem_row16_to_bf16(t_lane + TM_DQ + 64 * m + t.part * 16, p.dq + grow * p.lddq + t.h * 64 + t.part * 16, ok);
     }
   }
+  ATT_MARK(24);
   if (has_norm) reduce16_to_smem(dacc, s_dsqk + t.part * 16, t.lane);
   tc_fence_before_sync();
   __syncthreads();
   if (has_norm && t.tid < 64) atomicAdd(p.dsqk + t.h * 64 + t.tid, s_dsqk[t.tid] * p.sqk_mul);
+  ATT_MARK(25);
   if (t.warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -626,6 +649,12 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 
 using namespace nvit;
 
+static long long* g_att_dbg = nullptr;
+extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
+  g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
+  return NVIT_OK;
+}
+
 extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                                   const float* sqk, float sqk_mul, float scale, void* out, int64_t ldo, float* lse, int64_t B,
                                   int64_t H, int64_t T, int64_t D, void* stream) {
@@ -648,6 +677,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   p.TP = (int)((T + 15) / 16 * 16);
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
+  p.dbg = g_att_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
@@ -694,6 +724,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   p.TP = (int)((T + 15) / 16 * 16);
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
+  p.dbg = g_att_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
