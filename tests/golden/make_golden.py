@@ -78,9 +78,57 @@ def run(name, over, batch):
     return out
 
 
+KOHONEN_CASES = {
+    "micro_kohonen": ("micro", dict(use_kohonen=True, kohonen_nodes=32, kohonen_alpha=0.3), 4),
+}
+KOHONEN_WEIGHTS = dict(kohonen_consistency=0.1, kohonen_smoothness=0.1)     # settings.yaml:15-16
+
+
+def run_kohonen(name, over, batch):
+    """BASELINE config 5 shape of the forward: one training-mode forward+backward with the train.py:906-926 loss."""
+    cfg = O.named_config(name, **over)
+    sd = O.formula_state_dict(cfg)
+    m = ref.ViT(ref.ViTConfig(**cfg.as_dict()))
+    m.load_state_dict({**sd, **O.kohonen_buffers(cfg)}, strict=True)
+    m.train()
+    X, y = O.formula_batch(cfg, batch)
+    idx = {}
+    for tag in ("local", "global"):
+        mod = getattr(m, tag + "_kohonen")
+        mod.register_forward_hook(lambda _m, _i, out, tag=tag: idx.__setitem__(tag, out[1].detach().clone()))
+    logits, aux = m(X)
+    ce = F.cross_entropy(logits, y)
+    loss = ce + 0.1 * aux["kohonen_consistency"] + 0.1 * aux["kohonen_smoothness"] \
+        + cfg.local_quantization_weight * aux["local_quantization"] + cfg.global_quantization_weight * aux["global_quantization"] \
+        + cfg.reconstruction_weight * aux["reconstruction"]
+    loss.backward()
+    out = {"logits": logits.detach().numpy(), "ce": ce.detach().numpy(), "loss": loss.detach().numpy()}
+    for k, v in aux.items():
+        out["aux:" + k] = v.detach().numpy()
+    out["local_indices"], out["global_indices"] = idx["local"].numpy(), idx["global"].numpy()
+    print("   distinct units:", len(np.unique(out["local_indices"])), len(np.unique(out["global_indices"])))
+    out["local_nodes_after"] = m.local_kohonen.nodes.detach().numpy().copy()
+    out["global_nodes_after"] = m.global_kohonen.nodes.detach().numpy().copy()
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.detach().flatten()
+        out["gnorm:" + k] = np.float64(g.double().norm().item())
+        out["ghead:" + k] = g[:8].numpy().copy()
+    return out
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(1)
+    only = sys.argv[1:]
     for tag, (name, over, batch) in CASES.items():
+        if only and tag not in only:
+            continue
         np.savez_compressed(os.path.join(HERE, tag + ".npz"), **run(name, over, batch))
+        print("wrote", tag)
+    for tag, (name, over, batch) in KOHONEN_CASES.items():
+        if only and tag not in only:
+            continue
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **run_kohonen(name, over, batch))
         print("wrote", tag)
