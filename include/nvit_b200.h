@@ -140,6 +140,39 @@ int nvit_cross_entropy(const float* logits, const int64_t* target, float* loss, 
 int nvit_tanh_mse(const void* pred_bf16, const void* target_bf16, int64_t n, float inv_count, float* out_accum,
                   void* stream);
 
+/* ---- Kohonen maps (BASELINE config 5; /root/reference/nvit/kohonen.py, model.py:417-445, 482-561) ---------------------
+ * The token-to-node distance matrix is a GEMM: dots[M,G] = x[M,C] nodes[G,C]^T through nvit_gemm_bf16 on bf16 hi/lo
+ * splits (x_hi n_hi + x_hi n_lo + x_lo n_hi, fp32 accumulate: ~2^-17 relative, replacing torch.cdist kohonen.py:110). */
+/* x fp32 -> hi = bf16(x) (optional), lo = bf16(x - hi) */
+int nvit_split_bf16(const float* x, void* hi_bf16_or_null, void* lo_bf16, int64_t n, void* stream);
+/* per node: squared norm, bf16 hi/lo GEMM operands and a copy of the table before the in-forward update */
+int nvit_som_prepare(const float* nodes, int64_t G, int64_t C, float* node_sq, void* hi_bf16, void* lo_bf16, float* snapshot,
+                     void* stream);
+/* KohonenMap.forward (kohonen.py:100-119): idx[r] = argmin_g (node_sq[g] - 2 dots[r,g]) (lowest index on ties),
+ * repr[r] = nodes[idx[r]] (fp32 + bf16), optional int64 copy of idx, one-hot bf16 [M,G] and counts[g] += #tokens */
+int nvit_som_select(const float* dots, const float* node_sq, const float* nodes, int64_t M, int64_t G, int64_t C, int32_t* idx,
+                    int64_t* idx64_or_null, void* onehot_bf16_or_null, float* counts_or_null, float* repr32, void* repr_bf16,
+                    void* stream);
+/* kohonen.py:149-155: out[r] = mean(x[r*run : (r+1)*run]) */
+int nvit_som_pool(const float* x, int64_t rows, int64_t run, float* out, void* stream);
+/* KohonenMap.update_nodes (kohonen.py:121-165): for i < steps, in order: nodes += s_i (pooled[i] - nodes),
+ * s_i[g] = coef * exp(-torus_dist2(g, bmu[i]) / (2 sigma^2)); coef = lr * alpha is read from device memory */
+int nvit_som_update(float* nodes, const float* pooled, const int32_t* bmu, int64_t steps, int64_t grid_rows, int64_t grid_cols,
+                    int64_t C, const float* coef_dev, float sigma, void* stream);
+/* consistency + the two quantization (Huber) losses (model.py:437, 441-442, 491-500): sums3 += {sum cos, sum huber_l,
+ * sum huber_g}; with weights3 (device: consistency, local q., global q. weight x incoming gradient) the gradients are
+ * ADDED to d_repr_l, d_repr_g, d_x_l, d_x_g (fp32 [M,C]) */
+int nvit_som_pair_losses(const float* repr_l, const float* repr_g, const float* x_l, const float* x_g, int64_t M, int64_t C,
+                         float* sums3_or_null, const float* weights3_or_null, float* d_repr_l, float* d_repr_g, float* d_x_l,
+                         float* d_x_g, void* stream);
+/* map smoothness (model.py:503-561) from the unit histogram: loss += sum_g counts[g] sum_k ||n_g - n_nb(g,k)|| / (8 M);
+ * with a device weight the gradient is added to gnodes */
+int nvit_som_smoothness(const float* nodes, const float* counts, int64_t side, int64_t C, int64_t M, float* loss_accum,
+                        const float* weight_or_null, float* gnodes_or_null, void* stream);
+/* d/dpred of weight * mean((tanh(pred) - target)^2), bf16 (reconstruction head backward, train.py:925-926) */
+int nvit_tanh_mse_bwd(const void* pred_bf16, const void* target_bf16, int64_t n, float inv_count, const float* weight_dev,
+                      void* dpred_bf16, void* stream);
+
 /* ---- optimizer tail ------------------------------------------------------------------------------------------
  * AdamW over one flat fp32 buffer (torch.optim.AdamW semantics, model.py:369-385; clip train.py:935-938).
  * Elements [0,n_decay) get weight decay.  gnorm_sq (device scalar, may be NULL) holds sum(g^2); the clip coefficient

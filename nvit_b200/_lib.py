@@ -35,6 +35,14 @@ SIGNATURES = {
     "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],
     "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P],
     "nvit_attention_debug": [P],
+    "nvit_split_bf16": [P, P, P, I64, P],
+    "nvit_som_prepare": [P, I64, I64, P, P, P, P, P],
+    "nvit_som_select": [P, P, P, I64, I64, I64, P, P, P, P, P, P, P],
+    "nvit_som_pool": [P, I64, I64, P, P],
+    "nvit_som_update": [P, P, P, I64, I64, I64, I64, P, F32, P],
+    "nvit_som_pair_losses": [P, P, P, P, I64, I64, P, P, P, P, P, P, P],
+    "nvit_som_smoothness": [P, P, I64, I64, I64, P, P, P, P],
+    "nvit_tanh_mse_bwd": [P, P, I64, F32, P, P, P],
     "nvit_im2col_bf16": [P, P, I64, I64, I64, I64, I64, I64, P],
     "nvit_pool_ln_fwd": [P, P, P, F32, P, P, P, I64, I64, I64, P],
     "nvit_pool_ln_bwd": [P, P, P, P, P, P, P, I64, I64, I64, P],

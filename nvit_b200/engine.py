@@ -71,9 +71,14 @@ class Engine:
             order += [b + "query.weight", b + "key.weight", b + "value.weight", b + "att_c_proj.weight", b + "c_fc.weight",
                       b + "mlp_c_proj.weight"]
         order += ["mlp_head.1.weight"]
+        # the reconstruction loss joins the objective only with the Kohonen maps (train.py:909-926); then its head trains
+        self.rec_active = bool(cfg.use_kohonen)
+        if self.rec_active:
+            order += ["reconstruction_head.0.weight"]
         n_gemm = len(order)
         # region A': remaining weight-decayed parameters (dim >= 2)
-        inactive = {n for n in named if (cfg.use_nvit and ".rmsnorm_" in n) or n.startswith("reconstruction_head.")}
+        inactive = {n for n in named if (cfg.use_nvit and ".rmsnorm_" in n) or n == "map_balance"
+                    or (n.startswith("reconstruction_head.") and not self.rec_active)}
         rest = [n for n in named if n not in order and n not in inactive]
         order += [n for n in rest if named[n].dim() >= 2 and "sz" not in n]
         n_decay_names = len(order)
@@ -91,7 +96,8 @@ class Engine:
         order += sorted(nodecay, key=key)
         n_active_names = len(order)
         # region C: never receive a gradient: the reconstruction head first (it is a GEMM operand)
-        order += ["reconstruction_head.0.weight", "reconstruction_head.0.bias"]
+        if not self.rec_active:
+            order += ["reconstruction_head.0.weight", "reconstruction_head.0.bias"]
         order += sorted(n for n in inactive if not n.startswith("reconstruction_head."))
         assert len(order) == len(named) and set(order) == set(named), "parameter layout does not cover the model"
 
@@ -127,12 +133,15 @@ class Engine:
         self.P32 = P32
         # bf16 GEMM operands: region A + the reconstruction weight
         rec = self.slots["reconstruction_head.0.weight"]
-        self.W16 = torch.empty(self.n_gemm + _align(rec.numel, 8), device=device, dtype=BF16)
-        self._rec16_off = self.n_gemm
+        self.W16 = torch.empty(self.n_gemm + (0 if self.rec_active else _align(rec.numel, 8)), device=device, dtype=BF16)
+        self._rec16_off = rec.off if self.rec_active else self.n_gemm
         self._p16_version = None
         self._acts = {}
         self._build_norm_table()
-        self.scratch = torch.zeros(8, device=device, dtype=F32)   # [0] recon loss
+        self.scratch = torch.zeros(8, device=device, dtype=F32)   # [0] recon loss, [1:4] map pair-loss sums, [4] smoothness
+        # weights of the auxiliary losses times the incoming gradient: [0] reconstruction, [1] consistency,
+        # [2] local quantization, [3] global quantization, [4] smoothness; [5] Kohonen lr * alpha (device-side for graphs)
+        self.aux_w = torch.zeros(8, device=device, dtype=F32)
         self._ptrs = {n: s.param.data_ptr() for n, s in self.slots.items()}
 
     def _check_alias(self, device):
@@ -209,9 +218,11 @@ class Engine:
         if not force and ver == self._p16_version:
             return
         ops.cast_bf16(self.P32[:self.n_gemm], self.W16[:self.n_gemm])
-        rec = self.slots["reconstruction_head.0.weight"]
-        ops.cast_bf16(self.P32[rec.off:rec.off + rec.numel], self.W16[self._rec16_off:self._rec16_off + rec.numel])
-        self.launches += 2
+        self.launches += 1
+        if not self.rec_active:
+            rec = self.slots["reconstruction_head.0.weight"]
+            ops.cast_bf16(self.P32[rec.off:rec.off + rec.numel], self.W16[self._rec16_off:self._rec16_off + rec.numel])
+            self.launches += 1
         self._p16_version = ver
 
     # ------------------------------------------------------------------------------------------ activations
@@ -229,8 +240,8 @@ class Engine:
             return torch.empty(*shape, device=dev, dtype=dtype)
         a = {
             "A_l": e(M, Kl), "A_g": e(M, Kg), "local32": e(M, C, dtype=F32), "local16": e(M, C), "global16": e(M, C),
-            "ca_q": e(M, C), "ca_kv": e(M, 2 * C), "ca_att": e(M, C), "ca_lse": e(B, H, T, dtype=F32), "ca_uv": e(M, 2 * C),
-            "ca_x": e(M, C), "ca_o": e(M, C),
+            "ca": [{"q": e(M, C), "kv": e(M, 2 * C), "att": e(M, C), "lse": e(B, H, T, dtype=F32), "uv": e(M, 2 * C),
+                    "x": e(M, C), "o": e(M, C)} for _ in range(3 if cfg.use_kohonen else 1)],
             "h32": [e(M, C, dtype=F32) for _ in range(L + 1)], "h16": [e(M, C) for _ in range(L + 1)],
             "qkv": [e(M, 3 * C) for _ in range(L)], "att": [e(M, C) for _ in range(L)],
             "lse": [e(B, H, T, dtype=F32) for _ in range(L)], "h_att": [e(M, C) for _ in range(L)],
@@ -246,6 +257,18 @@ class Engine:
         if not cfg.use_nvit:
             a.update({"global32": e(M, C, dtype=F32), "y1_32": [e(M, C, dtype=F32) for _ in range(L)],
                       "y1_16": [e(M, C) for _ in range(L)], "dY1": e(M, C, dtype=F32)})
+        if cfg.use_kohonen:
+            Gn = self.slots["local_kohonen.nodes"].shape[0]
+            a["global32"] = e(M, C, dtype=F32)
+            a["som"] = {tag: {"node_sq": e(Gn, dtype=F32), "hi": e(Gn, C), "lo": e(Gn, C), "snap": e(Gn, C, dtype=F32),
+                              "xlo": e(M, C), "dots": e(M, Gn, dtype=F32), "idx": e(M, dtype=torch.int32),
+                              "idx64": e(B, T, dtype=torch.int64), "onehot": e(M, Gn), "counts": e(Gn, dtype=F32),
+                              "repr32": e(M, C, dtype=F32), "repr16": e(M, C), "pooled": e(B, C, dtype=F32)}
+                        for tag in ("local", "global")}
+            a.update({"ln32": e(M, C, dtype=F32), "ln16": e(M, C), "gn32": e(M, C, dtype=F32), "gn16": e(M, C),
+                      "k32a": e(M, C, dtype=F32), "k32b": e(M, C, dtype=F32), "dpred": e(M, Kl)})
+        for k, v in a["ca"][0].items():      # the original-ViT branch addresses its single cross-attention call by these names
+            a["ca_" + k] = v
         self._acts = {B: a}      # keep one batch size resident
         return a
 
@@ -280,20 +303,24 @@ class Engine:
         ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
         ops.linear_fwd(a["A_l"], w16("local_patch_embed.weight"), a["local32"], bias=p("local_patch_embed.bias"),
                        rowadd=p("local_pos_embed").view(T, C), rowadd_period=T, c2=a["local16"])
-        ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global16"], bias=p("global_patch_embed.1.bias"),
-                       rowadd=p("global_pos_embed").view(T, C), rowadd_period=T)
+        if cfg.use_kohonen:      # the maps and the quantization loss read the fp32 global embedding as well
+            ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global32"], bias=p("global_patch_embed.1.bias"),
+                           rowadd=p("global_pos_embed").view(T, C), rowadd_period=T, c2=a["global16"])
+        else:
+            ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global16"], bias=p("global_patch_embed.1.bias"),
+                           rowadd=p("global_pos_embed").view(T, C), rowadd_period=T)
         self.launches += 4
 
-        # ---- cross attention (model.py:219-275): q <- local, k,v <- global
-        ca = "cross_attention."
-        ops.linear_fwd(a["local16"], w16(ca + "q_local.weight"), a["ca_q"], bias=p(ca + "q_local.bias") if bias else None)
-        ops.linear_fwd(a["global16"], w16(ca + "k_global.weight", rows=2 * C), a["ca_kv"],
-                       bias=self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None)
-        ops.attention_fwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], p(ca + "sqk"), smul, att_scale, a["ca_att"], a["ca_lse"], B, H, T)
-        self._gated_fwd(a["ca_att"], w16(ca + "proj.weight"), p(ca + "proj.bias") if bias else None, None, 1.0, a["ca_uv"], a["ca_x"], C)
-        ops.linear_fwd(a["ca_x"], w16(ca + "out_proj.weight"), a["ca_o"], bias=p(ca + "out_proj.bias") if bias else None)
-        ops.residual_fwd(a["local32"], a["ca_o"], p(ca + "attn_alpha"), amul, a["h32"][0], a["h16"][0])
-        self.launches += 5
+        # ---- cross attention (model.py:219-275): q <- local, k,v <- global; three shared-weight calls around the Kohonen
+        # maps (model.py:424-445), one without them (model.py:448)
+        if cfg.use_kohonen:
+            self._kohonen_fwd(a, B, T)
+            som = a["som"]
+            self._ca_fwd(a["ca"][0], B, T, som["local"]["repr32"], som["local"]["repr16"], a["local16"], a["ln32"], a["ln16"])
+            self._ca_fwd(a["ca"][1], B, T, som["global"]["repr32"], som["global"]["repr16"], a["global16"], a["gn32"], a["gn16"])
+            self._ca_fwd(a["ca"][2], B, T, a["ln32"], a["ln16"], a["gn16"], a["h32"][0], a["h16"][0])
+        else:
+            self._ca_fwd(a["ca"][0], B, T, a["local32"], a["local16"], a["global16"], a["h32"][0], a["h16"][0])
 
         # ---- transformer blocks + norm_skip (model.py:92-169, 84-87, 450-452)
         for i in range(L):
@@ -322,7 +349,86 @@ class Engine:
         self.launches += 5
         self.last_forward_launches = self.launches - n0
         self._saved = (B, T) if save else None
+        self.last_aux = self._kohonen_aux(B * T) if cfg.use_kohonen else {}
         return a["logits"].clone(), self.scratch[0].clone()
+
+    def _ca_fwd(self, s, B, T, loc32, loc16, glob16, out32, out16):
+        """CrossAttentionBlock.forward, nViT mode (model.py:219-275); `s` holds this call's saved activations."""
+        cfg = self.cfg
+        C, H = cfg.n_embd, cfg.n_head
+        p, w16, bias = self.p, self.w16, cfg.bias
+        ca = "cross_attention."
+        ops.linear_fwd(loc16, w16(ca + "q_local.weight"), s["q"], bias=p(ca + "q_local.bias") if bias else None)
+        ops.linear_fwd(glob16, w16(ca + "k_global.weight", rows=2 * C), s["kv"],
+                       bias=self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None)
+        ops.attention_fwd(s["q"], s["kv"][:, :C], s["kv"][:, C:], p(ca + "sqk"), 1.0 / cfg.base_scale, float(C // H) ** 0.5, s["att"],
+                          s["lse"], B, H, T)
+        self._gated_fwd(s["att"], w16(ca + "proj.weight"), p(ca + "proj.bias") if bias else None, None, 1.0, s["uv"], s["x"], C)
+        ops.linear_fwd(s["x"], w16(ca + "out_proj.weight"), s["o"], bias=p(ca + "out_proj.bias") if bias else None)
+        ops.residual_fwd(loc32, s["o"], p(ca + "attn_alpha"), 0.05 / cfg.base_scale, out32, out16)
+        self.launches += 5
+
+    # ------------------------------------------------------------------------------------------ Kohonen maps (config 5)
+    def som_geometry(self):
+        """Grid rows/columns and neighbourhood width of one map (kohonen.py:52-69)."""
+        per_map = self.cfg.kohonen_nodes // 2
+        m = int(per_map ** 0.5)
+        n = per_map // m
+        return m, n, (m * n) ** 0.5 / 2.0
+
+    def _kohonen_fwd(self, a, B, T):
+        """Best-matching units, representations and (training mode) the in-forward map update (model.py:417-431).
+
+        Distances on tcgen05: dots = x n^T from bf16 hi/lo splits of both fp32 operands (three GEMMs, fp32 accumulate)."""
+        cfg, model = self.cfg, self.model
+        C = cfg.n_embd
+        M = B * T
+        gm, gn, sigma = self.som_geometry()
+        alpha = cfg.kohonen_scheduler_min_lr if cfg.kohonen_scheduler_enabled else cfg.kohonen_alpha     # model.py:316, 321
+        if model.training:
+            self.aux_w[5:6].fill_(float(model.get_kohonen_lr(model.step)) * alpha)
+        for tag, x32, x16 in (("local", a["local32"], a["local16"]), ("global", a["global32"], a["global16"])):
+            s = a["som"][tag]
+            nodes = self.p(tag + "_kohonen.nodes")
+            Gn = nodes.shape[0]
+            ops.som_prepare(nodes, s["node_sq"], s["hi"], s["lo"], s["snap"])
+            ops.split_bf16(x32, None, s["xlo"])
+            for k, (xa, nb) in enumerate(((x16, s["hi"]), (x16, s["lo"]), (s["xlo"], s["hi"]))):
+                ops.gemm(xa, nb, s["dots"], M=M, N=Gn, K=C, lda=C, ldb=C, ldc=Gn, accumulate=(k > 0))
+            s["counts"].zero_()
+            ops.som_select(s["dots"], s["node_sq"], s["snap"], s["idx"], s["idx64"], s["onehot"], s["counts"], s["repr32"], s["repr16"])
+            self.launches += 6
+            if model.training:
+                # kohonen.py:138-165: update i pairs image i with the unit of flattened token i, for i < min(B*T, B)
+                ops.som_pool(x32, B * C, T, s["pooled"])
+                ops.som_update(nodes, s["pooled"], s["idx"], min(M, B), gm, gn, self.aux_w[5:6], sigma)
+                self.launches += 2
+
+    def _kohonen_aux(self, M):
+        """The four Kohonen losses (model.py:437-442) as device scalars; smoothness sees the UPDATED nodes."""
+        cfg = self.cfg
+        C = cfg.n_embd
+        a = self._acts[next(iter(self._acts))]
+        som = a["som"]
+        side = int(math.sqrt(cfg.kohonen_nodes // 2))
+        if side * side != cfg.kohonen_nodes // 2:
+            raise ValueError(f"Number of nodes per map ({cfg.kohonen_nodes // 2}) must be a perfect square. "
+                             f"Got {cfg.kohonen_nodes} total nodes.")
+        self.scratch[1:5].zero_()
+        ops.som_pair_losses(som["local"]["repr32"], som["global"]["repr32"], a["local32"], a["global32"], self.scratch[1:4])
+        for tag in ("local", "global"):
+            ops.som_smoothness(self.p(tag + "_kohonen.nodes"), som[tag]["counts"], side, M, self.scratch[4:5])
+        self.launches += 3
+        sums = self.scratch.clone()
+        return {"kohonen_consistency": 1.0 - sums[1] / M, "kohonen_smoothness": sums[4],
+                "local_quantization": sums[2] / (M * C), "global_quantization": sums[3] / (M * C),
+                "local_indices": som["local"]["idx64"], "global_indices": som["global"]["idx64"]}
+
+    def set_aux_weights(self, reconstruction=0.0, consistency=0.0, local_quantization=0.0, global_quantization=0.0, smoothness=0.0):
+        """Weights (times the incoming gradient scale) of the auxiliary losses for the next backward; device-resident."""
+        self.param_list()
+        self.aux_w[:5].copy_(torch.tensor([reconstruction, consistency, local_quantization, global_quantization, smoothness],
+                                          dtype=F32), non_blocking=True)
 
     def _cat_bias(self, first_name, n):
         s = self.slots[first_name]
@@ -377,6 +483,13 @@ class Engine:
         ops.pool_ln_bwd(a["dy16"], p("mlp_head.0.weight"), a["xhat"], a["rstd"], a["G"], g("mlp_head.0.weight"), g("mlp_head.0.bias"), B, T, C)
         self.launches += 4
         G, dHin, dH1 = a["G"], a["dHin"], a["dH1"]
+        if self.rec_active:
+            # reconstruction head backward (model.py:459-464 in the objective, train.py:925-926)
+            ops.tanh_mse_bwd(a["pred"], a["A_l"], self.aux_w[0:1], a["dpred"])
+            self._wgrad(a["dpred"], a["h16"][L], g2d("reconstruction_head.0.weight"))
+            ops.colsum(a["dpred"], g("reconstruction_head.0.bias"))
+            ops.linear_dgrad(a["dpred"], w16("reconstruction_head.0.weight"), G, accumulate=True)
+            self.launches += 3
 
         # ---- blocks, last to first
         for i in reversed(range(L)):
@@ -412,35 +525,11 @@ class Engine:
                 self.grad_ready_hook(*self.block_grad_range(i))
 
         # ---- cross attention: G = dL/d(h0)
-        ca = "cross_attention."
-        dLocal = dHin            # fp32 [M,C], written by the residual backward
-        dO, dX = a["d_c16"], a["d_c16b"]
-        ops.residual_bwd(G, a["local32"], a["ca_o"], p(ca + "attn_alpha"), amul, dLocal, dO, g(ca + "attn_alpha"))
-        self._wgrad(dO, a["ca_x"], g2d(ca + "out_proj.weight"))
-        if bias:
-            ops.colsum(dO, g(ca + "out_proj.bias"))
-        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
-        duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)     # contiguous [M, 2C] scratch
-        ops.swiglu_bwd(dX, a["ca_uv"], None, 1.0, duv, None)
-        self._wgrad(duv, a["ca_att"], g2d(ca + "proj.weight"))
-        if bias:
-            ops.colsum(duv, g(ca + "proj.bias"))
-        dAtt = a["d_c16"]
-        ops.linear_dgrad(duv, w16(ca + "proj.weight"), dAtt)
-        dq = a["d_c16b"]
-        dkv = a["d_3c"].view(-1)[:M * 2 * C].view(M, 2 * C)
-        ops.attention_bwd(a["ca_q"], a["ca_kv"][:, :C], a["ca_kv"][:, C:], p(ca + "sqk"), smul, att_scale, a["ca_att"], dAtt, a["ca_lse"],
-                          dq, dkv[:, :C], dkv[:, C:], g(ca + "sqk"), B, H, T)
-        self._wgrad(dq, a["local16"], g2d(ca + "q_local.weight"))
-        self._wgrad(dkv, a["global16"], g2d(ca + "k_global.weight", rows=2 * C))
-        if bias:
-            ops.colsum(dq, g(ca + "q_local.bias"))
-            ops.colsum(dkv, self._cat_grad(ca + "k_global.bias", 2 * C))
-            self.launches += 4
-        ops.linear_dgrad(dq, w16(ca + "q_local.weight"), dLocal, accumulate=True)
-        dGlobal = G              # fp32 scratch (G is dead now)
-        ops.linear_dgrad(dkv, w16(ca + "k_global.weight", rows=2 * C), dGlobal)
-        self.launches += 7
+        if cfg.use_kohonen:
+            dLocal, dGlobal = self._kohonen_bwd(a, B, T, G, dHin, dH1)
+        else:
+            dLocal, dGlobal = dHin, dH1
+            self._ca_bwd(a["ca"][0], B, T, G, a["local32"], a["local16"], a["global16"], dLocal, dGlobal)
 
         # ---- patch embeddings: position / bias gradients and the two conv weight gradients (no dX: images need none)
         for dX32, A, wname, bname, pos in ((dLocal, a["A_l"], "local_patch_embed.weight", "local_patch_embed.bias", "local_pos_embed"),
@@ -455,6 +544,72 @@ class Engine:
             self.grad_ready_hook(0, self.block_grad_range(0)[0])
             self.grad_ready_hook(self.block_grad_range(cfg.n_layer - 1)[1], self.n_active)
 
+
+    def _ca_bwd(self, s, B, T, G, loc32, loc16, glob16, dLoc, dGlob):
+        """Backward of one cross-attention call: G = dL/d(out) -> dLoc = dL/d(local) and dGlob = dL/d(global), both fp32
+        [M, C] and WRITTEN; parameter gradients accumulate (the three Kohonen-mode calls share weights)."""
+        cfg = self.cfg
+        C, H = cfg.n_embd, cfg.n_head
+        M = B * T
+        a = self._acts[B]
+        p, g, w16, g2d, bias = self.p, self.g, self.w16, self.g2d, cfg.bias
+        ca = "cross_attention."
+        dO, dX = a["d_c16"], a["d_c16b"]
+        ops.residual_bwd(G, loc32, s["o"], p(ca + "attn_alpha"), 0.05 / cfg.base_scale, dLoc, dO, g(ca + "attn_alpha"))
+        self._wgrad(dO, s["x"], g2d(ca + "out_proj.weight"))
+        if bias:
+            ops.colsum(dO, g(ca + "out_proj.bias"))
+        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
+        duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)     # contiguous [M, 2C] scratch
+        ops.swiglu_bwd(dX, s["uv"], None, 1.0, duv, None)
+        self._wgrad(duv, s["att"], g2d(ca + "proj.weight"))
+        if bias:
+            ops.colsum(duv, g(ca + "proj.bias"))
+        dAtt = a["d_c16"]
+        ops.linear_dgrad(duv, w16(ca + "proj.weight"), dAtt)
+        dq = a["d_c16b"]
+        dkv = a["d_3c"].view(-1)[:M * 2 * C].view(M, 2 * C)
+        ops.attention_bwd(s["q"], s["kv"][:, :C], s["kv"][:, C:], p(ca + "sqk"), 1.0 / cfg.base_scale, float(C // H) ** 0.5, s["att"], dAtt,
+                          s["lse"], dq, dkv[:, :C], dkv[:, C:], g(ca + "sqk"), B, H, T)
+        self._wgrad(dq, loc16, g2d(ca + "q_local.weight"))
+        self._wgrad(dkv, glob16, g2d(ca + "k_global.weight", rows=2 * C))
+        if bias:
+            ops.colsum(dq, g(ca + "q_local.bias"))
+            ops.colsum(dkv, self._cat_grad(ca + "k_global.bias", 2 * C))
+            self.launches += 4
+        ops.linear_dgrad(dq, w16(ca + "q_local.weight"), dLoc, accumulate=True)
+        ops.linear_dgrad(dkv, w16(ca + "k_global.weight", rows=2 * C), dGlob)
+        self.launches += 7
+
+    def _kohonen_bwd(self, a, B, T, G, f1, f2):
+        """Backward of model.py:417-445: the three shared-weight cross-attention calls, the map losses and the scatter
+        of the representation gradients into the node tables.  Returns (dL/d local patches, dL/d global patches)."""
+        som = a["som"]
+        M = B * T
+        free = [f1, f2, a["k32a"], a["k32b"]]                 # fp32 [M, C] scratch besides G
+        d_ln, d_gn = free.pop(), free.pop()
+        self._ca_bwd(a["ca"][2], B, T, G, a["ln32"], a["ln16"], a["gn16"], d_ln, d_gn)
+        free.append(G)
+        d_rg, d_xg = free.pop(), free.pop()
+        self._ca_bwd(a["ca"][1], B, T, d_gn, som["global"]["repr32"], som["global"]["repr16"], a["global16"], d_rg, d_xg)
+        free.append(d_gn)
+        d_rl, d_xl = free.pop(), free.pop()
+        self._ca_bwd(a["ca"][0], B, T, d_ln, som["local"]["repr32"], som["local"]["repr16"], a["local16"], d_rl, d_xl)
+        # consistency and quantization gradients join the representation / patch gradients (model.py:437, 441-442)
+        ops.som_pair_losses(som["local"]["repr32"], som["global"]["repr32"], a["local32"], a["global32"], None, self.aux_w[1:4],
+                            d_rl, d_rg, d_xl, d_xg)
+        side = int(math.sqrt(self.cfg.kohonen_nodes // 2))
+        hi, lo = a["d_c16"], a["d_c16b"]
+        for tag, d_r in (("local", d_rl), ("global", d_rg)):
+            # nodes[idx] gather backward = onehot^T dRepr on the tensor cores, dRepr as bf16 hi + lo
+            gn = self.g2d(tag + "_kohonen.nodes")
+            ops.split_bf16(d_r, hi, lo)
+            self._wgrad(som[tag]["onehot"], hi, gn)
+            self._wgrad(som[tag]["onehot"], lo, gn)
+            ops.som_smoothness(self.p(tag + "_kohonen.nodes"), som[tag]["counts"], side, M, self.scratch[5:6], self.aux_w[4:5], gn)
+            self.launches += 2
+        self.launches += 1
+        return d_xl, d_xg
 
     # ------------------------------------------------------------------------------------------ original-ViT branch
     # config.use_nvit = False (BASELINE config 4): RMSNorm pre-norm that OVERWRITES h, plain residual adds, 1/sqrt(D)
@@ -611,20 +766,33 @@ class Engine:
 
 
 class NViTFunction(torch.autograd.Function):
-    """One autograd node for the whole model: forward/backward are the engine's hand-scheduled passes."""
+    """One autograd node for the whole model: forward/backward are the engine's hand-scheduled passes.
+
+    Outputs (logits, reconstruction) or, with Kohonen maps, (logits, reconstruction, consistency, smoothness, local
+    quantization, global quantization); the gradients arriving for the scalar losses become the device-side weights of
+    the fused loss-gradient kernels."""
+
+    AUX = ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization")
 
     @staticmethod
     def forward(ctx, engine, img, *params):
         logits, recon = engine.forward(img, save=True)
         ctx.engine = engine
         ctx.n_params = len(params)
-        ctx.mark_non_differentiable(recon)
-        return logits, recon
+        if not engine.cfg.use_kohonen:
+            ctx.mark_non_differentiable(recon)      # not in the objective without the maps (train.py:909-926)
+            return logits, recon
+        return (logits, recon, *(engine.last_aux[k] for k in NViTFunction.AUX))
 
     @staticmethod
-    def backward(ctx, dlogits, _drecon):
+    def backward(ctx, dlogits, *daux):
         eng = ctx.engine
         eng.zero_grad()
+        if eng.cfg.use_kohonen:
+            drec, dcons, dsmooth, dlq, dgq = ((d if d is not None else eng.aux_w.new_zeros(())) for d in daux)
+            eng.aux_w[:5].copy_(torch.stack([drec, dcons, dlq, dgq, dsmooth]).to(F32))
+        if dlogits is None:
+            dlogits = torch.zeros_like(eng._acts[next(iter(eng._acts))]["logits"])
         eng.backward(dlogits)
         grads = []
         for n in eng.order:

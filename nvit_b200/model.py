@@ -18,6 +18,8 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
+from .kohonen import KohonenMap
+
 
 @dataclass
 class ViTConfig:
@@ -145,8 +147,8 @@ class ViT(nn.Module):
         self.total_steps = 0
         if config.n_embd % config.n_head != 0 or config.n_embd // config.n_head != 64:
             raise ValueError("nvit_b200 attention kernels need head_dim = n_embd / n_head = 64")
-        if config.use_kohonen:
-            raise NotImplementedError("the Kohonen branch (BASELINE config 5) is not built yet; see DESIGN.md")
+        if config.use_kohonen and not config.use_nvit:
+            raise NotImplementedError("Kohonen maps are built for the nViT branch (BASELINE config 5); use_nvit=False + use_kohonen is not")
         C, P, G = config.n_embd, config.local_patch_size, config.global_patch_size
         self.local_patch_embed = nn.Conv2d(config.channels, C, kernel_size=P, stride=P)
         self.global_patch_embed = nn.Sequential(
@@ -156,6 +158,11 @@ class ViT(nn.Module):
         n_patches = (config.image_size // P) ** 2
         self.local_pos_embed = nn.Parameter(torch.zeros(1, n_patches, C))
         self.global_pos_embed = nn.Parameter(torch.zeros(1, n_patches, C))
+        if config.use_kohonen:      # model.py:312-325
+            a0 = config.kohonen_alpha if not config.kohonen_scheduler_enabled else config.kohonen_scheduler_min_lr
+            self.local_kohonen = KohonenMap(C, config.kohonen_nodes // 2, a0)
+            self.global_kohonen = KohonenMap(C, config.kohonen_nodes // 2, a0)
+            self.map_balance = nn.Parameter(torch.tensor(config.map_balance_weight))
         self.cross_attention = CrossAttentionBlock(config)
         self.reconstruction_head = nn.Sequential(nn.Linear(C, P * P * config.channels), nn.Tanh())
         self.transformer = nn.ModuleDict({
@@ -215,7 +222,22 @@ class ViT(nn.Module):
         return flops_achieved / 312e12, flops_achieved
 
     def get_kohonen_lr(self, step: int) -> float:
-        return self.config.kohonen_alpha
+        """Learning rate of the map update (nvit/model.py:563-581): constant, or linear warm-up then cosine decay."""
+        cfg = self.config
+        if not cfg.kohonen_scheduler_enabled:
+            return cfg.kohonen_alpha
+        w, d = cfg.kohonen_scheduler_warmup_steps, cfg.kohonen_scheduler_decay_steps
+        lo, hi = cfg.kohonen_scheduler_min_lr, cfg.kohonen_alpha
+        if step < w:
+            return lo + (hi - lo) * (step / w)
+        if step > d:
+            return lo
+        return lo + 0.5 * (1.0 + math.cos(math.pi * (step - w) / (d - w))) * (hi - lo)
+
+    def combine_representations(self, local_repr: torch.Tensor, global_repr: torch.Tensor) -> torch.Tensor:
+        """nvit/model.py:477-480 (API surface used by the reference's debug tooling; not on the training path)."""
+        combined = local_repr * global_repr
+        return combined / combined.norm(p=2, dim=-1, keepdim=True)
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -240,7 +262,15 @@ class ViT(nn.Module):
         eng = self.engine
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad:
-            logits, recon = NViTFunction.apply(eng, img, *eng.param_list())
+            out = NViTFunction.apply(eng, img, *eng.param_list())
         else:
             logits, recon = eng.forward(img, save=False)
-        return logits, {"reconstruction": recon}
+            out = (logits, recon, *(eng.last_aux[k] for k in AUX_KEYS)) if self.config.use_kohonen else (logits, recon)
+        aux = {}
+        if self.config.use_kohonen:      # same keys, same order as nvit/model.py:437-442, 464
+            aux.update(zip(AUX_KEYS, out[2:]))
+        aux["reconstruction"] = out[1]
+        return out[0], aux
+
+
+AUX_KEYS = ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization")

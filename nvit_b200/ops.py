@@ -162,6 +162,46 @@ def tanh_mse(pred, target, out):
     _lib.call("nvit_tanh_mse", _p(pred), _p(target), n, 1.0 / n, _p(out), _stream())
 
 
+def tanh_mse_bwd(pred, target, weight_dev, dpred):
+    n = pred.numel()
+    _lib.call("nvit_tanh_mse_bwd", _p(pred), _p(target), n, 1.0 / n, _p(weight_dev), _p(dpred), _stream())
+
+
+# ---- Kohonen maps (BASELINE config 5)
+def split_bf16(x, hi, lo):
+    _lib.call("nvit_split_bf16", _p(x), _p(hi), _p(lo), x.numel(), _stream())
+
+
+def som_prepare(nodes, node_sq, hi, lo, snapshot):
+    G, C = nodes.shape
+    _lib.call("nvit_som_prepare", _p(nodes), G, C, _p(node_sq), _p(hi), _p(lo), _p(snapshot), _stream())
+
+
+def som_select(dots, node_sq, nodes, idx, idx64, onehot, counts, repr32, repr16):
+    M, G = dots.shape
+    _lib.call("nvit_som_select", _p(dots), _p(node_sq), _p(nodes), M, G, nodes.shape[1], _p(idx), _p(idx64), _p(onehot), _p(counts),
+              _p(repr32), _p(repr16), _stream())
+
+
+def som_pool(x, rows, run, out):
+    _lib.call("nvit_som_pool", _p(x), rows, run, _p(out), _stream())
+
+
+def som_update(nodes, pooled, bmu, steps, grid_rows, grid_cols, coef_dev, sigma):
+    _lib.call("nvit_som_update", _p(nodes), _p(pooled), _p(bmu), steps, grid_rows, grid_cols, nodes.shape[1], _p(coef_dev), float(sigma),
+              _stream())
+
+
+def som_pair_losses(repr_l, repr_g, x_l, x_g, sums, weights=None, d_repr_l=None, d_repr_g=None, d_x_l=None, d_x_g=None):
+    M, C = repr_l.shape
+    _lib.call("nvit_som_pair_losses", _p(repr_l), _p(repr_g), _p(x_l), _p(x_g), M, C, _p(sums), _p(weights), _p(d_repr_l), _p(d_repr_g),
+              _p(d_x_l), _p(d_x_g), _stream())
+
+
+def som_smoothness(nodes, counts, side, M, loss, weight=None, gnodes=None):
+    _lib.call("nvit_som_smoothness", _p(nodes), _p(counts), side, nodes.shape[1], M, _p(loss), _p(weight), _p(gnodes), _stream())
+
+
 def adamw_flat(p, g, m, v, n_decay, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0, dev_lr_step=None):
     _lib.call("nvit_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), n_decay, float(lr), float(beta1), float(beta2), float(eps),
               float(weight_decay), step, _p(gnorm_sq), float(max_norm), _p(dev_lr_step), _stream())

@@ -83,12 +83,15 @@ class Trainer:
 
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
                  eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
-                 cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = True, sm_budget: int = 0):
+                 cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = True, sm_budget: int = 0,
+                 consistency_weight: float = 0.1, smoothness_weight: float = 0.1):
         import torch.distributed as dist
         self.model = model
         self.engine = model.engine
         self.lr, self.betas, self.wd, self.clip, self.eps = learning_rate, betas, weight_decay, grad_clip, eps
         self.grad_accum = gradient_accumulation_steps
+        # weights of the Kohonen losses (settings.training.*, train.py:909-926); the other three come from the model config
+        self.consistency_weight, self.smoothness_weight = consistency_weight, smoothness_weight
         self.iter_num = 0
         self.opt_step = 0
         if data_parallel is None:
@@ -105,7 +108,8 @@ class Trainer:
             _lib.call("nvit_set_sm_budget", int(sm_budget))
         # CUDA-graph replay of the whole step (single rank): the ~275 launches, their tensor-map encodes and the Python
         # between them are captured once; learning rate and step count then live in device memory (self.hyper)
-        self.use_graph = bool(cuda_graph) and not self.dp
+        # (the Kohonen learning-rate schedule is host-side state, so that mode runs eagerly)
+        self.use_graph = bool(cuda_graph) and not self.dp and not model.config.use_kohonen
         self.graph_warmup_steps = max(1, graph_warmup_steps)
         self._graph = None
         self._graph_inputs = None
@@ -124,6 +128,12 @@ class Trainer:
             self.hyper = torch.tensor([self.lr, float(self.opt_step)], device=eng.P32.device, dtype=F32)   # {lr, step}
             self._state_for = eng.P32
             self._graph = None
+            cfg = self.model.config
+            if cfg.use_kohonen:
+                k = 1.0 / (self.grad_accum * self.world)
+                eng.set_aux_weights(reconstruction=cfg.reconstruction_weight * k, consistency=self.consistency_weight * k,
+                                    local_quantization=cfg.local_quantization_weight * k,
+                                    global_quantization=cfg.global_quantization_weight * k, smoothness=self.smoothness_weight * k)
             if self.dp:
                 self.reducer = GradReducer(eng.G32, self.group)
                 self._broadcast_params()
@@ -142,6 +152,8 @@ class Trainer:
         """forward + loss + backward of one micro-batch; gradients accumulate in the flat buffer (train.py:898-933)."""
         eng = self.engine
         self._ensure_state()
+        if self.model.training:
+            self.model.step += 1               # ViT.forward's own counter (model.py:404-405): drives the Kohonen schedule
         logits, recon = eng.forward(X, save=True)
         B, N = logits.shape
         dlogits = eng._acts[B].setdefault("dlogits", torch.empty(B, N, device=logits.device, dtype=F32))
@@ -151,6 +163,7 @@ class Trainer:
         eng.grad_ready_hook = self.reducer.ready if (self.dp and last and self.overlap) else None
         eng.backward(dlogits)
         self.last_recon = recon
+        self.last_aux = eng.last_aux
         return logits
 
     def optimizer_step(self):

@@ -1,0 +1,290 @@
+"""BASELINE config 5 (nViT + Kohonen maps) on a B200 (-m gpu): kernels, model and training step against the oracle.
+
+Units: the best-matching unit is a discrete choice.  The CUDA path computes the distances on the tensor cores from
+bf16 hi/lo splits (~2^-17 relative); the tests demand the SAME unit as an fp64 evaluation wherever the margin between
+the best and the second-best squared distance exceeds 1e-4 of the distance, and an argmin-equivalent unit elsewhere.
+Model-level cases are chosen so that no token sits on such a near-tie, then everything downstream (representations,
+the five auxiliary losses, logits, every gradient incl. the node tables, the in-forward map update) is held to the same
+bf16 tolerances as tests/test_model_gpu.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from nvit_b200 import ViT, ViTConfig, Trainer, ops  # noqa: E402
+from nvit_b200.kohonen import KohonenMap  # noqa: E402
+from oracle import nvit_oracle as O  # noqa: E402
+
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WEIGHTS = dict(kohonen_consistency=0.1, kohonen_smoothness=0.1)
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("M,G,C,scale", [(64, 16, 64, 0.1), (1000, 256, 768, 0.05), (50176, 256, 768, 0.03), (333, 64, 192, 1.0)])
+def test_bmu_matches_fp64_argmin(M, G, C, scale):
+    torch.manual_seed(M + G)
+    km = KohonenMap(C, G).to(DEV)
+    with torch.no_grad():
+        km.nodes.mul_(scale)
+    x = torch.randn(M, C, device=DEV) * 0.05
+    rep, idx = km(x)
+    d2 = torch.cdist(x.double(), km.nodes.detach().double()) ** 2
+    best, ref = d2.min(dim=1)
+    assert idx.dtype == torch.int64 and idx.shape == (M,)
+    mine = d2.gather(1, idx[:, None])[:, 0]
+    assert float(((mine - best) / best).max()) <= 1e-4                     # always an argmin up to the stated margin
+    top2 = d2.topk(2, dim=1, largest=False).values
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-4 * top2[:, 0]
+    assert bool((idx[clear] == ref[clear]).all()) and float(clear.float().mean()) > 0.99
+    assert len(torch.unique(idx)) > 1
+    assert torch.equal(rep, km.nodes.detach()[idx])
+
+
+def test_bmu_ties_pick_lowest_index_and_batched_input():
+    km = KohonenMap(64, 16).to(DEV)
+    with torch.no_grad():
+        km.nodes.copy_(torch.randn(4, 64, device=DEV).repeat(4, 1))        # nodes g and g+4k identical
+    x = torch.randn(3, 5, 64, device=DEV)
+    rep, idx = km(x)
+    assert idx.shape == (3, 5) and rep.shape == (3, 5, 64)
+    assert int(idx.max()) < 4
+
+
+@pytest.mark.parametrize("B,T,C,G,lr", [(4, 16, 64, 16, 0.3), (20, 16, 64, 16, 0.05), (7, 64, 192, 64, 0.1), (256, 196, 768, 256, 0.01)])
+def test_map_update_matches_oracle(B, T, C, G, lr):
+    """KohonenMap.update_nodes (kohonen.py:121-165): sequential, pairs image i with the unit of flattened token i."""
+    torch.manual_seed(B)
+    cfg = O.OracleConfig(n_embd=C, kohonen_nodes=2 * G, kohonen_alpha=0.5)
+    km = KohonenMap(C, G, alpha=0.5).to(DEV).train()
+    x = torch.randn(B, T, C, device=DEV)
+    idx = torch.randint(0, G, (B, T), device=DEV)
+    ref = km.nodes.detach().clone()
+    O.kohonen_update(ref, cfg, x, idx, lr)
+    before = km.nodes.detach().clone()
+    km.update_nodes(x, idx, lr)
+    assert float((km.nodes.detach() - before).abs().max()) > 0
+    torch.testing.assert_close(km.nodes.detach(), ref, rtol=2e-5, atol=2e-6)
+    km.eval()
+    frozen = km.nodes.detach().clone()
+    km.update_nodes(x, idx, lr)
+    assert torch.equal(frozen, km.nodes.detach())
+
+
+@pytest.mark.parametrize("M,C", [(64, 64), (777, 192), (4096, 768), (300, 1024)])
+def test_pair_losses_and_gradients(M, C):
+    torch.manual_seed(C)
+    a, b, xl, xg = (torch.randn(M, C, device=DEV) * s for s in (0.7, 0.9, 0.8, 2.0))      # xg large: Huber's linear branch too
+    w = torch.tensor([0.3, 0.7, 1.1], device=DEV)
+    ta, tb, txl, txg = (t.clone().requires_grad_(True) for t in (a, b, xl, xg))
+    cons = O.kohonen_consistency(ta, tb)
+    hl, hg = F.huber_loss(ta, txl), F.huber_loss(tb, txg)
+    (w[0] * cons + w[1] * hl + w[2] * hg).backward()
+    sums = torch.zeros(3, device=DEV)
+    ops.som_pair_losses(a, b, xl, xg, sums)
+    assert abs(float(1 - sums[0] / M) - float(cons)) < 1e-5
+    assert abs(float(sums[1] / (M * C)) - float(hl)) < 1e-5 * float(hl) + 1e-7
+    assert abs(float(sums[2] / (M * C)) - float(hg)) < 1e-5 * float(hg) + 1e-7
+    base = [torch.randn(M, C, device=DEV) for _ in range(4)]
+    outs = [t.clone() for t in base]
+    ops.som_pair_losses(a, b, xl, xg, None, w, *outs)
+    for o, b0, t in zip(outs, base, (ta, tb, txl, txg)):
+        torch.testing.assert_close(o - b0, t.grad, rtol=1e-4, atol=1e-9 + 1e-5 * float(t.grad.abs().max()))
+
+
+@pytest.mark.parametrize("G,C,M", [(16, 64, 64), (256, 768, 50176), (64, 192, 1000)])
+def test_smoothness_loss_and_gradient(G, C, M):
+    torch.manual_seed(G)
+    cfg = O.OracleConfig(n_embd=C, kohonen_nodes=2 * G)
+    nodes = torch.randn(G, C, device=DEV)
+    idx = torch.randint(0, G, (M,), device=DEV)
+    tn = nodes.clone().requires_grad_(True)
+    ref = O.kohonen_smoothness(cfg, tn, idx.view(1, M))
+    (0.37 * ref).backward()
+    counts = torch.bincount(idx, minlength=G).float()
+    loss = torch.zeros(1, device=DEV)
+    gn = torch.zeros_like(nodes)
+    ops.som_smoothness(nodes, counts, int(G ** 0.5), M, loss, torch.tensor([0.37], device=DEV), gn)
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    torch.testing.assert_close(gn, tn.grad, rtol=1e-4, atol=1e-6 * float(tn.grad.abs().max()))
+
+
+def test_tanh_mse_backward():
+    torch.manual_seed(0)
+    pred = (torch.randn(1000, 48, device=DEV)).bfloat16()
+    tgt = torch.randn(1000, 48, device=DEV).bfloat16()
+    t = pred.float().requires_grad_(True)
+    (0.5 * F.mse_loss(torch.tanh(t), tgt.float())).backward()
+    out = torch.empty_like(pred)
+    ops.tanh_mse_bwd(pred, tgt, torch.tensor([0.5], device=DEV), out)
+    assert rel(out.float(), t.grad) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ model
+def build(cfg, sd):
+    m = ViT(ViTConfig(**cfg.as_dict()))
+    m.load_state_dict({**sd, **O.kohonen_buffers(cfg)}, strict=True)
+    return m.to(DEV).train()
+
+
+def total_loss(cfg, logits, aux, y):
+    return F.cross_entropy(logits, y) + 0.1 * aux["kohonen_consistency"] + 0.1 * aux["kohonen_smoothness"] \
+        + cfg.local_quantization_weight * aux["local_quantization"] + cfg.global_quantization_weight * aux["global_quantization"] \
+        + cfg.reconstruction_weight * aux["reconstruction"]
+
+
+def case(name, over, batch, seed, node_scale):
+    cfg = O.named_config(name, use_kohonen=True, **over)
+    if isinstance(seed, str):
+        sd = O.formula_state_dict(cfg)
+        X, y = O.formula_batch(cfg, batch)
+    else:
+        sd = O.init_state_dict(cfg, seed)
+        for k in sd:
+            if k.endswith("nodes"):
+                sd[k].mul_(node_scale)
+        g = torch.Generator().manual_seed(1234)
+        X = torch.randn(batch, cfg.channels, cfg.image_size, cfg.image_size, generator=g)
+        y = torch.randint(0, cfg.num_classes, (batch,), generator=g)
+    return cfg, sd, X.to(DEV), y.to(DEV)
+
+
+MODEL_CASES = [
+    ("micro", dict(kohonen_nodes=32, kohonen_alpha=0.3), 4, "formula", 1.0),
+    ("tiny", dict(kohonen_nodes=128, kohonen_alpha=0.2), 16, 0, 0.02),
+    ("tiny", dict(kohonen_nodes=32, kohonen_alpha=0.2, bias=True, kohonen_scheduler_enabled=True), 70, 1, 0.02),   # B > T
+    ("tiny", dict(kohonen_nodes=512), 8, 2, 1.0),              # reference init: N(0,1) nodes, every token picks the same unit
+    ("b16", dict(kohonen_nodes=512, kohonen_alpha=0.1), 2, 0, 0.02),
+]
+
+
+@pytest.mark.parametrize("name,over,batch,seed,node_scale", MODEL_CASES)
+def test_kohonen_forward_backward_matches_oracle(name, over, batch, seed, node_scale):
+    cfg, sd, X, y = case(name, over, batch, seed, node_scale)
+    p = {k: v.detach().to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
+    ref_logits, ref_aux = O.vit_forward(p, cfg, X, training=True, step=1)
+    total_loss(cfg, ref_logits, ref_aux, y).backward()
+
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    assert list(aux) == ["kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization", "reconstruction"]
+    total_loss(cfg, logits, aux, y).backward()
+    got = model.engine.last_aux
+    for tag in ("local", "global"):
+        same = (got[tag + "_indices"] == ref_aux["_" + tag + "_indices"]).float().mean()
+        assert float(same) == 1.0, f"{tag}: {float(same):.4f} of the units agree"
+    formula = isinstance(seed, str)
+    assert rel(logits.detach(), ref_logits.detach()) <= (2e-2 if formula else 1e-2)
+    for k in ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization", "reconstruction"):
+        assert abs(float(aux[k]) - float(ref_aux[k])) <= 1e-2 * abs(float(ref_aux[k])) + 1e-6, (k, float(aux[k]), float(ref_aux[k]))
+    # in-forward map update
+    for tag in ("local", "global"):
+        k = tag + "_kohonen.nodes"
+        mine, ref = dict(model.named_parameters())[k].detach(), p[k].detach()
+        assert float((ref - sd[k].to(DEV)).abs().max()) > 0
+        assert rel(mine - sd[k].to(DEV), ref - sd[k].to(DEV)) <= 1e-2, (k, rel(mine - sd[k].to(DEV), ref - sd[k].to(DEV)))
+    # every gradient
+    ref_grads = {k: v.grad for k, v in p.items()}
+    gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values() if g is not None)))
+    n = 0
+    tol = 6e-2 if formula else 3e-2
+    for k, prm in model.named_parameters():
+        rg = ref_grads[k]
+        if rg is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
+            continue
+        assert prm.grad is not None, k
+        n += 1
+        err = float((prm.grad.double() - rg.double()).norm())
+        if err <= 1e-3 * gnorm and float(rg.norm()) < 3e-2 * gnorm:
+            continue
+        assert rel(prm.grad, rg) <= tol, (k, rel(prm.grad, rg), float(rg.norm()), gnorm)
+    assert n > 25
+    assert model.map_balance.grad is None
+    assert model.reconstruction_head[0].weight.grad is not None and model.local_kohonen.nodes.grad is not None
+
+
+def test_kohonen_golden_from_reference():
+    """tests/golden/micro_kohonen.npz: outputs of the real reference (make_golden.py) on formula weights."""
+    cfg, sd, X, y = case("micro", dict(kohonen_nodes=32, kohonen_alpha=0.3), 4, "formula", 1.0)
+    gold = dict(np.load(os.path.join(GOLDEN, "micro_kohonen.npz")))
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    got = model.engine.last_aux
+    assert np.array_equal(got["local_indices"].cpu().numpy(), gold["local_indices"])
+    assert np.array_equal(got["global_indices"].cpu().numpy(), gold["global_indices"])
+    assert rel(logits.detach().cpu(), torch.from_numpy(gold["logits"])) <= 3e-2
+    for k in ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization", "reconstruction"):
+        assert abs(float(aux[k]) - float(gold["aux:" + k])) <= 1e-2 * abs(float(gold["aux:" + k])), k
+    for tag in ("local", "global"):
+        after = dict(model.named_parameters())[tag + "_kohonen.nodes"].detach().cpu()
+        ref_after, before = torch.from_numpy(gold[tag + "_nodes_after"]), sd[tag + "_kohonen.nodes"]
+        assert rel(after - before, ref_after - before) <= 1e-2
+
+
+def test_kohonen_eval_mode_has_no_update_and_no_grad_path():
+    cfg, sd, X, y = case("tiny", dict(kohonen_nodes=128), 8, 0, 0.02)
+    model = build(cfg, sd).eval()
+    before = model.local_kohonen.nodes.detach().clone()
+    with torch.no_grad():
+        l1, a1 = model(X)
+        l2, a2 = model(X)
+    assert torch.equal(before, model.local_kohonen.nodes.detach())
+    assert torch.equal(l1, l2) and model.step == 0
+    p = {k: v.detach().to(DEV).clone() for k, v in sd.items()}
+    with torch.no_grad():
+        rl, ra = O.vit_forward(p, cfg, X, training=False)
+    assert rel(l1, rl) <= 1e-2
+    assert abs(float(a1["kohonen_smoothness"]) - float(ra["kohonen_smoothness"])) <= 1e-3 * float(ra["kohonen_smoothness"])
+
+
+def test_kohonen_trainer_steps_match_oracle():
+    """Two train.py steps (total loss of train.py:906-926, clip, AdamW, normalize) through nvit_b200.Trainer."""
+    cfg, sd, X, y = case("tiny", dict(kohonen_nodes=128, kohonen_alpha=0.2, kohonen_scheduler_enabled=True,
+                                      kohonen_scheduler_warmup_steps=2, kohonen_scheduler_decay_steps=6), 16, 3, 0.02)
+    model = build(cfg, sd)
+    tr = Trainer(model, learning_rate=1e-3)
+    ot = O.OracleTrainer({k: v.to(DEV) for k, v in sd.items()}, cfg, lr=1e-3)
+    for it in range(2):
+        loss = tr.step(X, y)
+        oloss, _, oaux = ot.step(X, y)
+        for tag in ("local", "global"):
+            assert torch.equal(tr.last_aux[tag + "_indices"], oaux["_" + tag + "_indices"]), (it, tag)
+        for k in ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization"):
+            assert abs(float(tr.last_aux[k]) - float(oaux[k])) <= 1e-2 * abs(float(oaux[k])) + 1e-6, (it, k)
+    assert model.step == 2
+    mine = dict(model.named_parameters())
+    for k, v in ot.sd.items():
+        d_ref = v.detach() - sd[k].to(DEV)
+        if float(d_ref.abs().max()) == 0:
+            continue
+        # Adam's normalised update amplifies bf16 noise on near-zero gradients: compare the parameters, not the deltas,
+        # to lr-sized tolerance, and the bulk of the update direction by cosine
+        assert float((mine[k].detach() - v.detach()).abs().max()) <= 2.5e-3, k
+        if v.dim() >= 2 and "kohonen" not in k:
+            d_mine = mine[k].detach() - sd[k].to(DEV)
+            cos = float((d_mine.flatten().double() @ d_ref.flatten().double()) / (d_mine.norm().double() * d_ref.norm().double()))
+            assert cos > 0.9, (k, cos)
+    for i in range(cfg.n_layer):
+        for nm, dim in O.NORMALIZED:
+            w = mine[f"transformer.h.{i}.{nm}.weight"].detach()
+            assert float((w.norm(dim=dim) - 1).abs().max()) <= 1e-3
+
+
+def test_kohonen_rejected_outside_nvit_mode():
+    with pytest.raises(NotImplementedError):
+        ViT(ViTConfig(image_size=16, n_layer=1, n_head=1, n_embd=64, local_patch_size=4, global_patch_size=8, use_kohonen=True,
+                      kohonen_nodes=32, use_nvit=False))

@@ -24,18 +24,24 @@ def test_config_fields_match_reference(reference_model_module):
 
 
 @pytest.mark.parametrize("name,over", [("micro", {}), ("micro", {"bias": True}), ("tiny", {}), ("mini", {"base_scale": 1 / 32}),
-                                       ("micro", {"use_nvit": False}), ("tiny", {"use_nvit": False, "bias": True})])
+                                       ("micro", {"use_nvit": False}), ("tiny", {"use_nvit": False, "bias": True}),
+                                       ("micro", {"use_kohonen": True, "kohonen_nodes": 32}), ("tiny", {"use_kohonen": True})])
 def test_state_dict_keys_shapes_match_oracle(name, over):
     cfg = O.named_config(name, **over)
     m = ViT(ViTConfig(**cfg.as_dict()))
     sd = m.state_dict()
-    shapes = O.param_shapes(cfg)
-    assert set(sd) == set(shapes)
+    shapes = dict(O.param_shapes(cfg))
+    buffers = O.kohonen_buffers(cfg) if cfg.use_kohonen else {}
+    assert set(sd) == set(shapes) | set(buffers)
     for k, v in sd.items():
-        assert tuple(v.shape) == tuple(shapes[k]) and v.dtype == torch.float32, k
+        if k in buffers:
+            assert torch.equal(v, buffers[k]) and v.dtype == torch.int64, k
+        else:
+            assert tuple(v.shape) == tuple(shapes[k]) and v.dtype == torch.float32, k
 
 
-@pytest.mark.parametrize("name,over", [("micro", {}), ("tiny", {"bias": True})])
+@pytest.mark.parametrize("name,over", [("micro", {}), ("tiny", {"bias": True}),
+                                       ("micro", {"use_kohonen": True, "kohonen_nodes": 32, "kohonen_scheduler_enabled": True})])
 def test_same_seed_gives_the_reference_initialisation(reference_model_module, name, over):
     """Modules are created in the reference's order, so the RNG stream — and every initial value — is identical."""
     ref = reference_model_module
@@ -108,3 +114,28 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 16, 16))
     with pytest.raises(ValueError, match="head_dim"):
         ViT(ViTConfig(n_embd=96, n_head=2, use_nvit=True))
+
+
+def test_kohonen_surface_matches_reference(reference_model_module):
+    """BASELINE config 5 API: map attributes, learning-rate schedule, optimizer groups, layout of the flat buffers."""
+    ref = reference_model_module
+    cfg = O.named_config("micro", use_kohonen=True, kohonen_nodes=32, kohonen_scheduler_enabled=True,
+                         kohonen_scheduler_warmup_steps=5, kohonen_scheduler_decay_steps=20, kohonen_alpha=0.3)
+    mine, theirs = ViT(ViTConfig(**cfg.as_dict())), ref.ViT(ref.ViTConfig(**cfg.as_dict()))
+    for attr in ("m", "n", "grid_size", "input_dim", "alpha", "sigma", "periodic"):
+        assert getattr(mine.local_kohonen, attr) == getattr(theirs.local_kohonen, attr), attr
+    for step in (0, 1, 4, 5, 6, 12, 20, 21, 1000):
+        assert mine.get_kohonen_lr(step) == theirs.get_kohonen_lr(step) == O.kohonen_lr(cfg, step)
+    a, b = torch.randn(2, 3, 8), torch.randn(2, 3, 8)
+    assert torch.equal(mine.combine_representations(a, b), theirs.combine_representations(a, b))
+    go, gr = (m.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu").param_groups for m in (mine, theirs))
+    assert [len(g["params"]) for g in go] == [len(g["params"]) for g in gr]
+    from nvit_b200.engine import Engine
+    eng = Engine(mine)
+    eng._build_layout()
+    s = eng.slots
+    assert eng.rec_active and s["reconstruction_head.0.weight"].off < eng.n_gemm
+    assert s["local_kohonen.nodes"].off < eng.n_decay and s["reconstruction_head.0.bias"].off < eng.n_active
+    assert s["map_balance"].off >= eng.n_active          # never receives a gradient (SURVEY.md 8b)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mine.local_kohonen(torch.zeros(4, 64))
