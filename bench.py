@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 
 METRIC = "nViT-B/16 train images/sec"
 UNIT = "images/s"
+VARIANT_NAME = {"nvit": "nViT", "orig": "original-ViT-branch", "kohonen": "nViT+Kohonen(512 nodes)"}
 
 
 def flops_per_image(cfg, kohonen: bool = False) -> float:
@@ -33,8 +34,12 @@ def flops_per_image(cfg, kohonen: bool = False) -> float:
     C, L, P, G = cfg.n_embd, cfg.n_layer, cfg.local_patch_size, cfg.global_patch_size
     T = (cfg.image_size // P) ** 2
     Kl, Kg = 3 * P * P, 3 * G * G
-    n_ca = 1
+    kohonen = kohonen or bool(getattr(cfg, "use_kohonen", False))
+    n_ca = 3 if kohonen else 1
     fwd = 2 * T * C * (Kl + Kg + 6 * C * n_ca + 16 * C * L + Kl) + 4 * T * T * C * (L + n_ca) + 2 * C * cfg.num_classes
+    if kohonen:
+        bmu = 2 * (2 * T * C * (cfg.kohonen_nodes // 2))           # the two distance GEMMs (algorithmic: one product each)
+        return float(3 * (fwd + bmu) - 2 * T * C * (Kl + Kg) - 2 * bmu)   # recon head trains; the argmin has no backward
     train = 3 * fwd - 2 * T * C * (Kl + Kg) - 4 * T * C * Kl
     return float(train)
 
@@ -161,8 +166,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="b16", choices=["b16", "l16", "tiny"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--variant", default="nvit", choices=["nvit", "orig"],
-                    help="nvit = normalized ViT (headline); orig = the reference's use_nvit=False branch (BASELINE config 4 A/B)")
+    ap.add_argument("--variant", default="nvit", choices=["nvit", "orig", "kohonen"],
+                    help="nvit = normalized ViT (headline); orig = the reference's use_nvit=False branch (BASELINE config 4 A/B); "
+                         "kohonen = nViT + Kohonen maps, 512 nodes (BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
@@ -188,7 +194,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    ocfg = O.named_config(args.config, use_nvit=(args.variant == "nvit"))
+    ocfg = O.named_config(args.config, use_nvit=(args.variant != "orig"), use_kohonen=(args.variant == "kohonen"))
     cfg = ViTConfig(**ocfg.as_dict())
     torch.manual_seed(0)
     model = ViT(cfg).to(dev).train()
@@ -293,11 +299,11 @@ def main():
         fpi = flops_per_image(cfg)
         line = {
             "metric": METRIC if (args.config == "b16" and args.variant == "nvit") else
-                      f"{'nViT' if args.variant == 'nvit' else 'ViT(original branch)'}-{args.config.upper()} train images/sec",
+                      f"{VARIANT_NAME[args.variant]}-{args.config.upper()} train images/sec",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{'nViT' if args.variant == 'nvit' else 'original-ViT-branch'}-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
+            "config": {"workload": f"{VARIANT_NAME[args.variant]}-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
                                    f"bf16 GEMM/attention + fp32 residual, random-init weights",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~20 GB of activations) is far larger than the 126 MB L2, no explicit flush",

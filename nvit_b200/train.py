@@ -188,6 +188,14 @@ class Trainer:
         eng._p16_version = None
         eng.zero_grad()
         self.normalize_matrices()
+        if self.dp and self.model.config.use_kohonen:
+            # the in-forward map update (kohonen.py:121-165) saw different images on every rank: average the node tables so
+            # that the replicas stay identical (the reference's DDP would leave them diverged)
+            import torch.distributed as dist
+            for tag in ("local", "global"):
+                nodes = eng.p(tag + "_kohonen.nodes")
+                dist.all_reduce(nodes, op=dist.ReduceOp.SUM, group=self.group)
+                nodes.mul_(1.0 / self.world)
 
     def set_lr(self, lr: float):
         """Learning-rate schedule hook (train.py:874-876 sets it per epoch); safe with a captured graph."""

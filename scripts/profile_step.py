@@ -1,5 +1,5 @@
 """One profiled training step of the bench workload, bracketed by cudaProfilerStart/Stop (use with
-`ncu --profile-from-start off ...`).  Usage: python scripts/profile_step.py [config] [batch] [warm steps]"""
+`ncu --profile-from-start off ...`).  Usage: python scripts/profile_step.py [config] [batch] [warm steps] [nvit|orig|kohonen]"""
 import os
 import sys
 
@@ -11,7 +11,8 @@ from oracle import nvit_oracle as O
 name = sys.argv[1] if len(sys.argv) > 1 else "b16"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-cfg = ViTConfig(**O.named_config(name).as_dict())
+variant = sys.argv[4] if len(sys.argv) > 4 else "nvit"
+cfg = ViTConfig(**O.named_config(name, use_nvit=(variant != "orig"), use_kohonen=(variant == "kohonen")).as_dict())
 torch.manual_seed(0)
 model = ViT(cfg).cuda().train()
 tr = Trainer(model)
