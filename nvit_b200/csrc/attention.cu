@@ -175,12 +175,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   ATT_MARK(0);
 
   if (t.tid == 0) {
-    tma_prefetch_desc(&p.tq);
-    tma_prefetch_desc(&p.tk);
-    tma_prefetch_desc(&p.tv);
+    // the loads go out first: barrier set-up, TMEM allocation and the sqk fetch below hide under their latency
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(bar_tma, 3 * ATT_TILE_BYTES);
+    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
   }
   if (t.warp == 0) {
     tmem_alloc(tmem_ptr, 512);
@@ -201,13 +203,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
   const float bound = s_misc[0];
   const bool two_pass = !has_norm || !(bound <= 60.f);
-
-  if (t.tid == 0) {
-    mbar_arrive_expect_tx(bar_tma, 3 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
-  }
   ATT_MARK(1);
   mbar_wait(bar_tma, 0);
   ATT_MARK(2);
@@ -399,9 +394,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   float* s_dsqk = s_scale + 64;                                // [64]
   float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
   float* s_dot = s_rscale + 64;                                // [4][128] partial row dots of the normalisation backward
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dot + 512);
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dot + 512);   // q, k tiles
   uint64_t* bar_mma = bar_tma + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_tma2 = bar_mma + 1;                                // v, dO, O tiles
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tma2 + 1);
 
   const AttnThread t = attn_thread(p);
   const int T = p.T, TP = p.TP;
@@ -409,14 +405,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   ATT_MARK(0);
 
   if (t.tid == 0) {
-    tma_prefetch_desc(&p.tq);
-    tma_prefetch_desc(&p.tk);
-    tma_prefetch_desc(&p.tv);
-    tma_prefetch_desc(&p.tdo);
-    tma_prefetch_desc(&p.to);
+    // the loads go out first (q, k on their own barrier: the normalisation and the first MMA need only those)
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_tma2, 1);
     fence_barrier_init();
+    mbar_arrive_expect_tx(bar_tma, 2 * ATT_TILE_BYTES);
+    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
+    mbar_arrive_expect_tx(bar_tma2, 3 * ATT_TILE_BYTES);
+    tma_load_3d(&p.tv, bar_tma2, sV, t.h * 64, 0, t.b);
+    tma_load_3d(&p.tdo, bar_tma2, sDO, t.h * 64, 0, t.b);
+    tma_load_3d(&p.to, bar_tma2, sP, t.h * 64, 0, t.b);   // O parks in the (not yet used) P buffer for the delta pass
   }
   if (t.warp == 0) {
     tmem_alloc(tmem_ptr, 512);
@@ -428,29 +428,46 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     s_rscale[t.tid] = sc != 0.f ? 1.f / sc : 0.f;
     s_dsqk[t.tid] = 0.f;
   }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (t.tid == 0) {
-    mbar_arrive_expect_tx(bar_tma, 5 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tdo, bar_tma, sDO, t.h * 64, 0, t.b);
-    tma_load_3d(&p.to, bar_tma, sP, t.h * 64, 0, t.b);   // O parks in the (not yet used) P buffer for the delta pass
-  }
-  // while the tiles fly: lse; then delta = rowsum(dO * O) from the shared tiles, and a clean P buffer
-  if (t.tid < 256) {
-    const int r = t.tid;  // one thread per (padded) token row
+  if (t.tid >= 256) {
+    const int r = t.tid - 256;  // one thread per (padded) token row
     s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E : 0.f;
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
   }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
   ATT_MARK(1);
   mbar_wait(bar_tma, 0);
   ATT_MARK(2);
+  if (has_norm) {
+    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
+      if (j < T) s_invq[j] = normalize_row(sQ, j, s_scale);
+      else s_invk[j - T] = normalize_row(sK, j - T, s_scale);
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
+  const float sl2 = p.scale * LOG2E;
+  const int nks_q = TP >> 4;  // k-steps over the q axis
+  uint32_t mma_phase = 0;
+  float dacc[16];   // dL/d(sqk) partials for this thread's 16 channels
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
+
+  constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+  // ---- S^T_0 = Kh_0 Qh^T goes to the tensor pipe; delta = rowsum(dO * O) is computed from the shared tiles meanwhile
+  if (t.warp == 0) {
+    tc_fence_after_sync();
+    mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
+    mma_commit(bar_mma);
+  }
+  mbar_wait(bar_tma2, 0);
   if (t.tid < 256) {
     const int r = t.tid;
     float d = 0.f;
@@ -464,42 +481,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     }
     s_delta[r] = d;
   }
-  __syncthreads();
-  for (int i = t.tid; i < ATT_PB_BYTES / 16; i += ATT_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
-
-  if (has_norm) {
-    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
-      if (j < T) s_invq[j] = normalize_row(sQ, j, s_scale);
-      else s_invk[j - T] = normalize_row(sK, j - T, s_scale);
-    }
-  }
-  fence_proxy_async_smem();
+  // No clearing of the P buffer: kv rows >= T and q columns >= T of P^T are written as zeros by the P pass, and whatever
+  // else lies beyond column TP only reaches accumulator rows (q >= TP) that are never read.
   __syncthreads();
   ATT_MARK(3);
-
-  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
-  const float sl2 = p.scale * LOG2E;
-  const int nks_q = TP >> 4;  // k-steps over the q axis
-  uint32_t mma_phase = 0;
-  float dacc[16];   // dL/d(sqk) partials for this thread's 16 channels
-#pragma unroll
-  for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
-
-  constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
   for (int j = 0; j < p.nK; ++j) {
     const int kv = j * 128 + t.row;
     const bool kv_ok = kv < T;
-    // ---- S^T_j = Kh_j Qh^T
-    if (t.warp == 0) {
+    if (j == 0) {       // S^T_j for j > 0 was issued behind the dK/dQ products of tile j-1 and waited for there
+      mbar_wait(bar_mma, mma_phase);
+      mma_phase ^= 1;
       tc_fence_after_sync();
-      mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + j * 16384, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
-      mma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after_sync();
     ATT_MARK(4 + 8 * j);
     // ---- P^T = exp(scale S^T - lse)   (four threads per kv row, columns = q)
     for (int c = t.c_begin; c < t.c_end; ++c) {
@@ -576,17 +570,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
       for (int m = 0; m < p.nQ; ++m)
         mma_seq(tmem_base + TM_DQ + 64 * m, umma_smem_desc(sP_a + 2 * m * 16384, 16384, 1024), 128,
                 umma_smem_desc(sK_a + j * 16384, 8192, 1024), 128, IDESC_MM(64), kv_steps, j > 0);
+      if (j + 1 < p.nK)   // the score tile of the next kv block rides behind: its region (dP^T) has just been consumed
+        mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + (j + 1) * 16384, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
       mma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after_sync();
-    ATT_MARK(8 + 8 * j);
-    // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both
+    // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both; dV_j is complete already and is
+    // stored while the tensor pipe works on dK/dQ
     {
       const int kvc = kv_ok ? kv : 0;
       const long long grow = static_cast<long long>(t.b) * T + kvc;
       tmem_row16_to_bf16(t_lane + TM_DV + t.part * 16, p.dv + grow * p.lddv + t.h * 64 + t.part * 16, kv_ok);
+      mbar_wait(bar_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after_sync();
+      ATT_MARK(8 + 8 * j);
       if (has_norm) {
         float g[16], n[16];
         s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DK + t.part * 16, sK, kvc, t.part, s_scale, s_rscale, g, n, dacc, kv_ok);
