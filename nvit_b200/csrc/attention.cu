@@ -108,6 +108,7 @@ struct AttnThread {
   int tid, warp, lane, wq, part, row, b, h;
   int c_begin, c_end, nch;  // this thread's 16-column chunks of a score row
 };
+template <int PARTS = ATT_PARTS>
 __device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
   AttnThread t;
   t.tid = threadIdx.x;
@@ -119,8 +120,8 @@ __device__ __forceinline__ AttnThread attn_thread(const AttnParams& p) {
   t.b = blockIdx.x / p.H;
   t.h = blockIdx.x % p.H;
   t.nch = p.TP >> 4;
-  t.c_begin = (t.part * t.nch) / ATT_PARTS;
-  t.c_end = ((t.part + 1) * t.nch) / ATT_PARTS;
+  t.c_begin = (t.part * t.nch) / PARTS;
+  t.c_end = ((t.part + 1) * t.nch) / PARTS;
   return t;
 }
 
@@ -153,23 +154,48 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (64 + 512 + 8) * 4 + 64;
+// One CTA of 256 threads per (batch, head), TWO CTAs per SM: the phases of one head are a serial chain (load ->
+// normalise -> S MMA -> softmax -> PV MMA -> store), so two resident CTAs keep the CUDA cores of the SM busy while the
+// other one waits for the tensor pipe or for TMA.  That needs <= 113 KB of shared memory and <= 256 TMEM columns per CTA:
+// the probabilities never go to shared memory - they are written back to TMEM as packed bf16 pairs over the (dead)
+// score columns and feed the PV product as its A operand straight from tensor memory, and O reuses score columns too:
+//   columns [0, TP)      S  = Qh Kh^T            (fp32)
+//   columns [0, TP/2)    P  = exp2(...)           (bf16 pairs; written only after every thread has read its S columns)
+//   columns [128, 192)   O  = P V                 (fp32; TP/2 <= 128)
+constexpr int ATT_FWD_THREADS = 256;
+constexpr int ATT_FWD_PARTS = 2;      // two threads share a TMEM lane (a score row) and split its columns
+constexpr int ATT_FWD_MAXCH = 8;      // 16-column chunks per thread at TP = 256
+constexpr uint32_t TMF_O = 128;
+constexpr int ATT_FWD_SMEM = 3 * ATT_TILE_BYTES + 1024 /*align*/ + (64 + 2 * 128 + 8) * 4 + 64;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// D[tmem] (+)= A[tmem, bf16 pairs, 8 columns per k-step] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_TILE_BYTES;
-  float* s_scale = reinterpret_cast<float*>(sP + ATT_PB_BYTES);  // [64]
-  float* s_part = s_scale + 64;                                  // [4][128] partial row sums / maxima
-  float* s_misc = s_part + 512;                                  // [0] = log2-domain logit bound
+  float* s_scale = reinterpret_cast<float*>(sV + ATT_TILE_BYTES);  // [64]
+  float* s_part = s_scale + 64;                                    // [2][128] partial row sums / maxima
+  float* s_misc = s_part + 256;                                    // [0] = log2-domain logit bound
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
-  const AttnThread t = attn_thread(p);
+  const AttnThread t = attn_thread<ATT_FWD_PARTS>(p);
   const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
   ATT_MARK(0);
@@ -185,7 +211,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
   }
   if (t.warp == 0) {
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, 256);
     tmem_relinquish();
   }
   if (t.warp == 1) {
@@ -208,7 +234,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   ATT_MARK(2);
 
   if (has_norm) {
-    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
+    for (int j = t.tid; j < 2 * T; j += ATT_FWD_THREADS) {
       if (j < T) normalize_row(sQ, j, s_scale);
       else normalize_row(sK, j - T, s_scale);
     }
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   __syncthreads();
   ATT_MARK(3);
 
-  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sP_a = smem_u32(sP);
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
   const float sl2 = p.scale * LOG2E;
   uint32_t mma_phase = 0;
@@ -247,57 +273,75 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       }
       s_part[t.part * 128 + t.row] = mx;
       __syncthreads();
-      m2 = fmaxf(fmaxf(s_part[t.row], s_part[128 + t.row]), fmaxf(s_part[256 + t.row], s_part[384 + t.row])) * sl2;
+      m2 = fmaxf(s_part[t.row], s_part[128 + t.row]) * sl2;
       __syncthreads();
     }
+    // ---- read this thread's score columns, exponentiate, keep the bf16 pairs in registers
+    uint32_t pk[ATT_FWD_MAXCH][8];
     float sum = 0.f;
-    for (int c = t.c_begin; c < t.c_end; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + c * 16, r);
-      tmem_wait_ld();
-      float pv[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(r[e]), sl2, -m2));
-      if (c == t.nch - 1) {
+    for (int cc = 0; cc < ATT_FWD_MAXCH; ++cc) {
+      const int c = t.c_begin + cc;
+      if (c < t.c_end) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + c * 16, r);
+        tmem_wait_ld();
+        float pv[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (c * 16 + e >= T) pv[e] = 0.f;
+        for (int e = 0; e < 16; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(r[e]), sl2, -m2));
+        if (c == t.nch - 1) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c * 16 + e >= T) pv[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sum += pv[e];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
       }
-#pragma unroll
-      for (int e = 0; e < 16; ++e) sum += pv[e];
-      uint8_t* blk = sP + (c >> 2) * 16384;
-      const int ch = (c & 3) * 2;
-      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch)) = pack8(pv);
-      *reinterpret_cast<uint4*>(blk + sw128(t.row, ch + 1)) = pack8(pv + 8);
     }
     s_part[t.part * 128 + t.row] = sum;
     tc_fence_before_sync();
-    fence_proxy_async_smem();
+    __syncthreads();           // every score column has been read: P may now overwrite them
+    tc_fence_after_sync();
+#pragma unroll
+    for (int cc = 0; cc < ATT_FWD_MAXCH; ++cc) {
+      const int c = t.c_begin + cc;
+      if (c < t.c_end) tmem_st_32x32b_x8(t_lane + c * 8, pk[cc]);
+    }
+    tmem_wait_st();
+    tc_fence_before_sync();
     __syncthreads();
     ATT_MARK(5 + 4 * i);
 
     if (t.warp == 0) {
       tc_fence_after_sync();
-      mma_seq_pk(tmem_base + 256, umma_smem_desc(sP_a, 16, 1024), umma_smem_desc(sV_a, 8192, 1024), 128, IDESC_KM(64), TP >> 4);
+      uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
+      const int nks = TP >> 4;
+#pragma unroll 1
+      for (int ks = 0; ks < nks; ++ks) {
+        if (elect_one()) umma_bf16_ts(tmem_base + TMF_O, tmem_base + ks * 8, dv, IDESC_KM(64), ks > 0 ? 1u : 0u);
+        dv += 128;
+      }
       mma_commit(bar_mma);
     }
-    const float total = (s_part[t.row] + s_part[128 + t.row]) + (s_part[256 + t.row] + s_part[384 + t.row]);
+    const float total = s_part[t.row] + s_part[128 + t.row];
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
     ATT_MARK(6 + 4 * i);
     {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(t_lane + 256 + t.part * 16, r);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_lane + TMF_O + t.part * 32, r);
       tmem_wait_ld();
       if (qtok < T) {
         const float inv = 1.f / total;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.part * 16;
-        float o[16];
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.part * 32;
+        float o[32];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]) * inv;
-        *reinterpret_cast<uint4*>(dst) = pack8(o);
-        *reinterpret_cast<uint4*>(dst + 8) = pack8(o + 8);
+        for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(r[e]) * inv;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + 8 * q4) = pack8(o + 8 * q4);
         if (t.part == 0) p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + qtok] = (m2 + log2f(total)) * LN2;
       }
     }
@@ -308,7 +352,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 
   if (t.warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -399,7 +443,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   uint64_t* bar_tma2 = bar_mma + 1;                                // v, dO, O tiles
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tma2 + 1);
 
-  const AttnThread t = attn_thread(p);
+  const AttnThread t = attn_thread<>(p);
   const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
   ATT_MARK(0);
@@ -680,7 +724,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<<<(unsigned)(B * H), ATT_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_fwd_kernel<<<(unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
