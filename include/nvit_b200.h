@@ -114,6 +114,18 @@ int nvit_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq,
                        const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
                        float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, void* stream);
 
+/* Gate backward fused behind the mlp_c_proj / out_proj dgrad GEMM (model.py:152-155, 260-262 backward):
+ *   dx = dY[M,K] W[K,F]            (W = the projection weight as it lies, [K, F] bf16; dx stays on chip, fp32)
+ *   d_uv[:, :F]  = dx * silu(v sv) * su          d_uv[:, F:] = dx * (u su) * silu'(v sv) * sv
+ * with u|v = uv_raw[M, 2F] (bf16, the c_fc / proj output saved by the forward pass) and su|sv = suv * suv_mul (suv NULL:
+ * ones).  F must be a multiple of 64.  dL/dsuv is NOT produced here: see nvit_rowdot_div. */
+int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_raw, const float* suv, float suv_mul, void* d_uv,
+                       int64_t M, int64_t F, int64_t K, int64_t ld_dy, int64_t ld_w, int64_t ld_uv, int64_t ld_duv, void* stream);
+/* out[r] = sum_k w[r,k] dw[r,k] / div[r] (0 where div == 0), overwriting out.  With w = c_fc.weight, dw = its gradient and
+ * div = suv this is dL/dsuv (uv = suv mul (h W^T) makes dL/dsuv[c] = W[c,:].dW[c,:] / suv[c]): a 19 MB read instead of a
+ * column reduction over [M, 8C] (model.py:148-151 backward). */
+int nvit_rowdot_div(const float* w, const float* dw, const float* div, float* out, int64_t rows, int64_t cols, void* stream);
+
 /* Measurement aid: device buffer of 256 int64 receiving clock64() phase marks of the first 8 CTAs of the next attention
  * launches (NULL switches it off). */
 int nvit_attention_debug(void* dev_buf_256_int64);

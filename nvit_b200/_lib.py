@@ -35,6 +35,8 @@ SIGNATURES = {
     "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],
     "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P],
     "nvit_attention_debug": [P],
+    "nvit_gemm_gate_bwd": [P, P, P, P, F32, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "nvit_rowdot_div": [P, P, P, P, I64, I64, P],
     "nvit_split_bf16": [P, P, P, I64, P],
     "nvit_som_prepare": [P, I64, I64, P, P, P, P, P],
     "nvit_som_select": [P, P, P, I64, I64, I64, P, P, P, P, P, P, P],

@@ -36,6 +36,8 @@ struct alignas(64) GemmParams {
   const float* bias;      // [N] or null
   const float* colscale;  // [N] ([2F] for swiglu) or null
   const float* rowadd;    // [rowadd_period, N] or null
+  const __nv_bfloat16* gate_uv;   // GATEB: raw u|v of the forward pass, [M, 2F] bf16 (F = swiglu_half)
+  long long ld_uv;
   long long ldc, ldc2;
   int M, N, K;
   int out_f32, accumulate, atomic;
@@ -45,7 +47,7 @@ struct alignas(64) GemmParams {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool CG2 = false>
+template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false>
 struct GemmTraits {
   static constexpr int BM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int BK = 64;
@@ -58,7 +60,7 @@ struct GemmTraits {
 #define NVIT_GEMM_NBUF 1
 #endif
   // epilogue staging: NBUF 16 KB buffers per epilogue group (two groups); what is left of the 224 KB goes to the TMA ring
-  static constexpr int NBUF = (CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1;
+  static constexpr int NBUF = GATEB ? 2 : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1);   // GATEB: one buffer each for du and dv
   static constexpr int STAGING_BYTES = 2 * NBUF * 16384;
   static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int ACC_STAGES = 2;
@@ -75,6 +77,11 @@ struct GemmTraits {
   static constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
 };
 
+__device__ __forceinline__ float tanh_approx_(float x) {
+  float y;
+  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));   // volatile: keep ptxas from recomputing it per use
+  return y;
+}
 __device__ __forceinline__ float silu_mul(float u, float v) { return __fdividef(u * v, 1.f + __expf(-v)); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -93,9 +100,10 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2>
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
 __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB>;
+  static_assert(!GATEB || (BN == 256 && !SWIGLU), "gate-backward epilogue: 128x256 tiles");
   // CG2: the kernel runs as clusters of two CTAs (one SM pair); the pair computes a 256 x BN tile with
   // tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its own 128 rows of A and half of B.
   const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0;
@@ -270,6 +278,36 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec2_ok = (p.C2 == nullptr) || ((p.ldc2 & 7) == 0);
     const bool use_vec = (p.bias != nullptr) || (p.colscale != nullptr);
+    // GATEB: raw u / v of this group's NEXT 64-column chunk, fetched a whole chunk ahead.  The loads are warp-cooperative
+    // so that every request is a full 128-byte line (instruction k: lane l takes 16 bytes `l & 7` of row 4k + l/8 of the
+    // warp's 32 rows); the pieces reach their owner threads through the group's staging buffers.  MEASURED: the obvious
+    // per-thread form (each thread reading its own row, 32 bytes at a time) made this kernel 2.5x slower than its main
+    // loop - 32 sector requests per warp instruction against an L2 request rate the operand loads already saturate.
+    uint4 un[GATEB ? 8 : 1], vn[GATEB ? 8 : 1];
+    auto gate_fetch = [&](int mb, int nb, int s2) {
+      if constexpr (GATEB) {
+        const int col = nb * BN + (eg + 2 * s2) * 64 + (lane & 7) * 8;
+        const __nv_bfloat16* base = p.gate_uv + (static_cast<long long>(mb) * T::BM + q * 32 + (lane >> 3)) * p.ld_uv + col;
+        const int rows_left = p.M - (mb * T::BM + q * 32 + (lane >> 3));   // row 4k + l/8 is valid iff 4k < rows_left
+        const bool col_ok = col < p.N && p.dbg != 3;      // dbg 3 (measurement aid): no u|v loads
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (col_ok && 4 * k < rows_left) {
+            un[k] = ldg_u4_stream(base + static_cast<long long>(4 * k) * p.ld_uv);
+            vn[k] = ldg_u4_stream(base + static_cast<long long>(4 * k) * p.ld_uv + p.swiglu_half);
+          } else {
+            un[k] = make_uint4(0u, 0u, 0u, 0u);
+            vn[k] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+    };
+    if constexpr (GATEB) {
+      if (unit0 < total_units && p.dbg != 1) {
+        const int t0 = unit0 / p.splits;
+        gate_fetch((t0 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t0 % p.tiles_n, 0);
+      }
+    }
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int t = u / p.splits;
       const int n_blk = t % p.tiles_n;
@@ -282,7 +320,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
           int j = n_blk * TILE_N + (SWIGLU ? (et & 127) : et);
           j = min(j, p.N - 1);
           if (SWIGLU) j += (et >> 7) * p.swiglu_half;   // entries 0..127: u scales, 128..255: v scales
-          if (SWIGLU || et < BN) {
+          if constexpr (GATEB) {      // [0,256): u scales of the tile's columns, [256,512): v scales
+            s_vec[et] = __ldg(p.colscale + j) * p.colscale_mul;
+            s_vec[256 + et] = __ldg(p.colscale + p.swiglu_half + j) * p.colscale_mul;
+          } else if (SWIGLU || et < BN) {
             s_vec[et] = p.colscale ? __ldg(p.colscale + j) * p.colscale_mul : 1.f;
             s_vec[256 + et] = p.bias ? __ldg(p.bias + j) : 0.f;
           }
@@ -326,7 +367,95 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
       // Sending the staged tile out through coalesced LSU stores instead was slower still (qkv 1151 -> 941 TFLOP/s), and
       // two or three staging buffers per group (at the price of ring stages) changed nothing: the cost follows the
       // output bytes, not the mechanism.
-      if (p.dbg == 1) {                      // measurement aid: main loop only
+      if constexpr (GATEB) {
+        // Backward of x = (u su) * silu(v sv) fused behind dx = dy W (model.py:148-155 backward): the accumulator holds
+        // dL/dx for 256 gate columns; this thread combines its row with the raw u, v of the forward pass and emits
+        // dL/du_raw and dL/dv_raw as two [128 x 64] bf16 tiles per chunk.  (dL/dsuv follows from the c_fc weight
+        // gradient: nvit_rowdot_div.)
+        if (p.dbg == 1) {
+          release_tmem();
+        } else {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int c = eg + 2 * s2;
+            const int n0 = n_blk * BN + c * 64;
+            const bool live = n0 < p.N;   // uniform over the group
+            if (live) {
+              if (issuer) bulk_wait_group_read<0>();     // the previous stores have drained both buffers
+              named_bar_sync(bar_id, 128);
+              // hand the prefetched pieces to their owner rows: staging buffer 0 <- u chunk, buffer 1 <- v chunk
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int rr = q * 32 + 4 * k + (lane >> 3);
+                const uint32_t off = rr * 128 + (((lane & 7) ^ (rr & 7)) << 4);
+                *reinterpret_cast<uint4*>(gbuf + off) = un[k];
+                *reinterpret_cast<uint4*>(gbuf + 16384 + off) = vn[k];
+              }
+              __syncwarp();       // a warp's 32 rows are loaded and consumed by that warp alone
+            }
+            if (s2 == 0) {
+              gate_fetch(m_blk, n_blk, 1);
+            } else if (u + unit_stride < total_units) {
+              const int t2 = (u + unit_stride) / p.splits;
+              gate_fetch((t2 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t2 % p.tiles_n, 0);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr + c * 64 + hh * 32, r);
+              tmem_wait_ld();
+              if (s2 == 1 && hh == 1) release_tmem();
+              if (live && p.dbg != 4) {                         // dbg 4 (measurement aid): no gate arithmetic
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t off = erow * 128 + (((hh * 4 + j) ^ (erow & 7)) << 4);
+                  const uint4 u8 = *reinterpret_cast<const uint4*>(gbuf + off);
+                  const uint4 v8 = *reinterpret_cast<const uint4*>(gbuf + 16384 + off);
+                  const uint32_t uc[4] = {u8.x, u8.y, u8.z, u8.w}, vc[4] = {v8.x, v8.y, v8.z, v8.w};
+                  uint32_t ou[4], ov[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int cc = c * 64 + hh * 32 + 8 * j + 2 * e;      // column within the tile
+                    float2 su = make_float2(1.f, 1.f), sv = su;
+                    if (use_vec) {
+                      su = *reinterpret_cast<const float2*>(s_vec + cc);
+                      sv = *reinterpret_cast<const float2*>(s_vec + 256 + cc);
+                    }
+                    float du2[2], dv2[2];
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl) {
+                      const float ur = hl ? bf16hi(uc[e]) : bf16lo(uc[e]);
+                      const float vr = hl ? bf16hi(vc[e]) : bf16lo(vc[e]);
+                      const float g = __uint_as_float(r[8 * j + 2 * e + hl]);
+                      const float s_u = hl ? su.y : su.x, s_v = hl ? sv.y : sv.x;
+                      const float uh = ur * s_u, vh = vr * s_v;
+                      const float sg = fmaf(0.5f, tanh_approx_(0.5f * vh), 0.5f);
+                      const float sl = vh * sg;                               // silu(vh)
+                      const float gu = g * sl;                                // dL/d(u scaled)
+                      const float gv = g * uh * fmaf(sl, 1.f - sg, sg);       // dL/d(v scaled): silu' = sg + silu (1 - sg)
+                      du2[hl] = gu * s_u;
+                      dv2[hl] = gv * s_v;
+                    }
+                    ou[e] = pack_bf16(du2[0], du2[1]);
+                    ov[e] = pack_bf16(dv2[0], dv2[1]);
+                  }
+                  *reinterpret_cast<uint4*>(gbuf + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+                  *reinterpret_cast<uint4*>(gbuf + 16384 + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                }
+              }
+            }
+            if (live) {
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, 128);
+              if (issuer && p.dbg != 2) {                       // dbg 2 (measurement aid): no stores
+                tma_store_2d(&p.tma_c, gbuf, n0, m_blk * T::BM);
+                tma_store_2d(&p.tma_c, gbuf + 16384, p.swiglu_half + n0, m_blk * T::BM);
+                bulk_commit_group();
+              }
+            }
+          }
+        }
+      } else if (p.dbg == 1) {                      // measurement aid: main loop only
         release_tmem();
       } else if (!p.direct) {
         if constexpr (SWIGLU) {
@@ -639,9 +768,9 @@ static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, u
   return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2>
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
 static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB>;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&p.tma_a, A, p.K, p.M, lda, T::BK, T::BM);
   else       rc = make_tmap_bf16_2d(&p.tma_a, A, p.M, p.K, lda, 64, T::BK);
@@ -652,7 +781,11 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   if (rc) return rc;
   // output maps for the staged epilogue (fall back to direct stores when the output is not TMA-addressable)
   p.direct = 1;
-  if (SWIGLU) {
+  if (GATEB) {
+    // one map over d(uv) [M, 2F]: the du tile of a chunk goes to column n0, its dv tile to column F + n0
+    if ((rc = make_out_tmap(&p.tma_c, p.C, false, true, 2ull * p.swiglu_half, p.M, p.ldc, 64))) return rc;
+    p.direct = 0;
+  } else if (SWIGLU) {
     const bool ok = tma_addressable(p.C, p.ldc, 2) && (!p.C2 || (tma_addressable(p.C2, p.ldc2, 2) && (p.swiglu_half % 8) == 0));
     if (ok) {
       if ((rc = make_out_tmap(&p.tma_c, p.C, false, true, p.N, p.M, p.ldc, 64))) return rc;
@@ -703,7 +836,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          T::SMEM_BYTES));
     attr_set = true;
   }
@@ -722,7 +855,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2>, p));
+  NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB>, p));
   return NVIT_OK;
 }
 
@@ -797,6 +930,36 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
     case 6: return launch_gemm<256, true, false, false, false>(p, A, B, lda, ldb, st);
     default: return launch_gemm<256, true, true, false, false>(p, A, B, lda, ldb, st);
   }
+}
+
+// d(uv_raw)[M, 2F] = backward of x = (u su) silu(v sv) applied to dx = dY W, dx never leaving the SM.
+extern "C" int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_raw, const float* suv, float suv_mul, void* d_uv,
+                                  int64_t M, int64_t F, int64_t K, int64_t ld_dy, int64_t ld_w, int64_t ld_uv, int64_t ld_duv,
+                                  void* stream) {
+  NVIT_REQUIRE(dY && W && uv_raw && d_uv, "nvit_gemm_gate_bwd: null operand");
+  NVIT_REQUIRE(M > 0 && F > 0 && K > 0 && M < (1ll << 31) && F < (1ll << 30) && K < (1ll << 31), "nvit_gemm_gate_bwd: bad sizes");
+  NVIT_REQUIRE((F % 64) == 0, "nvit_gemm_gate_bwd: F must be a multiple of 64 (got %lld)", (long long)F);
+  NVIT_REQUIRE((ld_uv % 8) == 0 && (reinterpret_cast<uintptr_t>(uv_raw) & 15) == 0,
+               "nvit_gemm_gate_bwd: uv_raw rows must be 16-byte aligned");
+  NVIT_REQUIRE(tma_addressable(d_uv, ld_duv, 2), "nvit_gemm_gate_bwd: d_uv must be 16-byte aligned with a 16-byte row pitch");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = d_uv;
+  p.ldc = ld_duv;
+  p.colscale = suv;
+  p.colscale_mul = suv_mul;
+  p.gate_uv = static_cast<const __nv_bfloat16*>(uv_raw);
+  p.ld_uv = ld_uv;
+  p.M = (int)M; p.N = (int)F; p.K = (int)K;
+  p.rowadd_period = 1;
+  p.splits = 1;
+  p.swiglu_half = (int)F;
+  p.dbg = g_dbg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the heavy epilogue wants the smaller operand traffic of CTA pairs (and their deeper TMA ring)
+  const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128);
+  if (cg2) return launch_gemm<256, false, true, false, true, true>(p, dY, W, ld_dy, ld_w, st);
+  return launch_gemm<256, false, true, false, false, true>(p, dY, W, ld_dy, ld_w, st);
 }
 
 extern "C" int nvit_gemm_debug(int mode) {   // measurement aid, results are WRONG when non-zero

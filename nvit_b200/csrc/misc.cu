@@ -206,6 +206,25 @@ __global__ void __launch_bounds__(128) swiglu_bwd_kernel(const __nv_bfloat16* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dL/dsuv from dL/dW
+// uv = (suv mul) * (h W^T)  =>  dL/dsuv[c] = sum_k W[c,k] dW[c,k] / suv[c]  (dW = dL/dW of the same step, any number of
+// accumulated micro-batches), which replaces a column reduction over all M rows of d(uv) * uv.  One warp per row.
+__global__ void __launch_bounds__(256) rowdot_div_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                                         const float* __restrict__ div, float* __restrict__ out, int rows, int cols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = blockIdx.x * nwarp + warp; r < rows; r += gridDim.x * nwarp) {
+    const float* a = w + 1ll * r * cols;
+    const float* b = dw + 1ll * r * cols;
+    float acc = 0.f;
+    for (int k = lane; k < cols; k += 32) acc += a[k] * b[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float d = div[r];
+      out[r] = d != 0.f ? acc / d : 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ im2col
 __device__ __forceinline__ int reflect_idx(int i, int S) {
   if (i < 0) i = -i;
@@ -622,6 +641,14 @@ extern "C" int nvit_swiglu_bwd(const void* dx, const void* uv, const float* suv,
   slab_grid(M, F, &grid, &rps);
   swiglu_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
                                                   static_cast<__nv_bfloat16*>(duv), dsuv_accum, (int)M, (int)F, rps);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_rowdot_div(const float* w, const float* dw, const float* div, float* out, int64_t rows, int64_t cols, void* stream) {
+  NVIT_REQUIRE(w && dw && div && out && rows >= 0 && cols > 0, "nvit_rowdot_div: bad arguments");
+  if (rows == 0) return NVIT_OK;
+  rowdot_div_kernel<<<stream_grid(rows * 32, 256), 256, 0, ST(stream)>>>(w, dw, div, out, (int)rows, (int)cols);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

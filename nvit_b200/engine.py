@@ -17,6 +17,7 @@ Memory layout (HBM):
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -49,6 +50,8 @@ class Engine:
         self.launches = 0
         self._p16_version = None
         self.probe = None               # list to receive (start, end) CUDA event pairs around the c_fc GEMM (bench.py)
+        # SiLU-gate backward inside the dgrad GEMM epilogue (nvit_gemm_gate_bwd); NVIT_FUSE_GATE_BWD=0 keeps the two-kernel path
+        self.fuse_gate_bwd = os.environ.get("NVIT_FUSE_GATE_BWD", "1") != "0"
 
     # ------------------------------------------------------------------------------------------ parameter layout
     def invalidate(self):
@@ -500,9 +503,16 @@ class Engine:
             self._wgrad(dHmlp, a["x"][i], g2d(b + "mlp_c_proj.weight"))
             if bias:
                 ops.colsum(dHmlp, g(b + "mlp_c_proj.bias"))
-            ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
-            ops.swiglu_bwd(a["d_4c"], a["uv"][i], p(b + "suv"), math.sqrt(C), a["d_8c"], g(b + "suv"))
-            self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
+            if self.fuse_gate_bwd and not bias:
+                # dx = dHmlp W stays on chip: the dgrad GEMM's epilogue applies the gate backward against the saved raw u|v;
+                # dL/dsuv[c] = W_fc[c,:] . dW_fc[c,:] / suv[c] follows from the weight gradient (18 MB instead of [M, 8C])
+                ops.gemm_gate_bwd(dHmlp, w16(b + "mlp_c_proj.weight"), a["uv"][i], p(b + "suv"), math.sqrt(C), a["d_8c"])
+                self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
+                ops.rowdot_div(p(b + "c_fc.weight"), g(b + "c_fc.weight"), p(b + "suv"), g(b + "suv"))
+            else:
+                ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
+                ops.swiglu_bwd(a["d_4c"], a["uv"][i], p(b + "suv"), math.sqrt(C), a["d_8c"], g(b + "suv"))
+                self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
             if bias:
                 ops.colsum(a["d_8c"], g(b + "c_fc.bias"))
             ops.linear_dgrad(a["d_8c"], w16(b + "c_fc.weight"), dH1, accumulate=True)
@@ -559,9 +569,12 @@ class Engine:
         self._wgrad(dO, s["x"], g2d(ca + "out_proj.weight"))
         if bias:
             ops.colsum(dO, g(ca + "out_proj.bias"))
-        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
         duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)     # contiguous [M, 2C] scratch
-        ops.swiglu_bwd(dX, s["uv"], None, 1.0, duv, None)
+        if self.fuse_gate_bwd and C % 64 == 0:
+            ops.gemm_gate_bwd(dO, w16(ca + "out_proj.weight"), s["uv"], None, 1.0, duv)
+        else:
+            ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
+            ops.swiglu_bwd(dX, s["uv"], None, 1.0, duv, None)
         self._wgrad(duv, s["att"], g2d(ca + "proj.weight"))
         if bias:
             ops.colsum(duv, g(ca + "proj.bias"))
@@ -579,7 +592,7 @@ class Engine:
             self.launches += 4
         ops.linear_dgrad(dq, w16(ca + "q_local.weight"), dLoc, accumulate=True)
         ops.linear_dgrad(dkv, w16(ca + "k_global.weight", rows=2 * C), dGlob)
-        self.launches += 7
+        self.launches += 6 if (self.fuse_gate_bwd and C % 64 == 0) else 7
 
     def _kohonen_bwd(self, a, B, T, G, f1, f2):
         """Backward of model.py:417-445: the three shared-weight cross-attention calls, the map losses and the scatter
@@ -693,8 +706,11 @@ class Engine:
             self._wgrad(dHmlp, a["x"][i], g2d(b + "mlp_c_proj.weight"))
             if bias:
                 ops.colsum(dHmlp, g(b + "mlp_c_proj.bias"))
-            ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
-            ops.swiglu_bwd(a["d_4c"], a["uv"][i], None, 1.0, a["d_8c"], None)
+            if self.fuse_gate_bwd:
+                ops.gemm_gate_bwd(dHmlp, w16(b + "mlp_c_proj.weight"), a["uv"][i], None, 1.0, a["d_8c"])
+            else:
+                ops.linear_dgrad(dHmlp, w16(b + "mlp_c_proj.weight"), a["d_4c"])
+                ops.swiglu_bwd(a["d_4c"], a["uv"][i], None, 1.0, a["d_8c"], None)
             self._wgrad(a["d_8c"], a["h1_16"][i], g2d(b + "c_fc.weight"))
             if bias:
                 ops.colsum(a["d_8c"], g(b + "c_fc.bias"))
@@ -724,9 +740,12 @@ class Engine:
         self._wgrad(dO, a["ca_x"], g2d(ca + "out_proj.weight"))
         if bias:
             ops.colsum(dO, g(ca + "out_proj.bias"))
-        ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
         duv = a["d_8c"].view(-1)[:M * 2 * C].view(M, 2 * C)
-        ops.swiglu_bwd(dX, a["ca_uv"], None, 1.0, duv, None)
+        if self.fuse_gate_bwd and C % 64 == 0:
+            ops.gemm_gate_bwd(dO, w16(ca + "out_proj.weight"), a["ca_uv"], None, 1.0, duv)
+        else:
+            ops.linear_dgrad(dO, w16(ca + "out_proj.weight"), dX)
+            ops.swiglu_bwd(dX, a["ca_uv"], None, 1.0, duv, None)
         self._wgrad(duv, a["ca_att"], g2d(ca + "proj.weight"))
         if bias:
             ops.colsum(duv, g(ca + "proj.bias"))

@@ -65,6 +65,19 @@ def linear_wgrad(dy, x, dw, *, splits=1, accumulate=False):
          accumulate=accumulate)
 
 
+def gemm_gate_bwd(dy, w, uv, suv, suv_mul, duv):
+    """duv[M, 2F] = gate backward of (dy[M,K] @ w[K,F]) against the saved raw u|v (see nvit_gemm_gate_bwd)."""
+    M, K = dy.shape
+    F = w.shape[1]
+    _lib.call("nvit_gemm_gate_bwd", _p(dy), _p(w), _p(uv), _p(suv), float(suv_mul), _p(duv), M, F, K, dy.stride(0), w.stride(0),
+              uv.stride(0), duv.stride(0), _stream())
+
+
+def rowdot_div(w, dw, div, out):
+    rows = w.shape[0]
+    _lib.call("nvit_rowdot_div", _p(w), _p(dw), _p(div), _p(out), rows, w.numel() // rows, _stream())
+
+
 def cast_bf16(src, dst):
     _lib.call("nvit_cast_f32_to_bf16", _p(src), _p(dst), src.numel(), _stream())
 

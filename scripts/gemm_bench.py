@@ -11,7 +11,7 @@ M = 50176
 SHAPES = [  # name, N, K, kind
     ("qkv fwd", 2304, 768, "fwd"), ("att_c_proj fwd", 768, 768, "fwd"), ("mlp_c_proj fwd", 768, 3072, "fwd"),
     ("c_fc swiglu", 3072, 768, "swiglu"), ("mlp_c_proj dgrad", 3072, 768, "dgrad"), ("c_fc dgrad acc", 768, 6144, "dgrad_acc"),
-    ("c_fc wgrad", 6144, 768, "wgrad"), ("qkv wgrad", 2304, 768, "wgrad"),
+    ("c_fc wgrad", 6144, 768, "wgrad"), ("qkv wgrad", 2304, 768, "wgrad"), ("mlp_c_proj dgrad+gate", 3072, 768, "gate_bwd"),
 ]
 
 
@@ -28,6 +28,14 @@ def run(name, N, K, kind, iters=20):
         w = torch.randn(K, N, device=dev, dtype=torch.bfloat16)
         dx = torch.zeros(M, N, device=dev, dtype=torch.float32 if kind == "dgrad_acc" else torch.bfloat16)
         f = lambda: ops.linear_dgrad(dy, w, dx, accumulate=(kind == "dgrad_acc"))
+        flops = 2.0 * M * N * K
+    elif kind == "gate_bwd":     # d(uv)[M, 2N] = gate backward of dY[M,K] W[K,N]
+        dy = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(K, N, device=dev, dtype=torch.bfloat16)
+        uv = torch.randn(M, 2 * N, device=dev, dtype=torch.bfloat16)
+        suv = torch.ones(2 * N, device=dev)
+        duv = torch.empty(M, 2 * N, device=dev, dtype=torch.bfloat16)
+        f = lambda: ops.gemm_gate_bwd(dy, w, uv, suv, 1.0, duv)
         flops = 2.0 * M * N * K
     elif kind == "swiglu":
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
@@ -60,7 +68,10 @@ if __name__ == "__main__":
     modes = [int(x) for x in os.environ.get("DBG_MODES", "0,1,2").split(",")]
     cgs = [int(x) for x in os.environ.get("CG_MODES", "1,2").split(",")]
     print(f"{'shape':22s} " + " ".join(f"cg{cg}/dbg{d:<7d}" for cg in cgs for d in modes))
+    only = os.environ.get("ONLY")
     for name, N, K, kind in SHAPES:
+        if only and only not in name:
+            continue
         cells = []
         for cg in cgs:
             for dbg in modes:

@@ -248,6 +248,60 @@ def test_swiglu_fwd_bwd(with_suv):
         assert rel(dsuv, suv.grad) < 1e-3
 
 
+# ---------------------------------------------------------------------------------------------- gate backward in the dgrad GEMM
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,Fh,K,with_suv", [(515, 768, 192, True), (1000, 3072, 768, True), (300, 64, 64, False), (4096, 768, 768, False),
+                                             (129, 256, 136, True)])
+def test_gemm_gate_backward(M, Fh, K, with_suv, cta_group):
+    """nvit_gemm_gate_bwd: d(uv_raw) = gate backward of dx = dY W against the saved raw u|v, dx never leaving the SM."""
+    from nvit_b200 import _lib
+    _lib.call("nvit_gemm_force_cta_group", cta_group)
+    try:
+        dy = randn(M, K, seed=40, dtype=torch.bfloat16) * 0.5
+        w = (randn(K, Fh, seed=41) * (1.0 / K ** 0.5)).to(torch.bfloat16)
+        uvb = randn(M, 2 * Fh, seed=42, dtype=torch.bfloat16)
+        uv = uvb.float().requires_grad_(True)
+        suv = (1.0 + 0.2 * randn(2 * Fh, seed=43)).requires_grad_(True) if with_suv else None
+        mul = 1.3
+        s = uv * (suv * mul) if with_suv else uv
+        x = s[:, :Fh] * F.silu(s[:, Fh:])
+        dx = dy.float() @ w.float()
+        x.backward(dx)
+        duv = torch.full((M, 2 * Fh), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.gemm_gate_bwd(dy, w, uvb, None if suv is None else suv.detach(), mul, duv)
+        torch.cuda.synchronize()
+        assert torch.isfinite(duv.float()).all()
+        assert rel(duv, uv.grad) < 6e-3, rel(duv, uv.grad)
+        # the two-kernel composition it replaces (dx rounded to bf16 in between) agrees to bf16 rounding
+        dxb = torch.empty(M, Fh, device=DEV, dtype=torch.bfloat16)
+        ops.linear_dgrad(dy, w, dxb)
+        duv2 = torch.empty_like(duv)
+        dsuv = torch.zeros(2 * Fh, device=DEV) if with_suv else None
+        ops.swiglu_bwd(dxb, uvb, None if suv is None else suv.detach(), mul, duv2, dsuv)
+        assert rel(duv, duv2) < 8e-3
+    finally:
+        _lib.call("nvit_gemm_force_cta_group", 0)
+
+
+def test_rowdot_div_gives_the_suv_gradient():
+    """dL/dsuv[c] = W[c,:] . dW[c,:] / suv[c] when uv = (suv mul) * (h W^T): checked against autograd through the whole gate."""
+    M, C, Fh = 700, 192, 384
+    h = randn(M, C, seed=50)
+    W = (randn(2 * Fh, C, seed=51) * C ** -0.5).requires_grad_(True)
+    suv = (1.0 + 0.3 * randn(2 * Fh, seed=52)).requires_grad_(True)
+    mul = C ** 0.5
+    uvs = (h @ W.t()) * (suv * mul)
+    x = uvs[:, :Fh] * F.silu(uvs[:, Fh:])
+    (x * randn(M, Fh, seed=53)).sum().backward()
+    out = torch.full((2 * Fh,), float("nan"), device=DEV)
+    ops.rowdot_div(W.detach().contiguous(), W.grad.contiguous(), suv.detach(), out)
+    assert rel(out, suv.grad) < 1e-4
+    suv0 = suv.detach().clone()
+    suv0[3] = 0.0
+    ops.rowdot_div(W.detach().contiguous(), W.grad.contiguous(), suv0, out)
+    assert float(out[3]) == 0.0 and torch.isfinite(out).all()
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def attention_reference(q, k, v, sqk, sqk_mul, scale, B, H, T):
     D = 64
