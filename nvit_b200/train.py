@@ -245,6 +245,49 @@ class Trainer:
         self.launches += self._graph_launches
         return self.loss_buf
 
+    # ---- checkpoint interchange (train.py:629-655 saves {"model", "optimizer", "model_args", "iter_num", ...})
+    def _torch_optimizer(self):
+        dev = self.engine.P32.device.type
+        return self.model.configure_optimizers(self.wd, self.lr, self.betas, dev)
+
+    def optimizer_state_dict(self) -> dict:
+        """The flat AdamW moments in torch.optim.AdamW's state_dict layout over ViT.configure_optimizers' groups, i.e. what
+        the reference stores under checkpoint["optimizer"] (train.py:641).  Parameters that never receive a gradient
+        have no entry, as in torch."""
+        self._ensure_state()
+        eng, opt = self.engine, self._torch_optimizer()
+        by_param = {id(s.param): s for s in eng.slots.values()}
+        if self.opt_step > 0:
+            for group in opt.param_groups:
+                for prm in group["params"]:
+                    s = by_param[id(prm)]
+                    if s.off >= eng.n_active:
+                        continue
+                    opt.state[prm] = {"step": torch.tensor(float(self.opt_step), device=prm.device),
+                                      "exp_avg": self.m[s.off:s.off + s.numel].view(s.shape).clone(),
+                                      "exp_avg_sq": self.v[s.off:s.off + s.numel].view(s.shape).clone()}
+        return opt.state_dict()
+
+    def load_optimizer_state_dict(self, state: dict) -> None:
+        """Inverse of optimizer_state_dict: accepts the reference's checkpoint["optimizer"] (train.py:380)."""
+        self._ensure_state()
+        eng, opt = self.engine, self._torch_optimizer()
+        opt.load_state_dict(state)
+        by_param = {id(s.param): s for s in eng.slots.values()}
+        self.m.zero_()
+        self.v.zero_()
+        step = 0
+        for prm, st in opt.state.items():
+            s = by_param[id(prm)]
+            self.m[s.off:s.off + s.numel].copy_(st["exp_avg"].reshape(-1))
+            self.v[s.off:s.off + s.numel].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        group = opt.param_groups[0]
+        self.lr, self.betas, self.eps = group["lr"], tuple(group["betas"]), group["eps"]
+        self.opt_step = step
+        self.hyper.copy_(torch.tensor([self.lr, float(step)], dtype=F32))
+        self._graph = None
+
     @property
     def total_launches(self) -> int:
         return self.launches + self.engine.launches

@@ -139,3 +139,49 @@ def test_kohonen_surface_matches_reference(reference_model_module):
     assert s["map_balance"].off >= eng.n_active          # never receives a gradient
     with pytest.raises(RuntimeError, match="CUDA"):
         mine.local_kohonen(torch.zeros(4, 64))
+
+
+@pytest.mark.parametrize("over", [{}, {"use_kohonen": True, "kohonen_nodes": 32}, {"use_nvit": False}])
+def test_checkpoint_interchange_with_the_reference(reference_model_module, tmp_path, over):
+    """a checkpoint written the reference's way (train.py:629-655: model / optimizer / model_args) loads
+    into this package the reference's way (train.py:375-381), and the other way round."""
+    import dataclasses
+    import torch.nn.functional as F
+    ref = reference_model_module
+    cfg = O.named_config("micro", **over)
+    torch.manual_seed(1)
+    theirs = ref.ViT(ref.ViTConfig(**cfg.as_dict()))
+    if not cfg.use_nvit:
+        for blk in theirs.transformer.h:
+            blk.rmsnorm_att, blk.rmsnorm_mlp = ref.RMSNorm(cfg.n_embd), ref.RMSNorm(cfg.n_embd)
+    opt = theirs.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu")
+    logits, _ = theirs(torch.randn(2, 3, cfg.image_size, cfg.image_size))
+    F.cross_entropy(logits, torch.tensor([1, 2])).backward()
+    opt.step()                                        # non-trivial optimizer state
+    path = tmp_path / "checkpoint_latest.pt"
+    torch.save({"model": theirs.state_dict(), "optimizer": opt.state_dict(), "model_args": dataclasses.asdict(theirs.config),
+                "iter_num": 7}, path)
+    ck = torch.load(path, map_location="cpu")
+    mine = ViT(ViTConfig(**ck["model_args"]))
+    mine.load_state_dict(ck["model"])                 # strict
+    my_opt = mine.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu")
+    my_opt.load_state_dict(ck["optimizer"])
+    named_theirs, named_mine = dict(theirs.named_parameters()), dict(mine.named_parameters())
+    assert list(named_theirs) == list(named_mine)
+    n_state = 0
+    for k, prm in named_theirs.items():
+        assert torch.equal(prm, named_mine[k]), k
+        if prm in opt.state:
+            assert torch.equal(opt.state[prm]["exp_avg"], my_opt.state[named_mine[k]]["exp_avg"]), k
+            n_state += 1
+    assert n_state > 20
+    # and back: what this package saves loads into the reference
+    path2 = tmp_path / "checkpoint_b200.pt"
+    torch.save({"model": mine.state_dict(), "optimizer": my_opt.state_dict(), "model_args": dataclasses.asdict(mine.config)}, path2)
+    ck2 = torch.load(path2, map_location="cpu")
+    back = ref.ViT(ref.ViTConfig(**ck2["model_args"]))
+    if not cfg.use_nvit:
+        for blk in back.transformer.h:
+            blk.rmsnorm_att, blk.rmsnorm_mlp = ref.RMSNorm(cfg.n_embd), ref.RMSNorm(cfg.n_embd)
+    back.load_state_dict(ck2["model"])
+    back.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu").load_state_dict(ck2["optimizer"])

@@ -214,3 +214,33 @@ def test_state_dict_roundtrip_and_device_move():
     assert torch.equal(a, b)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(X)                                              # CPU tensor: no fallback
+
+
+def test_trainer_optimizer_state_round_trips_through_the_torch_layout():
+    """the flat fused-AdamW state exports to / imports from torch.optim.AdamW's state_dict (the layout of the
+    reference's checkpoint["optimizer"], train.py:641): a resumed trainer continues exactly like the original."""
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 3)
+    g = torch.Generator().manual_seed(99)
+    X = torch.randn(16, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (16,), generator=g).to(DEV)
+    m1 = build(cfg, sd)
+    t1 = Trainer(m1, learning_rate=2e-3)
+    t1.step(X, y)
+    t1.step(X, y)
+    state = t1.optimizer_state_dict()
+    assert len(state["state"]) > 20 and state["param_groups"][0]["lr"] == 2e-3
+    some = next(iter(state["state"].values()))
+    assert set(some) >= {"step", "exp_avg", "exp_avg_sq"} and float(some["step"]) == 2.0
+    # resume in a fresh model/trainer from (model state_dict, optimizer state_dict)
+    m2 = build(cfg, {k: v.detach().cpu() for k, v in m1.state_dict().items()})
+    t2 = Trainer(m2, learning_rate=1e-3)
+    t2.load_optimizer_state_dict(state)
+    assert t2.opt_step == 2 and t2.lr == 2e-3
+    l1 = float(t1.step(X, y))
+    l2 = float(t2.step(X, y))
+    assert abs(l1 - l2) <= 1e-6 * abs(l1)
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert rel(b.detach(), a.detach()) <= 1e-5, k
+    # a torch AdamW can take the state over too (what the reference's load_checkpoint does)
+    m1.configure_optimizers(0.1, 2e-3, (0.9, 0.95), "cuda").load_state_dict(t1.optimizer_state_dict())
