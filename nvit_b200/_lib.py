@@ -18,6 +18,7 @@ P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 SIGNATURES = {
     "nvit_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, I32, I32, I32, I32, P, P, F32, P, I64, I64, P],
     "nvit_gemm_force_cta_group": [I32],
+    "nvit_gemm_swiglu_cta_group": [I32],
     "nvit_set_sm_budget": [I32],
     "nvit_gemm_debug": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
@@ -76,6 +77,9 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    mode = os.environ.get("NVIT_SWIGLU_CTA_GROUP")    # benchmarking hook: CTA-group mode of the gate GEMM
+    if mode in ("1", "2"):
+        lib.nvit_gemm_swiglu_cta_group(int(mode))
     mode = os.environ.get("NVIT_GEMM_CTA_GROUP")      # benchmarking hook: pin cta_group::1 or ::2 GEMM tiles
     if mode in ("1", "2"):
         lib.nvit_gemm_force_cta_group(int(mode))

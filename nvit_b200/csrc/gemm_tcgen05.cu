@@ -60,7 +60,12 @@ struct GemmTraits {
 #define NVIT_GEMM_NBUF 1
 #endif
   // epilogue staging: NBUF 16 KB buffers per epilogue group (two groups); what is left of the 224 KB goes to the TMA ring
-  static constexpr int NBUF = GATEB ? 2 : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1);   // GATEB: one buffer each for du and dv
+#ifndef NVIT_GATEB_SETS
+#define NVIT_GATEB_SETS 2
+#endif
+  // GATEB: NVIT_GATEB_SETS sets of {du, dv} buffers per group, so a chunk's stores drain while the next chunk is computed
+  static constexpr int GATE_SETS = (GATEB && CG2) ? NVIT_GATEB_SETS : 1;
+  static constexpr int NBUF = GATEB ? 2 * GATE_SETS : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1);
   static constexpr int STAGING_BYTES = 2 * NBUF * 16384;
   static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int ACC_STAGES = 2;
@@ -380,16 +385,18 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             const int c = eg + 2 * s2;
             const int n0 = n_blk * BN + c * 64;
             const bool live = n0 < p.N;   // uniform over the group
+            uint8_t* const sbuf = gbuf + (store_ctr % T::GATE_SETS) * 32768;    // this chunk's {du, dv} buffer set
             if (live) {
-              if (issuer) bulk_wait_group_read<0>();     // the previous stores have drained both buffers
+              ++store_ctr;
+              if (issuer) bulk_wait_group_read<T::GATE_SETS - 1>();     // the stores that last used this set have drained it
               named_bar_sync(bar_id, 128);
               // hand the prefetched pieces to their owner rows: staging buffer 0 <- u chunk, buffer 1 <- v chunk
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int rr = q * 32 + 4 * k + (lane >> 3);
                 const uint32_t off = rr * 128 + (((lane & 7) ^ (rr & 7)) << 4);
-                *reinterpret_cast<uint4*>(gbuf + off) = un[k];
-                *reinterpret_cast<uint4*>(gbuf + 16384 + off) = vn[k];
+                *reinterpret_cast<uint4*>(sbuf + off) = un[k];
+                *reinterpret_cast<uint4*>(sbuf + 16384 + off) = vn[k];
               }
               __syncwarp();       // a warp's 32 rows are loaded and consumed by that warp alone
             }
@@ -409,8 +416,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint32_t off = erow * 128 + (((hh * 4 + j) ^ (erow & 7)) << 4);
-                  const uint4 u8 = *reinterpret_cast<const uint4*>(gbuf + off);
-                  const uint4 v8 = *reinterpret_cast<const uint4*>(gbuf + 16384 + off);
+                  const uint4 u8 = *reinterpret_cast<const uint4*>(sbuf + off);
+                  const uint4 v8 = *reinterpret_cast<const uint4*>(sbuf + 16384 + off);
                   const uint32_t uc[4] = {u8.x, u8.y, u8.z, u8.w}, vc[4] = {v8.x, v8.y, v8.z, v8.w};
                   uint32_t ou[4], ov[4];
 #pragma unroll
@@ -439,8 +446,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
                     ou[e] = pack_bf16(du2[0], du2[1]);
                     ov[e] = pack_bf16(dv2[0], dv2[1]);
                   }
-                  *reinterpret_cast<uint4*>(gbuf + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-                  *reinterpret_cast<uint4*>(gbuf + 16384 + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                  *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+                  *reinterpret_cast<uint4*>(sbuf + 16384 + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
                 }
               }
             }
@@ -448,8 +455,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
               fence_proxy_async_smem();
               named_bar_sync(bar_id, 128);
               if (issuer && p.dbg != 2) {                       // dbg 2 (measurement aid): no stores
-                tma_store_2d(&p.tma_c, gbuf, n0, m_blk * T::BM);
-                tma_store_2d(&p.tma_c, gbuf + 16384, p.swiglu_half + n0, m_blk * T::BM);
+                tma_store_2d(&p.tma_c, sbuf, n0, m_blk * T::BM);
+                tma_store_2d(&p.tma_c, sbuf + 16384, p.swiglu_half + n0, m_blk * T::BM);
                 bulk_commit_group();
               }
             }
@@ -864,6 +871,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
 using namespace nvit;
 
 static int g_force_cg = 0;  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
+static int g_swiglu_cg = 2; // CTA-group mode of the gate GEMM under the auto policy (nvit_gemm_swiglu_cta_group)
 static int g_dbg = 0;       // see GemmParams::dbg
 
 extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
@@ -900,9 +908,12 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
   p.dbg = g_dbg;
   // CTA pairs (256-row tiles, cta_group::2) pay off for long reductions and fp32 outputs (wgrad, accumulating dgrad);
   // MEASURED on the nViT-B/16 shapes, single-CTA 128-row tiles are a few percent faster for bf16 outputs with
-  // K < 2048 (qkv / att_c_proj forward, the gate GEMM, mlp_c_proj dgrad).  nvit_gemm_force_cta_group pins either mode.
+  // K < 2048 (qkv / att_c_proj forward, plain mlp_c_proj dgrad).  The two gate GEMMs (swiglu forward, gate backward) have
+  // epilogue-heavy tiles and run as pairs (MEASURED in situ: 49.0 / 49.6 vs 49.4 / 50.2 ms per step for the forward one).
+  // nvit_gemm_force_cta_group pins either mode.
   const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128 && (out_f32 || K >= 2048));
   if (swiglu_half > 0) {
+    const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128 && g_swiglu_cg == 2);
     NVIT_REQUIRE(N == swiglu_half, "nvit_gemm_bf16: swiglu needs N == F");
     NVIT_REQUIRE(!a_mn_major && !b_mn_major && !out_f32 && !accumulate && splits <= 1 && !bias && !rowadd,
                  "nvit_gemm_bf16: swiglu supports K-major operands, bf16 output and the colscale epilogue only");
@@ -960,6 +971,12 @@ extern "C" int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_
   const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128);
   if (cg2) return launch_gemm<256, false, true, false, true, true>(p, dY, W, ld_dy, ld_w, st);
   return launch_gemm<256, false, true, false, false, true>(p, dY, W, ld_dy, ld_w, st);
+}
+
+extern "C" int nvit_gemm_swiglu_cta_group(int mode) {   // benchmarking hook: 1 or 2 (default 2)
+  NVIT_REQUIRE(mode == 1 || mode == 2, "nvit_gemm_swiglu_cta_group: mode must be 1 or 2");
+  g_swiglu_cg = mode;
+  return NVIT_OK;
 }
 
 extern "C" int nvit_gemm_debug(int mode) {   // measurement aid, results are WRONG when non-zero
