@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
       // MEASURED (scripts/gemm_bench.py, nvit_gemm_debug): main loop alone 1555-1700 TFLOP/s; + TMEM reads and conversion
       // -7 %; + staging and barriers -6 %; + the TMA stores themselves -13 % (plain bf16) to -25 % (gate, three outputs).
       // Sending the staged tile out through coalesced LSU stores instead was slower still (qkv 1151 -> 941 TFLOP/s), and
-      // two or three staging buffers per group (at the price of ring stages) changed nothing: the cost follows the
-      // output bytes, not the mechanism.
+      // two or three staging buffers per group (at the price of ring stages) changed nothing, nor did an L2 evict_first
+      // hint on the stores (createpolicy + .L2::cache_hint): the cost follows the output bytes, not the mechanism.
       if constexpr (GATEB) {
         // Backward of x = (u su) * silu(v sv) fused behind dx = dy W (model.py:148-155 backward): the accumulator holds
         // dL/dx for 256 gate columns; this thread combines its row with the raw u, v of the forward pass and emits
