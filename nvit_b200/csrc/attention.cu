@@ -46,6 +46,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// MEASURED: moving every 2nd / 3rd / 4th exponential of the softmax passes from the SFU to a degree-4 polynomial on the
+// FMA pipe (the FlashAttention-4 trade) made both kernels slower (fwd 150 -> 166 / 159 / 157 us, bwd 490 -> 505 / 494 /
+// 496 us): these passes are bound by issue slots and latency, not by ex2 throughput.
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a 128B-swizzled tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
