@@ -126,7 +126,8 @@ int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_raw, const 
  * column reduction over [M, 8C] (model.py:148-151 backward). */
 int nvit_rowdot_div(const float* w, const float* dw, const float* div, float* out, int64_t rows, int64_t cols, void* stream);
 
-/* Benchmarking hook: CTA-group mode (1 or 2, default 2) of the swiglu gate GEMM under the automatic policy. */
+/* Benchmarking hook: CTA-group mode (1 or 2, default 2) of the swiglu gate GEMM under the automatic policy; 11 or 12 set
+ * the mode of the fused gate-backward GEMM. */
 int nvit_gemm_swiglu_cta_group(int mode);
 
 /* Measurement aid: device buffer of 256 int64 receiving clock64() phase marks of the first 8 CTAs of the next attention

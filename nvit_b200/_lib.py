@@ -80,6 +80,9 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_SWIGLU_CTA_GROUP")    # benchmarking hook: CTA-group mode of the gate GEMM
     if mode in ("1", "2"):
         lib.nvit_gemm_swiglu_cta_group(int(mode))
+    mode = os.environ.get("NVIT_GATEB_CTA_GROUP")     # ... and of the fused gate-backward GEMM
+    if mode in ("1", "2"):
+        lib.nvit_gemm_swiglu_cta_group(10 + int(mode))
     mode = os.environ.get("NVIT_GEMM_CTA_GROUP")      # benchmarking hook: pin cta_group::1 or ::2 GEMM tiles
     if mode in ("1", "2"):
         lib.nvit_gemm_force_cta_group(int(mode))
