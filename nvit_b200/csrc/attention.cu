@@ -40,6 +40,10 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -88,6 +92,7 @@ __device__ __forceinline__ float normalize_row(uint8_t* tile, int row, const flo
 
 struct alignas(64) AttnParams {
   CUtensorMap tq, tk, tv, tdo, to;
+  CUtensorMap tdq, tdk, tdv;   // backward outputs: [128 tokens][64] boxes, stored from the (dead) operand tiles
   const __nv_bfloat16 *q, *k, *o, *dout;  // raw rows for the normalisation backward / delta
   __nv_bfloat16 *out, *dq, *dk, *dv;
   const float* sqk;
@@ -339,20 +344,27 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
       tmem_ld_32x32b_x32(t_lane + TMF_O + t.part * 32, r);
       tmem_wait_ld();
       if (qtok < T) {
+        // O leaves through the (dead) Qh rows of this tile: one TMA store per [128 x 64] tile instead of per-thread
+        // 16-byte stores at a 1.5 KB row stride
         const float inv = 1.f / total;
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(t.b) * T + qtok) * p.ldo + t.h * 64 + t.part * 32;
         float o[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(r[e]) * inv;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + 8 * q4) = pack8(o + 8 * q4);
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(sQ + sw128(qtok, t.part * 4 + q4)) = pack8(o + 8 * q4);
         if (t.part == 0) p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + qtok] = (m2 + log2f(total)) * LN2;
       }
     }
     tc_fence_before_sync();
+    fence_proxy_async_smem();
     __syncthreads();
+    if (t.tid == 0) {
+      tma_store_3d(&p.to, sQ + i * 16384, t.h * 64, i * 128, t.b);
+      bulk_commit_group();
+    }
     ATT_MARK(7 + 4 * i);
   }
+  if (t.tid == 0) bulk_wait_group_read<0>();   // the staged O tiles have left shared memory before the CTA retires
 
   if (t.warp == 0) {
     tc_fence_after_sync();
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 192 + 512) * 4 + 64;
+constexpr int ATT_BWD_SMEM = 4 * ATT_TILE_BYTES + ATT_PB_BYTES + 1024 /*align*/ + (4 * 256 + 192 + 1024) * 4 + 64;
 
 // Backward of y = s * x/||x|| for one row, four threads per row, each owning 16 of the 64 channels.  dL/dy sits in TMEM
 // (16 columns at `taddr` for this thread); the unit vector n = x/||x|| is recovered from the normalised bf16 row still
@@ -388,24 +400,27 @@ __device__ __forceinline__ float norm_bwd_load(uint32_t taddr, const uint8_t* ti
   }
   return dot;
 }
-__device__ __forceinline__ void norm_bwd_store(const float (&g)[16], const float (&n)[16], float dot, float inv, __nv_bfloat16* dst) {
+// The backward outputs leave through shared memory: every thread writes its 16 channels (two 16-byte chunks) of its row
+// into a dead 128B-swizzled operand tile and one TMA store ships the [128 x 64] tile (rows >= T are clipped by the map).
+// MEASURED: per-thread 16-byte global stores at a 1.5 KB row stride (32 sectors per warp instruction) made the dQ epilogue
+// 4.9 k cycles long.
+__device__ __forceinline__ void norm_bwd_store(const float (&g)[16], const float (&n)[16], float dot, float inv, uint8_t* tile, int trow,
+                                               int part) {
   float d[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) d[e] = (g[e] - n[e] * dot) * inv;
-  *reinterpret_cast<uint4*>(dst) = pack8(d);
-  *reinterpret_cast<uint4*>(dst + 8) = pack8(d + 8);
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part)) = pack8(d);
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part + 1)) = pack8(d + 8);
 }
-__device__ __forceinline__ void tmem_row16_to_bf16(uint32_t taddr, __nv_bfloat16* dst, bool valid) {
+__device__ __forceinline__ void tmem_row16_to_tile(uint32_t taddr, uint8_t* tile, int trow, int part) {
   uint32_t r[16];
   tmem_ld_32x32b_x16(taddr, r);
   tmem_wait_ld();
-  if (valid) {
-    float g[16];
+  float g[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) g[e] = __uint_as_float(r[e]);
-    *reinterpret_cast<uint4*>(dst) = pack8(g);
-    *reinterpret_cast<uint4*>(dst + 8) = pack8(g + 8);
-  }
+  for (int e = 0; e < 16; ++e) g[e] = __uint_as_float(r[e]);
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part)) = pack8(g);
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part + 1)) = pack8(g + 8);
 }
 
 // Sum 16 per-lane partials over the 32 lanes of a warp by recursive halving and add them to s_out[16].
@@ -441,8 +456,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   float* s_scale = s_invk + 256;                               // [64]
   float* s_dsqk = s_scale + 64;                                // [64]
   float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
-  float* s_dot = s_rscale + 64;                                // [4][128] partial row dots of the normalisation backward
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dot + 512);   // q, k tiles
+  float* s_dot = s_rscale + 64;                                // [2][4][128] partial row dots of the normalisation backward
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_dot + 1024);   // q, k tiles
   uint64_t* bar_mma = bar_tma + 1;
   uint64_t* bar_tma2 = bar_mma + 1;                                // v, dO, O tiles
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tma2 + 1);
@@ -481,6 +496,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E : 0.f;
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
+    s_delta[r] = 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -489,14 +505,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   ATT_MARK(1);
   mbar_wait(bar_tma, 0);
   ATT_MARK(2);
-  if (has_norm) {
-    for (int j = t.tid; j < 2 * T; j += ATT_THREADS) {
-      if (j < T) s_invq[j] = normalize_row(sQ, j, s_scale);
-      else s_invk[j - T] = normalize_row(sK, j - T, s_scale);
+  // One pool of row jobs over all threads: 2T normalisations (q rows, then k rows) followed by T delta rows
+  // (delta = rowsum(dO * O) from the shared tiles; O parks in the P buffer).  With T = 196 the threads beyond the 392
+  // normalisation rows start on delta at once, so the second load group is consumed as it lands.
+  {
+    const int njobs = (has_norm ? 2 * T : 0) + T, base = has_norm ? 2 * T : 0;
+    bool waited2 = false;
+    for (int j = t.tid; j < njobs; j += ATT_THREADS) {
+      if (j < base) {
+        if (j < T) s_invq[j] = normalize_row(sQ, j, s_scale);
+        else s_invk[j - T] = normalize_row(sK, j - T, s_scale);
+      } else {
+        if (!waited2) { mbar_wait(bar_tma2, 0); waited2 = true; }
+        const int r = j - base;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a[8], g[8];
+          unpack8(*reinterpret_cast<const uint4*>(sP + sw128(r, c)), a);
+          unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, c)), g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d += a[e] * g[e];
+        }
+        s_delta[r] = d;
+      }
     }
   }
+  mbar_wait(bar_tma2, 0);      // every thread observes the second load group before it touches v / dO / the P buffer
+  // No clearing of the P buffer: kv rows >= T and q columns >= T of P^T are written as zeros by the P pass, and whatever
+  // else lies beyond column TP only reaches accumulator rows (q >= TP) that are never read.
   fence_proxy_async_smem();
   __syncthreads();
+  ATT_MARK(3);
 
   const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
@@ -509,30 +549,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
 
   constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
-  // ---- S^T_0 = Kh_0 Qh^T goes to the tensor pipe; delta = rowsum(dO * O) is computed from the shared tiles meanwhile
+  // ---- S^T_0 = Kh_0 Qh^T
   if (t.warp == 0) {
     tc_fence_after_sync();
     mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
     mma_commit(bar_mma);
   }
-  mbar_wait(bar_tma2, 0);
-  if (t.tid < 256) {
-    const int r = t.tid;
-    float d = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float a[8], g[8];
-      unpack8(*reinterpret_cast<const uint4*>(sP + sw128(r, c)), a);    // rows >= T are zero-filled by the TMA
-      unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, c)), g);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) d += a[e] * g[e];
-    }
-    s_delta[r] = d;
-  }
-  // No clearing of the P buffer: kv rows >= T and q columns >= T of P^T are written as zeros by the P pass, and whatever
-  // else lies beyond column TP only reaches accumulator rows (q >= TP) that are never read.
-  __syncthreads();
-  ATT_MARK(3);
 
   for (int j = 0; j < p.nK; ++j) {
     const int kv = j * 128 + t.row;
@@ -622,52 +644,72 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + (j + 1) * 16384, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
       mma_commit(bar_mma);
     }
-    // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both; dV_j is complete already and is
-    // stored while the tensor pipe works on dK/dQ
+    // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both.  dV_j is complete already and is staged
+    // (in the V_j rows, dead since dP^T) while the tensor pipe works on dK/dQ; dK_j replaces the K_j rows in place.
     {
-      const int kvc = kv_ok ? kv : 0;
-      const long long grow = static_cast<long long>(t.b) * T + kvc;
-      tmem_row16_to_bf16(t_lane + TM_DV + t.part * 16, p.dv + grow * p.lddv + t.h * 64 + t.part * 16, kv_ok);
+      tmem_row16_to_tile(t_lane + TM_DV + t.part * 16, sV + j * 16384, t.row, t.part);
       mbar_wait(bar_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after_sync();
       ATT_MARK(8 + 8 * j);
       if (has_norm) {
         float g[16], n[16];
-        s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DK + t.part * 16, sK, kvc, t.part, s_scale, s_rscale, g, n, dacc, kv_ok);
+        s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DK + t.part * 16, sK, kv_ok ? kv : 0, t.part, s_scale, s_rscale, g, n, dacc, kv_ok);
         __syncthreads();
         const float dot = (s_dot[t.row] + s_dot[128 + t.row]) + (s_dot[256 + t.row] + s_dot[384 + t.row]);
-        if (kv_ok) norm_bwd_store(g, n, dot, s_invk[kvc], p.dk + grow * p.lddk + t.h * 64 + t.part * 16);
+        if (kv_ok) norm_bwd_store(g, n, dot, s_invk[kv], sK, kv, t.part);
       } else {
-        tmem_row16_to_bf16(t_lane + TM_DK + t.part * 16, p.dk + grow * p.lddk + t.h * 64 + t.part * 16, kv_ok);
+        tmem_row16_to_tile(t_lane + TM_DK + t.part * 16, sK + j * 16384, t.row, t.part);
       }
     }
     tc_fence_before_sync();
+    fence_proxy_async_smem();
     __syncthreads();
+    if (t.tid == 0) {
+      tma_store_3d(&p.tdv, sV + j * 16384, t.h * 64, j * 128, t.b);
+      tma_store_3d(&p.tdk, sK + j * 16384, t.h * 64, j * 128, t.b);
+      bulk_commit_group();
+    }
     ATT_MARK(9 + 8 * j);
   }
 
-  // ---- dQ rows, one 128-row q tile at a time, 16 channels per thread
-  for (int m = 0; m < p.nQ; ++m) {
-    const int qi = m * 128 + t.row;
-    const bool ok = qi < T;
-    const int qc = ok ? qi : 0;
-    const long long grow = static_cast<long long>(t.b) * T + qc;
-    if (has_norm) {
-      float g[16], n[16];
-      s_dot[t.part * 128 + t.row] = norm_bwd_load(t_lane + TM_DQ + 64 * m + t.part * 16, sQ, qc, t.part, s_scale, s_rscale, g, n, dacc, ok);
-      __syncthreads();
-      const float dot = (s_dot[t.row] + s_dot[128 + t.row]) + (s_dot[256 + t.row] + s_dot[384 + t.row]);
-      if (ok) norm_bwd_store(g, n, dot, s_invq[qc], p.dq + grow * p.lddq + t.h * 64 + t.part * 16);
-      __syncthreads();
-    } else {
-      tmem_row16_to_bf16(t_lane + TM_DQ + 64 * m + t.part * 16, p.dq + grow * p.lddq + t.h * 64 + t.part * 16, ok);
+  // ---- dQ rows: both 128-row q tiles in one pass (loads and partial dots for both, ONE exchange), staged in place over Qh
+  if (has_norm) {
+    float g[2][16], n[2][16];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (m < p.nQ) {
+        const int qi = m * 128 + t.row;
+        const bool ok = qi < T;
+        s_dot[m * 512 + t.part * 128 + t.row] =
+            norm_bwd_load(t_lane + TM_DQ + 64 * m + t.part * 16, sQ, ok ? qi : 0, t.part, s_scale, s_rscale, g[m], n[m], dacc, ok);
+      }
     }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (m < p.nQ) {
+        const int qi = m * 128 + t.row;
+        if (qi < T) {
+          const float* sd = s_dot + m * 512;
+          const float dot = (sd[t.row] + sd[128 + t.row]) + (sd[256 + t.row] + sd[384 + t.row]);
+          norm_bwd_store(g[m], n[m], dot, s_invq[qi], sQ, qi, t.part);
+        }
+      }
+    }
+  } else {
+    for (int m = 0; m < p.nQ; ++m) tmem_row16_to_tile(t_lane + TM_DQ + 64 * m + t.part * 16, sQ + m * 16384, t.row, t.part);
   }
+  fence_proxy_async_smem();
   ATT_MARK(24);
   if (has_norm) reduce16_to_smem(dacc, s_dsqk + t.part * 16, t.lane);
   tc_fence_before_sync();
   __syncthreads();
+  if (t.tid == 0) {
+    for (int m = 0; m < p.nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, t.h * 64, m * 128, t.b);
+    bulk_commit_group();
+    bulk_wait_group_read<0>();      // all staged tiles have left shared memory before the CTA retires
+  }
   if (has_norm && t.tid < 64) atomicAdd(p.dsqk + t.h * 64 + t.tid, s_dsqk[t.tid] * p.sqk_mul);
   ATT_MARK(25);
   if (t.warp == 0) {
@@ -676,10 +718,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
 }
 
-static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int T) {
+static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int T, int box_rows = ATT_ROWS) {
   const uint64_t dims[3] = {static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
   const uint64_t strides[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * T};
-  const uint32_t box[3] = {64, ATT_ROWS, 1};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return make_tmap_bf16(m, base, 3, dims, strides, box);
 }
 
@@ -712,6 +754,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   if ((rc = make_head_tmap(&p.tq, q, ldq, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
+  if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T, 128))) return rc;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
@@ -752,6 +795,9 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tdo, dout, ldo, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T))) return rc;
+  if ((rc = make_head_tmap(&p.tdq, dq, lddq, (int)B, (int)H, (int)T, 128))) return rc;
+  if ((rc = make_head_tmap(&p.tdk, dk, lddk, (int)B, (int)H, (int)T, 128))) return rc;
+  if ((rc = make_head_tmap(&p.tdv, dv, lddv, (int)B, (int)H, (int)T, 128))) return rc;
   p.q = static_cast<const __nv_bfloat16*>(q);
   p.k = static_cast<const __nv_bfloat16*>(k);
   p.o = static_cast<const __nv_bfloat16*>(out);
