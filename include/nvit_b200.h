@@ -105,14 +105,28 @@ int nvit_swiglu_bwd(const void* dx_bf16, const void* uv_bf16, const float* suv, 
  *   qh = s * N_D(q), kh = s * N_D(k) with s = sqk * sqk_mul ([H*D]; sqk NULL -> no normalization, s = 1),
  *   out[B*T, H*D] = softmax(scale * qh kh^T) v  (non-causal).  lse [B,H,T] (fp32) is saved for backward.
  *   bwd: dq, dk, dv (bf16, same layouts) and dsqk[H*D] += (w.r.t. stored sqk).
+ *   inv_q / inv_k (both or neither; need sqk): q and k are ALREADY qh / kh (written by nvit_gemm_qknorm) and
+ *   inv_*[token * ld_inv_* + h] = 1 / ||x|| of the raw projection: the kernels skip their normalisation pass; dq / dk are
+ *   still the gradients w.r.t. the raw projections.
  */
 int nvit_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                        const float* sqk, float sqk_mul, float scale, void* out, int64_t ldo, float* lse, int64_t B,
-                       int64_t H, int64_t T, int64_t D, void* stream);
+                       int64_t H, int64_t T, int64_t D, const float* inv_q, const float* inv_k, int64_t ld_inv_q,
+                       int64_t ld_inv_k, void* stream);
 int nvit_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                        const float* sqk, float sqk_mul, float scale, const void* out, const void* dout, int64_t ldo,
                        const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
-                       float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, void* stream);
+                       float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, const float* inv_q, const float* inv_k,
+                       int64_t ld_inv_q, int64_t ld_inv_k, void* stream);
+
+/* q/k/v projection with the unit-norm treatment of nViT in the epilogue (model.py:99-119, 226-249):
+ *   C[M,N] = A[M,K] B[N,K]^T (+ bias);  for columns < norm_cols every 64-column head h of a row becomes
+ *   scale[col % scale_period] * scale_mul * x / ||x||  and  inv_out[row * ld_inv + col / 64] = 1 / ||x||  (0 for a zero row);
+ * columns >= norm_cols (the value projection) are stored as they are.  The attention kernels then take the normalised q/k
+ * and the inverse norms (inv_q / inv_k arguments) and skip their own normalisation pass. */
+int nvit_gemm_qknorm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                     const float* bias, const float* scale, float scale_mul, int64_t scale_period, int64_t norm_cols, float* inv_out,
+                     int64_t ld_inv, void* stream);
 
 /* Gate backward fused behind the mlp_c_proj / out_proj dgrad GEMM (model.py:152-155, 260-262 backward):
  *   dx = dY[M,K] W[K,F]            (W = the projection weight as it lies, [K, F] bf16; dx stays on chip, fp32)

@@ -33,9 +33,10 @@ SIGNATURES = {
     "nvit_add_skipnorm_bwd": [P, P, P, P, P, P, P, P, P, I64, I64, P],
     "nvit_swiglu_fwd": [P, P, F32, P, I64, I64, P],
     "nvit_swiglu_bwd": [P, P, P, F32, P, P, I64, I64, P],
-    "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P],
-    "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P],
+    "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P, P, I64, I64, P],
+    "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P, P, I64, I64, P],
     "nvit_attention_debug": [P],
+    "nvit_gemm_qknorm": [P, P, P, I64, I64, I64, I64, I64, I64, P, P, F32, I64, I64, P, I64, P],
     "nvit_gemm_gate_bwd": [P, P, P, P, F32, P, I64, I64, I64, I64, I64, I64, I64, P],
     "nvit_rowdot_div": [P, P, P, P, I64, I64, P],
     "nvit_split_bf16": [P, P, P, I64, P],

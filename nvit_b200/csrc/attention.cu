@@ -96,6 +96,8 @@ struct alignas(64) AttnParams {
   const __nv_bfloat16 *q, *k, *o, *dout;  // raw rows for the normalisation backward / delta
   __nv_bfloat16 *out, *dq, *dk, *dv;
   const float* sqk;
+  const float *inv_q, *inv_k;   // non-null: q / k arrive normalised (nvit_gemm_qknorm) with 1/||x|| at [token * ld_inv + head]
+  long long ld_inv_q, ld_inv_k;
   float* lse;
   float* dsqk;
   long long ldq, ldk, ldo, lddq, lddk, lddv;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
   mbar_wait(bar_tma, 0);
   ATT_MARK(2);
 
-  if (has_norm) {
+  if (has_norm && p.inv_q == nullptr) {
     for (int j = t.tid; j < 2 * T; j += ATT_FWD_THREADS) {
       if (j < T) normalize_row(sQ, j, s_scale);
       else normalize_row(sK, j - T, s_scale);
@@ -494,8 +496,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   if (t.tid >= 256) {
     const int r = t.tid - 256;  // one thread per (padded) token row
     s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(t.b) * p.H + t.h) * T + r] * LOG2E : 0.f;
-    s_invq[r] = 0.f;
-    s_invk[r] = 0.f;
+    // q / k normalised by the projection GEMM: only their inverse norms are needed, fetched under the tile loads
+    const bool pre = p.inv_q != nullptr && r < T;
+    s_invq[r] = pre ? p.inv_q[(static_cast<long long>(t.b) * T + r) * p.ld_inv_q + t.h] : 0.f;
+    s_invk[r] = pre ? p.inv_k[(static_cast<long long>(t.b) * T + r) * p.ld_inv_k + t.h] : 0.f;
     s_delta[r] = 0.f;
   }
   tc_fence_before_sync();
@@ -505,11 +509,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   ATT_MARK(1);
   mbar_wait(bar_tma, 0);
   ATT_MARK(2);
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
+  const float sl2 = p.scale * LOG2E;
+  const int nks_q = TP >> 4;  // k-steps over the q axis
+  uint32_t mma_phase = 0;
+  float dacc[16];   // dL/d(sqk) partials for this thread's 16 channels
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
+  constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+  // S^T_0 = Kh_0 Qh^T: straight away when q / k need no normalisation here (already normalised by the projection GEMM, or
+  // the un-normalised model), otherwise behind the normalisation jobs
+  const bool qk_ready = !has_norm || p.inv_q != nullptr;
+  auto issue_st0 = [&]() {
+    if (t.warp == 0) {
+      tc_fence_after_sync();
+      mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
+      mma_commit(bar_mma);
+    }
+  };
+  if (qk_ready) issue_st0();
   // One pool of row jobs over all threads: 2T normalisations (q rows, then k rows) followed by T delta rows
   // (delta = rowsum(dO * O) from the shared tiles; O parks in the P buffer).  With T = 196 the threads beyond the 392
   // normalisation rows start on delta at once, so the second load group is consumed as it lands.
   {
-    const int njobs = (has_norm ? 2 * T : 0) + T, base = has_norm ? 2 * T : 0;
+    const int base = (has_norm && p.inv_q == nullptr) ? 2 * T : 0, njobs = base + T;
     bool waited2 = false;
     for (int j = t.tid; j < njobs; j += ATT_THREADS) {
       if (j < base) {
@@ -537,24 +561,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   fence_proxy_async_smem();
   __syncthreads();
   ATT_MARK(3);
-
-  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sP_a = smem_u32(sP);
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(t.wq * 32) << 16);
-  const float sl2 = p.scale * LOG2E;
-  const int nks_q = TP >> 4;  // k-steps over the q axis
-  uint32_t mma_phase = 0;
-  float dacc[16];   // dL/d(sqk) partials for this thread's 16 channels
-#pragma unroll
-  for (int i = 0; i < 16; ++i) dacc[i] = 0.f;
-
-  constexpr uint32_t TM_S = 0, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
-
-  // ---- S^T_0 = Kh_0 Qh^T
-  if (t.warp == 0) {
-    tc_fence_after_sync();
-    mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a, 16, 1024), 2, umma_smem_desc(sQ_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
-    mma_commit(bar_mma);
-  }
+  if (!qk_ready) issue_st0();
 
   for (int j = 0; j < p.nK; ++j) {
     const int kv = j * 128 + t.row;
@@ -744,8 +751,10 @@ extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement 
 
 extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                                   const float* sqk, float sqk_mul, float scale, void* out, int64_t ldo, float* lse, int64_t B,
-                                  int64_t H, int64_t T, int64_t D, void* stream) {
+                                  int64_t H, int64_t T, int64_t D, const float* inv_q, const float* inv_k, int64_t ld_inv_q,
+                                  int64_t ld_inv_k, void* stream) {
   NVIT_REQUIRE(q && k && v && out && lse, "nvit_attention_fwd: null argument");
+  NVIT_REQUIRE((inv_q == nullptr) == (inv_k == nullptr) && (!inv_q || sqk), "nvit_attention_fwd: inv_q / inv_k go together and need sqk");
   int rc = attn_check("nvit_attention_fwd", B, H, T, D);
   if (rc) return rc;
   NVIT_REQUIRE((ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "nvit_attention_fwd: out must be 16-byte aligned rows");
@@ -758,6 +767,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
+  p.inv_q = inv_q; p.inv_k = inv_k; p.ld_inv_q = ld_inv_q; p.ld_inv_k = ld_inv_k;
   p.sqk = sqk;
   p.sqk_mul = sqk_mul;
   p.scale = scale;
@@ -779,8 +789,10 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
 extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                                   const float* sqk, float sqk_mul, float scale, const void* out, const void* dout, int64_t ldo,
                                   const float* lse, void* dq, void* dk, void* dv, int64_t lddq, int64_t lddk, int64_t lddv,
-                                  float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, void* stream) {
+                                  float* dsqk_accum, int64_t B, int64_t H, int64_t T, int64_t D, const float* inv_q, const float* inv_k,
+                                  int64_t ld_inv_q, int64_t ld_inv_k, void* stream) {
   NVIT_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv, "nvit_attention_bwd: null argument");
+  NVIT_REQUIRE((inv_q == nullptr) == (inv_k == nullptr) && (!inv_q || sqk), "nvit_attention_bwd: inv_q / inv_k go together and need sqk");
   NVIT_REQUIRE((sqk == nullptr) == (dsqk_accum == nullptr), "nvit_attention_bwd: sqk and dsqk go together");
   int rc = attn_check("nvit_attention_bwd", B, H, T, D);
   if (rc) return rc;
@@ -807,6 +819,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   p.dv = static_cast<__nv_bfloat16*>(dv);
   p.ldq = ldq; p.ldk = ldk; p.ldo = ldo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.lse = const_cast<float*>(lse);
+  p.inv_q = inv_q; p.inv_k = inv_k; p.ld_inv_q = ld_inv_q; p.ld_inv_k = ld_inv_k;
   p.sqk = sqk;
   p.dsqk = dsqk_accum;
   p.sqk_mul = sqk_mul;

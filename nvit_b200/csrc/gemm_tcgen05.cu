@@ -38,6 +38,11 @@ struct alignas(64) GemmParams {
   const float* rowadd;    // [rowadd_period, N] or null
   const __nv_bfloat16* gate_uv;   // GATEB: raw u|v of the forward pass, [M, 2F] bf16 (F = swiglu_half)
   long long ld_uv;
+  // unit-norm q/k epilogue (nvit_gemm_qknorm): output columns [0, qk_cols) are normalised per 64-column head and scaled
+  // by colscale[col % qk_period] * colscale_mul; 1/||x|| goes to qk_inv[row * ld_inv + col / 64]
+  int qk_cols, qk_period;
+  float* qk_inv;
+  long long ld_inv;
   long long ldc, ldc2;
   int M, N, K;
   int out_f32, accumulate, atomic;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             s_vec[et] = __ldg(p.colscale + j) * p.colscale_mul;
             s_vec[256 + et] = __ldg(p.colscale + p.swiglu_half + j) * p.colscale_mul;
           } else if (SWIGLU || et < BN) {
-            s_vec[et] = p.colscale ? __ldg(p.colscale + j) * p.colscale_mul : 1.f;
+            s_vec[et] = p.colscale ? __ldg(p.colscale + (p.qk_cols > 0 ? j % p.qk_period : j)) * p.colscale_mul : 1.f;
             s_vec[256 + et] = p.bias ? __ldg(p.bias + j) : 0.f;
           }
         }
@@ -524,6 +529,32 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
             const int n0 = n_blk * BN + c * 64;
             if (n0 >= p.N) continue;
             uint32_t o[32];
+            if (p.qk_cols > 0) {
+              // unit-norm q/k (model.py:108-119): this chunk is one head of one token; the whole row segment is in registers
+              const bool normed = n0 < p.qk_cols;      // uniform over the group
+              float ss = 0.f;
+#pragma unroll
+              for (int i = 0; i < 64; ++i) {
+                float v = __uint_as_float(i < 32 ? r[i] : r2[i - 32]) + (p.bias ? s_vec[256 + c * 64 + i] : 0.f);
+                if (i < 32) r[i] = __float_as_uint(v); else r2[i - 32] = __float_as_uint(v);
+                ss += v * v;
+              }
+              const float inv = (normed && ss > 0.f) ? rsqrtf(ss) : (normed ? 0.f : 1.f);
+#pragma unroll
+              for (int i = 0; i < 64; i += 2) {
+                float v0 = __uint_as_float(i < 32 ? r[i] : r2[i - 32]) * inv;
+                float v1 = __uint_as_float(i < 32 ? r[i + 1] : r2[i - 31]) * inv;
+                if (normed) {
+                  const float2 cs = *reinterpret_cast<const float2*>(s_vec + c * 64 + i);
+                  v0 *= cs.x;
+                  v1 *= cs.y;
+                }
+                o[i >> 1] = pack_bf16(v0, v1);
+              }
+              if (normed && row < p.M) p.qk_inv[static_cast<long long>(row) * p.ld_inv + (n0 >> 6)] = inv;
+              stage_store(o, &p.tma_c, n0, false);
+              continue;
+            }
 #pragma unroll
             for (int i = 0; i < 64; i += 2) {
               float v0 = __uint_as_float(i < 32 ? r[i] : r2[i - 32]);
@@ -951,6 +982,37 @@ extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf
     case 6: return launch_gemm<256, true, false, false, false>(p, A, B, lda, ldb, st);
     default: return launch_gemm<256, true, true, false, false>(p, A, B, lda, ldb, st);
   }
+}
+
+// C = A B^T (+bias) with the unit-norm q/k treatment of nViT applied in the epilogue (see include/nvit_b200.h).
+extern "C" int nvit_gemm_qknorm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                int64_t ldc, const float* bias, const float* scale, float scale_mul, int64_t scale_period,
+                                int64_t norm_cols, float* inv_out, int64_t ld_inv, void* stream) {
+  NVIT_REQUIRE(A && B && C && scale && inv_out, "nvit_gemm_qknorm: null operand");
+  NVIT_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "nvit_gemm_qknorm: bad sizes");
+  NVIT_REQUIRE((N % 64) == 0 && (norm_cols % 64) == 0 && norm_cols > 0 && norm_cols <= N && scale_period > 0 && (scale_period % 64) == 0,
+               "nvit_gemm_qknorm: N, norm_cols and scale_period must be multiples of the head size 64");
+  NVIT_REQUIRE(ld_inv >= norm_cols / 64, "nvit_gemm_qknorm: inv_out rows too short");
+  NVIT_REQUIRE(tma_addressable(C, ldc, 2), "nvit_gemm_qknorm: C must be 16-byte aligned with a 16-byte row pitch");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C;
+  p.ldc = ldc;
+  p.bias = bias;
+  p.colscale = scale;
+  p.colscale_mul = scale_mul;
+  p.qk_cols = (int)norm_cols;
+  p.qk_period = (int)scale_period;
+  p.qk_inv = inv_out;
+  p.ld_inv = ld_inv;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.rowadd_period = 1;
+  p.splits = 1;
+  p.dbg = g_dbg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128 && K >= 2048);
+  if (cg2) return launch_gemm<256, false, false, false, true>(p, A, B, lda, ldb, st);
+  return launch_gemm<256, false, false, false, false>(p, A, B, lda, ldb, st);
 }
 
 // d(uv_raw)[M, 2F] = backward of x = (u su) silu(v sv) applied to dx = dY W, dx never leaving the SM.

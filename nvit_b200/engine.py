@@ -52,6 +52,9 @@ class Engine:
         self.probe = None               # list to receive (start, end) CUDA event pairs around the c_fc GEMM (bench.py)
         # SiLU-gate backward inside the dgrad GEMM epilogue (nvit_gemm_gate_bwd); NVIT_FUSE_GATE_BWD=0 keeps the two-kernel path
         self.fuse_gate_bwd = os.environ.get("NVIT_FUSE_GATE_BWD", "1") != "0"
+        # q/k normalised and sqk-scaled in the projection GEMM's epilogue (nvit_gemm_qknorm) instead of inside the attention
+        # kernels; NVIT_FUSE_QKNORM=0 keeps the in-kernel normalisation
+        self.fuse_qknorm = os.environ.get("NVIT_FUSE_QKNORM", "1") != "0"
 
     # ------------------------------------------------------------------------------------------ parameter layout
     def invalidate(self):
@@ -244,7 +247,8 @@ class Engine:
         a = {
             "A_l": e(M, Kl), "A_g": e(M, Kg), "local32": e(M, C, dtype=F32), "local16": e(M, C), "global16": e(M, C),
             "ca": [{"q": e(M, C), "kv": e(M, 2 * C), "att": e(M, C), "lse": e(B, H, T, dtype=F32), "uv": e(M, 2 * C),
-                    "x": e(M, C), "o": e(M, C)} for _ in range(3 if cfg.use_kohonen else 1)],
+                    "x": e(M, C), "o": e(M, C), "inv": e(M, 2 * H, dtype=F32)} for _ in range(3 if cfg.use_kohonen else 1)],
+            "qk_inv": [e(M, 2 * H, dtype=F32) for _ in range(L)],
             "h32": [e(M, C, dtype=F32) for _ in range(L + 1)], "h16": [e(M, C) for _ in range(L + 1)],
             "qkv": [e(M, 3 * C) for _ in range(L)], "att": [e(M, C) for _ in range(L)],
             "lse": [e(B, H, T, dtype=F32) for _ in range(L)], "h_att": [e(M, C) for _ in range(L)],
@@ -328,10 +332,14 @@ class Engine:
         # ---- transformer blocks + norm_skip (model.py:92-169, 84-87, 450-452)
         for i in range(L):
             b = f"transformer.h.{i}."
-            ops.linear_fwd(a["h16"][i], w16(b + "query.weight", rows=3 * C), a["qkv"][i],
-                           bias=self._cat_bias(b + "query.bias", 3 * C) if bias else None)
-            qkv = a["qkv"][i]
-            ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], p(b + "sqk"), smul, att_scale, a["att"][i], a["lse"][i], B, H, T)
+            qkv, inv = a["qkv"][i], (a["qk_inv"][i] if self.fuse_qknorm else None)
+            qkv_bias = self._cat_bias(b + "query.bias", 3 * C) if bias else None
+            if inv is not None:
+                ops.gemm_qknorm(a["h16"][i], w16(b + "query.weight", rows=3 * C), qkv, p(b + "sqk"), smul, C, 2 * C, inv, bias=qkv_bias)
+            else:
+                ops.linear_fwd(a["h16"][i], w16(b + "query.weight", rows=3 * C), qkv, bias=qkv_bias)
+            ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], p(b + "sqk"), smul, att_scale, a["att"][i], a["lse"][i], B, H, T,
+                              inv_q=None if inv is None else inv[:, :H], inv_k=None if inv is None else inv[:, H:])
             ops.linear_fwd(a["att"][i], w16(b + "att_c_proj.weight"), a["h_att"][i], bias=p(b + "att_c_proj.bias") if bias else None)
             ops.residual_fwd(a["h32"][i], a["h_att"][i], p(b + "attn_alpha"), amul, a["h1_32"][i], a["h1_16"][i])
             self._gated_fwd(a["h1_16"][i], w16(b + "c_fc.weight"), p(b + "c_fc.bias") if bias else None, p(b + "suv"), math.sqrt(C),
@@ -361,11 +369,18 @@ class Engine:
         C, H = cfg.n_embd, cfg.n_head
         p, w16, bias = self.p, self.w16, cfg.bias
         ca = "cross_attention."
-        ops.linear_fwd(loc16, w16(ca + "q_local.weight"), s["q"], bias=p(ca + "q_local.bias") if bias else None)
-        ops.linear_fwd(glob16, w16(ca + "k_global.weight", rows=2 * C), s["kv"],
-                       bias=self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None)
-        ops.attention_fwd(s["q"], s["kv"][:, :C], s["kv"][:, C:], p(ca + "sqk"), 1.0 / cfg.base_scale, float(C // H) ** 0.5, s["att"],
-                          s["lse"], B, H, T)
+        smul = 1.0 / cfg.base_scale
+        inv = s["inv"] if self.fuse_qknorm else None
+        kv_bias = self._cat_bias(ca + "k_global.bias", 2 * C) if bias else None
+        if inv is not None:
+            ops.gemm_qknorm(loc16, w16(ca + "q_local.weight"), s["q"], p(ca + "sqk"), smul, C, C, inv[:, :H],
+                            bias=p(ca + "q_local.bias") if bias else None)
+            ops.gemm_qknorm(glob16, w16(ca + "k_global.weight", rows=2 * C), s["kv"], p(ca + "sqk"), smul, C, C, inv[:, H:], bias=kv_bias)
+        else:
+            ops.linear_fwd(loc16, w16(ca + "q_local.weight"), s["q"], bias=p(ca + "q_local.bias") if bias else None)
+            ops.linear_fwd(glob16, w16(ca + "k_global.weight", rows=2 * C), s["kv"], bias=kv_bias)
+        ops.attention_fwd(s["q"], s["kv"][:, :C], s["kv"][:, C:], p(ca + "sqk"), smul, float(C // H) ** 0.5, s["att"],
+                          s["lse"], B, H, T, inv_q=None if inv is None else inv[:, :H], inv_k=None if inv is None else inv[:, H:])
         self._gated_fwd(s["att"], w16(ca + "proj.weight"), p(ca + "proj.bias") if bias else None, None, 1.0, s["uv"], s["x"], C)
         ops.linear_fwd(s["x"], w16(ca + "out_proj.weight"), s["o"], bias=p(ca + "out_proj.bias") if bias else None)
         ops.residual_fwd(loc32, s["o"], p(ca + "attn_alpha"), 0.05 / cfg.base_scale, out32, out16)
@@ -523,8 +538,10 @@ class Engine:
                 ops.colsum(dHatt, g(b + "att_c_proj.bias"))
             ops.linear_dgrad(dHatt, w16(b + "att_c_proj.weight"), dAtt)
             qkv, dqkv = a["qkv"][i], a["d_3c"]
+            inv = a["qk_inv"][i] if self.fuse_qknorm else None
             ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], p(b + "sqk"), smul, att_scale, a["att"][i], dAtt, a["lse"][i],
-                              dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], g(b + "sqk"), B, H, T)
+                              dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], g(b + "sqk"), B, H, T,
+                              inv_q=None if inv is None else inv[:, :H], inv_k=None if inv is None else inv[:, H:])
             self._wgrad(dqkv, a["h16"][i], g2d(b + "query.weight", rows=3 * C))
             if bias:
                 ops.colsum(dqkv, self._cat_grad(b + "query.bias", 3 * C))
@@ -582,8 +599,10 @@ class Engine:
         ops.linear_dgrad(duv, w16(ca + "proj.weight"), dAtt)
         dq = a["d_c16b"]
         dkv = a["d_3c"].view(-1)[:M * 2 * C].view(M, 2 * C)
+        inv = s["inv"] if self.fuse_qknorm else None
         ops.attention_bwd(s["q"], s["kv"][:, :C], s["kv"][:, C:], p(ca + "sqk"), 1.0 / cfg.base_scale, float(C // H) ** 0.5, s["att"], dAtt,
-                          s["lse"], dq, dkv[:, :C], dkv[:, C:], g(ca + "sqk"), B, H, T)
+                          s["lse"], dq, dkv[:, :C], dkv[:, C:], g(ca + "sqk"), B, H, T,
+                          inv_q=None if inv is None else inv[:, :H], inv_k=None if inv is None else inv[:, H:])
         self._wgrad(dq, loc16, g2d(ca + "q_local.weight"))
         self._wgrad(dkv, glob16, g2d(ca + "k_global.weight", rows=2 * C))
         if bias:

@@ -65,6 +65,15 @@ def linear_wgrad(dy, x, dw, *, splits=1, accumulate=False):
          accumulate=accumulate)
 
 
+def gemm_qknorm(x, w, out, scale, scale_mul, scale_period, norm_cols, inv, *, bias=None):
+    """out[M,N] = x @ w^T (+bias) with columns [0, norm_cols) normalised per 64-column head and scaled (nvit_gemm_qknorm);
+    inv[M, norm_cols / 64] receives 1/||x||."""
+    M, K = x.shape
+    N = w.shape[0]
+    _lib.call("nvit_gemm_qknorm", _p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), out.stride(0), _p(bias), _p(scale),
+              float(scale_mul), scale_period, norm_cols, _p(inv), inv.stride(0), _stream())
+
+
 def gemm_gate_bwd(dy, w, uv, suv, suv_mul, duv):
     """duv[M, 2F] = gate backward of (dy[M,K] @ w[K,F]) against the saved raw u|v (see nvit_gemm_gate_bwd)."""
     M, K = dy.shape
@@ -135,16 +144,19 @@ def swiglu_bwd(dx, uv, suv, suv_mul, duv, dsuv):
     _lib.call("nvit_swiglu_bwd", _p(dx), _p(uv), _p(suv), float(suv_mul), _p(duv), _p(dsuv), M, F2 // 2, _stream())
 
 
-def attention_fwd(q, k, v, sqk, sqk_mul, scale, out, lse, B, H, T, D=64):
+def attention_fwd(q, k, v, sqk, sqk_mul, scale, out, lse, B, H, T, D=64, inv_q=None, inv_k=None):
+    """inv_q / inv_k ([M, *] fp32 views, head h at column h): q / k are already normalised (gemm_qknorm)."""
     _lib.call("nvit_attention_fwd", _p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(sqk), float(sqk_mul), float(scale),
-              _p(out), out.stride(0), _p(lse), B, H, T, D, _stream())
+              _p(out), out.stride(0), _p(lse), B, H, T, D, _p(inv_q), _p(inv_k), 0 if inv_q is None else inv_q.stride(0),
+              0 if inv_k is None else inv_k.stride(0), _stream())
 
 
-def attention_bwd(q, k, v, sqk, sqk_mul, scale, out, dout, lse, dq, dk, dv, dsqk, B, H, T, D=64):
+def attention_bwd(q, k, v, sqk, sqk_mul, scale, out, dout, lse, dq, dk, dv, dsqk, B, H, T, D=64, inv_q=None, inv_k=None):
     assert out.stride(0) == dout.stride(0)
     _lib.call("nvit_attention_bwd", _p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(sqk), float(sqk_mul), float(scale),
               _p(out), _p(dout), out.stride(0), _p(lse), _p(dq), _p(dk), _p(dv), dq.stride(0), dk.stride(0), dv.stride(0), _p(dsqk),
-              B, H, T, D, _stream())
+              B, H, T, D, _p(inv_q), _p(inv_k), 0 if inv_q is None else inv_q.stride(0), 0 if inv_k is None else inv_k.stride(0),
+              _stream())
 
 
 def im2col(img, out, ksize, stride, pad):

@@ -17,9 +17,11 @@ do = torch.randn(M, C, device=dev, dtype=torch.bfloat16) * 0.1
 dqkv = torch.empty(M, 3 * C, device=dev, dtype=torch.bfloat16)
 dsqk = torch.zeros(C, device=dev)
 buf = torch.zeros(256, dtype=torch.int64, device=dev)
-fwd = lambda: ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.036, 8.0, out, lse, B, H, T)
+inv = torch.rand(M, 2 * H, device=dev) + 0.5 if os.environ.get("PRENORM") == "1" else None    # timing only: values arbitrary
+kw = {} if inv is None else dict(inv_q=inv[:, :H], inv_k=inv[:, H:])
+fwd = lambda: ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.036, 8.0, out, lse, B, H, T, **kw)
 bwd = lambda: ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.036, 8.0, out, do, lse,
-                                dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dsqk, B, H, T)
+                                dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dsqk, B, H, T, **kw)
 for name, f, marks in (("fwd", fwd, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]), ("bwd", bwd, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 24, 25])):
     for _ in range(3):
         f()

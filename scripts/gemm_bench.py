@@ -11,7 +11,7 @@ M = 50176
 SHAPES = [  # name, N, K, kind
     ("qkv fwd", 2304, 768, "fwd"), ("att_c_proj fwd", 768, 768, "fwd"), ("mlp_c_proj fwd", 768, 3072, "fwd"),
     ("c_fc swiglu", 3072, 768, "swiglu"), ("mlp_c_proj dgrad", 3072, 768, "dgrad"), ("c_fc dgrad acc", 768, 6144, "dgrad_acc"),
-    ("c_fc wgrad", 6144, 768, "wgrad"), ("qkv wgrad", 2304, 768, "wgrad"), ("mlp_c_proj dgrad+gate", 3072, 768, "gate_bwd"),
+    ("qkv fwd + qk norm", 2304, 768, "qknorm"), ("c_fc wgrad", 6144, 768, "wgrad"), ("qkv wgrad", 2304, 768, "wgrad"), ("mlp_c_proj dgrad+gate", 3072, 768, "gate_bwd"),
 ]
 
 
@@ -28,6 +28,14 @@ def run(name, N, K, kind, iters=20):
         w = torch.randn(K, N, device=dev, dtype=torch.bfloat16)
         dx = torch.zeros(M, N, device=dev, dtype=torch.float32 if kind == "dgrad_acc" else torch.bfloat16)
         f = lambda: ops.linear_dgrad(dy, w, dx, accumulate=(kind == "dgrad_acc"))
+        flops = 2.0 * M * N * K
+    elif kind == "qknorm":
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        sc = torch.ones(K, device=dev)
+        inv = torch.empty(M, 2 * K // 64, device=dev)
+        f = lambda: ops.gemm_qknorm(x, w, out, sc, 1.0, K, 2 * K, inv)
         flops = 2.0 * M * N * K
     elif kind == "gate_bwd":     # d(uv)[M, 2N] = gate backward of dY[M,K] W[K,N]
         dy = torch.randn(M, K, device=dev, dtype=torch.bfloat16)

@@ -56,7 +56,7 @@ def test_argument_errors_are_reported_not_thrown(lib):
     with pytest.raises(RuntimeError, match="null operand"):
         _lib.call("nvit_gemm_bf16", None, None, None, None, 1, 1, 1, 8, 8, 8, 0, 0, 0, 0, 0, 1, None, None, 1.0, None, 0, 0, None)
     with pytest.raises(RuntimeError, match="head_dim must be 64"):
-        _lib.call("nvit_attention_fwd", 16, 16, 16, 8, 8, 8, None, 1.0, 1.0, 16, 8, 16, 1, 1, 4, 32, None)
+        _lib.call("nvit_attention_fwd", 16, 16, 16, 8, 8, 8, None, 1.0, 1.0, 16, 8, 16, 1, 1, 4, 32, None, None, 0, 0, None)
     with pytest.raises(RuntimeError, match="multiple of 4"):
         _lib.call("nvit_residual_fwd", 16, 16, 16, 1.0, None, None, 16, None, 4, 7, None)
 

@@ -302,6 +302,40 @@ def test_rowdot_div_gives_the_suv_gradient():
     assert float(out[3]) == 0.0 and torch.isfinite(out).all()
 
 
+# ---------------------------------------------------------------------------------------------- q/k normalisation in the GEMM
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,C,K,norm_cols,with_bias", [(515, 192, 192, 128, False), (1000, 768, 768, 512, True), (300, 64, 64, 64, False),
+                                                       (196, 2304, 768, 1536, False)])
+def test_gemm_qknorm(M, C, K, norm_cols, with_bias, cta_group):
+    """nvit_gemm_qknorm: projection + per-head unit norm + sqk scale in the epilogue, 1/||x|| as a side output."""
+    from nvit_b200 import _lib
+    _lib.call("nvit_gemm_force_cta_group", cta_group)
+    try:
+        N = C
+        period = 64 * max(1, norm_cols // 128)
+        x = randn(M, K, seed=60, dtype=torch.bfloat16)
+        w = (randn(N, K, seed=61) * K ** -0.5).to(torch.bfloat16)
+        bias = 0.1 * randn(N, seed=62) if with_bias else None
+        scale = 1.0 + 0.3 * randn(period, seed=63)
+        mul = 1.7
+        y = x.float() @ w.float().t()
+        if bias is not None:
+            y = y + bias
+        heads = y[:, :norm_cols].reshape(M, norm_cols // 64, 64)
+        nrm = heads.norm(dim=-1, keepdim=True)
+        s_full = (scale * mul).repeat(norm_cols // period).view(1, norm_cols // 64, 64)
+        ref = torch.cat([(heads / nrm * s_full).reshape(M, norm_cols), y[:, norm_cols:]], dim=1)
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        inv = torch.full((M, norm_cols // 64 + 3), float("nan"), device=DEV)
+        ops.gemm_qknorm(x, w, out, scale, mul, period, norm_cols, inv, bias=bias)
+        torch.cuda.synchronize()
+        assert rel(out, ref) < 6e-3, rel(out, ref)
+        assert rel(inv[:, :norm_cols // 64], 1.0 / nrm[..., 0]) < 2e-3
+        assert torch.isnan(inv[:, norm_cols // 64:]).all()
+    finally:
+        _lib.call("nvit_gemm_force_cta_group", 0)
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def attention_reference(q, k, v, sqk, sqk_mul, scale, B, H, T):
     D = 64
@@ -345,6 +379,41 @@ def test_attention_fwd_bwd(B, H, T, normed):
         assert rel(dqkv[:, sl], qkv.grad[:, sl]) < 3e-2, (name, rel(dqkv[:, sl], qkv.grad[:, sl]))
     if normed:
         assert rel(dsqk, sqk.grad) < 3e-2
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 2, 196), (3, 1, 64), (1, 2, 256)])
+def test_attention_with_prenormalised_qk(B, H, T):
+    """inv_q / inv_k: q, k arrive as s * x / ||x|| (what nvit_gemm_qknorm writes) with 1/||x|| on the side; outputs and the
+    gradients w.r.t. the RAW q, k must match the in-kernel normalisation path and the reference."""
+    C = H * 64
+    M = B * T
+    qkvb = randn(M, 3 * C, seed=44, scale=0.5, dtype=torch.bfloat16)
+    qkv = qkvb.float().requires_grad_(True)
+    sqk = (1.0 + 0.2 * randn(C, seed=45)).mul(0.03).requires_grad_(True)
+    sqk_mul, scale = 1.0 / 0.03, 8.0
+    ref = attention_reference(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, sqk_mul, scale, B, H, T)
+    gb = randn(M, C, seed=46, scale=0.1, dtype=torch.bfloat16)
+    ref.backward(gb.float())
+    with torch.no_grad():
+        heads = qkvb[:, :2 * C].float().view(M, 2 * H, 64)
+        nrm = heads.norm(dim=-1, keepdim=True)
+        s = (sqk.detach() * sqk_mul).view(1, H, 64).repeat(1, 2, 1)
+        pre = qkvb.clone()
+        pre[:, :2 * C] = (heads / nrm * s).reshape(M, 2 * C).to(torch.bfloat16)
+        inv = (1.0 / nrm[..., 0]).contiguous()                       # [M, 2H]: q heads, then k heads
+    out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device=DEV)
+    ops.attention_fwd(pre[:, :C], pre[:, C:2 * C], pre[:, 2 * C:], sqk.detach(), sqk_mul, scale, out, lse, B, H, T,
+                      inv_q=inv[:, :H], inv_k=inv[:, H:])
+    assert rel(out, ref) < 1e-2, rel(out, ref)
+    dqkv = torch.zeros(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    dsqk = torch.zeros(C, device=DEV)
+    ops.attention_bwd(pre[:, :C], pre[:, C:2 * C], pre[:, 2 * C:], sqk.detach(), sqk_mul, scale, out, gb, lse,
+                      dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dsqk, B, H, T, inv_q=inv[:, :H], inv_k=inv[:, H:])
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        assert rel(dqkv[:, sl], qkv.grad[:, sl]) < 3e-2, (name, rel(dqkv[:, sl], qkv.grad[:, sl]))
+    assert rel(dsqk, sqk.grad) < 3e-2
 
 
 # ---------------------------------------------------------------------------------------------- misc kernels
