@@ -202,9 +202,10 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
   float* s_scale = reinterpret_cast<float*>(sV + ATT_TILE_BYTES);  // [64]
   float* s_part = s_scale + 64;                                    // [2][128] partial row sums / maxima
   float* s_misc = s_part + 256;                                    // [0] = log2-domain logit bound
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_misc + 8);
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(s_misc + 8);   // q, k
   uint64_t* bar_mma = bar_tma + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_tmav = bar_mma + 1;                               // v: only the PV product waits for it
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_tmav + 1);
 
   const AttnThread t = attn_thread<ATT_FWD_PARTS>(p);
   const int T = p.T, TP = p.TP;
@@ -215,11 +216,13 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
     // the loads go out first: barrier set-up, TMEM allocation and the sqk fetch below hide under their latency
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_tmav, 1);
     fence_barrier_init();
-    mbar_arrive_expect_tx(bar_tma, 3 * ATT_TILE_BYTES);
+    mbar_arrive_expect_tx(bar_tma, 2 * ATT_TILE_BYTES);
     tma_load_3d(&p.tq, bar_tma, sQ, t.h * 64, 0, t.b);
     tma_load_3d(&p.tk, bar_tma, sK, t.h * 64, 0, t.b);
-    tma_load_3d(&p.tv, bar_tma, sV, t.h * 64, 0, t.b);
+    mbar_arrive_expect_tx(bar_tmav, ATT_TILE_BYTES);
+    tma_load_3d(&p.tv, bar_tmav, sV, t.h * 64, 0, t.b);
   }
   if (t.warp == 0) {
     tmem_alloc(tmem_ptr, 256);
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
     ATT_MARK(5 + 4 * i);
 
     if (t.warp == 0) {
+      if (i == 0) mbar_wait(bar_tmav, 0);
       tc_fence_after_sync();
       uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
       const int nks = TP >> 4;
