@@ -52,7 +52,7 @@ struct alignas(64) GemmParams {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false>
+template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false, bool SWIGLU = false>
 struct GemmTraits {
   static constexpr int BM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int BK = 64;
@@ -70,7 +70,9 @@ struct GemmTraits {
 #endif
   // GATEB: NVIT_GATEB_SETS sets of {du, dv} buffers per group, so a chunk's stores drain while the next chunk is computed
   static constexpr int GATE_SETS = (GATEB && CG2) ? NVIT_GATEB_SETS : 1;
-  static constexpr int NBUF = GATEB ? 2 * GATE_SETS : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1);
+  // The pair-mode gate GEMM sends three tiles (x, raw u, raw v) per group and tile: three buffers let them drain side
+  // by side (MEASURED: 436 -> 421 -> 417 us with 1 / 2 / 3 buffers; no effect on the one-output kernels).
+  static constexpr int NBUF = GATEB ? 2 * GATE_SETS : ((SWIGLU && CG2) ? 3 : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1));
   static constexpr int STAGING_BYTES = 2 * NBUF * 16384;
   static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int ACC_STAGES = 2;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v
 
 template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
 __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU>;
   static_assert(!GATEB || (BN == 256 && !SWIGLU), "gate-backward epilogue: 128x256 tiles");
   // CG2: the kernel runs as clusters of two CTAs (one SM pair); the pair computes a 256 x BN tile with
   // tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its own 128 rows of A and half of B.
@@ -312,10 +314,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
         }
       }
     };
+    float gate_su = 1.f, gate_sv = 1.f;      // GATEB: this thread's entries of the next tile's scale vectors
     if constexpr (GATEB) {
       if (unit0 < total_units && p.dbg != 1) {
         const int t0 = unit0 / p.splits;
         gate_fetch((t0 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t0 % p.tiles_n, 0);
+      }
+      if (unit0 < total_units && use_vec) {
+        const int j0 = min((unit0 / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
+        gate_su = __ldg(p.colscale + j0) * p.colscale_mul;
+        gate_sv = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
       }
     }
     for (int u = unit0; u < total_units; u += unit_stride) {
@@ -325,20 +333,32 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
       const int row = m_blk * T::BM + erow;
       if (use_vec) {
         // per-tile column vectors (bias, scale) staged once in shared memory instead of per-element global loads
+        if constexpr (GATEB) {
+          // [0,256): u scales of the tile's columns, [256,512): v scales.  The values were fetched one tile ahead
+          // (gate_su / gate_sv), so no global-load latency sits between the two barriers.
+          named_bar_sync(3, 256);
+          s_vec[et] = gate_su;
+          s_vec[256 + et] = gate_sv;
+          if (u + unit_stride < total_units) {
+            const int jn = min(((u + unit_stride) / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
+            gate_su = __ldg(p.colscale + jn) * p.colscale_mul;
+            gate_sv = __ldg(p.colscale + p.swiglu_half + jn) * p.colscale_mul;
+          }
+          named_bar_sync(3, 256);
+        } else {
         named_bar_sync(3, 256);  // both groups are done with the previous tile's vectors
         {
           int j = n_blk * TILE_N + (SWIGLU ? (et & 127) : et);
           j = min(j, p.N - 1);
           if (SWIGLU) j += (et >> 7) * p.swiglu_half;   // entries 0..127: u scales, 128..255: v scales
-          if constexpr (GATEB) {      // [0,256): u scales of the tile's columns, [256,512): v scales
-            s_vec[et] = __ldg(p.colscale + j) * p.colscale_mul;
-            s_vec[256 + et] = __ldg(p.colscale + p.swiglu_half + j) * p.colscale_mul;
+          if constexpr (GATEB) {
           } else if (SWIGLU || et < BN) {
             s_vec[et] = p.colscale ? __ldg(p.colscale + (p.qk_cols > 0 ? j % p.qk_period : j)) * p.colscale_mul : 1.f;
             s_vec[256 + et] = p.bias ? __ldg(p.bias + j) : 0.f;
           }
         }
         named_bar_sync(3, 256);
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -418,11 +438,19 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
               tmem_wait_ld();
               if (s2 == 1 && hh == 1) release_tmem();
               if (live && p.dbg != 4) {                         // dbg 4 (measurement aid): no gate arithmetic
+                // the results go back to the addresses the inputs came from, so the compiler may not move the next
+                // piece's loads above this piece's stores: fetch one piece ahead by hand
+                uint4 u_nx = *reinterpret_cast<const uint4*>(sbuf + erow * 128 + (((hh * 4) ^ (erow & 7)) << 4));
+                uint4 v_nx = *reinterpret_cast<const uint4*>(sbuf + 16384 + erow * 128 + (((hh * 4) ^ (erow & 7)) << 4));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint32_t off = erow * 128 + (((hh * 4 + j) ^ (erow & 7)) << 4);
-                  const uint4 u8 = *reinterpret_cast<const uint4*>(sbuf + off);
-                  const uint4 v8 = *reinterpret_cast<const uint4*>(sbuf + 16384 + off);
+                  const uint4 u8 = u_nx, v8 = v_nx;
+                  if (j < 3) {
+                    const uint32_t off2 = erow * 128 + (((hh * 4 + j + 1) ^ (erow & 7)) << 4);
+                    u_nx = *reinterpret_cast<const uint4*>(sbuf + off2);
+                    v_nx = *reinterpret_cast<const uint4*>(sbuf + 16384 + off2);
+                  }
                   const uint32_t uc[4] = {u8.x, u8.y, u8.z, u8.w}, vc[4] = {v8.x, v8.y, v8.z, v8.w};
                   uint32_t ou[4], ov[4];
 #pragma unroll
@@ -811,7 +839,7 @@ static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, u
 
 template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
 static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU>;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&p.tma_a, A, p.K, p.M, lda, T::BK, T::BM);
   else       rc = make_tmap_bf16_2d(&p.tma_a, A, p.M, p.K, lda, 64, T::BK);
