@@ -49,6 +49,7 @@ class Engine:
         self.grad_ready_hook = None     # callable(lo, hi): flat-gradient range [lo, hi) is final (data-parallel overlap)
         self.launches = 0
         self._p16_version = None
+        self.last_aux = {}              # Kohonen-map losses / units of the last forward (empty without the maps)
         self.probe = None               # list to receive (start, end) CUDA event pairs around the c_fc GEMM (bench.py)
         # SiLU-gate backward inside the dgrad GEMM epilogue (nvit_gemm_gate_bwd); NVIT_FUSE_GATE_BWD=0 keeps the two-kernel path
         self.fuse_gate_bwd = os.environ.get("NVIT_FUSE_GATE_BWD", "1") != "0"

@@ -244,3 +244,20 @@ def test_trainer_optimizer_state_round_trips_through_the_torch_layout():
         assert rel(b.detach(), a.detach()) <= 1e-5, k
     # a torch AdamW can take the state over too (what the reference's load_checkpoint does)
     m1.configure_optimizers(0.1, 2e-3, (0.9, 0.95), "cuda").load_state_dict(t1.optimizer_state_dict())
+
+
+def test_trainer_steps_in_the_original_vit_branch():
+    """BASELINE config 4 through nvit_b200.Trainer (bench.py --variant orig): two steps against the oracle's step."""
+    cfg = O.named_config("tiny", use_nvit=False)
+    sd = O.init_state_dict(cfg, 7)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(16, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (16,), generator=g).to(DEV)
+    ref = O.OracleTrainer({k: v.to(DEV) for k, v in sd.items()}, cfg, lr=1e-3)
+    model = build(cfg, sd)
+    tr = Trainer(model, learning_rate=1e-3)
+    for it in range(2):
+        ref_loss, _, _ = ref.step(X, y)
+        loss = tr.step(X, y)
+        assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss)), (it, float(loss), float(ref_loss))
+    assert tr.last_aux == {}
