@@ -153,6 +153,11 @@ int nvit_attention_debug(void* dev_buf_256_int64);
  */
 int nvit_im2col_bf16(const float* img, void* out_bf16, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
                      int64_t pad, void* stream);
+/* The same operand straight from uint8 HWC images ([B, S, S, ch], what the data loader holds before torchvision's ToTensor),
+ * with ToTensor + Normalize folded in (train.py:266-273, 1081-1092): value = pixel * scale + shift, e.g. scale = 1/(255 std),
+ * shift = -mean/std.  One byte per sample crosses PCIe instead of four. */
+int nvit_im2col_u8(const void* img_u8_nhwc, void* out_bf16, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
+                   int64_t pad, float scale, float shift, void* stream);
 
 /* ---- classifier head (model.py:455-456, 466-468): mean over T -> LayerNorm(eps) -> (GEMM) ------------------- */
 int nvit_pool_ln_fwd(const float* h, const float* gamma, const float* beta, float eps, void* y_bf16, float* xhat,

@@ -6,7 +6,7 @@ hand-written CUDA kernels behind the C ABI of ``libnvit_b200.so`` (include/nvit_
 """
 from .model import ViTConfig, ViT, Block, CrossAttentionBlock, RMSNorm, justnorm  # noqa: F401
 from .kohonen import KohonenMap  # noqa: F401
-from .train import Trainer, GradReducer  # noqa: F401
+from .train import Trainer, GradReducer, DeviceLoader  # noqa: F401
 from . import ops  # noqa: F401
 
-__all__ = ["ViTConfig", "ViT", "Block", "CrossAttentionBlock", "RMSNorm", "justnorm", "KohonenMap", "Trainer", "GradReducer", "ops"]
+__all__ = ["ViTConfig", "ViT", "Block", "CrossAttentionBlock", "RMSNorm", "justnorm", "KohonenMap", "Trainer", "GradReducer", "DeviceLoader", "ops"]

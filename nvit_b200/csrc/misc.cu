@@ -268,6 +268,32 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
   }
 }
 
+// The same operand straight from the loader's uint8 HWC images (torchvision ToTensor + Normalize(mean, std) of
+// train.py:266-273, 1081-1092 folded in: value = pixel * scale + shift), so the host sends 1 byte per sample instead of 4:
+//   out[(b,i,j), (c,kh,kw)] = img[b, refl(i*st + kh - pad), refl(j*st + kw - pad), c] * scale + shift
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int ch,
+                                                        int S, int ks, int st, int pad, int g, long long total_pairs, float scale,
+                                                        float shift) {
+  const int K = ch * ks * ks;
+  const int halfK = K / 2;
+  for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += 1ll * gridDim.x * blockDim.x) {
+    const long long m = idx / halfK;
+    const int k = (int)(idx - m * halfK) * 2;
+    const int c = k / (ks * ks);
+    const int rem = k - c * ks * ks;
+    const int kh = rem / ks, kw = rem - kh * ks;
+    const int b = (int)(m / (g * g));
+    const int ij = (int)(m - 1ll * b * g * g);
+    const int i = ij / g, j = ij - i * g;
+    const int y = reflect_idx(i * st + kh - pad, S);
+    const int x0 = j * st + kw - pad;
+    const uint8_t* src = img + ((1ll * b * S + y) * S) * ch + c;
+    const float v0 = (float)__ldg(src + 1ll * reflect_idx(x0, S) * ch) * scale + shift;
+    const float v1 = (float)__ldg(src + 1ll * reflect_idx(x0 + 1, S) * ch) * scale + shift;
+    *reinterpret_cast<uint32_t*>(out + m * K + k) = pack_bf16(v0, v1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pooled LayerNorm head
 // One CTA per image: mean over T (coalesced over C), LayerNorm over C; saves xhat and rstd for backward.
 __global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
@@ -667,6 +693,21 @@ extern "C" int nvit_im2col_bf16(const float* img, void* out, int64_t B, int64_t 
   else
     im2col_kernel<2><<<stream_grid(total / 2, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
                                                                              (int)ksize, (int)stride, (int)pad, g, total / 2);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_im2col_u8(const void* img_u8_nhwc, void* out, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
+                              int64_t pad, float scale, float shift, void* stream) {
+  NVIT_REQUIRE(img_u8_nhwc && out && B > 0 && ch > 0 && S > 0 && ksize > 0 && stride > 0 && pad >= 0, "nvit_im2col_u8: bad arguments");
+  NVIT_REQUIRE((ksize % 2) == 0, "nvit_im2col_u8: kernel size must be even");
+  NVIT_REQUIRE(pad < S, "nvit_im2col_u8: reflect padding must be smaller than the image");
+  NVIT_REQUIRE((S + 2 * pad - ksize) % stride == 0, "nvit_im2col_u8: (S + 2 pad - k) must be a multiple of the stride");
+  const int g = (int)((S + 2 * pad - ksize) / stride + 1);
+  const long long total = 1ll * B * g * g * ch * ksize * ksize;
+  im2col_u8_kernel<<<stream_grid(total / 2, 256, 16), 256, 0, ST(stream)>>>(static_cast<const uint8_t*>(img_u8_nhwc), static_cast<__nv_bfloat16*>(out),
+                                                                           (int)B, (int)ch, (int)S, (int)ksize, (int)stride, (int)pad, g, total / 2,
+                                                                           scale, shift);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

@@ -288,12 +288,20 @@ class Engine:
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, save: bool = True):
         cfg = self.cfg
-        if img.dtype != F32:
+        # uint8 [B, S, S, channels] (HWC, as the data loader holds images before ToTensor): normalised on the fly by the
+        # im2col kernels with input_mean / input_std (Normalize(0.5, 0.5) of train.py:1081-1092 by default)
+        self._u8 = img.dtype == torch.uint8
+        if self._u8:
+            if img.dim() != 4 or img.shape[-1] != cfg.channels:
+                raise ValueError("uint8 input must be [B, S, S, channels] (HWC)")
+        elif img.dtype != F32:
             img = img.float()
         img = img.contiguous()
         self._check_alias(img.device)
         self.refresh_operands()
         B = img.shape[0]
+        if self._u8 and img.shape[1] != cfg.image_size:
+            raise ValueError("uint8 input must be [B, S, S, channels] with S = image_size")
         if not cfg.use_nvit:
             return self._forward_orig(img, save)
         C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
@@ -307,8 +315,7 @@ class Engine:
         n0 = self.launches
 
         # ---- dual patch embedding as im2col + GEMM, bias and position embedding in the epilogue (model.py:407-415)
-        ops.im2col(img, a["A_l"], P, P, 0)
-        ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
+        self._im2col(img, a, P, G)
         ops.linear_fwd(a["A_l"], w16("local_patch_embed.weight"), a["local32"], bias=p("local_patch_embed.bias"),
                        rowadd=p("local_pos_embed").view(T, C), rowadd_period=T, c2=a["local16"])
         if cfg.use_kohonen:      # the maps and the quantization loss read the fp32 global embedding as well
@@ -363,6 +370,18 @@ class Engine:
         self._saved = (B, T) if save else None
         self.last_aux = self._kohonen_aux(B * T) if cfg.use_kohonen else {}
         return a["logits"].clone(), self.scratch[0].clone()
+
+    input_mean, input_std = 0.5, 0.5      # Normalize(mean, std) applied to uint8 inputs (train.py:1081-1092)
+
+    def _im2col(self, img, a, P, G):
+        """Patch operands of the two embeddings (model.py:286-304): local P x P, global G x G reflect-padded, stride P."""
+        if self._u8:
+            scale, shift = 1.0 / (255.0 * self.input_std), -self.input_mean / self.input_std
+            ops.im2col_u8(img, a["A_l"], P, P, 0, scale, shift)
+            ops.im2col_u8(img, a["A_g"], G, P, (G - P) // 2, scale, shift)
+        else:
+            ops.im2col(img, a["A_l"], P, P, 0)
+            ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
 
     def _ca_fwd(self, s, B, T, loc32, loc16, glob16, out32, out16):
         """CrossAttentionBlock.forward, nViT mode (model.py:219-275); `s` holds this call's saved activations."""
@@ -659,8 +678,7 @@ class Engine:
         att_scale = 1.0 / float(C // H) ** 0.5
         eps = 1e-6
         n0 = self.launches
-        ops.im2col(img, a["A_l"], P, P, 0)
-        ops.im2col(img, a["A_g"], G, P, (G - P) // 2)
+        self._im2col(img, a, P, G)
         ops.linear_fwd(a["A_l"], w16("local_patch_embed.weight"), a["local32"], bias=p("local_patch_embed.bias"),
                        rowadd=p("local_pos_embed").view(T, C), rowadd_period=T)
         ops.linear_fwd(a["A_g"], w16("global_patch_embed.1.weight"), a["global32"], bias=p("global_patch_embed.1.bias"),

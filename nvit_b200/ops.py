@@ -164,6 +164,14 @@ def im2col(img, out, ksize, stride, pad):
     _lib.call("nvit_im2col_bf16", _p(img), _p(out), B, ch, S, ksize, stride, pad, _stream())
 
 
+def im2col_u8(img_u8, out, ksize, stride, pad, scale, shift):
+    """img_u8: [B, S, S, ch] uint8 (HWC); value = pixel * scale + shift (ToTensor + Normalize folded in)."""
+    B, S, _, ch = img_u8.shape
+    if img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise TypeError("im2col_u8: expected a contiguous uint8 [B, S, S, ch] tensor")
+    _lib.call("nvit_im2col_u8", _p(img_u8), _p(out), B, ch, S, ksize, stride, pad, float(scale), float(shift), _stream())
+
+
 def pool_ln_fwd(h, gamma, beta, eps, y, xhat, rstd, B, T, C):
     _lib.call("nvit_pool_ln_fwd", _p(h), _p(gamma), _p(beta), float(eps), _p(y), _p(xhat), _p(rstd), B, T, C, _stream())
 

@@ -261,3 +261,38 @@ def test_trainer_steps_in_the_original_vit_branch():
         loss = tr.step(X, y)
         assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss)), (it, float(loss), float(ref_loss))
     assert tr.last_aux == {}
+
+
+def test_uint8_hwc_input_and_device_loader():
+    """SURVEY.md 8f (input pipeline on device): raw uint8 HWC batches, ToTensor + Normalize(0.5, 0.5) folded into the im2col
+    kernels (train.py:266-273, 1081-1092), staged through the double-buffered DeviceLoader."""
+    from nvit_b200 import DeviceLoader
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 11)
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randint(0, 256, (8, 32, 32, 3), generator=g, dtype=torch.uint8), torch.randint(0, 10, (8,), generator=g))
+               for _ in range(5)]
+    m_u8, m_f = build(cfg, sd).eval(), build(cfg, sd).eval()
+    seen = 0
+    with torch.no_grad():
+        for (Xd, yd), (Xh, yh) in zip(DeviceLoader(batches, DEV), batches):
+            assert Xd.is_cuda and Xd.dtype == torch.uint8 and torch.equal(Xd.cpu(), Xh) and torch.equal(yd.cpu(), yh)
+            lu, au = m_u8(Xd)
+            Xf = ((Xh.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5          # torchvision ToTensor + Normalize(0.5, 0.5)
+            lf, af = m_f(Xf.to(DEV))
+            assert rel(lu, lf) <= 2e-3, rel(lu, lf)
+            assert abs(float(au["reconstruction"]) - float(af["reconstruction"])) <= 2e-3 * float(af["reconstruction"])
+            # and against the oracle on the normalised float image
+            lo, _ = O.vit_forward({k: v.to(DEV) for k, v in sd.items()}, cfg, Xf.to(DEV))
+            assert rel(lu, lo) <= 1e-2
+            seen += 1
+    assert seen == len(batches)
+    # training step straight from uint8
+    model = build(cfg, sd)
+    tr = Trainer(model)
+    Xd, yd = batches[0][0].to(DEV), batches[0][1].to(DEV)
+    l0 = float(tr.step(Xd, yd))
+    l1 = float(tr.step(Xd, yd))
+    assert l1 < l0
+    with pytest.raises(ValueError, match="HWC"):
+        model(torch.zeros(2, 3, 32, 32, dtype=torch.uint8, device=DEV))
