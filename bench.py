@@ -315,10 +315,10 @@ def main():
                                  "frac_of_sustained_peak": fpi * value / world / 1e12 / peak},
             "roofline": {"kernel": "gemm_tcgen05_kernel<256,K,K,SWIGLU> (c_fc GEMM + suv*SiLU gate epilogue, forward)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": (955.66e6 if (args.config == "b16" and B == 256) else None), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
+                         "traffic": (952.49e6 if (args.config == "b16" and B == 256) else None), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
                          "launches_timed": len(probe), "avg_launch_ms": kern_ms, "flop_per_launch": gemm_flops,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                                           "profiles/r01_ncu_full_cfc_swiglu_gemm_raw.csv (bytes; algorithmic 1011e6)",
+                                           "profiles/r01_ncu_full_cfc_swiglu_gemm_final_raw.csv (bytes; algorithmic 1011e6)",
                          "probe": f"CUDA events around each c_fc launch over {probe_steps} eager steps of the same workload"
                                   + (" (the timed region replays a CUDA graph, where events cannot be timed)" if trainer.use_graph else "")},
         }

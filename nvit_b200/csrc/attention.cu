@@ -4,20 +4,22 @@
 //   O  = softmax(scale * qh kh^T) v,  non-causal                           (nvit/model.py:121-127, 252-258)
 //
 // The sequence is short and fixed by the patch grid (T = 196 for 224/16, 64 for the CIFAR config), so one CTA owns one
-// (batch, head): Q, K, V (and dO) tiles of up to 256 tokens x 64 channels are TMA-loaded into 128B-swizzled shared
-// memory, the q/k row normalisation and sqk scaling run in place on those tiles (the reference spends ~8 eager kernels
-// and fp32 temporaries on it), and every matmul is a tcgen05.mma whose operands are just different descriptor views
-// (K-major or MN-major) of the same shared tiles:
-//   forward : S = Qh Kh^T (M=128 q rows, N=Tpad)  -> row softmax by the threads owning the TMEM lane -> P (bf16, smem)
-//             O = P V      (B operand = V as it lies, MN-major)
+// (batch, head): Q, K, V (and dO, O) tiles of up to 256 tokens x 64 channels are TMA-loaded into 128B-swizzled shared
+// memory, q/k arrive either raw (normalised and sqk-scaled in place on those tiles) or already normalised by the
+// projection GEMM (nvit_gemm_qknorm, with 1/||x|| on the side), and every matmul is a tcgen05.mma whose operands are
+// different descriptor views (K-major or MN-major) of the same shared tiles - or, for P in the forward pass, tensor memory:
+//   forward : S = Qh Kh^T (M=128 q rows, N=Tpad) -> row softmax by the threads owning the TMEM lane -> P (bf16 pairs
+//             written back over the dead score columns) ; O = P V (A from TMEM, B = V as it lies, MN-major).
+//             256 threads, 96 KB shared memory, 256 TMEM columns: two CTAs per SM overlap each other's serial phases.
 //   backward (per 128-row kv tile j, scores kept transposed so that dV and dK complete per tile):
 //             S^T = Kh_j Qh^T ; P^T = exp(scale S^T - lse) ; dV_j = P^T dO ; dP^T = V_j dO^T ;
-//             dS^T = P^T (dP^T - delta) scale ; dK_j = dS^T Qh ; dQ += dS Kh_j (A = dS^T viewed MN-major)
-//             then the backward of the row normalisation and the sqk gradient.
-// 512 threads per CTA: four threads share a TMEM lane (score row) and split its columns (and, in the epilogues, its 64
-// channels), which quarters the serial per-thread work and gives every scheduler four warps to hide ALU latency.  With unit-norm q/k the logits are bounded by
-// scale * max(s^2), so the forward softmax needs no running max (one pass); the general two-pass form is kept for
-// un-normalised inputs and very large learned scales.
+//             dS^T = P^T (dP^T - delta) scale ; dK_j = dS^T Qh ; dQ += dS Kh_j (A = dS^T viewed MN-major, hence in
+//             shared memory) ; then the backward of the row normalisation and the sqk gradient.
+//             512 threads (four per TMEM lane), 202 KB shared memory, 464 TMEM columns: one CTA per SM, overlapped by
+//             hand (split load barriers, next score tile behind dK/dQ, dV staged under the tensor pipe).
+// Outputs are staged in operand rows that are dead by then and leave as [128 x 64] TMA stores.  With unit-norm q/k the
+// logits are bounded by scale * max(s^2), so the forward softmax needs no running max (one pass); the general two-pass
+// form is kept for un-normalised inputs and very large learned scales.
 #include "common.cuh"
 #include <string.h>
 
@@ -93,8 +95,6 @@ __device__ __forceinline__ float normalize_row(uint8_t* tile, int row, const flo
 struct alignas(64) AttnParams {
   CUtensorMap tq, tk, tv, tdo, to;
   CUtensorMap tdq, tdk, tdv;   // backward outputs: [128 tokens][64] boxes, stored from the (dead) operand tiles
-  const __nv_bfloat16 *q, *k, *o, *dout;  // raw rows for the normalisation backward / delta
-  __nv_bfloat16 *out, *dq, *dk, *dv;
   const float* sqk;
   const float *inv_q, *inv_k;   // non-null: q / k arrive normalised (nvit_gemm_qknorm) with 1/||x|| at [token * ld_inv + head]
   long long ld_inv_q, ld_inv_k;
@@ -768,7 +768,6 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
   if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T, 128))) return rc;
-  p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.lse = lse;
   p.inv_q = inv_q; p.inv_k = inv_k; p.ld_inv_q = ld_inv_q; p.ld_inv_k = ld_inv_k;
@@ -814,13 +813,6 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   if ((rc = make_head_tmap(&p.tdq, dq, lddq, (int)B, (int)H, (int)T, 128))) return rc;
   if ((rc = make_head_tmap(&p.tdk, dk, lddk, (int)B, (int)H, (int)T, 128))) return rc;
   if ((rc = make_head_tmap(&p.tdv, dv, lddv, (int)B, (int)H, (int)T, 128))) return rc;
-  p.q = static_cast<const __nv_bfloat16*>(q);
-  p.k = static_cast<const __nv_bfloat16*>(k);
-  p.o = static_cast<const __nv_bfloat16*>(out);
-  p.dout = static_cast<const __nv_bfloat16*>(dout);
-  p.dq = static_cast<__nv_bfloat16*>(dq);
-  p.dk = static_cast<__nv_bfloat16*>(dk);
-  p.dv = static_cast<__nv_bfloat16*>(dv);
   p.ldq = ldq; p.ldk = ldk; p.ldo = ldo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.lse = const_cast<float*>(lse);
   p.inv_q = inv_q; p.inv_k = inv_k; p.ld_inv_q = ld_inv_q; p.ld_inv_k = ld_inv_k;
