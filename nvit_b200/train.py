@@ -264,6 +264,8 @@ class Trainer:
         self.loss_buf.zero_()
         for k in range(self.grad_accum):
             self.micro_step(X, y, last=(k == self.grad_accum - 1))
+        if self.grad_accum > 1:
+            self.loss_buf.mul_(1.0 / self.grad_accum)      # mean over the micro-steps (each adds its mean CE)
         self.optimizer_step()
         return self.loss_buf
 

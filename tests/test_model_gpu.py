@@ -296,3 +296,31 @@ def test_uint8_hwc_input_and_device_loader():
     assert l1 < l0
     with pytest.raises(ValueError, match="HWC"):
         model(torch.zeros(2, 3, 32, 32, dtype=torch.uint8, device=DEV))
+
+
+def test_gradient_accumulation_matches_single_step():
+    """train.py:898-933 runs `gradient_accumulation_steps` micro-steps on the SAME batch with loss / steps: the accumulated
+    gradient equals the single-step one, so both trainers must take the same optimizer step (this also pins the
+    overwrite semantics of dL/dsuv = rowdot(W_fc, dW_fc) / suv over accumulated weight gradients)."""
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 21)
+    g = torch.Generator().manual_seed(8)
+    X = torch.randn(16, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (16,), generator=g).to(DEV)
+    m1, m2 = build(cfg, sd), build(cfg, sd)
+    t1 = Trainer(m1, learning_rate=1e-3, grad_clip=0.0)
+    t2 = Trainer(m2, learning_rate=1e-3, grad_clip=0.0, gradient_accumulation_steps=2)
+    # compare the accumulated gradients before the optimizer consumes them
+    for t in (t1, t2):
+        t._ensure_state()
+        t.loss_buf.zero_()
+        t.engine.zero_grad()
+        for k in range(t.grad_accum):
+            t.micro_step(X, y, last=(k == t.grad_accum - 1))
+    torch.cuda.synchronize()
+    for n, _ in m1.named_parameters():
+        s = m1.engine.slots[n]
+        if s.off >= m1.engine.n_active:
+            continue
+        assert rel(m2.engine.g(n), m1.engine.g(n)) <= 5e-3, (n, rel(m2.engine.g(n), m1.engine.g(n)))
+    assert abs(float(t2.loss_buf) / 2 - float(t1.loss_buf)) <= 1e-5 * abs(float(t1.loss_buf))     # one mean CE added per micro-step
