@@ -114,25 +114,21 @@ class DeviceLoader:
     def __iter__(self):
         pending = None
         for i, (X, y) in enumerate(self.batches):
-            slot = self._stage(i, X, y)
+            slot = self._stage(i, X, y)          # batch i goes out while the consumer still works on batch i-1
             if pending is not None:
                 yield self._hand_out(pending)
+                self._release(pending)           # back from the consumer: its work on `pending` is enqueued
             pending = slot
         if pending is not None:
             yield self._hand_out(pending)
 
     def _hand_out(self, slot):
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(slot["ready"])
-        # whatever the consumer enqueues on the current stream before asking for the next batch reads dx / dy; the event is
-        # recorded lazily at the next hand-out of this slot's successor, i.e. after that work has been enqueued
-        for other in self.slots:
-            if other is not None and other is not slot and other.get("handed"):
-                other["free"] = torch.cuda.Event()
-                other["free"].record(cur)
-                other["handed"] = False
-        slot["handed"] = True
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
         return slot["dx"], slot["dy"]
+
+    def _release(self, slot):
+        slot["free"] = torch.cuda.Event()
+        slot["free"].record(torch.cuda.current_stream(self.device))
 
 
 class Trainer:

@@ -296,6 +296,15 @@ def test_uint8_hwc_input_and_device_loader():
     assert l1 < l0
     with pytest.raises(ValueError, match="HWC"):
         model(torch.zeros(2, 3, 32, 32, dtype=torch.uint8, device=DEV))
+    # asynchronous consumption: training steps fed by the loader == the same steps fed by blocking copies
+    many = [batches[i % len(batches)] for i in range(12)]
+    ma, mb = build(cfg, sd), build(cfg, sd)
+    ta, tb = Trainer(ma), Trainer(mb)
+    for Xd, yd in DeviceLoader(many, DEV):
+        la = ta.step(Xd, yd)
+    for Xh, yh in many:
+        lb = tb.step(Xh.to(DEV), yh.to(DEV))
+    assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(lb)), (float(la), float(lb))
 
 
 def test_gradient_accumulation_matches_single_step():
