@@ -82,6 +82,9 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_SWIGLU_CTA_GROUP")    # benchmarking hook: CTA-group mode of the gate GEMM
     if mode in ("1", "2"):
         lib.nvit_gemm_swiglu_cta_group(int(mode))
+    mode = os.environ.get("NVIT_GATEB_GROUPS")        # epilogue groups (2 or 4) of the fused gate-backward GEMM
+    if mode in ("2", "4"):
+        lib.nvit_gemm_swiglu_cta_group(20 + int(mode))
     mode = os.environ.get("NVIT_GATEB_CTA_GROUP")     # ... and of the fused gate-backward GEMM
     if mode in ("1", "2"):
         lib.nvit_gemm_swiglu_cta_group(10 + int(mode))

@@ -52,8 +52,9 @@ struct alignas(64) GemmParams {
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false, bool SWIGLU = false>
+template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false, bool SWIGLU = false, int NG = 2>
 struct GemmTraits {
+  static constexpr int GROUPS = NG;            // epilogue groups of four warps (CTA = 64 + 128 * NG threads)
   static constexpr int BM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int BK = 64;
   static constexpr int UMMA_K = 16;
@@ -69,11 +70,11 @@ struct GemmTraits {
 #define NVIT_GATEB_SETS 2
 #endif
   // GATEB: NVIT_GATEB_SETS sets of {du, dv} buffers per group, so a chunk's stores drain while the next chunk is computed
-  static constexpr int GATE_SETS = (GATEB && CG2) ? NVIT_GATEB_SETS : 1;
+  static constexpr int GATE_SETS = (GATEB && CG2 && NG == 2) ? NVIT_GATEB_SETS : 1;
   // The pair-mode gate GEMM sends three tiles (x, raw u, raw v) per group and tile: three buffers let them drain side
   // by side (MEASURED: 436 -> 421 -> 417 us with 1 / 2 / 3 buffers; no effect on the one-output kernels).
   static constexpr int NBUF = GATEB ? 2 * GATE_SETS : ((SWIGLU && CG2) ? 3 : ((CG2 || BN == 128) ? NVIT_GEMM_NBUF : 1));
-  static constexpr int STAGING_BYTES = 2 * NBUF * 16384;
+  static constexpr int STAGING_BYTES = NG * NBUF * 16384;
   static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: powers of two
@@ -112,9 +113,10 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
-__global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU>;
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false, int NG = 2>
+__global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU, NG>;
+  static_assert(NG == 2 || GATEB, "four epilogue groups exist for the gate-backward epilogue only");
   static_assert(!GATEB || (BN == 256 && !SWIGLU), "gate-backward epilogue: 128x256 tiles");
   // CG2: the kernel runs as clusters of two CTAs (one SM pair); the pair computes a 256 x BN tile with
   // tcgen05.mma.cta_group::2 issued by the rank-0 CTA.  Each CTA stages its own 128 rows of A and half of B.
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < T::ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], CG2 ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tmem_empty[i], (CG2 ? 8 : 4) * NG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int eg = (warp - 2) >> 2;  // epilogue group
     const int erow = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..255 over the epilogue threads
+    const int et = threadIdx.x - 64;  // 0 .. 128 NG - 1 over the epilogue threads
     const bool issuer = (lane == 0) && (((warp - 2) & 3) == 0);
     uint8_t* const gbuf = stg + eg * (T::NBUF * 16384);   // this group's staging buffers
     uint32_t store_ctr = 0;
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     uint4 un[GATEB ? 8 : 1], vn[GATEB ? 8 : 1];
     auto gate_fetch = [&](int mb, int nb, int s2) {
       if constexpr (GATEB) {
-        const int col = nb * BN + (eg + 2 * s2) * 64 + (lane & 7) * 8;
+        const int col = nb * BN + (eg + NG * s2) * 64 + (lane & 7) * 8;
         const __nv_bfloat16* base = p.gate_uv + (static_cast<long long>(mb) * T::BM + q * 32 + (lane >> 3)) * p.ld_uv + col;
         const int rows_left = p.M - (mb * T::BM + q * 32 + (lane >> 3));   // row 4k + l/8 is valid iff 4k < rows_left
         const bool col_ok = col < p.N && p.dbg != 3;      // dbg 3 (measurement aid): no u|v loads
@@ -316,11 +318,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
     };
     float gate_su = 1.f, gate_sv = 1.f;      // GATEB: this thread's entries of the next tile's scale vectors
     if constexpr (GATEB) {
-      if (unit0 < total_units && p.dbg != 1) {
+      if (NG == 2 && unit0 < total_units && p.dbg != 1) {
         const int t0 = unit0 / p.splits;
         gate_fetch((t0 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t0 % p.tiles_n, 0);
       }
-      if (unit0 < total_units && use_vec) {
+      if (unit0 < total_units && use_vec && et < 256) {
         const int j0 = min((unit0 / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
         gate_su = __ldg(p.colscale + j0) * p.colscale_mul;
         gate_sv = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
@@ -336,15 +338,17 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
         if constexpr (GATEB) {
           // [0,256): u scales of the tile's columns, [256,512): v scales.  The values were fetched one tile ahead
           // (gate_su / gate_sv), so no global-load latency sits between the two barriers.
-          named_bar_sync(3, 256);
-          s_vec[et] = gate_su;
-          s_vec[256 + et] = gate_sv;
-          if (u + unit_stride < total_units) {
-            const int jn = min(((u + unit_stride) / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
-            gate_su = __ldg(p.colscale + jn) * p.colscale_mul;
-            gate_sv = __ldg(p.colscale + p.swiglu_half + jn) * p.colscale_mul;
+          named_bar_sync(3, 128 * NG);
+          if (et < 256) {
+            s_vec[et] = gate_su;
+            s_vec[256 + et] = gate_sv;
+            if (u + unit_stride < total_units) {
+              const int jn = min(((u + unit_stride) / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
+              gate_su = __ldg(p.colscale + jn) * p.colscale_mul;
+              gate_sv = __ldg(p.colscale + p.swiglu_half + jn) * p.colscale_mul;
+            }
           }
-          named_bar_sync(3, 256);
+          named_bar_sync(3, 128 * NG);
         } else {
         named_bar_sync(3, 256);  // both groups are done with the previous tile's vectors
         {
@@ -406,10 +410,13 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
           release_tmem();
         } else {
 #pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            const int c = eg + 2 * s2;
+          for (int s2 = 0; s2 < 4 / NG; ++s2) {
+            const int c = eg + NG * s2;
             const int n0 = n_blk * BN + c * 64;
             const bool live = n0 < p.N;   // uniform over the group
+            // four groups: one chunk per group and tile, fetched here and now - with four warps per scheduler the other
+            // groups' work covers the load latency, and no registers are held across the arithmetic
+            if constexpr (NG == 4) gate_fetch(m_blk, n_blk, 0);
             uint8_t* const sbuf = gbuf + (store_ctr % T::GATE_SETS) * 32768;    // this chunk's {du, dv} buffer set
             if (live) {
               ++store_ctr;
@@ -425,18 +432,20 @@ __global__ void __launch_bounds__(320, 1) gemm_tcgen05_kernel(const __grid_const
               }
               __syncwarp();       // a warp's 32 rows are loaded and consumed by that warp alone
             }
-            if (s2 == 0) {
-              gate_fetch(m_blk, n_blk, 1);
-            } else if (u + unit_stride < total_units) {
-              const int t2 = (u + unit_stride) / p.splits;
-              gate_fetch((t2 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t2 % p.tiles_n, 0);
+            if constexpr (NG == 2) {
+              if (s2 == 0) {
+                gate_fetch(m_blk, n_blk, 1);
+              } else if (u + unit_stride < total_units) {
+                const int t2 = (u + unit_stride) / p.splits;
+                gate_fetch((t2 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t2 % p.tiles_n, 0);
+              }
             }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(taddr + c * 64 + hh * 32, r);
               tmem_wait_ld();
-              if (s2 == 1 && hh == 1) release_tmem();
+              if (s2 == 4 / NG - 1 && hh == 1) release_tmem();
               if (live && p.dbg != 4) {                         // dbg 4 (measurement aid): no gate arithmetic
                 // the results go back to the addresses the inputs came from, so the compiler may not move the next
                 // piece's loads above this piece's stores: fetch one piece ahead by hand
@@ -837,9 +846,9 @@ static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, u
   return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false>
+template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false, int NG = 2>
 static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
-  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU>;
+  using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU, NG>;
   int rc;
   if (!A_MN) rc = make_tmap_bf16_2d(&p.tma_a, A, p.K, p.M, lda, T::BK, T::BM);
   else       rc = make_tmap_bf16_2d(&p.tma_a, A, p.M, p.K, lda, 64, T::BK);
@@ -911,7 +920,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   }
   static bool attr_set = false;
   if (!attr_set) {
-    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          T::SMEM_BYTES));
     attr_set = true;
   }
@@ -920,7 +929,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(CG2 ? 2 * nwork : nwork);
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(64 + 128 * NG);
   cfg.dynamicSmemBytes = T::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -930,7 +939,7 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB>, p));
+  NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB, NG>, p));
   return NVIT_OK;
 }
 
@@ -941,6 +950,7 @@ using namespace nvit;
 static int g_force_cg = 0;  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
 static int g_swiglu_cg = 2; // CTA-group mode of the gate GEMM under the auto policy (nvit_gemm_swiglu_cta_group)
 static int g_gateb_cg = 2;  // ... and of the fused gate-backward GEMM (mode + 10 through the same hook)
+static int g_gateb_groups = 4;  // epilogue groups of the fused gate-backward GEMM (mode 22 / 24 through the same hook)
 static int g_dbg = 0;       // see GemmParams::dbg
 
 extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
@@ -1069,13 +1079,19 @@ extern "C" int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // the heavy epilogue wants the smaller operand traffic of CTA pairs (and their deeper TMA ring)
   const bool cg2 = (g_force_cg == 2) || (g_force_cg == 0 && M > 128 && g_gateb_cg == 2);
+  if (g_gateb_groups == 4) {
+    if (cg2) return launch_gemm<256, false, true, false, true, true, 4>(p, dY, W, ld_dy, ld_w, st);
+    return launch_gemm<256, false, true, false, false, true, 4>(p, dY, W, ld_dy, ld_w, st);
+  }
   if (cg2) return launch_gemm<256, false, true, false, true, true>(p, dY, W, ld_dy, ld_w, st);
   return launch_gemm<256, false, true, false, false, true>(p, dY, W, ld_dy, ld_w, st);
 }
 
 extern "C" int nvit_gemm_swiglu_cta_group(int mode) {   // benchmarking hook: 1 or 2 (default 2)
-  NVIT_REQUIRE(mode == 1 || mode == 2 || mode == 11 || mode == 12, "nvit_gemm_swiglu_cta_group: mode must be 1, 2 (forward gate GEMM) or 11, 12 (gate backward)");
-  if (mode > 10) g_gateb_cg = mode - 10;
+  NVIT_REQUIRE(mode == 1 || mode == 2 || mode == 11 || mode == 12 || mode == 22 || mode == 24,
+               "nvit_gemm_swiglu_cta_group: mode must be 1, 2 (forward gate GEMM), 11, 12 (gate backward) or 22, 24 (its epilogue groups)");
+  if (mode > 20) g_gateb_groups = mode - 20;
+  else if (mode > 10) g_gateb_cg = mode - 10;
   else g_swiglu_cg = mode;
   return NVIT_OK;
 }
