@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--bucket-blocks", type=int, default=1, help="data parallel: transformer blocks per overlapped all-reduce bucket")
     ap.add_argument("--sm-budget", type=int, default=0, help="data parallel: SMs the persistent kernels may use (0 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -199,7 +200,7 @@ def main():
     torch.manual_seed(0)
     model = ViT(cfg).to(dev).train()
     trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
-                      overlap_allreduce=not args.no_overlap, sm_budget=args.sm_budget)
+                      overlap_allreduce=not args.no_overlap, sm_budget=args.sm_budget, bucket_blocks=args.bucket_blocks)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     X_host = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g).pin_memory()

@@ -29,13 +29,17 @@ class GradReducer:
     flushed at `finish()`.
     """
 
-    def __init__(self, flat: torch.Tensor, group=None, min_bucket: int = 1 << 20):
+    def __init__(self, flat: torch.Tensor, group=None, min_bucket: int = 1 << 20, bucket_elems: int = 0):
+        """`bucket_elems` > 0 merges adjacent large ranges (consecutive transformer blocks arrive back to front) until a
+        bucket holds at least that many elements: fewer, longer collectives beside the backward pass."""
         import torch.distributed as dist
         self.dist = dist
         self.flat = flat
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.min_bucket = min_bucket
+        self.bucket_elems = bucket_elems
+        self.acc: list[int] | None = None          # [lo, hi) of the bucket being filled
         self.pending = []
         self.small: list[tuple[int, int]] = []
         self.comm_stream = torch.cuda.Stream() if flat.is_cuda else None
@@ -57,12 +61,27 @@ class GradReducer:
 
     def ready(self, lo: int, hi: int):
         if hi - lo >= self.min_bucket:
-            self._issue(lo, hi)
+            if self.bucket_elems <= 0:
+                self._issue(lo, hi)
+                return
+            if self.acc is not None and (hi == self.acc[0] or lo == self.acc[1]):
+                self.acc = [min(lo, self.acc[0]), max(hi, self.acc[1])]
+            else:
+                self._flush_acc()
+                self.acc = [lo, hi]
+            if self.acc[1] - self.acc[0] >= self.bucket_elems:
+                self._flush_acc()
         elif hi > lo:
             self.small.append((lo, hi))
 
+    def _flush_acc(self):
+        if self.acc is not None:
+            self._issue(*self.acc)
+            self.acc = None
+
     def finish(self):
         """Flush coalesced small ranges and make the current stream wait for every collective."""
+        self._flush_acc()
         self.small.sort()
         merged: list[list[int]] = []
         for lo, hi in self.small:
@@ -137,6 +156,7 @@ class Trainer:
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
                  eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
                  cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = True, sm_budget: int = 0,
+                 bucket_blocks: int = 1,
                  consistency_weight: float = 0.1, smoothness_weight: float = 0.1):
         import torch.distributed as dist
         self.model = model
@@ -156,6 +176,7 @@ class Trainer:
         self.reducer = None
         self.launches = 0
         self.overlap = overlap_allreduce      # bucketed all-reduce behind the backward pass vs one all-reduce after it
+        self.bucket_blocks = max(1, bucket_blocks)   # transformer blocks per overlapped bucket
         if self.dp and sm_budget:
             from . import _lib
             _lib.call("nvit_set_sm_budget", int(sm_budget))
@@ -188,7 +209,9 @@ class Trainer:
                                     local_quantization=cfg.local_quantization_weight * k,
                                     global_quantization=cfg.global_quantization_weight * k, smoothness=self.smoothness_weight * k)
             if self.dp:
-                self.reducer = GradReducer(eng.G32, self.group)
+                lo, hi = eng.block_grad_range(0)
+                self.reducer = GradReducer(eng.G32, self.group,
+                                           bucket_elems=(hi - lo) * self.bucket_blocks if self.bucket_blocks > 1 else 0)
                 self._broadcast_params()
 
     def _broadcast_params(self):

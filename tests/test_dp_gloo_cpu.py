@@ -50,7 +50,18 @@ def _reducer_worker(rank, world, port, q):
     others = [torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
     expect = sum(others)
     ok = torch.allclose(flat[:4900], expect[:4900], atol=1e-6) and torch.equal(flat[4900:], mine[4900:])
-    q.put((rank, bool(ok), red.reduced_elems))
+    # the same hand-over with adjacent large ranges merged into buckets of >= 2500 elements: fewer collectives, same sums
+    flat2 = mine.clone()
+    red2 = GradReducer(flat2, min_bucket=1000, bucket_elems=2500)
+    issued = []
+    orig_issue = red2._issue
+    red2._issue = lambda lo, hi: (issued.append((lo, hi)), orig_issue(lo, hi))[1]
+    for lo, hi in [(3000, 4200), (1500, 3000), (300, 1500), (0, 100), (100, 300), (4200, 4300), (4300, 4900)]:
+        red2.ready(lo, hi)
+    red2.finish()
+    ok2 = torch.allclose(flat2[:4900], expect[:4900], atol=1e-6) and torch.equal(flat2[4900:], mine[4900:])
+    ok2 = ok2 and issued[0] == (1500, 4200) and red2.reduced_elems == red.reduced_elems
+    q.put((rank, bool(ok and ok2), red.reduced_elems))
     dist.destroy_process_group()
 
 
