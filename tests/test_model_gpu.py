@@ -333,3 +333,76 @@ def test_gradient_accumulation_matches_single_step():
             continue
         assert rel(m2.engine.g(n), m1.engine.g(n)) <= 5e-3, (n, rel(m2.engine.g(n), m1.engine.g(n)))
     assert abs(float(t2.loss_buf) / 2 - float(t1.loss_buf)) <= 1e-5 * abs(float(t1.loss_buf))     # one mean CE added per micro-step
+
+
+def test_full_size_b16_batch256_sample_independence_linearity_and_step():
+    """BASELINE config 2 at its FULL size (nViT-B/16, 224 px, batch 256, the bench workload), checked through
+    size-independent properties, with the oracle anchoring one slice:
+      * samples are independent (no batch statistics anywhere): the logits of the 256-image batch equal the
+        logits of its 32-image slices run on their own;
+      * the mean-CE gradient of the whole batch is the mean of the slices' gradients (linearity of the backward pass);
+      * the first slice matches the fp32 oracle (logits and every gradient, the usual tolerance);
+      * one full-size Trainer.step (graph-less) leaves every normalised weight row at unit norm and lowers the loss.
+    """
+    cfg = O.named_config("b16")
+    sd = O.init_state_dict(cfg, 0)
+    B, S = 256, 32
+    g = torch.Generator().manual_seed(1234)
+    X = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g).to(DEV)
+    y = torch.randint(0, cfg.num_classes, (B,), generator=g).to(DEV)
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    assert logits.shape == (B, cfg.num_classes) and bool(torch.isfinite(logits).all())
+    F.cross_entropy(logits, y).backward()
+    full = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    full_logits = logits.detach().clone()
+    del logits, aux
+    acc = {n: torch.zeros_like(v, dtype=torch.float64) for n, v in full.items()}
+    for s in range(0, B, S):
+        model.zero_grad(set_to_none=True)
+        ls, _ = model(X[s:s + S])
+        # row results do not depend on which other rows share the launch: tiles never mix rows
+        assert rel(ls.detach(), full_logits[s:s + S]) <= 1e-4, (s, rel(ls.detach(), full_logits[s:s + S]))
+        F.cross_entropy(ls, y[s:s + S]).backward()
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                acc[n] += p.grad.double()
+        if s == 0:
+            ref_logits, _, _, ref_grads = oracle_grads(cfg, sd, X[:S], y[:S])
+            assert rel(ls.detach(), ref_logits) <= 1e-2
+            check_grads(model, ref_grads)
+            del ref_grads
+    gnorm = float(torch.sqrt(sum((v.double() ** 2).sum() for v in full.values())))
+    for n, v in full.items():
+        mean = acc[n] / (B // S)
+        err = float((v.double() - mean).norm())
+        # bf16 operands are rounded per element, not per batch: only fp32 / split-K summation order differs
+        assert err <= 2e-2 * float(mean.norm()) + 1e-4 * gnorm, (n, err, float(mean.norm()))
+    del full, acc
+    model.zero_grad(set_to_none=True)
+    tr = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0)
+    l0 = float(tr.step(X, y))
+    l1 = float(tr.step(X, y))
+    assert np.isfinite(l0) and l1 < l0, (l0, l1)
+    params = dict(model.named_parameters())
+    for i in range(cfg.n_layer):
+        for nm, dim in O.NORMALIZED:
+            w = params[f"transformer.h.{i}.{nm}.weight"].detach()
+            assert float((w.norm(dim=dim) - 1).abs().max()) <= 1e-3, (i, nm)
+
+
+def test_l16_shapes_match_oracle():
+    """BASELINE config 3 shapes (nViT-L/16: C = 1024, 24 blocks, 16 heads) on a small batch against the fp32 oracle."""
+    cfg = O.named_config("l16")
+    sd = O.init_state_dict(cfg, 1)
+    g = torch.Generator().manual_seed(4321)
+    X = torch.randn(2, cfg.channels, cfg.image_size, cfg.image_size, generator=g).to(DEV)
+    y = torch.randint(0, cfg.num_classes, (2,), generator=g).to(DEV)
+    ref_logits, ref_recon, ref_loss, ref_grads = oracle_grads(cfg, sd, X, y)
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    loss = F.cross_entropy(logits, y)
+    loss.backward()
+    assert rel(logits.detach(), ref_logits) <= 1e-2, rel(logits.detach(), ref_logits)
+    assert abs(float(aux["reconstruction"]) - float(ref_recon)) <= 1e-2 * float(ref_recon)
+    check_grads(model, ref_grads)
