@@ -28,6 +28,12 @@ int nvit_version(void);
 int nvit_sm_count(void);
 /* Size persistent grids for at most n SMs (0 = all): leaves SMs free for concurrent NCCL kernels in data-parallel runs. */
 int nvit_set_sm_budget(int n);
+/* Programmatic dependent launch: with on != 0 every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so its on-chip set-up (barriers, TMEM allocation, descriptor
+ * prefetch) and the launch latency overlap the tail of the previous kernel in the stream; each kernel executes
+ * griddepcontrol.wait before its first global-memory access, so results are those of plain stream order.  Process-wide;
+ * takes effect for launches (and graph captures) made after the call.  Default off. */
+int nvit_set_pdl(int on);
 
 /* ---- GEMM: nn.Linear / nn.Conv2d-as-GEMM forward, dgrad and wgrad (model.py:99-101,130,148,155,226-228,259,262,
  *      286-304,329-332,341-344 and their autograd backward) ------------------------------------------------------

@@ -26,6 +26,14 @@ int nvit_num_sms() {
   return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
 }
 
+// Programmatic dependent launch (common.cuh: pdl_wait / nvit::launch).  Off unless nvit_set_pdl(1).
+static int g_pdl = 0;
+int nvit_pdl_enabled() { return g_pdl; }
+extern "C" int nvit_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return NVIT_OK;
+}
+
 extern "C" const char* nvit_last_error(void) { return g_err; }
 extern "C" int nvit_version(void) { return 100; }
 extern "C" int nvit_sm_count(void) { return nvit_num_sms(); }

@@ -196,6 +196,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  pdl_enter();   // the tile loads are the first thing this kernel does: nothing to set up ahead of the previous grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -450,6 +451,7 @@ __device__ __forceinline__ void reduce16_to_smem(float (&v)[16], float* s_out, i
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -786,7 +788,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<<<(unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  launch(attn_fwd_kernel, (unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), p);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -832,7 +834,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
     attr_set = true;
   }
-  attn_bwd_kernel<<<(unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  launch(attn_bwd_kernel, (unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), p);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

@@ -7,6 +7,8 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <utility>
 
 #define NVIT_OK 0
 #define NVIT_ERR_ARG -1
@@ -32,6 +34,7 @@
 
 void nvit_set_error(const char* fmt, ...);
 int nvit_num_sms();
+int nvit_pdl_enabled();   // programmatic dependent launch on/off (nvit_set_pdl, api.cu)
 
 namespace nvit {
 
@@ -40,6 +43,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library is launched through nvit::launch (below), which - when nvit_set_pdl(1) is in force - marks
+// the launch as programmatically serialised: its CTAs may become resident while the previous kernel in the stream is
+// still draining, so barrier initialisation, TMEM allocation, descriptor prefetch and the launch latency itself overlap
+// that kernel's tail.  The contract that keeps this identical to plain stream order: a kernel touches NO global memory
+// (loads, stores, atomics, TMA) before pdl_wait(), which returns once the preceding grid has completed and its writes
+// are visible.  pdl_trigger() right behind it lets the next kernel in turn start its own prologue.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -322,6 +337,24 @@ __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u &
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ----------------------------------------------------------------------------- host: kernel launch
+// One launch path for the whole library (replaces <<< >>>): optional cluster width, optional programmatic serialisation.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = nvit_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace nvit

@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
   if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch, the cluster handshake) touches no global
+  // memory and may run under the tail of the previous kernel; operands, scale vectors and outputs come after this.
+  pdl_enter();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -932,13 +935,15 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   cfg.blockDim = dim3(64 + 128 * NG);
   cfg.dynamicSmemBytes = T::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in common.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = nvit_pdl_enabled() ? 2 : 1;
   NVIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB, NG>, p));
   return NVIT_OK;
 }

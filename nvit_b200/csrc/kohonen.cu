@@ -17,6 +17,7 @@ static inline int som_grid(long long work_items, int threads, int per_sm = 8) {
 // x = hi + lo + O(2^-17 |x|): two bf16 GEMM operands that together carry ~16 mantissa bits of an fp32 tensor.
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, long long n) {
+  pdl_enter();
   const long long n4 = n >> 2;
   const long long stride = 1ll * gridDim.x * blockDim.x;
   for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) som_prepare_kernel(const float* __restrict__ nodes, int C, float* __restrict__ nn,
                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                           float* __restrict__ snapshot) {
+  pdl_enter();
   __shared__ float red[4];
   const int g = blockIdx.x;
   const float* row = nodes + 1ll * g * C;
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) som_select_kernel(const float* __restrict
                                                          int* __restrict__ idx, long long* __restrict__ idx64,
                                                          __nv_bfloat16* __restrict__ onehot, float* __restrict__ counts,
                                                          float* __restrict__ repr32, __nv_bfloat16* __restrict__ repr16) {
+  pdl_enter();
   extern __shared__ float s_hist[];   // [G]
   for (int g = threadIdx.x; g < G; g += blockDim.x) s_hist[g] = 0.f;
   __syncthreads();
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(256) som_select_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------ pooled update inputs
 // kohonen.py:149-155: image b's [T, C] patch matrix, flattened, averaged over runs of `run` = T consecutive elements.
 __global__ void __launch_bounds__(256) som_pool_kernel(const float* __restrict__ x, long long rows, int run, float* __restrict__ out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const float inv = 1.f / (float)run;
   for (long long r = 1ll * blockIdx.x * nwarp + warp; r < rows; r += 1ll * gridDim.x * nwarp) {
@@ -132,6 +136,7 @@ constexpr int SOM_CHUNK = 256;
 __global__ void __launch_bounds__(256) som_update_kernel(float* __restrict__ nodes, const float* __restrict__ v,
                                                          const int* __restrict__ bmu, int steps, int C, int gm, int gn,
                                                          const float* __restrict__ coef_dev, float two_sigma2) {
+  pdl_enter();
   __shared__ float s_str[SOM_CHUNK];
   const int g = blockIdx.x;
   const int gr = g / gn, gc = g % gn;
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(256) som_pair_kernel(const float* __restrict__
                                                        const float* __restrict__ xl, const float* __restrict__ xg, long long M, int C,
                                                        float* __restrict__ sums, const float* __restrict__ w, float* __restrict__ d_a,
                                                        float* __restrict__ d_b, float* __restrict__ d_xl, float* __restrict__ d_xg) {
+  pdl_enter();
   __shared__ float red[3][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float t_cos = 0.f, t_hl = 0.f, t_hg = 0.f;
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(256) som_pair_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) som_smooth_kernel(const float* __restrict__ nodes, const float* __restrict__ counts, int side,
                                                          int C, float inv_8m, float* __restrict__ loss, const float* __restrict__ w,
                                                          float* __restrict__ gnodes) {
+  pdl_enter();
   __shared__ float red[4];
   const int g = blockIdx.x >> 3, k = blockIdx.x & 7;
   const float cnt = counts[g];
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(128) som_smooth_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) tanh_mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
                                                            long long n, float two_inv_count, const float* __restrict__ w,
                                                            __nv_bfloat16* __restrict__ dpred) {
+  pdl_enter();
   const float k = two_inv_count * w[0];
   const long long n8 = n >> 3;
   const long long stride = 1ll * gridDim.x * blockDim.x;
@@ -339,14 +347,14 @@ extern "C" int nvit_split_bf16(const float* x, void* hi_or_null, void* lo, int64
   NVIT_REQUIRE(((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(lo) & 7) | (reinterpret_cast<uintptr_t>(hi_or_null) & 7)) == 0,
                "nvit_split_bf16: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
   if (n == 0) return NVIT_OK;
-  split_bf16_kernel<<<som_grid(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, static_cast<__nv_bfloat16*>(hi_or_null), static_cast<__nv_bfloat16*>(lo), n);
+  launch(split_bf16_kernel, som_grid(n / 4 + 1, 256), 256, 0, ST(stream), x, static_cast<__nv_bfloat16*>(hi_or_null), static_cast<__nv_bfloat16*>(lo), n);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
 
 extern "C" int nvit_som_prepare(const float* nodes, int64_t G, int64_t C, float* node_sq, void* hi, void* lo, float* snapshot, void* stream) {
   NVIT_REQUIRE(nodes && node_sq && hi && lo && snapshot && G > 0 && C > 0, "nvit_som_prepare: bad arguments");
-  som_prepare_kernel<<<(int)G, 128, 0, ST(stream)>>>(nodes, (int)C, node_sq, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), snapshot);
+  launch(som_prepare_kernel, (int)G, 128, 0, ST(stream), nodes, (int)C, node_sq, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), snapshot);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -356,7 +364,7 @@ extern "C" int nvit_som_select(const float* dots, const float* node_sq, const fl
   NVIT_REQUIRE(dots && node_sq && nodes && idx && repr32 && repr16, "nvit_som_select: null argument");
   NVIT_REQUIRE(M >= 0 && G > 0 && G <= 8192 && C > 0, "nvit_som_select: bad sizes M=%lld G=%lld C=%lld", (long long)M, (long long)G, (long long)C);
   if (M == 0) return NVIT_OK;
-  som_select_kernel<<<som_grid(M * 32, 256, 4), 256, (size_t)G * sizeof(float), ST(stream)>>>(
+  launch(som_select_kernel, som_grid(M * 32, 256, 4), 256, (size_t)G * sizeof(float), ST(stream), 
       dots, node_sq, nodes, M, (int)G, (int)C, idx, reinterpret_cast<long long*>(idx64_or_null), static_cast<__nv_bfloat16*>(onehot_or_null),
       counts_or_null, repr32, static_cast<__nv_bfloat16*>(repr16));
   NVIT_CUDA_CHECK(cudaGetLastError());
@@ -366,7 +374,7 @@ extern "C" int nvit_som_select(const float* dots, const float* node_sq, const fl
 extern "C" int nvit_som_pool(const float* x, int64_t rows, int64_t run, float* out, void* stream) {
   NVIT_REQUIRE(x && out && rows >= 0 && run > 0 && run < (1ll << 31), "nvit_som_pool: bad arguments");
   if (rows == 0) return NVIT_OK;
-  som_pool_kernel<<<som_grid(rows * 32, 256), 256, 0, ST(stream)>>>(x, rows, (int)run, out);
+  launch(som_pool_kernel, som_grid(rows * 32, 256), 256, 0, ST(stream), x, rows, (int)run, out);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -376,7 +384,7 @@ extern "C" int nvit_som_update(float* nodes, const float* pooled, const int32_t*
   NVIT_REQUIRE(nodes && pooled && bmu && coef_dev, "nvit_som_update: null argument");
   NVIT_REQUIRE(steps >= 0 && grid_rows > 0 && grid_cols > 0 && C > 0 && sigma > 0.f, "nvit_som_update: bad sizes");
   if (steps == 0) return NVIT_OK;
-  som_update_kernel<<<(int)(grid_rows * grid_cols), 256, 0, ST(stream)>>>(nodes, pooled, bmu, (int)steps, (int)C, (int)grid_rows, (int)grid_cols,
+  launch(som_update_kernel, (int)(grid_rows * grid_cols), 256, 0, ST(stream), nodes, pooled, bmu, (int)steps, (int)C, (int)grid_rows, (int)grid_cols,
                                                                            coef_dev, 2.f * sigma * sigma);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -391,7 +399,7 @@ extern "C" int nvit_som_pair_losses(const float* repr_l, const float* repr_g, co
   if (M == 0) return NVIT_OK;
   const int grid = som_grid(M * 32, 256, 4);
   const int nv = (int)((C + 127) / 128);
-#define LAUNCH(NV) som_pair_kernel<NV><<<grid, 256, 0, ST(stream)>>>(repr_l, repr_g, x_l, x_g, M, (int)C, sums3_or_null, weights3_or_null, d_repr_l, d_repr_g, d_x_l, d_x_g)
+#define LAUNCH(NV) launch(som_pair_kernel<NV>, grid, 256, 0, ST(stream), repr_l, repr_g, x_l, x_g, M, (int)C, sums3_or_null, weights3_or_null, d_repr_l, d_repr_g, d_x_l, d_x_g)
   if (nv <= 1) LAUNCH(1);
   else if (nv <= 2) LAUNCH(2);
   else if (nv <= 4) LAUNCH(4);
@@ -405,7 +413,7 @@ extern "C" int nvit_som_pair_losses(const float* repr_l, const float* repr_g, co
 extern "C" int nvit_som_smoothness(const float* nodes, const float* counts, int64_t side, int64_t C, int64_t M, float* loss_accum,
                                    const float* weight_or_null, float* gnodes_or_null, void* stream) {
   NVIT_REQUIRE(nodes && counts && loss_accum && side > 0 && C > 0 && M > 0, "nvit_som_smoothness: bad arguments");
-  som_smooth_kernel<<<(int)(side * side * 8), 128, 0, ST(stream)>>>(nodes, counts, (int)side, (int)C, 1.f / (8.f * (float)M), loss_accum,
+  launch(som_smooth_kernel, (int)(side * side * 8), 128, 0, ST(stream), nodes, counts, (int)side, (int)C, 1.f / (8.f * (float)M), loss_accum,
                                                                    weight_or_null, gnodes_or_null);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -415,7 +423,7 @@ extern "C" int nvit_tanh_mse_bwd(const void* pred, const void* target, int64_t n
                                  void* stream) {
   NVIT_REQUIRE(pred && target && weight_dev && dpred && n >= 0, "nvit_tanh_mse_bwd: bad arguments");
   if (n == 0) return NVIT_OK;
-  tanh_mse_bwd_kernel<<<som_grid(n / 8 + 1, 256, 4), 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(target),
+  launch(tanh_mse_bwd_kernel, som_grid(n / 8 + 1, 256, 4), 256, 0, ST(stream), static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(target),
                                                                           n, 2.f * inv_count, weight_dev, static_cast<__nv_bfloat16*>(dpred));
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;

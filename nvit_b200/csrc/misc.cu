@@ -40,6 +40,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ------------------------------------------------------------------------------------------------ cast
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                             long long n) {
+  pdl_enter();
   const long long n8 = n >> 3;
   const long long stride = 1ll * gridDim.x * blockDim.x;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------ sum of squares
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[32];
   const long long stride = 1ll * gridDim.x * blockDim.x;
   float acc = 0.f;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 // grid.x over 256-column chunks (thread = column), grid.y over row slabs.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ldx,
                                                           float* __restrict__ out, int rows_per_slab) {
+  pdl_enter();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= N) return;
   const int r0 = blockIdx.y * rows_per_slab;
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // dpos[t,c] += sum_b dx[b,t,c]; dbias[c] += the same, summed over t.   grid (T, ceil(C/256)).
 __global__ void __launch_bounds__(256) pos_bias_grad_kernel(const float* __restrict__ dx, int B, int T, int C,
                                                             float* __restrict__ dpos, float* __restrict__ dbias) {
+  pdl_enter();
   const int t = blockIdx.x;
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= C) return;
@@ -114,6 +118,7 @@ __device__ __forceinline__ float sigmoidf_(float v) {
 __global__ void __launch_bounds__(128) swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ uv, const float* __restrict__ suv,
                                                          float suv_mul, __nv_bfloat16* __restrict__ xo, int M, int F,
                                                          int rows_per_slab) {
+  pdl_enter();
   const int c8 = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (c8 >= F) return;
   float su[8], sv[8];
@@ -142,6 +147,7 @@ __global__ void __launch_bounds__(128) swiglu_bwd_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ suv, float suv_mul,
                                                          __nv_bfloat16* __restrict__ duv, float* __restrict__ dsuv, int M, int F,
                                                          int rows_per_slab) {
+  pdl_enter();
   const int c8 = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (c8 >= F) return;
   float su[8], sv[8], gsu[8], gsv[8];
@@ -211,6 +217,7 @@ __global__ void __launch_bounds__(128) swiglu_bwd_kernel(const __nv_bfloat16* __
 // accumulated micro-batches), which replaces a column reduction over all M rows of d(uv) * uv.  One warp per row.
 __global__ void __launch_bounds__(256) rowdot_div_kernel(const float* __restrict__ w, const float* __restrict__ dw,
                                                          const float* __restrict__ div, float* __restrict__ out, int rows, int cols) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int r = blockIdx.x * nwarp + warp; r < rows; r += gridDim.x * nwarp) {
     const float* a = w + 1ll * r * cols;
@@ -236,6 +243,7 @@ __device__ __forceinline__ int reflect_idx(int i, int S) {
 template <int V>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int ch,
                                                      int S, int ks, int st, int pad, int g, long long total_vec) {
+  pdl_enter();
   const int K = ch * ks * ks;
   const int vecK = K / V;
   for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec; idx += 1ll * gridDim.x * blockDim.x) {
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
 __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int ch,
                                                         int S, int ks, int st, int pad, int g, long long total_pairs, float scale,
                                                         float shift) {
+  pdl_enter();
   const int K = ch * ks * ks;
   const int halfK = K / 2;
   for (long long idx = 1ll * blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += 1ll * gridDim.x * blockDim.x) {
@@ -299,6 +308,7 @@ __global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restric
 __global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
                                                           float* __restrict__ xhat, float* __restrict__ rstd, int T, int C) {
+  pdl_enter();
   extern __shared__ float s_pool[];  // [C]
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(256) pool_ln_bwd_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                           float* __restrict__ dh, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta, int T, int C) {
+  pdl_enter();
   extern __shared__ float s_dp[];  // [C]
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(256) head_scale_bwd_kernel(const float* __rest
                                                              const float* __restrict__ sz, float sz_mul,
                                                              __nv_bfloat16* __restrict__ draw, float* __restrict__ dsz, int B, int N,
                                                              long long ld) {
+  pdl_enter();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float s = sz ? sz[n] * sz_mul : 1.f;
@@ -382,6 +394,7 @@ __global__ void __launch_bounds__(256) head_scale_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                                             float* __restrict__ loss, float* __restrict__ dlogits, float gscale, int B,
                                                             int N) {
+  pdl_enter();
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* row = logits + 1ll * b * N;
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) tanh_mse_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
                                                        long long n, float inv_count, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[32];
   const long long n8 = n >> 3;
   const long long stride = 1ll * gridDim.x * blockDim.x;
@@ -431,6 +445,7 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
                                                          float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                          const float* __restrict__ gnorm_sq, float max_norm,
                                                          const float* __restrict__ dev_lr_step) {
+  pdl_enter();
   if (dev_lr_step) {   // CUDA-graph friendly: learning rate and 1-based step count live in device memory
     lr = dev_lr_step[0];
     const float t = dev_lr_step[1];
@@ -485,6 +500,7 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
 //           slab (rows x 512 B, L2 resident) to scale it.
 __global__ void __launch_bounds__(256) weight_norm_multi_kernel(const long long* __restrict__ table, int n_tensors,
                                                                 long long total_units) {
+  pdl_enter();
   __shared__ float4 s_part[8][32];
   __shared__ float4 s_inv[32];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
@@ -605,7 +621,7 @@ using namespace nvit;
 extern "C" int nvit_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   NVIT_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "nvit_cast_f32_to_bf16: bad arguments");
   if (n == 0) return NVIT_OK;
-  cast_f32_bf16_kernel<<<stream_grid(n / 8 + 1, 256), 256, 0, ST(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  launch(cast_f32_bf16_kernel, stream_grid(n / 8 + 1, 256), 256, 0, ST(stream), src, static_cast<__nv_bfloat16*>(dst), n);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -613,7 +629,7 @@ extern "C" int nvit_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
 extern "C" int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream) {
   NVIT_REQUIRE(n >= 0 && out_accum && (n == 0 || x), "nvit_sumsq_f32: bad arguments");
   if (n == 0) return NVIT_OK;
-  sumsq_kernel<<<stream_grid(n / 4 + 1, 256, 4), 256, 0, ST(stream)>>>(x, n, out_accum);
+  launch(sumsq_kernel, stream_grid(n / 4 + 1, 256, 4), 256, 0, ST(stream), x, n, out_accum);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -626,7 +642,7 @@ extern "C" int nvit_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ldx
   if (slabs > M) slabs = (int)M;
   const int rps = (int)((M + slabs - 1) / slabs);
   dim3 grid(gx, (unsigned)((M + rps - 1) / rps));
-  colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), (int)M, (int)N, ldx, out_accum, rps);
+  launch(colsum_bf16_kernel, grid, 256, 0, ST(stream), static_cast<const __nv_bfloat16*>(x), (int)M, (int)N, ldx, out_accum, rps);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -634,7 +650,7 @@ extern "C" int nvit_colsum_bf16(const void* x, int64_t M, int64_t N, int64_t ldx
 extern "C" int nvit_pos_bias_grad(const float* dx, int64_t B, int64_t T, int64_t C, float* dpos, float* dbias_accum, void* stream) {
   NVIT_REQUIRE(dx && dpos && B > 0 && T > 0 && C > 0, "nvit_pos_bias_grad: bad arguments");
   dim3 grid((unsigned)T, (unsigned)((C + 255) / 256));
-  pos_bias_grad_kernel<<<grid, 256, 0, ST(stream)>>>(dx, (int)B, (int)T, (int)C, dpos, dbias_accum);
+  launch(pos_bias_grad_kernel, grid, 256, 0, ST(stream), dx, (int)B, (int)T, (int)C, dpos, dbias_accum);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -653,7 +669,7 @@ extern "C" int nvit_swiglu_fwd(const void* uv, const float* suv, float suv_mul, 
   if (M == 0) return NVIT_OK;
   dim3 grid; int rps;
   slab_grid(M, F, &grid, &rps);
-  swiglu_fwd_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(uv), suv, suv_mul, static_cast<__nv_bfloat16*>(x), (int)M, (int)F, rps);
+  launch(swiglu_fwd_kernel, grid, 128, 0, ST(stream), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul, static_cast<__nv_bfloat16*>(x), (int)M, (int)F, rps);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -665,7 +681,7 @@ extern "C" int nvit_swiglu_bwd(const void* dx, const void* uv, const float* suv,
   if (M == 0) return NVIT_OK;
   dim3 grid; int rps;
   slab_grid(M, F, &grid, &rps);
-  swiglu_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
+  launch(swiglu_bwd_kernel, grid, 128, 0, ST(stream), static_cast<const __nv_bfloat16*>(dx), static_cast<const __nv_bfloat16*>(uv), suv, suv_mul,
                                                   static_cast<__nv_bfloat16*>(duv), dsuv_accum, (int)M, (int)F, rps);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -674,7 +690,7 @@ extern "C" int nvit_swiglu_bwd(const void* dx, const void* uv, const float* suv,
 extern "C" int nvit_rowdot_div(const float* w, const float* dw, const float* div, float* out, int64_t rows, int64_t cols, void* stream) {
   NVIT_REQUIRE(w && dw && div && out && rows >= 0 && cols > 0, "nvit_rowdot_div: bad arguments");
   if (rows == 0) return NVIT_OK;
-  rowdot_div_kernel<<<stream_grid(rows * 32, 256), 256, 0, ST(stream)>>>(w, dw, div, out, (int)rows, (int)cols);
+  launch(rowdot_div_kernel, stream_grid(rows * 32, 256), 256, 0, ST(stream), w, dw, div, out, (int)rows, (int)cols);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -688,10 +704,10 @@ extern "C" int nvit_im2col_bf16(const float* img, void* out, int64_t B, int64_t 
   const int g = (int)((S + 2 * pad - ksize) / stride + 1);
   const long long total = 1ll * B * g * g * ch * ksize * ksize;
   if ((ksize % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-    im2col_kernel<8><<<stream_grid(total / 8, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
+    launch(im2col_kernel<8>, stream_grid(total / 8, 256, 16), 256, 0, ST(stream), img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
                                                                              (int)ksize, (int)stride, (int)pad, g, total / 8);
   else
-    im2col_kernel<2><<<stream_grid(total / 2, 256, 16), 256, 0, ST(stream)>>>(img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
+    launch(im2col_kernel<2>, stream_grid(total / 2, 256, 16), 256, 0, ST(stream), img, static_cast<__nv_bfloat16*>(out), (int)B, (int)ch, (int)S,
                                                                              (int)ksize, (int)stride, (int)pad, g, total / 2);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -705,7 +721,7 @@ extern "C" int nvit_im2col_u8(const void* img_u8_nhwc, void* out, int64_t B, int
   NVIT_REQUIRE((S + 2 * pad - ksize) % stride == 0, "nvit_im2col_u8: (S + 2 pad - k) must be a multiple of the stride");
   const int g = (int)((S + 2 * pad - ksize) / stride + 1);
   const long long total = 1ll * B * g * g * ch * ksize * ksize;
-  im2col_u8_kernel<<<stream_grid(total / 2, 256, 16), 256, 0, ST(stream)>>>(static_cast<const uint8_t*>(img_u8_nhwc), static_cast<__nv_bfloat16*>(out),
+  launch(im2col_u8_kernel, stream_grid(total / 2, 256, 16), 256, 0, ST(stream), static_cast<const uint8_t*>(img_u8_nhwc), static_cast<__nv_bfloat16*>(out),
                                                                            (int)B, (int)ch, (int)S, (int)ksize, (int)stride, (int)pad, g, total / 2,
                                                                            scale, shift);
   NVIT_CUDA_CHECK(cudaGetLastError());
@@ -716,7 +732,7 @@ extern "C" int nvit_pool_ln_fwd(const float* h, const float* gamma, const float*
                                 int64_t B, int64_t T, int64_t C, void* stream) {
   NVIT_REQUIRE(h && gamma && beta && y && xhat && rstd && B > 0 && T > 0 && C > 0, "nvit_pool_ln_fwd: bad arguments");
   NVIT_REQUIRE(C * sizeof(float) <= 48 * 1024, "nvit_pool_ln_fwd: C too large");
-  pool_ln_fwd_kernel<<<(unsigned)B, 256, C * sizeof(float), ST(stream)>>>(h, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), xhat, rstd, (int)T, (int)C);
+  launch(pool_ln_fwd_kernel, (unsigned)B, 256, C * sizeof(float), ST(stream), h, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), xhat, rstd, (int)T, (int)C);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -725,7 +741,7 @@ extern "C" int nvit_pool_ln_bwd(const void* dy, const float* gamma, const float*
                                 float* dbeta, int64_t B, int64_t T, int64_t C, void* stream) {
   NVIT_REQUIRE(dy && gamma && xhat && rstd && dh && dgamma && dbeta && B > 0 && T > 0 && C > 0, "nvit_pool_ln_bwd: bad arguments");
   NVIT_REQUIRE((C % 4) == 0 && C * sizeof(float) <= 48 * 1024, "nvit_pool_ln_bwd: C must be a multiple of 4 and fit shared memory");
-  pool_ln_bwd_kernel<<<(unsigned)B, 256, C * sizeof(float), ST(stream)>>>(static_cast<const __nv_bfloat16*>(dy), gamma, xhat, rstd, dh, dgamma, dbeta, (int)T, (int)C);
+  launch(pool_ln_bwd_kernel, (unsigned)B, 256, C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(dy), gamma, xhat, rstd, dh, dgamma, dbeta, (int)T, (int)C);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -733,7 +749,7 @@ extern "C" int nvit_pool_ln_bwd(const void* dy, const float* gamma, const float*
 extern "C" int nvit_head_scale_bwd(const float* dlogits, const float* raw, const float* sz, float sz_mul, void* draw, float* dsz,
                                    int64_t B, int64_t N, int64_t ld_draw, void* stream) {
   NVIT_REQUIRE(dlogits && raw && draw && B > 0 && N > 0 && ld_draw >= N, "nvit_head_scale_bwd: bad arguments");
-  head_scale_bwd_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)(B < 32 ? B : 32)), 256, 0, ST(stream)>>>(dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
+  launch(head_scale_bwd_kernel, dim3((unsigned)((N + 255) / 256), (unsigned)(B < 32 ? B : 32)), 256, 0, ST(stream), dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -741,7 +757,7 @@ extern "C" int nvit_head_scale_bwd(const float* dlogits, const float* raw, const
 extern "C" int nvit_cross_entropy(const float* logits, const int64_t* target, float* loss, float* dlogits, float gscale, int64_t B,
                                   int64_t N, void* stream) {
   NVIT_REQUIRE(logits && target && B > 0 && N > 0 && (loss || dlogits), "nvit_cross_entropy: bad arguments");
-  cross_entropy_kernel<<<(unsigned)B, 256, 0, ST(stream)>>>(logits, reinterpret_cast<const long long*>(target), loss, dlogits, gscale, (int)B, (int)N);
+  launch(cross_entropy_kernel, (unsigned)B, 256, 0, ST(stream), logits, reinterpret_cast<const long long*>(target), loss, dlogits, gscale, (int)B, (int)N);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -749,7 +765,7 @@ extern "C" int nvit_cross_entropy(const float* logits, const int64_t* target, fl
 extern "C" int nvit_tanh_mse(const void* pred, const void* target, int64_t n, float inv_count, float* out_accum, void* stream) {
   NVIT_REQUIRE(pred && target && out_accum && n >= 0, "nvit_tanh_mse: bad arguments");
   if (n == 0) return NVIT_OK;
-  tanh_mse_kernel<<<stream_grid(n / 8 + 1, 256, 4), 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(target), n, inv_count, out_accum);
+  launch(tanh_mse_kernel, stream_grid(n / 8 + 1, 256, 4), 256, 0, ST(stream), static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(target), n, inv_count, out_accum);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -764,7 +780,7 @@ extern "C" int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int
   if (n == 0) return NVIT_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adamw_flat_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, n_decay, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+  launch(adamw_flat_kernel, stream_grid(n / 4 + 1, 256), 256, 0, ST(stream), p, g, m, v, n, n_decay, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                                                        (float)sqrt(bc2), gnorm_sq, max_norm, dev_lr_step);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -774,7 +790,7 @@ extern "C" int nvit_weight_norm_multi(const int64_t* table_dev, int64_t n_tensor
   NVIT_REQUIRE(table_dev && n_tensors > 0 && total_units > 0, "nvit_weight_norm_multi: bad arguments");
   const long long cap = 1ll * nvit_num_sms() * 8;
   const int grid = (int)(total_units < cap ? total_units : cap);
-  weight_norm_multi_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table_dev), (int)n_tensors, total_units);
+  launch(weight_norm_multi_kernel, grid, 256, 0, ST(stream), reinterpret_cast<const long long*>(table_dev), (int)n_tensors, total_units);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) residual_fwd_kernel(const float* __restri
                                                            const float* __restrict__ h0, const float* __restrict__ skip,
                                                            float* __restrict__ out32, __nv_bfloat16* __restrict__ out16,
                                                            int M, int C) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) residual_bwd_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ dx,
                                                            float* __restrict__ dh0, float* __restrict__ dalpha,
                                                            float* __restrict__ dskip, int M, int C) {
+  pdl_enter();
   extern __shared__ float s_dlr[];  // [C] per-CTA reduction of d lr, then [C] lr
   float* s_lr = s_dlr + C;
   __shared__ float s_dskip;
@@ -307,8 +309,8 @@ extern "C" int nvit_residual_fwd(const float* h, const void* x_bf16, const float
   auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto ob = static_cast<__nv_bfloat16*>(out_bf16);
   NVIT_DISPATCH_NV(C, {
-    if (h0) residual_fwd_kernel<NV, true><<<grid, 256, 0, st>>>(h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
-    else    residual_fwd_kernel<NV, false><<<grid, 256, 0, st>>>(h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
+    if (h0) launch(residual_fwd_kernel<NV, true>, grid, 256, 0, st, h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
+    else    launch(residual_fwd_kernel<NV, false>, grid, 256, 0, st, h, xb, alpha, alpha_mul, h0, skip, out_f32, ob, (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -329,10 +331,10 @@ extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_b
   auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto dxb = static_cast<__nv_bfloat16*>(dx_bf16);
   NVIT_DISPATCH_NV(C, {
-    if (h0 && dh_accumulate)       residual_bwd_kernel<NV, true, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
-    else if (h0)                   residual_bwd_kernel<NV, true, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
-    else if (dh_accumulate)        residual_bwd_kernel<NV, false, true><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
-    else                           residual_bwd_kernel<NV, false, false><<<grid, 256, smem, st>>>(g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    if (h0 && dh_accumulate)       launch(residual_bwd_kernel<NV, true, true>, grid, 256, smem, st, g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else if (h0)                   launch(residual_bwd_kernel<NV, true, false>, grid, 256, smem, st, g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else if (dh_accumulate)        launch(residual_bwd_kernel<NV, false, true>, grid, 256, smem, st, g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
+    else                           launch(residual_bwd_kernel<NV, false, false>, grid, 256, smem, st, g, h, xb, alpha, alpha_mul, h0, skip, dh, dxb, dh0, dalpha_accum, dskip_accum, (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;

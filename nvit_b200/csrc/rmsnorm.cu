@@ -27,6 +27,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) add_rmsnorm_fwd_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ w, float eps, float* __restrict__ y32,
                                                               __nv_bfloat16* __restrict__ y16, int M, int C) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) add_rmsnorm_bwd_kernel(const float* __res
                                                               const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                               float eps, float* dh, __nv_bfloat16* __restrict__ dx,
                                                               float* __restrict__ dw, int M, int C) {
+  pdl_enter();
   extern __shared__ float s_dw[];  // [C]
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -164,6 +166,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) add_skipnorm_fwd_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ x,
                                                                const float* __restrict__ h0, const float* __restrict__ skip,
                                                                float* __restrict__ out32, __nv_bfloat16* __restrict__ out16, int M, int C) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(256) add_skipnorm_bwd_kernel(const float* __re
                                                                const float* __restrict__ skip, float* __restrict__ dh,
                                                                __nv_bfloat16* __restrict__ dx, float* __restrict__ dh0,
                                                                float* __restrict__ dskip, int M, int C) {
+  pdl_enter();
   __shared__ float s_ds;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -302,7 +306,7 @@ extern "C" int nvit_add_rmsnorm_fwd(const float* h, const void* x_bf16, const fl
   if (M == 0) return NVIT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NVIT_RN_DISPATCH(C, {
-    add_rmsnorm_fwd_kernel<NV><<<rn_grid((int)M), 256, 0, st>>>(h, static_cast<const __nv_bfloat16*>(x_bf16), w, eps, y_f32,
+    launch(add_rmsnorm_fwd_kernel<NV>, rn_grid((int)M), 256, 0, st, h, static_cast<const __nv_bfloat16*>(x_bf16), w, eps, y_f32,
                                                                static_cast<__nv_bfloat16*>(y_bf16), (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
@@ -321,8 +325,8 @@ extern "C" int nvit_add_rmsnorm_bwd(const float* dy, const float* h, const void*
   auto xb = static_cast<const __nv_bfloat16*>(x_bf16);
   auto dxb = static_cast<__nv_bfloat16*>(dx_bf16);
   NVIT_RN_DISPATCH(C, {
-    if (dh_accumulate) add_rmsnorm_bwd_kernel<NV, true><<<rn_grid((int)M), 256, smem, st>>>(dy, h, xb, w, eps, dh, dxb, dw_accum, (int)M, (int)C);
-    else               add_rmsnorm_bwd_kernel<NV, false><<<rn_grid((int)M), 256, smem, st>>>(dy, h, xb, w, eps, dh, dxb, dw_accum, (int)M, (int)C);
+    if (dh_accumulate) launch(add_rmsnorm_bwd_kernel<NV, true>, rn_grid((int)M), 256, smem, st, dy, h, xb, w, eps, dh, dxb, dw_accum, (int)M, (int)C);
+    else               launch(add_rmsnorm_bwd_kernel<NV, false>, rn_grid((int)M), 256, smem, st, dy, h, xb, w, eps, dh, dxb, dw_accum, (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
@@ -336,7 +340,7 @@ extern "C" int nvit_add_skipnorm_fwd(const float* h, const void* x_bf16, const f
   if (M == 0) return NVIT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NVIT_RN_DISPATCH(C, {
-    add_skipnorm_fwd_kernel<NV><<<rn_grid((int)M), 256, 0, st>>>(h, static_cast<const __nv_bfloat16*>(x_bf16), h0, skip, out_f32,
+    launch(add_skipnorm_fwd_kernel<NV>, rn_grid((int)M), 256, 0, st, h, static_cast<const __nv_bfloat16*>(x_bf16), h0, skip, out_f32,
                                                                 static_cast<__nv_bfloat16*>(out_bf16), (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
@@ -351,7 +355,7 @@ extern "C" int nvit_add_skipnorm_bwd(const float* g, const float* h, const void*
   if (M == 0) return NVIT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NVIT_RN_DISPATCH(C, {
-    add_skipnorm_bwd_kernel<NV><<<rn_grid((int)M), 256, 0, st>>>(g, h, static_cast<const __nv_bfloat16*>(x_bf16), h0, skip, dh,
+    launch(add_skipnorm_bwd_kernel<NV>, rn_grid((int)M), 256, 0, st, g, h, static_cast<const __nv_bfloat16*>(x_bf16), h0, skip, dh,
                                                                 static_cast<__nv_bfloat16*>(dx_bf16), dh0, dskip_accum, (int)M, (int)C);
   });
   NVIT_CUDA_CHECK(cudaGetLastError());
