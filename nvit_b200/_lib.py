@@ -21,6 +21,7 @@ SIGNATURES = {
     "nvit_gemm_swiglu_cta_group": [I32],
     "nvit_set_sm_budget": [I32],
     "nvit_set_pdl": [I32],
+    "nvit_residual_bwd_staged": [I32],
     "nvit_gemm_debug": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
@@ -89,6 +90,9 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_GATEB_CTA_GROUP")     # ... and of the fused gate-backward GEMM
     if mode in ("1", "2"):
         lib.nvit_gemm_swiglu_cta_group(10 + int(mode))
+    mode = os.environ.get("NVIT_RESIDUAL_STAGED")     # form of the residual backward kernel (see include/nvit_b200.h)
+    if mode in ("0", "1"):
+        lib.nvit_residual_bwd_staged(int(mode))
     mode = os.environ.get("NVIT_PDL")                 # programmatic dependent launch of every kernel (see include/nvit_b200.h)
     if mode in ("0", "1"):
         lib.nvit_set_pdl(int(mode))

@@ -196,16 +196,22 @@ class Engine:
         last = self.slots[b + "mlp_c_proj.weight"]
         return lo, last.off + last.numel
 
-    def _build_norm_table(self):
+    def _build_norm_table(self, columns_first: bool = True):
         """Device table for nvit_weight_norm_multi (Trainer.normalize_matrices, train.py:461-480)."""
         rows, first = [], 0
-        for i in range(self.cfg.n_layer if self.cfg.use_nvit else 0):
-            b = f"transformer.h.{i}."
-            for nm, axis in (("query", 1), ("key", 1), ("value", 1), ("att_c_proj", 0), ("c_fc", 1), ("mlp_c_proj", 0)):
-                s = self.slots[b + nm + ".weight"]
-                r, c = s.shape
-                rows.append([self.P32.data_ptr() + 4 * s.off, 0, r, c, axis, first])
-                first += (r + 7) // 8 if axis == 1 else (c + 127) // 128
+        # Units are handed to CTAs in table order.  A column unit (axis 0: 128 columns x all rows, two passes) runs ~15x
+        # longer than a row unit (8 rows), so the column-normalised matrices come first: their units start at t = 0 and
+        # the short row units fill in behind them, instead of a handful of long units forming the tail of the launch.
+        for want in ((0, 1) if columns_first else (None,)):      # None: plain block order (scripts/wnorm_bench.py A/B)
+            for i in range(self.cfg.n_layer if self.cfg.use_nvit else 0):
+                b = f"transformer.h.{i}."
+                for nm, axis in (("query", 1), ("key", 1), ("value", 1), ("att_c_proj", 0), ("c_fc", 1), ("mlp_c_proj", 0)):
+                    if want is not None and axis != want:
+                        continue
+                    s = self.slots[b + nm + ".weight"]
+                    r, c = s.shape
+                    rows.append([self.P32.data_ptr() + 4 * s.off, 0, r, c, axis, first])
+                    first += (r + 7) // 8 if axis == 1 else (c + 127) // 128
         self.norm_table = torch.tensor(rows if rows else [[0] * 6], dtype=torch.int64, device=self.device)
         self.norm_units = first
 

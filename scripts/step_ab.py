@@ -1,6 +1,8 @@
-"""Same-box A/B of programmatic dependent launch (nvit_set_pdl): nViT-B/16, batch 256, one GPU.
+"""Same-box A/B of a process-wide on/off hook of the library on the training step: nViT-B/16, batch 256, one GPU.
 
-    python scripts/pdl_ab.py [--steps 10] [--reps 3] [--config b16] [--batch 256]
+    python scripts/step_ab.py [--hook nvit_set_pdl] [--steps 10] [--reps 3] [--config b16] [--batch 256] [--graph-only]
+
+Hooks: nvit_set_pdl (programmatic dependent launch), nvit_residual_bwd_staged (form of the residual backward kernel).
 
 Alternates the two modes inside one process (same clocks, same allocations): for each mode the step graph is captured
 again and `steps` replays are timed with CUDA events; the eager (launch-from-Python) path is timed the same way.
@@ -22,6 +24,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--config", default="b16")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--hook", default="nvit_set_pdl")
+    ap.add_argument("--graph-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = ViTConfig(**O.named_config(args.config).as_dict())
@@ -41,20 +45,20 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n, float(loss)
 
-    for graph in (True, False):
+    for graph in ((True,) if args.graph_only else (True, False)):
         tr = Trainer(model, learning_rate=1e-3, cuda_graph=graph)
         for _ in range(3):
             tr.step(X, y)
         for rep in range(args.reps):
             for mode in (0, 1):
-                _lib.call("nvit_set_pdl", mode)
+                _lib.call(args.hook, mode)
                 tr._graph = None                 # capture again under the new launch attribute
                 tr.step(X, y)
                 tr.step(X, y)
                 ms, loss = timed(tr, args.steps)
-                print(f"{'graph' if graph else 'eager'} pdl={mode} rep={rep}: {ms:.3f} ms/step  ({args.batch / ms * 1e3:.0f} images/s)  loss {loss:.4f}",
+                print(f"{'graph' if graph else 'eager'} {args.hook}={mode} rep={rep}: {ms:.3f} ms/step  ({args.batch / ms * 1e3:.0f} images/s)  loss {loss:.4f}",
                       flush=True)
-    _lib.call("nvit_set_pdl", 0)
+    _lib.call(args.hook, 0)
 
 
 if __name__ == "__main__":

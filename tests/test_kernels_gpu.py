@@ -5,6 +5,7 @@ Tolerances (stated per north_star: bf16 kernels vs an fp32 reference): GEMM/atte
 gradients rel-L2 <= 3e-2; fp32 streaming kernels <= 1e-5 relative.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -134,9 +135,23 @@ def test_gemm_swiglu_epilogue(M, C, with_suv, cta_group):
 
 
 # ---------------------------------------------------------------------------------------------- residual
-@pytest.mark.parametrize("M,C", [(64, 64), (333, 128), (777, 192), (2048, 768), (512, 1024)])
+RESIDUAL_STAGED_DEFAULT = "0"     # the library's default form of nvit_residual_bwd
+
+
+@pytest.fixture
+def residual_form(request):
+    """nvit_residual_bwd in both forms: rows in registers (0) and rows staged in shared memory by bulk copies (1)."""
+    _lib.call("nvit_residual_bwd_staged", request.param)
+    yield request.param
+    _lib.call("nvit_residual_bwd_staged", int(os.environ.get("NVIT_RESIDUAL_STAGED", RESIDUAL_STAGED_DEFAULT)))
+
+
+# (20011, 768) and (9001, 1024): enough rows per warp of the persistent grid for the stage ring to wrap several times
+@pytest.mark.parametrize("M,C", [(64, 64), (333, 128), (777, 192), (2048, 768), (512, 1024), (20011, 768), (9001, 1024)])
 @pytest.mark.parametrize("skip", [False, True])
-def test_residual_fwd_bwd(M, C, skip):
+@pytest.mark.parametrize("acc", [True, False])
+@pytest.mark.parametrize("residual_form", [0, 1], indirect=True)
+def test_residual_fwd_bwd(M, C, skip, acc, residual_form):
     cfg = O.named_config("micro", n_embd=C, base_scale=C ** -0.5)
     h = randn(M, C, seed=20).requires_grad_(True)
     xb = randn(M, C, seed=21, scale=0.3, dtype=torch.bfloat16)
@@ -163,10 +178,10 @@ def test_residual_fwd_bwd(M, C, skip):
     dh0 = torch.empty(M, C, device=DEV) if skip else None
     dalpha = torch.zeros(C, device=DEV)
     dskip = torch.zeros(1, device=DEV) if skip else None
-    ops.residual_bwd(g, h.detach(), xb, alpha.detach(), alpha_mul, dh, dx, dalpha, dh_accumulate=True,
+    ops.residual_bwd(g, h.detach(), xb, alpha.detach(), alpha_mul, dh, dx, dalpha, dh_accumulate=acc,
                      h0=None if h0 is None else h0.detach(), skip=None if sk is None else sk.detach(), dh0=dh0, dskip=dskip)
     torch.cuda.synchronize()
-    assert rel(dh - 0.25, h.grad) < 1e-4
+    assert rel(dh - (0.25 if acc else 0.0), h.grad) < 1e-4
     assert rel(dx, x.grad) < 6e-3
     assert rel(dalpha, alpha.grad) < 1e-3
     if skip:
