@@ -84,8 +84,9 @@ int nvit_residual_bwd(const float* g, const float* h, const void* x_bf16, const 
                       float* dalpha_accum, float* dskip_accum, int64_t M, int64_t C, void* stream);
 /* Form of nvit_residual_bwd: 0 = each warp holds its row of every stream in registers (direct global loads);
  * 1 = the rows of the next iterations arrive through per-warp rings of 1-D bulk copies (cp.async.bulk + mbarrier) in
- * shared memory, one persistent CTA per SM.  Same arithmetic, same results.  Process-wide. */
-int nvit_residual_bwd_staged(int on);
+ * shared memory, one persistent CTA per SM; 2 (default) = whichever was measured faster for the variant and width
+ * (staged for C >= 512 except the skip form without accumulation).  Same arithmetic, same results.  Process-wide. */
+int nvit_residual_bwd_staged(int mode);
 
 /* ---- original-ViT branch (config.use_nvit = False; BASELINE config 4) -------------------------------------------------
  *   add_rmsnorm : t = h (+ x_bf16, may be NULL);  y = t * rsqrt(mean(t^2) + eps) * w      (RMSNorm, model.py:172-184, applied

@@ -91,7 +91,7 @@ def load() -> ctypes.CDLL:
     if mode in ("1", "2"):
         lib.nvit_gemm_swiglu_cta_group(10 + int(mode))
     mode = os.environ.get("NVIT_RESIDUAL_STAGED")     # form of the residual backward kernel (see include/nvit_b200.h)
-    if mode in ("0", "1"):
+    if mode in ("0", "1", "2"):
         lib.nvit_residual_bwd_staged(int(mode))
     mode = os.environ.get("NVIT_PDL")                 # programmatic dependent launch of every kernel (see include/nvit_b200.h)
     if mode in ("0", "1"):

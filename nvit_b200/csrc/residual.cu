@@ -382,7 +382,7 @@ static cudaError_t launch_bwd_staged(int grid, int threads, size_t smem, cudaStr
 
 using namespace nvit;
 
-static int g_bwd_staged = 0;   // nvit_residual_bwd_staged
+static int g_bwd_staged = 2;   // nvit_residual_bwd_staged: 0 registers, 1 staged, 2 automatic (default)
 
 #define NVIT_DISPATCH_NV(C, ...)                                  \
   do {                                                            \
@@ -431,7 +431,12 @@ extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_b
   // least two stages per warp; one persistent CTA per SM with as many warps (8, 6 or 4) and stages (<= 4) as 227 KB hold.
   const uintptr_t align_all = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(x_bf16) |
                               reinterpret_cast<uintptr_t>(h0) | reinterpret_cast<uintptr_t>(dh);
-  if (g_bwd_staged && (C % 8) == 0 && (align_all & 15) == 0) {
+  // MEASURED (scripts/hbm_kernels_bench.py, M = 50 176, registers -> staged): C = 768: plain 129 -> 114 us, += 140 -> 137,
+  // skip 168 -> 175, skip and += 302 -> 200; C = 1024: 177 -> 147, 245 -> 183, 238 -> 238, 404 -> 262.  The skip form
+  // without += is the one case the ring does not help (two stages only, the longest arithmetic chain per row), so the
+  // automatic mode keeps it in registers; small widths (tiny models, microsecond launches) stay on the register form too.
+  const bool want_staged = g_bwd_staged == 1 || (g_bwd_staged == 2 && C >= 512 && !(h0 && !dh_accumulate));
+  if (want_staged && (C % 8) == 0 && (align_all & 15) == 0) {
     const size_t stage = static_cast<size_t>(C) * 4 * (2 + (h0 ? 1 : 0) + (dh_accumulate ? 1 : 0)) + static_cast<size_t>(C) * 2;
     for (int W = 8; W >= 4; W -= 2) {
       int ns = 4;
@@ -465,7 +470,8 @@ extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_b
   return NVIT_OK;
 }
 
-extern "C" int nvit_residual_bwd_staged(int on) {   // 0: rows held in registers, 1: rows staged in shared memory by bulk copies
-  g_bwd_staged = on ? 1 : 0;
+extern "C" int nvit_residual_bwd_staged(int mode) {   // 0: rows held in registers, 1: rows staged in shared memory, 2: automatic
+  NVIT_REQUIRE(mode >= 0 && mode <= 2, "nvit_residual_bwd_staged: mode must be 0 (registers), 1 (staged) or 2 (automatic)");
+  g_bwd_staged = mode;
   return NVIT_OK;
 }

@@ -67,7 +67,7 @@ def residual_bwd(M, C):
                 res.setdefault(mode, []).append(us)
             line = "  ".join(f"staged={m}: " + " / ".join(f"{u:.1f}" for u in v) + f" us ({nbytes / min(v) / 1e3:.0f} GB/s)" for m, v in res.items())
             print(f"residual_bwd M={M} C={C} skip={sk} acc={acc} ({nbytes / 1e6:.0f} MB): {line}", flush=True)
-    _lib.call("nvit_residual_bwd_staged", 0)
+    _lib.call("nvit_residual_bwd_staged", 2)
 
 
 if __name__ == "__main__":

@@ -26,7 +26,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--hook", default="nvit_set_pdl")
     ap.add_argument("--graph-only", action="store_true")
+    ap.add_argument("--modes", default="0,1", help="the two hook values to alternate")
+    ap.add_argument("--restore", type=int, default=None, help="hook value to leave behind (default: the first mode)")
     args = ap.parse_args()
+    modes = [int(m) for m in args.modes.split(",")]
     dev = torch.device("cuda", 0)
     cfg = ViTConfig(**O.named_config(args.config).as_dict())
     torch.manual_seed(0)
@@ -50,7 +53,7 @@ def main():
         for _ in range(3):
             tr.step(X, y)
         for rep in range(args.reps):
-            for mode in (0, 1):
+            for mode in modes:
                 _lib.call(args.hook, mode)
                 tr._graph = None                 # capture again under the new launch attribute
                 tr.step(X, y)
@@ -58,7 +61,7 @@ def main():
                 ms, loss = timed(tr, args.steps)
                 print(f"{'graph' if graph else 'eager'} {args.hook}={mode} rep={rep}: {ms:.3f} ms/step  ({args.batch / ms * 1e3:.0f} images/s)  loss {loss:.4f}",
                       flush=True)
-    _lib.call(args.hook, 0)
+    _lib.call(args.hook, modes[0] if args.restore is None else args.restore)
 
 
 if __name__ == "__main__":

@@ -135,7 +135,7 @@ def test_gemm_swiglu_epilogue(M, C, with_suv, cta_group):
 
 
 # ---------------------------------------------------------------------------------------------- residual
-RESIDUAL_STAGED_DEFAULT = "0"     # the library's default form of nvit_residual_bwd
+RESIDUAL_STAGED_DEFAULT = "2"     # the library's default: automatic choice of the form of nvit_residual_bwd
 
 
 @pytest.fixture
