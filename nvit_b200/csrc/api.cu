@@ -12,25 +12,29 @@ void nvit_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_sm_budget = 0;  // 0 = all SMs
+static std::atomic<int> g_sm_budget{0};  // 0 = all SMs
 
 // Number of SMs the persistent kernels size their grids for: the device's SM count, or the budget set through
 // nvit_set_sm_budget (data-parallel runs leave a few SMs to the NCCL kernels that overlap the backward pass).
 int nvit_num_sms() {
-  static int n = 0;
+  static std::atomic<int> cached[128];      // per device; 0 = not queried yet
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) dev = -1;
+  if (dev >= 0) n = cached[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
+    if (dev >= 0) cached[dev].store(n, std::memory_order_relaxed);
   }
-  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+  const int budget = g_sm_budget.load(std::memory_order_relaxed);
+  return (budget > 0 && budget < n) ? budget : n;
 }
 
 // Programmatic dependent launch (common.cuh: pdl_wait / nvit::launch).  Off unless nvit_set_pdl(1).
-static int g_pdl = 0;
-int nvit_pdl_enabled() { return g_pdl; }
+static std::atomic<int> g_pdl{0};
+int nvit_pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
 extern "C" int nvit_set_pdl(int on) {
-  g_pdl = on ? 1 : 0;
+  g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
   return NVIT_OK;
 }
 
@@ -42,6 +46,6 @@ extern "C" int nvit_set_sm_budget(int n) {
     nvit_set_error("nvit_set_sm_budget: negative budget");
     return NVIT_ERR_ARG;
   }
-  g_sm_budget = n & ~1;  // CTA pairs: keep it even
+  g_sm_budget.store(n & ~1, std::memory_order_relaxed);  // CTA pairs: keep it even
   return NVIT_OK;
 }

@@ -783,10 +783,11 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
   p.dbg = g_att_dbg;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  int dev;
+  if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
-    attr_set = true;
+    once.mark(dev);
   }
   launch(attn_fwd_kernel, (unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), p);
   NVIT_CUDA_CHECK(cudaGetLastError());
@@ -829,10 +830,11 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
   p.dbg = g_att_dbg;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  int dev;
+  if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    attr_set = true;
+    once.mark(dev);
   }
   launch(attn_bwd_kernel, (unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), p);
   NVIT_CUDA_CHECK(cudaGetLastError());

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <utility>
+#include <atomic>
 
 #define NVIT_OK 0
 #define NVIT_ERR_ARG -1
@@ -338,6 +339,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+// ----------------------------------------------------------------------------- host: per-device once-flags
+// cudaFuncSetAttribute is per device and entry points are called from several host threads (the main thread, the
+// autograd engine's backward thread): one bit per device, set after the attribute call succeeded.  Two threads racing
+// on the first call both make the (idempotent) call; nobody launches before it has been made on their device.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done[2];     // devices 0..127
+  bool needed(int* dev_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) { *dev_out = -1; return true; }
+    *dev_out = dev;
+    return ((done[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0;
+  }
+  void mark(int dev) {
+    if (dev >= 0) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+};
 
 // ----------------------------------------------------------------------------- host: kernel launch
 // One launch path for the whole library (replaces <<< >>>): optional cluster width, optional programmatic serialisation.

@@ -779,15 +779,17 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
+  static std::atomic<PFN_encodeTiled> fn{nullptr};     // the entry point is process-wide; racing threads store the same value
+  PFN_encodeTiled f = fn.load(std::memory_order_acquire);
+  if (f) return f;
   void* ptr = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
       qres != cudaDriverEntryPointSuccess)
     return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  return fn;
+  f = reinterpret_cast<PFN_encodeTiled>(ptr);
+  fn.store(f, std::memory_order_release);
+  return f;
 }
 
 // Tensor map of rank 2 or 3 (dims innermost first, strides in elements for dims 1..rank-1).
@@ -921,11 +923,12 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
     if (!p.accumulate)  // partial sums are added into C: start from zero
       NVIT_CUDA_CHECK(cudaMemset2DAsync(p.C, p.ldc * sizeof(float), 0, p.N * sizeof(float), p.M, stream));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;      // per instantiation
+  int dev;
+  if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, SWIGLU, CG2, GATEB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          T::SMEM_BYTES));
-    attr_set = true;
+    once.mark(dev);
   }
   const long long units = 1ll * p.tiles_m * p.tiles_n * p.splits;
   const int nwork = (int)(units < workers ? units : workers);
@@ -952,11 +955,11 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
 
 using namespace nvit;
 
-static int g_force_cg = 0;  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
-static int g_swiglu_cg = 2; // CTA-group mode of the gate GEMM under the auto policy (nvit_gemm_swiglu_cta_group)
-static int g_gateb_cg = 2;  // ... and of the fused gate-backward GEMM (mode + 10 through the same hook)
-static int g_gateb_groups = 4;  // epilogue groups of the fused gate-backward GEMM (mode 22 / 24 through the same hook)
-static int g_dbg = 0;       // see GemmParams::dbg
+static std::atomic<int> g_force_cg{0};  // 0 auto, 1 single-CTA tiles, 2 CTA pairs
+static std::atomic<int> g_swiglu_cg{2}; // CTA-group mode of the gate GEMM under the auto policy (nvit_gemm_swiglu_cta_group)
+static std::atomic<int> g_gateb_cg{2};  // ... and of the fused gate-backward GEMM (mode + 10 through the same hook)
+static std::atomic<int> g_gateb_groups{4};  // epilogue groups of the fused gate-backward GEMM (mode 22 / 24 through the same hook)
+static std::atomic<int> g_dbg{0};       // see GemmParams::dbg
 
 extern "C" int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t M, int64_t N, int64_t K,
                               int64_t lda, int64_t ldb, int64_t ldc, int64_t ldc2, int a_mn_major, int b_mn_major,

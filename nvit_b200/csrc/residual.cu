@@ -368,12 +368,13 @@ constexpr size_t kStagedSmemMax = 232448 - 1024;   // 227 KB per CTA minus the k
 
 template <int NV, bool SKIP, bool ACC, typename... Args>
 static cudaError_t launch_bwd_staged(int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
-  static bool configured = false;    // per instantiation; the attribute is idempotent, so a race only repeats the call
-  if (!configured) {
+  static DeviceOnce once;    // per instantiation
+  int dev;
+  if (once.needed(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(residual_bwd_kernel<NV, SKIP, ACC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kStagedSmemMax);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark(dev);
   }
   return launch(residual_bwd_kernel<NV, SKIP, ACC, true>, grid, threads, smem, st, args...);
 }
@@ -382,7 +383,7 @@ static cudaError_t launch_bwd_staged(int grid, int threads, size_t smem, cudaStr
 
 using namespace nvit;
 
-static int g_bwd_staged = 2;   // nvit_residual_bwd_staged: 0 registers, 1 staged, 2 automatic (default)
+static std::atomic<int> g_bwd_staged{2};   // nvit_residual_bwd_staged: 0 registers, 1 staged, 2 automatic (default)
 
 #define NVIT_DISPATCH_NV(C, ...)                                  \
   do {                                                            \
