@@ -55,6 +55,11 @@ int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t
 /* Test/benchmark hook: 0 = choose automatically (default), 1 = single-CTA 128-row tiles (cta_group::1),
  * 2 = CTA-pair 256-row tiles (cta_group::2, cluster of two SMs).  Process-wide. */
 int nvit_gemm_force_cta_group(int mode);
+/* Tile order of the persistent GEMM grids: 0 = n fastest over the whole output width (default); G > 0 = bands of G tiles
+ * along n (inside a band n fastest, then m), applied where an output has more than G tiles along n, so that the tiles in
+ * flight share fewer distinct operand panels; -1 = automatic (bands where they cut the operand rows shared by the tiles
+ * in flight by >= 10 %: on the nViT shapes the gate GEMM, G = 8).  Results do not depend on it.  Process-wide. */
+int nvit_gemm_raster_group(int group);
 /* Measurement aid for scripts/gemm_bench.py (outputs are WRONG when non-zero): 1 = the epilogue returns the accumulator
  * without reading it (main-loop-only time), 2 = it reads and converts but neither stages nor stores. */
 int nvit_gemm_debug(int mode);

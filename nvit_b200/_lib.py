@@ -18,6 +18,7 @@ P, I64, I32, F32 = c_void_p, c_int64, c_int, c_float
 SIGNATURES = {
     "nvit_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I32, I32, I32, I32, I32, P, P, F32, P, I64, I64, P],
     "nvit_gemm_force_cta_group": [I32],
+    "nvit_gemm_raster_group": [I32],
     "nvit_gemm_swiglu_cta_group": [I32],
     "nvit_set_sm_budget": [I32],
     "nvit_set_pdl": [I32],
@@ -93,6 +94,9 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_RESIDUAL_STAGED")     # form of the residual backward kernel (see include/nvit_b200.h)
     if mode in ("0", "1", "2"):
         lib.nvit_residual_bwd_staged(int(mode))
+    mode = os.environ.get("NVIT_GEMM_RASTER_GROUP")   # tile order of the GEMMs: band width along n (0 = n fastest)
+    if mode is not None and mode.lstrip("-").isdigit():
+        lib.nvit_gemm_raster_group(int(mode))
     mode = os.environ.get("NVIT_PDL")                 # programmatic dependent launch of every kernel (see include/nvit_b200.h)
     if mode in ("0", "1"):
         lib.nvit_set_pdl(int(mode))

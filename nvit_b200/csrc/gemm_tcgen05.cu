@@ -50,7 +50,33 @@ struct alignas(64) GemmParams {
   int swiglu_half;
   float colscale_mul;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
+  int group_n;         // tile order: 0 = n fastest over the whole width, G > 0 = bands of G tiles along n (tile_coords)
 };
+
+// Tile index -> (m tile, n tile).  The persistent CTAs (or pairs) take consecutive indices, so the order decides which
+// operand panels the ~74 / 148 tiles in flight share.  n fastest: the tiles in flight span few A row-panels and the whole
+// width; with tiles_n = 24 (the gate GEMM) that is 3 + 24 distinct panels.  Bands of G tiles along n (inside a band n
+// fastest, then m) make the set in flight ~74/G x G: 9 + 8 panels for G = 8, i.e. fewer distinct bytes pulled through L2.
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_tile, int& n_blk) {
+  if (p.group_n <= 0) {
+    n_blk = t % p.tiles_n;
+    m_tile = t / p.tiles_n;
+    return;
+  }
+  const int band_tiles = p.tiles_m * p.group_n;
+  const int full_bands = p.tiles_n / p.group_n;
+  const int band = t / band_tiles;
+  if (band < full_bands) {
+    const int r = t - band * band_tiles;
+    m_tile = r / p.group_n;
+    n_blk = band * p.group_n + r % p.group_n;
+  } else {                                     // the last, narrower band
+    const int gw = p.tiles_n - full_bands * p.group_n;
+    const int r = t - full_bands * band_tiles;
+    m_tile = r / gw;
+    n_blk = full_bands * p.group_n + r % gw;
+  }
+}
 
 template <int BN, bool A_MN, bool B_MN, bool CG2 = false, bool GATEB = false, bool SWIGLU = false, int NG = 2>
 struct GemmTraits {
@@ -179,8 +205,9 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
       for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u % p.splits;
         const int t = u / p.splits;
-        const int n_blk = t % p.tiles_n;
-        const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;   // this CTA's 128-row block
+        int m_tile, n_blk;
+        tile_coords(p, t, m_tile, n_blk);
+        const int m_blk = m_tile * (CG2 ? 2 : 1) + (int)cta_rank;   // this CTA's 128-row block
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         const int a_row = m_blk * T::BM;
@@ -322,19 +349,23 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
     float gate_su = 1.f, gate_sv = 1.f;      // GATEB: this thread's entries of the next tile's scale vectors
     if constexpr (GATEB) {
       if (NG == 2 && unit0 < total_units && p.dbg != 1) {
-        const int t0 = unit0 / p.splits;
-        gate_fetch((t0 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t0 % p.tiles_n, 0);
+        int mt0, nb0;
+        tile_coords(p, unit0 / p.splits, mt0, nb0);
+        gate_fetch(mt0 * (CG2 ? 2 : 1) + (int)cta_rank, nb0, 0);
       }
       if (unit0 < total_units && use_vec && et < 256) {
-        const int j0 = min((unit0 / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
+        int mt0, nb0;
+        tile_coords(p, unit0 / p.splits, mt0, nb0);
+        const int j0 = min(nb0 * TILE_N + et, p.N - 1);
         gate_su = __ldg(p.colscale + j0) * p.colscale_mul;
         gate_sv = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
       }
     }
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int t = u / p.splits;
-      const int n_blk = t % p.tiles_n;
-      const int m_blk = (t / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank;
+      int m_tile, n_blk;
+      tile_coords(p, t, m_tile, n_blk);
+      const int m_blk = m_tile * (CG2 ? 2 : 1) + (int)cta_rank;
       const int row = m_blk * T::BM + erow;
       if (use_vec) {
         // per-tile column vectors (bias, scale) staged once in shared memory instead of per-element global loads
@@ -346,7 +377,9 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
             s_vec[et] = gate_su;
             s_vec[256 + et] = gate_sv;
             if (u + unit_stride < total_units) {
-              const int jn = min(((u + unit_stride) / p.splits % p.tiles_n) * TILE_N + et, p.N - 1);
+              int mtn, nbn;
+              tile_coords(p, (u + unit_stride) / p.splits, mtn, nbn);
+              const int jn = min(nbn * TILE_N + et, p.N - 1);
               gate_su = __ldg(p.colscale + jn) * p.colscale_mul;
               gate_sv = __ldg(p.colscale + p.swiglu_half + jn) * p.colscale_mul;
             }
@@ -439,8 +472,9 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
               if (s2 == 0) {
                 gate_fetch(m_blk, n_blk, 1);
               } else if (u + unit_stride < total_units) {
-                const int t2 = (u + unit_stride) / p.splits;
-                gate_fetch((t2 / p.tiles_n) * (CG2 ? 2 : 1) + (int)cta_rank, t2 % p.tiles_n, 0);
+                int mt2, nb2;
+                tile_coords(p, (u + unit_stride) / p.splits, mt2, nb2);
+                gate_fetch(mt2 * (CG2 ? 2 : 1) + (int)cta_rank, nb2, 0);
               }
             }
 #pragma unroll
@@ -851,6 +885,9 @@ static int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, u
   return make_tmap_bf16(m, base, 2, dims, strides, box);
 }
 
+static std::atomic<int> g_raster_group{0};   // nvit_gemm_raster_group: width of the n bands of the tile order (0 = n fastest)
+static int raster_group() { return g_raster_group.load(std::memory_order_relaxed); }
+
 template <int BN, bool A_MN, bool B_MN, bool SWIGLU, bool CG2, bool GATEB = false, int NG = 2>
 static int launch_gemm(GemmParams& p, const void* A, const void* B, long long lda, long long ldb, cudaStream_t stream) {
   using T = GemmTraits<BN, A_MN, B_MN, CG2, GATEB, SWIGLU, NG>;
@@ -900,6 +937,21 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
   p.tiles_m = (p.M + TILE_M - 1) / TILE_M;
   p.tiles_n = (p.N + TILE_N - 1) / TILE_N;
   p.kb_total = (p.K + T::BK - 1) / T::BK;
+  p.group_n = 0;
+  if (raster_group() > 0 && p.tiles_n > raster_group()) {
+    p.group_n = raster_group();
+  } else if (raster_group() < 0) {
+    // automatic: operand rows the tiles in flight pull in when they lie (in_flight / g) x g, for every band width g that
+    // divides tiles_n; bands are used when they beat n-fastest by >= 10 % (on the nViT shapes: the gate GEMM, 24 or 32
+    // tiles wide, g = 8)
+    const int in_flight = CG2 ? nvit_num_sms() / 2 : nvit_num_sms();
+    auto cost = [&](int g) { return (double)TILE_M * ((in_flight + g - 1) / g) + 256.0 * g; };   // B panels are 256 rows (BN, or u | v)
+    if (BN == 256 || SWIGLU) {
+      double best = 0.9 * cost(p.tiles_n < in_flight ? p.tiles_n : in_flight);
+      for (int g = 2; g < p.tiles_n; ++g)
+        if (p.tiles_n % g == 0 && cost(g) < best) { best = cost(g); p.group_n = g; }
+    }
+  }
   const int workers = CG2 ? nvit_num_sms() / 2 : nvit_num_sms();   // CTAs or CTA pairs
   int splits = p.splits;
   if (splits <= 0) {
@@ -1101,6 +1153,12 @@ extern "C" int nvit_gemm_swiglu_cta_group(int mode) {   // benchmarking hook: 1 
   if (mode > 20) g_gateb_groups = mode - 20;
   else if (mode > 10) g_gateb_cg = mode - 10;
   else g_swiglu_cg = mode;
+  return NVIT_OK;
+}
+
+extern "C" int nvit_gemm_raster_group(int group) {
+  NVIT_REQUIRE(group >= -1 && group <= 64, "nvit_gemm_raster_group: band width must be in [0, 64] (0 = n fastest) or -1 (automatic)");
+  nvit::g_raster_group.store(group, std::memory_order_relaxed);
   return NVIT_OK;
 }
 

@@ -42,6 +42,15 @@ def cta_group(request):
     _lib.call("nvit_gemm_force_cta_group", 0)
 
 
+@pytest.fixture(params=[0, 2, 5, 8, -1], ids=["n_fastest", "bands2", "bands5", "bands8", "auto"])
+def raster(request):
+    """Tile order of the persistent GEMM grids (nvit_gemm_raster_group): n fastest, bands of 2 / 5 / 8 tiles along n (with
+    the narrower last band whenever the tile count is not a multiple), or the automatic choice.  Results must not depend on it."""
+    _lib.call("nvit_gemm_raster_group", request.param)
+    yield request.param
+    _lib.call("nvit_gemm_raster_group", int(os.environ.get("NVIT_GEMM_RASTER_GROUP", "0")))
+
+
 GEMM_SHAPES = [
     (128, 128, 64), (256, 256, 128), (384, 768, 768), (200, 192, 192), (50, 1000, 768), (1024, 3072, 768),
     (256, 768, 3072), (333, 130, 72),
@@ -50,7 +59,7 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-def test_gemm_layouts(M, N, K, a_mn, b_mn, cta_group):
+def test_gemm_layouts(M, N, K, a_mn, b_mn, cta_group, raster):
     # leading dims must be multiples of 8 elements for TMA: pad the storage, use views
     def padded(rows, cols, seed):
         ld = (cols + 7) // 8 * 8
@@ -88,7 +97,7 @@ def test_gemm_epilogue_bias_scale_rowadd_and_bf16_copy(cta_group):
 
 
 @pytest.mark.parametrize("splits", [0, 1, 4, 13])
-def test_gemm_wgrad_splitk_and_accumulate(splits, cta_group):
+def test_gemm_wgrad_splitk_and_accumulate(splits, cta_group, raster):
     M, N, K = 6272, 768, 192   # dW[N,K] = dY[M,N]^T X[M,K]
     dy = randn(M, N, seed=8, scale=0.1, dtype=torch.bfloat16)
     x = randn(M, K, seed=9, scale=0.1, dtype=torch.bfloat16)
@@ -115,7 +124,7 @@ def test_gemm_dgrad_accumulates_into_fp32(cta_group):
 
 @pytest.mark.parametrize("M,C", [(300, 192), (1000, 768)])
 @pytest.mark.parametrize("with_suv", [True, False])
-def test_gemm_swiglu_epilogue(M, C, with_suv, cta_group):
+def test_gemm_swiglu_epilogue(M, C, with_suv, cta_group, raster):
     Fh = 4 * C
     x = randn(M, C, seed=13, scale=1.0 / math.sqrt(C), dtype=torch.bfloat16)
     w = randn(2 * Fh, C, seed=14, scale=1.0, dtype=torch.bfloat16)
@@ -267,7 +276,7 @@ def test_swiglu_fwd_bwd(with_suv):
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("M,Fh,K,with_suv", [(515, 768, 192, True), (1000, 3072, 768, True), (300, 64, 64, False), (4096, 768, 768, False),
                                              (129, 256, 136, True)])
-def test_gemm_gate_backward(M, Fh, K, with_suv, cta_group):
+def test_gemm_gate_backward(M, Fh, K, with_suv, cta_group, raster):
     """nvit_gemm_gate_bwd: d(uv_raw) = gate backward of dx = dY W against the saved raw u|v, dx never leaving the SM."""
     from nvit_b200 import _lib
     _lib.call("nvit_gemm_force_cta_group", cta_group)
@@ -321,7 +330,7 @@ def test_rowdot_div_gives_the_suv_gradient():
 @pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("M,C,K,norm_cols,with_bias", [(515, 192, 192, 128, False), (1000, 768, 768, 512, True), (300, 64, 64, 64, False),
                                                        (196, 2304, 768, 1536, False)])
-def test_gemm_qknorm(M, C, K, norm_cols, with_bias, cta_group):
+def test_gemm_qknorm(M, C, K, norm_cols, with_bias, cta_group, raster):
     """nvit_gemm_qknorm: projection + per-head unit norm + sqk scale in the epilogue, 1/||x|| as a side output."""
     from nvit_b200 import _lib
     _lib.call("nvit_gemm_force_cta_group", cta_group)
