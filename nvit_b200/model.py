@@ -147,6 +147,13 @@ class ViT(nn.Module):
         self.total_steps = 0
         if config.n_embd % config.n_head != 0 or config.n_embd // config.n_head != 64:
             raise ValueError("nvit_b200 attention kernels need head_dim = n_embd / n_head = 64")
+        if (config.image_size // config.local_patch_size) ** 2 > 256:
+            raise ValueError("nvit_b200 attention kernels hold one sequence per CTA: at most 256 tokens "
+                             f"(image_size {config.image_size} / patch {config.local_patch_size} gives "
+                             f"{(config.image_size // config.local_patch_size) ** 2})")
+        if config.n_embd > 1024 or config.n_embd % 64 != 0:
+            raise ValueError("nvit_b200 residual / norm kernels keep a token row in one warp's registers: n_embd must be a "
+                             f"multiple of 64, at most 1024 (got {config.n_embd})")
         if config.use_kohonen and not config.use_nvit:
             raise NotImplementedError("Kohonen maps are built for the nViT branch (BASELINE config 5); use_nvit=False + use_kohonen is not")
         C, P, G = config.n_embd, config.local_patch_size, config.global_patch_size

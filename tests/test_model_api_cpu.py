@@ -185,3 +185,17 @@ def test_checkpoint_interchange_with_the_reference(reference_model_module, tmp_p
             blk.rmsnorm_att, blk.rmsnorm_mlp = ref.RMSNorm(cfg.n_embd), ref.RMSNorm(cfg.n_embd)
     back.load_state_dict(ck2["model"])
     back.configure_optimizers(0.1, 1e-3, (0.9, 0.95), "cpu").load_state_dict(ck2["optimizer"])
+
+
+def test_unsupported_shapes_are_rejected_at_construction():
+    """Limits of the kernels (one sequence of <= 256 tokens per attention CTA, head_dim 64, rows of <= 1024 channels) raise
+    when the model is built, not as a kernel error in the middle of a step."""
+    from nvit_b200 import ViT, ViTConfig
+    base = O.named_config("tiny").as_dict()
+    with pytest.raises(ValueError, match="256 tokens"):
+        ViT(ViTConfig(**dict(base, image_size=136, local_patch_size=8, global_patch_size=16)))     # 17 x 17 = 289 tokens
+    with pytest.raises(ValueError, match="head_dim"):
+        ViT(ViTConfig(**dict(base, n_embd=192, n_head=4)))
+    with pytest.raises(ValueError, match="at most 1024"):
+        ViT(ViTConfig(**dict(base, n_embd=2048, n_head=32)))
+    ViT(ViTConfig(**dict(base, image_size=64, local_patch_size=4, global_patch_size=8)))             # 256 tokens: the limit
