@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--variant", default="nvit", choices=["nvit", "orig", "kohonen"],
                     help="nvit = normalized ViT (headline); orig = the reference's use_nvit=False branch (BASELINE config 4 A/B); "
                          "kohonen = nViT + Kohonen maps, 512 nodes (BASELINE config 5)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU (default); strong: --batch images in total, split evenly over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
@@ -202,6 +204,9 @@ def main():
     trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
                       overlap_allreduce=not args.no_overlap, sm_budget=args.sm_budget, bucket_blocks=args.bucket_blocks)
     B = args.batch
+    if args.scaling == "strong":
+        assert args.batch % world == 0, f"--scaling strong: --batch {args.batch} must divide by the {world} GPUs"
+        B = args.batch // world
     g = torch.Generator().manual_seed(1234 + rank)
     X_host = torch.randn(B, cfg.channels, cfg.image_size, cfg.image_size, generator=g).pin_memory()
     y_host = torch.randint(0, cfg.num_classes, (B,), generator=g).pin_memory()
@@ -302,7 +307,7 @@ def main():
             "metric": METRIC if (args.config == "b16" and args.variant == "nvit") else
                       f"{VARIANT_NAME[args.variant]}-{args.config.upper()} train images/sec",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"{VARIANT_NAME[args.variant]}-{args.config.upper()} {cfg.image_size}px train step (fwd+bwd+clip+AdamW+normalize), batch {B}/GPU, "
                                    f"bf16 GEMM/attention + fp32 residual, random-init weights",
