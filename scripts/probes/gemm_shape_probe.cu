@@ -9,7 +9,7 @@
 // peak at the running clock, and by how much?  The answer decides whether the long-K GEMMs (wgrad, c_fc dgrad,
 // mlp_c_proj) get such tiles (they can live without the TMEM double buffer the 512-column accumulators cost).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -I nvit_b200/csrc -o scripts/probes/gemm_shape_probe.bin scripts/probes/gemm_shape_probe.cu
-// Run:   scripts/probes/gemm_shape_probe.bin
+// Run:   scripts/probes/gemm_shape_probe.bin [1]      (1: random operands instead of zeros)
 #include "common.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -140,6 +140,18 @@ __global__ void __launch_bounds__(64, 1) shape_kernel(const __grid_constant__ Pr
   if (threadIdx.x == 0) { p.out[2 * blockIdx.x] = (unsigned long long)(c1 - c0); p.out[2 * blockIdx.x + 1] = t1 - t0; }
 }
 
+// pseudo-random bf16 in (-1, 1): with real operand bits the tensor pipe draws its real power, so the clock (and the rate)
+// is what a GEMM on activations sees; zeros show the pipe's rate at the highest clock
+__global__ void fill_random(uint16_t* p, size_t n, uint32_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const float v = (float)(h & 0xffff) / 32768.f - 1.f;
+    const __nv_bfloat16 b = __float2bfloat16(v);
+    p[i] = *reinterpret_cast<const uint16_t*>(&b);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -205,7 +217,8 @@ static void run(PFN_encodeTiled fn, void* A, void* B, int M, int N, int K, unsig
   fflush(stdout);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool random_fill = argc > 1 && atoi(argv[1]) != 0;     // gemm_shape_probe.bin 1: random operands (real power draw)
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   void* fnp = nullptr;
@@ -223,6 +236,12 @@ int main() {
   cudaMalloc(&out, 2 * 160 * sizeof(unsigned long long));
   cudaMemset(A, 0, (size_t)M * KMAX * 2);          // zeros: the rate does not depend on the values, and power is lowest
   cudaMemset(B, 0, (size_t)NMAX * KMAX * 2);
+  if (random_fill) {
+    fill_random<<<148 * 8, 256>>>(static_cast<uint16_t*>(A), (size_t)M * KMAX, 1u);
+    fill_random<<<148 * 8, 256>>>(static_cast<uint16_t*>(B), (size_t)NMAX * KMAX, 2u);
+    cudaDeviceSynchronize();
+  }
+  printf("operands: %s\n", random_fill ? "pseudo-random bf16 in (-1, 1)" : "zeros");
   // the step's shapes, forward orientation: c_fc (N 6144, K 768), mlp_c_proj (N 768 -> wide needs a multiple of 512: 1024), long K
   for (int rep = 0; rep < 2; ++rep) {
     run<0>(fn, A, B, M, 6144, 768, out, sms);
