@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """Headline benchmark: nViT-B/16 224px training images/sec on N B200s (BASELINE.json metric), plus the roofline of
-the dominant kernel and the CPU baseline.
+the dominant kernel group, a per-kernel-group table and the CPU baseline.
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the box's host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference model (baseline/_ref) on the box's host cores
 
 A "step" is one full training iteration of the step contract (train.py:885-993): forward, cross-entropy, backward,
 [gradient all-reduce], clip, AdamW, zero_grad, normalize_matrices, on a synthetic ImageNet-shaped batch of 256 images
 per GPU (weak scaling) with random-init weights.  `value` is measured with the batch resident in HBM; `e2e` goes through
-the public Trainer.step with pinned host batches copied in and the loss read back every step.
+the public Trainer.step with pinned host batches copied in and the loss read back every step.  At N > 1 a self-check
+outside the timed region (`dp_parity`) compares the N-rank NCCL step with a 1-rank step on the concatenated batch.
 """
 from __future__ import annotations
 
@@ -27,6 +28,21 @@ if ROOT not in sys.path:
 METRIC = "nViT-B/16 train images/sec"
 UNIT = "images/s"
 VARIANT_NAME = {"nvit": "nViT", "orig": "original-ViT-branch", "kohonen": "nViT+Kohonen(512 nodes)"}
+
+# BASELINE.json configs mapped onto ViTConfig fields; base_scale = n_embd ** -0.5
+SHAPES = {
+    "tiny": dict(image_size=32, n_layer=6, n_head=3, n_embd=192, num_classes=10, local_patch_size=4, global_patch_size=8),
+    "b16": dict(image_size=224, n_layer=12, n_head=12, n_embd=768, num_classes=1000, local_patch_size=16, global_patch_size=32),
+    "l16": dict(image_size=224, n_layer=24, n_head=16, n_embd=1024, num_classes=1000, local_patch_size=16, global_patch_size=32),
+}
+
+
+def config_dict(name: str, variant: str = "nvit") -> dict:
+    kw = dict(SHAPES[name])
+    kw["base_scale"] = kw["n_embd"] ** -0.5
+    kw["use_nvit"] = variant != "orig"
+    kw["use_kohonen"] = variant == "kohonen"
+    return kw
 
 
 def flops_per_image(cfg, kohonen: bool = False) -> float:
@@ -102,62 +118,223 @@ class ClockSampler:
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(cfg_name: str, budget_s: float = 20.0):
-    """The reference algorithm (oracle port of nvit/model.py + the train.py step) on this box's host cores."""
-    import torch
-    from oracle import nvit_oracle as O
-    cfg = O.named_config(cfg_name)
-    cores = os.cpu_count() or 1
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def _cpu_stepper_timer(cfg: dict):
+    """(time_fn, kind, description) of the reference's CPU implementation of the path: the UNMODIFIED reference model
+    from baseline/_ref driven by the restated step (baseline/ref_step.py) when it is staged, else the oracle port."""
     try:
-        cores = len(os.sched_getaffinity(0))
+        from baseline import ref_step, stage_ref
+        stage_ref.stage()               # copies from /root/reference where that exists (build container); no-op on the GPU box
+        ref_step.import_reference()
+        return (lambda batch, steps, warmup, threads: ref_step.time_cpu_steps(cfg, batch, steps, warmup, threads),
+                "reference", "reference nvit/model.py (baseline/_ref, unmodified) + train.py step restated in baseline/ref_step.py")
+    except Exception as e:      # not staged (should not happen: build() stages it): fall back to the port, and say so
+        from oracle import nvit_oracle as O
+        ocfg = O.OracleConfig(**cfg)
+        return (lambda batch, steps, warmup, threads: O.time_cpu_steps(ocfg, batch=batch, steps=steps, warmup=warmup, threads=threads),
+                "port", f"oracle port (reference not staged: {type(e).__name__})")
+
+
+def _host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
     except Exception:
-        pass
-    torch.set_num_threads(cores)
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(cfg_name: str, budget_s: float = 20.0):
+    """The reference's own CPU path on this box's host cores: a bounded sample (about `budget_s` seconds of CPU work)."""
+    cfg = config_dict(cfg_name)
+    timer, kind, what = _cpu_stepper_timer(cfg)
+    cores = _host_threads()
     t0 = time.perf_counter()
-    O.time_cpu_steps(cfg, batch=4, steps=1, warmup=0, threads=cores)           # page-in / warm-up, sizes the sample
+    timer(4, 1, 0, cores)                                          # page-in / warm-up, sizes the sample
     t4 = time.perf_counter() - t0
-    batch = int(max(4, min(32, 4 * (budget_s * 0.5) / max(t4, 1e-3))))
-    times, _ = O.time_cpu_steps(cfg, batch=batch, steps=1, warmup=0, threads=cores)
+    batch = int(max(4, min(32, 4 * (budget_s * 0.6) / max(t4, 1e-3))))
+    times, _ = timer(batch, 1, 0, cores)
     ips = batch / times[0]
-    return {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle (fp32 PyTorch restatement of nvit/model.py + train.py step) 1 step at batch {batch} of the same config, "
-                      f"{cores} threads"}
+    return {"value": ips, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{what}; fp32, eager, 1 step at batch {batch} of the same config, {cores} threads"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation (oracle port) timed on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle import nvit_oracle as O
-    cfg = O.named_config(args.config)
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    torch.set_num_threads(cores)
+    cfg = config_dict(args.config)
+    timer, kind, what = _cpu_stepper_timer(cfg)
+    cores = _host_threads()
     t0 = time.perf_counter()
-    O.time_cpu_steps(cfg, batch=2, steps=1, warmup=0, threads=cores)
+    timer(2, 1, 0, cores)
     t2 = time.perf_counter() - t0
     total = args.steps + args.warmup
-    batch = int(max(1, min(32, 2 * (150.0 / total) / max(t2, 1e-3))))
-    times, _ = O.time_cpu_steps(cfg, batch=batch, steps=args.steps, warmup=args.warmup, threads=cores)
+    # SURVEY.md 8d: batch 32 for the B/16-class shapes; smaller only if K + W steps of it would not end within ~4 minutes
+    target = 64 if args.config == "tiny" else 32
+    batch = int(max(1, min(target, 2 * (240.0 / max(total, 1)) / max(t2, 1e-3))))
+    times, _ = timer(batch, args.steps, args.warmup, cores)
     ms = 1000.0 * sum(times) / len(times)
     ips = batch / (ms / 1000.0)
-    sample = f"oracle port, fp32, {cores} threads, {args.steps} steps of batch {batch} (bounded sample of the batch-256 workload)"
+    sample = (f"{what}; fp32, eager, {cores} threads, {args.steps} steps of batch {batch} "
+              f"(bounded sample of the batch-{args.batch} workload)")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"nViT-{args.config} 224px train step, CPU", "batch_per_step": batch},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"nViT-{args.config.upper()} {cfg['image_size']}px train step (fwd+bwd+clip+AdamW+normalize), CPU",
+                   "batch_per_step": batch},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------- kernel groups
+def classify_call(name, a):
+    """Entry-point call -> (group label, bound, algorithmic FLOPs or bytes) from its arguments (see include/nvit_b200.h)."""
+    if name == "nvit_gemm_bf16":
+        M, N, K, a_mn, b_mn, out_f32, half = a[4], a[5], a[6], a[11], a[12], a[13], a[21]
+        fl = 2.0 * M * N * K * (2 if half else 1)
+        if half:
+            return "gemm c_fc + gate forward (swiglu epilogue)", "tensor", fl
+        if a_mn and b_mn:
+            return "gemm wgrad (split-K, TMA reduce-add)", "tensor", fl
+        if b_mn:
+            return ("gemm dgrad, fp32 += output" if out_f32 else "gemm dgrad, bf16 output"), "tensor", fl
+        return ("gemm forward, long K (>= 2048)" if K >= 2048 else "gemm forward, K < 2048"), "tensor", fl
+    if name == "nvit_gemm_qknorm":
+        return "gemm qkv + unit-norm q/k epilogue", "tensor", 2.0 * a[3] * a[4] * a[5]
+    if name == "nvit_gemm_gate_bwd":
+        return "gemm mlp_c_proj dgrad + gate backward epilogue", "tensor", 2.0 * a[6] * a[7] * a[8]
+    if name == "nvit_attention_fwd":
+        B, H, T, D = a[12], a[13], a[14], a[15]
+        return "attention forward", "tensor", 4.0 * B * H * T * T * D
+    if name == "nvit_attention_bwd":
+        B, H, T, D = a[20], a[21], a[22], a[23]
+        return "attention backward", "tensor", 10.0 * B * H * T * T * D
+    if name == "nvit_residual_fwd":
+        M, C, h0 = a[8], a[9], a[4]
+        return "residual forward", "hbm", float(M * C * (12 + (4 if h0 else 0)))
+    if name == "nvit_residual_bwd":
+        M, C, h0, acc = a[13], a[14], a[5], a[8]
+        return "residual backward", "hbm", float(M * C * (16 + (4 if acc else 0) + (8 if h0 else 0)))
+    if name == "nvit_adamw_norm_fused":
+        return "optimizer tail (clip+AdamW+normalize+bf16+zero, one pass)", "hbm", None     # bytes filled in by the caller
+    if name == "nvit_sumsq_f32":
+        return "gradient norm (sumsq)", "hbm", 4.0 * a[1]
+    return "other (" + name.replace("nvit_", "") + ")", "hbm", None
+
+
+def kernel_group_table(records, steps, peaks, tail_bytes):
+    groups = {}
+    for name, a, e0, e1 in records:
+        label, bound, work = classify_call(name, a)
+        if name == "nvit_adamw_norm_fused":
+            work = tail_bytes
+        g = groups.setdefault(label, {"bound": bound, "ms": 0.0, "n": 0, "work": 0.0, "known": True})
+        g["ms"] += e0.elapsed_time(e1)
+        g["n"] += 1
+        if work is None:
+            g["known"] = False
+        else:
+            g["work"] += work
+    total = sum(g["ms"] for g in groups.values())
+    rows = []
+    for label, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"group": label, "bound": g["bound"], "ms_per_step": g["ms"] / steps, "launches_per_step": g["n"] / steps,
+               "share": g["ms"] / total if total > 0 else 0.0}
+        if g["known"] and g["ms"] > 0:
+            if g["bound"] == "tensor":
+                ach = g["work"] / (g["ms"] * 1e-3) / 1e12
+                row.update(achieved=ach, unit="TFLOP/s", frac=ach / float(peaks["bf16_tflops_sustained"]))
+            else:
+                ach = g["work"] / (g["ms"] * 1e-3) / 1e9
+                row.update(achieved=ach, unit="GB/s", frac=ach / float(peaks["hbm_gbs"]))
+        rows.append(row)
+    return rows, total / steps
+
+
+# ---------------------------------------------------------------------------------------------------- dp parity
+def dp_parity_check(cfg, variant, world, rank, dev, trainer_kwargs, per_rank=8):
+    """Outside the timed region: an N-rank step over NCCL (the bench trainer's mode) on per-rank shards against a 1-rank
+    step on the concatenated batch (the multi-GPU oracle is "N-rank == 1-rank on the
+    concatenated batch"), plus bit-identity of the replicas after two optimizer steps (the second one graph-replayed
+    when the bench step is)."""
+    import torch
+    import torch.distributed as dist
+    from nvit_b200 import ViT, Trainer
+
+    def fresh(dp):
+        torch.manual_seed(0)
+        m = ViT(cfg).to(dev).train()
+        kw = dict(trainer_kwargs)
+        kw["graph_warmup_steps"] = 1
+        return m, Trainer(m, data_parallel=dp, **kw)
+
+    g = torch.Generator().manual_seed(4321 + rank)
+    Xr = torch.randn(per_rank, cfg.channels, cfg.image_size, cfg.image_size, generator=g).to(dev)
+    yr = torch.randint(0, cfg.num_classes, (per_rank,), generator=g).to(dev)
+    Xall = [torch.empty_like(Xr) for _ in range(world)]
+    yall = [torch.empty_like(yr) for _ in range(world)]
+    dist.all_gather(Xall, Xr)
+    dist.all_gather(yall, yr)
+
+    # (1) gradients: N-rank reduced gradient vs the 1-rank gradient of the concatenated batch
+    m_dp, t_dp = fresh(True)
+    t_dp._ensure_state()
+    t_dp.loss_buf.zero_()
+    t_dp.micro_step(Xr, yr, last=True)
+    t_dp._all_reduce_grads()
+    eng = m_dp.engine
+    g_dp = eng.G32[:eng.n_active].double().clone()
+    res = {}
+    if rank == 0:
+        m_1, t_1 = fresh(False)
+        t_1._ensure_state()
+        t_1.loss_buf.zero_()
+        t_1.micro_step(torch.cat(Xall), torch.cat(yall), last=True)
+        g_1 = m_1.engine.G32[:eng.n_active].double()
+        res["rel_l2_grad_err"] = float((g_dp - g_1).norm() / g_1.norm())
+        worst = 0.0
+        gn = float(g_1.norm())
+        for n in eng.order:
+            s = eng.slots[n]
+            if s.off >= eng.n_active:
+                continue
+            a, b = g_dp[s.off:s.off + s.numel], g_1[s.off:s.off + s.numel]
+            if float(b.norm()) > 1e-3 * gn:
+                worst = max(worst, float((a - b).norm() / b.norm()))
+        res["max_rel_grad_err"] = worst
+        res["loss_dp_rank0_vs_1rank"] = [float(t_dp.loss_buf), float(t_1.loss_buf)]
+        del m_1, t_1
+    eng.zero_grad()
+
+    # (2) two full steps (eager, then graph-replayed if enabled): replicas stay bit-identical, and match the 1-rank run
+    m_dp, t_dp = fresh(True)
+    for _ in range(2):
+        t_dp.step(Xr, yr)
+    torch.cuda.synchronize()
+    P = m_dp.engine.P32
+    digest = torch.stack([P.view(torch.int32).to(torch.int64).sum(), (P.view(torch.int32).to(torch.int64) * 31 % 1000003).sum()])
+    digests = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(digests, digest)
+    if rank == 0:
+        res["params_bit_identical_across_ranks"] = all(bool(torch.equal(d, digests[0])) for d in digests)
+        m_1, t_1 = fresh(False)
+        Xc, yc = torch.cat(Xall), torch.cat(yall)
+        for _ in range(2):
+            t_1.step(Xc, yc)
+        torch.cuda.synchronize()
+        P1 = m_1.engine.P32
+        na = m_dp.engine.n_active
+        res["rel_l2_param_err_after_2_steps"] = float((P[:na].double() - P1[:na].double()).norm() / P1[:na].double().norm())
+        res["steps_checked"] = "1 eager + 1 " + ("graph replay" if t_dp.use_graph else "eager")
+        res["per_rank_batch"] = per_rank
+        res["collective"] = "overlapped buckets" if t_dp.overlap else "one all-reduce after backward"
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,9 +351,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--overlap", action="store_true", help="data parallel: bucketed all-reduce overlapped with backward "
+                                                          "(default: one all-reduce after backward, measured faster)")
+    ap.add_argument("--no-overlap", action="store_true", help=argparse.SUPPRESS)      # the default now; kept for old command lines
+    ap.add_argument("--unfused-tail", action="store_true", help="separate sumsq / AdamW / normalize / cast kernels (A/B)")
     ap.add_argument("--bucket-blocks", type=int, default=1, help="data parallel: transformer blocks per overlapped all-reduce bucket")
     ap.add_argument("--sm-budget", type=int, default=0, help="data parallel: SMs the persistent kernels may use (0 = all)")
+    ap.add_argument("--no-dp-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -185,8 +366,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from nvit_b200 import ViT, ViTConfig, Trainer
-    from oracle import nvit_oracle as O          # config table only (shapes); nothing of the oracle runs on the GPU arm
+    from nvit_b200 import ViT, ViTConfig, Trainer, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,12 +377,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    ocfg = O.named_config(args.config, use_nvit=(args.variant != "orig"), use_kohonen=(args.variant == "kohonen"))
-    cfg = ViTConfig(**ocfg.as_dict())
+    cfg = ViTConfig(**config_dict(args.config, args.variant))
+    trainer_kwargs = dict(learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
+                          overlap_allreduce=args.overlap, sm_budget=args.sm_budget, bucket_blocks=args.bucket_blocks,
+                          fused_tail=not args.unfused_tail)
+
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp_parity = dp_parity_check(cfg, args.variant, world, rank, dev, trainer_kwargs)
+        torch.cuda.empty_cache()
+
     torch.manual_seed(0)
     model = ViT(cfg).to(dev).train()
-    trainer = Trainer(model, learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
-                      overlap_allreduce=not args.no_overlap, sm_budget=args.sm_budget, bucket_blocks=args.bucket_blocks)
+    trainer = Trainer(model, **trainer_kwargs)
     B = args.batch
     if args.scaling == "strong":
         assert args.batch % world == 0, f"--scaling strong: --batch {args.batch} must divide by the {world} GPUs"
@@ -251,19 +438,19 @@ def main():
     value = world * B * args.steps / (ms_total / 1000.0)
     final_loss = float(loss)
 
-    # ---------------- dominant-kernel probe: CUDA events around every c_fc GEMM launch.  Events cannot be timed inside a
-    # replayed graph, so when the step is graph-replayed the probe runs over extra eager steps of the same workload.
+    # ---------------- per-kernel probe: CUDA events around EVERY entry-point call.  Events cannot be timed inside a
+    # replayed graph, so the probe runs over extra eager steps of the same workload (rank 0 reports).
     probe_steps = min(args.steps, 3)
     was_graph = trainer.use_graph
     trainer.use_graph = False
-    eng.probe = []
+    trainer.step(X_res, y_res)                    # one un-probed eager step (the graph left the eager path cold)
+    barrier()
+    _lib.PROBE = []
     for _ in range(probe_steps):
         trainer.step(X_res, y_res)
     barrier()
-    probe = eng.probe
-    eng.probe = None
+    records, _lib.PROBE = _lib.PROBE, None
     trainer.use_graph = was_graph
-    kern_ms = sum(a.elapsed_time(b) for a, b in probe) / max(1, len(probe))
 
     # ---------------- end-to-end through the public API: pinned host batch -> H2D -> Trainer.step -> loss D2H, every step
     e2e = None
@@ -298,11 +485,24 @@ def main():
 
     if rank == 0:
         peaks, how = load_peaks()
-        M = B * (cfg.image_size // cfg.local_patch_size) ** 2
-        gemm_flops = 2.0 * M * (8 * cfg.n_embd) * cfg.n_embd
-        achieved = gemm_flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        peaks.setdefault("bf16_tflops_sustained", peak)
         fpi = flops_per_image(cfg)
+        n_trained = sum(s.numel for s in eng.slots.values() if s.off < eng.n_active)
+        n_emit = sum(s.numel for s in eng.slots.values() if s.off < eng.n_gemm)
+        tail_bytes = 32.0 * n_trained + 2.0 * n_emit          # p, g, m, v read; p, m, v, zeroed g written; bf16 operands
+        table, probed_ms = kernel_group_table(records, probe_steps, peaks, tail_bytes)
+        top = next((r for r in table if "frac" in r), None)
+        dominant = {"kernel": top["group"] if top else None, "bound": top["bound"] if top else None,
+                    "achieved": top.get("achieved") if top else None, "peak": (peak if top and top["bound"] == "tensor" else float(peaks["hbm_gbs"])),
+                    "unit": top.get("unit") if top else None, "frac": top.get("frac") if top else None, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json ({how}): bf16_tflops_sustained for tensor-bound groups, hbm_gbs for HBM-bound ones",
+                    "share_of_step": top.get("share") if top else None, "ms_per_step": top.get("ms_per_step") if top else None,
+                    "how": f"the kernel group with the largest share of the step; CUDA events around every launch over {probe_steps} eager "
+                           f"steps of the same workload"
+                           + (" (the timed region replays a CUDA graph, where events cannot be timed)" if trainer.use_graph else "")
+                           + "; algorithmic FLOPs / bytes from the call arguments; see kernel_groups for the rest and "
+                             "profiles/ for the ncu launch list and --set full captures"}
         line = {
             "metric": METRIC if (args.config == "b16" and args.variant == "nvit") else
                       f"{VARIANT_NAME[args.variant]}-{args.config.upper()} train images/sec",
@@ -313,21 +513,22 @@ def main():
                                    f"bf16 GEMM/attention + fp32 residual, random-init weights",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set (~20 GB of activations) is far larger than the 126 MB L2, no explicit flush",
-                       "launch": "CUDA graph replay of the whole step" if trainer.use_graph else "eager launches from Python"},
+                       "launch": "CUDA graph replay of the whole step" + (" (NCCL all-reduce captured)" if world > 1 else "")
+                                 if trainer.use_graph else "eager launches from Python",
+                       "collective": (None if world == 1 else ("bucketed all-reduce overlapped with backward" if trainer.overlap
+                                                               else "one NCCL all-reduce of the flat fp32 gradient buffer after backward")),
+                       "optimizer_tail": "one fused pass" if trainer.fused_tail else "separate kernels"},
             "clocks": clocks,
             "gpu_launches": launches,
             "final_loss": final_loss,
             "step_tensor_frac": {"flop_per_image": fpi, "achieved_tflops_per_gpu": fpi * value / world / 1e12,
                                  "frac_of_sustained_peak": fpi * value / world / 1e12 / peak},
-            "roofline": {"kernel": "gemm_tcgen05_kernel<256,K,K,SWIGLU> (c_fc GEMM + suv*SiLU gate epilogue, forward)",
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": (952.49e6 if (args.config == "b16" and B == 256) else None), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
-                         "launches_timed": len(probe), "avg_launch_ms": kern_ms, "flop_per_launch": gemm_flops,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
-                                           "profiles/r01_ncu_full_cfc_swiglu_gemm_final_raw.csv (bytes; algorithmic 1011e6)",
-                         "probe": f"CUDA events around each c_fc launch over {probe_steps} eager steps of the same workload"
-                                  + (" (the timed region replays a CUDA graph, where events cannot be timed)" if trainer.use_graph else "")},
+            "roofline": dominant,
+            "kernel_groups": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table[:8]],
+            "probed_ms_per_step": probed_ms,
         }
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

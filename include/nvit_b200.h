@@ -12,6 +12,8 @@
  *  - Return 0 on success, negative on error (never throws, never exits); nvit_last_error() gives the message of the
  *    last failure on the calling thread.
  *  - Entry points are re-entrant and stream-ordered.
+ *  - Tuning switches that select between equivalent kernel variants (tile mode, tile order) and the measurement-only
+ *    hooks are NOT part of this header: see include/nvit_b200_tuning.h.
  */
 #ifndef NVIT_B200_H_
 #define NVIT_B200_H_
@@ -52,17 +54,6 @@ int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t
                    int splits, const float* bias, const float* colscale, float colscale_mul, const float* rowadd,
                    int64_t rowadd_period, int64_t swiglu_half, void* stream);
 
-/* Test/benchmark hook: 0 = choose automatically (default), 1 = single-CTA 128-row tiles (cta_group::1),
- * 2 = CTA-pair 256-row tiles (cta_group::2, cluster of two SMs).  Process-wide. */
-int nvit_gemm_force_cta_group(int mode);
-/* Tile order of the persistent GEMM grids: 0 = n fastest over the whole output width (default); G > 0 = bands of G tiles
- * along n (inside a band n fastest, then m), applied where an output has more than G tiles along n, so that the tiles in
- * flight share fewer distinct operand panels; -1 = automatic (bands where they cut the operand rows shared by the tiles
- * in flight by >= 10 %: on the nViT shapes the gate GEMM, G = 8).  Results do not depend on it.  Process-wide. */
-int nvit_gemm_raster_group(int group);
-/* Measurement aid for scripts/gemm_bench.py (outputs are WRONG when non-zero): 1 = the epilogue returns the accumulator
- * without reading it (main-loop-only time), 2 = it reads and converts but neither stages nor stores. */
-int nvit_gemm_debug(int mode);
 
 /* ---- casts / reductions ------------------------------------------------------------------------------------- */
 /* autocast's weight/activation casts (torch.autocast around model.py:905 of train.py) */
@@ -156,14 +147,6 @@ int nvit_gemm_gate_bwd(const void* dY, const void* W, const void* uv_raw, const 
  * column reduction over [M, 8C] (model.py:148-151 backward). */
 int nvit_rowdot_div(const float* w, const float* dw, const float* div, float* out, int64_t rows, int64_t cols, void* stream);
 
-/* Benchmarking hook: CTA-group mode (1 or 2, default 2) of the swiglu gate GEMM under the automatic policy; 11 or 12 set
- * the mode of the fused gate-backward GEMM. */
-int nvit_gemm_swiglu_cta_group(int mode);
-
-/* Measurement aid: device buffer of 256 int64 receiving clock64() phase marks of the first 8 CTAs of the next attention
- * launches (NULL switches it off). */
-int nvit_attention_debug(void* dev_buf_256_int64);
-
 /* ---- patch embedding operand (model.py:286-304, 407-408; reconstruction target model.py:460-463) --------------
  *   out[(b,i,j), (c,kh,kw)] = reflect_pad(img, pad)[b, c, i*stride + kh, j*stride + kw]   as bf16, [B*g*g, ch*ksize^2]
  */
@@ -181,10 +164,13 @@ int nvit_pool_ln_fwd(const float* h, const float* gamma, const float* beta, floa
 /* dy bf16 [B,C] (grad wrt LayerNorm output) -> dh[B,T,C] (fp32, written), dgamma/dbeta += */
 int nvit_pool_ln_bwd(const void* dy_bf16, const float* gamma, const float* xhat, const float* rstd, float* dh,
                      float* dgamma_accum, float* dbeta_accum, int64_t B, int64_t T, int64_t C, void* stream);
+/* logits[B,N] = raw[B,N] * sz[N] * sz_mul (model.py:466-468): the head GEMM runs once and this scales its fp32 output */
+int nvit_head_scale_fwd(const float* raw, const float* sz, float sz_mul, float* logits, int64_t B, int64_t N, void* stream);
 /* logits = raw * sz_eff (model.py:466-468);  bwd: draw_bf16 = dlogits * sz_eff, dsz[N] += sum_b dlogits*raw*sz_mul */
 int nvit_head_scale_bwd(const float* dlogits, const float* raw, const float* sz, float sz_mul, void* draw_bf16,
                         float* dsz_accum, int64_t B, int64_t N, int64_t ld_draw, void* stream);
-/* softmax cross-entropy, mean over batch (train.py:906): loss[0] = mean CE; dlogits = (softmax - onehot)*gscale/B */
+/* softmax cross-entropy, mean over batch (train.py:906): loss[0] += mean CE; dlogits = (softmax - onehot)*gscale/B.
+ * A target outside [0, N) contributes no loss and a zero gradient row (never an out-of-bounds read); the mean divides by B. */
 int nvit_cross_entropy(const float* logits, const int64_t* target, float* loss, float* dlogits, float gscale,
                        int64_t B, int64_t N, void* stream);
 /* reconstruction loss (model.py:459-464): out[0] += sum (tanh(pred) - target)^2 * inv_count */
@@ -234,6 +220,19 @@ int nvit_tanh_mse_bwd(const void* pred_bf16, const void* target_bf16, int64_t n,
 int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int64_t n_decay, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, const float* gnorm_sq, float max_norm,
                     const float* dev_lr_step, void* stream);
+/* The whole optimizer tail in ONE pass (train.py:935-946 clip + AdamW + zero_grad, train.py:461-480
+ * normalize_matrices, and the bf16 weight casts of the next autocast forward): for every element p, g, m, v are read once,
+ * updated with nvit_adamw_flat's arithmetic, and - for the tensors normalize_matrices touches - the updated row / column
+ * is L2-normalised before it is written back as fp32 and as the bf16 GEMM operand; g is zeroed if zero_grad != 0.
+ * p, g, m, v are the flat buffers (same layout); w16 the flat bf16 operand buffer.  table_dev: n_segments entries of
+ * 8 x int64 {element offset, rows, cols, kind, bf16 element offset or -1, weight-decay flag, first_unit, 0}; kind 0 = plain
+ * (unit = 2048 elements), 1 = normalise every row over cols (unit = 8 rows), 2 = normalise every column over rows (unit =
+ * 128 columns); first_unit = running sum of units.  unit_counter_zeroed: device uint32 that must be 0 at launch (units
+ * are claimed dynamically).  The other arguments are those of nvit_adamw_flat. */
+int nvit_adamw_norm_fused(float* p, float* g, float* m, float* v, void* w16_bf16, const int64_t* table_dev, int64_t n_segments,
+                          int64_t total_units, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                          const float* gnorm_sq, float max_norm, const float* dev_lr_step, uint32_t* unit_counter_zeroed,
+                          int zero_grad, void* stream);
 /* Trainer.normalize_matrices (train.py:461-480) as ONE launch over a device table of n_tensors entries, each
  * 6 x int64: {w_f32 ptr, w_bf16 ptr or 0, rows, cols, axis, first_unit}.  axis = 1 normalizes every row over cols,
  * axis = 0 every column over rows (the reference's norm dims).  Units: 8 rows (axis 1) or 128 columns (axis 0) each;

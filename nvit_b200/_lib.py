@@ -23,7 +23,6 @@ SIGNATURES = {
     "nvit_set_sm_budget": [I32],
     "nvit_set_pdl": [I32],
     "nvit_residual_bwd_staged": [I32],
-    "nvit_gemm_debug": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
     "nvit_colsum_bf16": [P, I64, I64, I64, P, P],
@@ -38,7 +37,6 @@ SIGNATURES = {
     "nvit_swiglu_bwd": [P, P, P, F32, P, P, I64, I64, P],
     "nvit_attention_fwd": [P, P, P, I64, I64, I64, P, F32, F32, P, I64, P, I64, I64, I64, I64, P, P, I64, I64, P],
     "nvit_attention_bwd": [P, P, P, I64, I64, I64, P, F32, F32, P, P, I64, P, P, P, P, I64, I64, I64, P, I64, I64, I64, I64, P, P, I64, I64, P],
-    "nvit_attention_debug": [P],
     "nvit_gemm_qknorm": [P, P, P, I64, I64, I64, I64, I64, I64, P, P, F32, I64, I64, P, I64, P],
     "nvit_gemm_gate_bwd": [P, P, P, P, F32, P, I64, I64, I64, I64, I64, I64, I64, P],
     "nvit_rowdot_div": [P, P, P, P, I64, I64, P],
@@ -59,7 +57,11 @@ SIGNATURES = {
     "nvit_tanh_mse": [P, P, I64, F32, P, P],
     "nvit_adamw_flat": [P, P, P, P, I64, I64, F32, F32, F32, F32, F32, I64, P, F32, P, P],
     "nvit_weight_norm_multi": [P, I64, I64, P],
+    "nvit_adamw_norm_fused": [P, P, P, P, P, P, I64, I64, F32, F32, F32, F32, F32, I64, P, F32, P, P, I32, P],
+    "nvit_head_scale_fwd": [P, P, F32, P, I64, I64, P],
 }
+# measurement-only entry points: present only in -DNVIT_BENCH_HOOKS builds (include/nvit_b200_tuning.h, section 2)
+HOOK_SIGNATURES = {"nvit_gemm_debug": [I32], "nvit_attention_debug": [P]}
 LIBRARY_CALLS = {"nvit_last_error": ([], c_char_p), "nvit_version": ([], c_int), "nvit_sm_count": ([], c_int)}
 
 _lib = None
@@ -78,6 +80,11 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    for name, argtypes in HOOK_SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
     for name, (argtypes, restype) in LIBRARY_CALLS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -112,8 +119,21 @@ def last_error() -> str:
     return msg.decode() if msg else ""
 
 
+# Measurement aid (bench.py's per-kernel-group roofline table): when PROBE is a list, every entry-point call is bracketed by
+# CUDA events on the current stream and (name, args, start, end) is appended.  None (the default) costs one comparison.
+PROBE = None
+
+
 def call(name: str, *args) -> None:
     """Call an entry point; a non-zero status becomes a RuntimeError carrying nvit_last_error()."""
-    rc = getattr(load(), name)(*args)
+    if PROBE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        PROBE.append((name, args, e0, e1))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")

@@ -41,11 +41,23 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, hooks: bool = False) -> str:
+    """hooks=True builds nvit_b200/libnvit_b200_hooks.so with -DNVIT_BENCH_HOOKS (the measurement-only entry points of
+    include/nvit_b200_tuning.h, section 2) into its own object directory; the product library never contains them."""
+    global OBJ_DIR, LIB_PATH
+    if hooks:
+        saved = (OBJ_DIR, LIB_PATH, list(NVCC_FLAGS))
+        OBJ_DIR, LIB_PATH = os.path.join(ROOT, "build", "obj_hooks"), os.path.join(HERE, "libnvit_b200_hooks.so")
+        NVCC_FLAGS.append("-DNVIT_BENCH_HOOKS")
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            OBJ_DIR, LIB_PATH = saved[0], saved[1]
+            NVCC_FLAGS[:] = saved[2]
     os.makedirs(OBJ_DIR, exist_ok=True)
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers += [os.path.join(ROOT, "include", "nvit_b200.h")]
+    headers += [os.path.join(ROOT, "include", "nvit_b200.h"), os.path.join(ROOT, "include", "nvit_b200_tuning.h")]
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
@@ -71,4 +83,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, hooks="--hooks" in sys.argv))

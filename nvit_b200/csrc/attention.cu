@@ -108,7 +108,11 @@ struct alignas(64) AttnParams {
   long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
 };
 
+#ifdef NVIT_BENCH_HOOKS
 #define ATT_MARK(i) do { if (p.dbg && blockIdx.x < 8 && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + (i)] = clock64(); } while (0)
+#else
+#define ATT_MARK(i) do { } while (0)
+#endif
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
 __host__ __device__ constexpr uint32_t IDESC_MM(int N) { return umma_idesc_bf16(128, N, 1, 1); }  // A MN-major, B MN-major
@@ -752,10 +756,12 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 using namespace nvit;
 
 static long long* g_att_dbg = nullptr;
+#ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
   g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
   return NVIT_OK;
 }
+#endif
 
 extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
                                   const float* sqk, float sqk_mul, float scale, void* out, int64_t ldo, float* lse, int64_t B,

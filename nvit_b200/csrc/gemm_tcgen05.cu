@@ -23,6 +23,14 @@
 
 namespace nvit {
 
+// nvit_gemm_debug (WRONG outputs, measurement only) exists in -DNVIT_BENCH_HOOKS builds; the product library compiles the
+// debug branches away.
+#ifdef NVIT_BENCH_HOOKS
+#define NVIT_DBG(p) ((p).dbg)
+#else
+#define NVIT_DBG(p) 0
+#endif
+
 struct alignas(64) GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
         const int col = nb * BN + (eg + NG * s2) * 64 + (lane & 7) * 8;
         const __nv_bfloat16* base = p.gate_uv + (static_cast<long long>(mb) * T::BM + q * 32 + (lane >> 3)) * p.ld_uv + col;
         const int rows_left = p.M - (mb * T::BM + q * 32 + (lane >> 3));   // row 4k + l/8 is valid iff 4k < rows_left
-        const bool col_ok = col < p.N && p.dbg != 3;      // dbg 3 (measurement aid): no u|v loads
+        const bool col_ok = col < p.N && NVIT_DBG(p) != 3;      // dbg 3 (measurement aid): no u|v loads
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (col_ok && 4 * k < rows_left) {
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
     };
     float gate_su = 1.f, gate_sv = 1.f;      // GATEB: this thread's entries of the next tile's scale vectors
     if constexpr (GATEB) {
-      if (NG == 2 && unit0 < total_units && p.dbg != 1) {
+      if (NG == 2 && unit0 < total_units && NVIT_DBG(p) != 1) {
         int mt0, nb0;
         tile_coords(p, unit0 / p.splits, mt0, nb0);
         gate_fetch(mt0 * (CG2 ? 2 : 1) + (int)cta_rank, nb0, 0);
@@ -413,12 +421,12 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
       };
       // write 32 packed words (a [row][64 bf16] or [row][32 fp32] line) into this group's staging buffer and store it
       auto stage_store = [&](const uint32_t (&src)[32], const CUtensorMap* map, int n0, bool reduce) {
-        if (p.dbg == 2) return;                // measurement aid: TMEM reads + math, no staging / stores
+        if (NVIT_DBG(p) == 2) return;                // measurement aid: TMEM reads + math, no staging / stores
         uint8_t* buf = gbuf + (store_ctr % T::NBUF) * 16384;
         ++store_ctr;
         if (issuer) bulk_wait_group_read<T::NBUF - 1>();   // the store that last used this buffer has drained it
         named_bar_sync(bar_id, 128);
-        if (p.dbg != 4) {
+        if (NVIT_DBG(p) != 4) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(buf + erow * 128 + ((j ^ (erow & 7)) << 4)) =
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (issuer && p.dbg != 3) {
+        if (issuer && NVIT_DBG(p) != 3) {
           if (reduce) tma_reduce_add_2d(map, buf, n0, m_blk * T::BM);
           else tma_store_2d(map, buf, n0, m_blk * T::BM);
           bulk_commit_group();
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
         // dL/dx for 256 gate columns; this thread combines its row with the raw u, v of the forward pass and emits
         // dL/du_raw and dL/dv_raw as two [128 x 64] bf16 tiles per chunk.  (dL/dsuv follows from the c_fc weight
         // gradient: nvit_rowdot_div.)
-        if (p.dbg == 1) {
+        if (NVIT_DBG(p) == 1) {
           release_tmem();
         } else {
 #pragma unroll
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
               tmem_ld_32x32b_x32(taddr + c * 64 + hh * 32, r);
               tmem_wait_ld();
               if (s2 == 4 / NG - 1 && hh == 1) release_tmem();
-              if (live && p.dbg != 4) {                         // dbg 4 (measurement aid): no gate arithmetic
+              if (live && NVIT_DBG(p) != 4) {                         // dbg 4 (measurement aid): no gate arithmetic
                 // the results go back to the addresses the inputs came from, so the compiler may not move the next
                 // piece's loads above this piece's stores: fetch one piece ahead by hand
                 uint4 u_nx = *reinterpret_cast<const uint4*>(sbuf + erow * 128 + (((hh * 4) ^ (erow & 7)) << 4));
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
               // every warp ships its own 32 rows (tma_c2: box 64 x 32), so the warps of a group never wait for each other
               // (MEASURED: 397 -> 381 us single-CTA, 410 -> 404 us as pairs, against one 128-row store per group)
               __syncwarp();
-              if (lane == 0 && p.dbg != 2) {                    // dbg 2 (measurement aid): no stores
+              if (lane == 0 && NVIT_DBG(p) != 2) {                    // dbg 2 (measurement aid): no stores
                 tma_store_2d(&p.tma_c2, sbuf + q * 4096, n0, m_blk * T::BM + q * 32);
                 tma_store_2d(&p.tma_c2, sbuf + 16384 + q * 4096, p.swiglu_half + n0, m_blk * T::BM + q * 32);
                 bulk_commit_group();
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
             }
           }
         }
-      } else if (p.dbg == 1) {                      // measurement aid: main loop only
+      } else if (NVIT_DBG(p) == 1) {                      // measurement aid: main loop only
         release_tmem();
       } else if (!p.direct) {
         if constexpr (SWIGLU) {
@@ -1162,10 +1170,12 @@ extern "C" int nvit_gemm_raster_group(int group) {
   return NVIT_OK;
 }
 
+#ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_gemm_debug(int mode) {   // measurement aid, results are WRONG when non-zero
   g_dbg = mode;
   return NVIT_OK;
 }
+#endif
 
 extern "C" int nvit_gemm_force_cta_group(int mode) {
   NVIT_REQUIRE(mode == 0 || mode == 1 || mode == 2, "nvit_gemm_force_cta_group: mode must be 0 (auto), 1 or 2");

@@ -390,6 +390,14 @@ __global__ void __launch_bounds__(256) head_scale_bwd_kernel(const float* __rest
   if (dsz) atomicAdd(dsz + n, acc * sz_mul);
 }
 
+// logits = raw * sz_eff (model.py:466-468): the class-head GEMM runs once, its scaled copy is this B x N pass
+__global__ void __launch_bounds__(256) head_scale_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ sz, float sz_mul,
+                                                             float* __restrict__ logits, long long total, int N) {
+  pdl_enter();
+  for (long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x)
+    logits[i] = raw[i] * (sz[i % N] * sz_mul);
+}
+
 // softmax cross-entropy, one CTA per sample
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                                             float* __restrict__ loss, float* __restrict__ dlogits, float gscale, int B,
@@ -405,10 +413,12 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
   for (int n = threadIdx.x; n < N; n += blockDim.x) se += __expf(row[n] - mx);
   se = block_sum(se, red);
   const float lse = mx + __logf(se);
-  const int t = (int)target[b];
-  if (threadIdx.x == 0 && loss) atomicAdd(loss, (lse - row[t]) / (float)B);
+  const long long t64 = target[b];
+  const bool valid = t64 >= 0 && t64 < N;      // out of range (e.g. ignore_index -100): no loss, zero gradient row
+  const int t = valid ? (int)t64 : -1;
+  if (threadIdx.x == 0 && loss && valid) atomicAdd(loss, (lse - row[t]) / (float)B);
   if (dlogits) {
-    const float k = gscale / (float)B;
+    const float k = valid ? gscale / (float)B : 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x)
       dlogits[1ll * b * N + n] = (__expf(row[n] - lse) - (n == t ? 1.f : 0.f)) * k;
   }
@@ -750,6 +760,13 @@ extern "C" int nvit_head_scale_bwd(const float* dlogits, const float* raw, const
                                    int64_t B, int64_t N, int64_t ld_draw, void* stream) {
   NVIT_REQUIRE(dlogits && raw && draw && B > 0 && N > 0 && ld_draw >= N, "nvit_head_scale_bwd: bad arguments");
   launch(head_scale_bwd_kernel, dim3((unsigned)((N + 255) / 256), (unsigned)(B < 32 ? B : 32)), 256, 0, ST(stream), dlogits, raw, sz, sz_mul, static_cast<__nv_bfloat16*>(draw), dsz, (int)B, (int)N, ld_draw);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_head_scale_fwd(const float* raw, const float* sz, float sz_mul, float* logits, int64_t B, int64_t N, void* stream) {
+  NVIT_REQUIRE(raw && sz && logits && B > 0 && N > 0, "nvit_head_scale_fwd: bad arguments");
+  launch(head_scale_fwd_kernel, stream_grid(B * N, 256), 256, 0, ST(stream), raw, sz, sz_mul, logits, (long long)(B * N), (int)N);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

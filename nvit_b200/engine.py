@@ -44,7 +44,10 @@ class Engine:
         self.model = model
         self.cfg = model.config
         self.P32 = None
-        self._acts = {}
+        self._acts = {}                 # batch size -> activation set (insertion order = least recently used first)
+        self._pinned = set()            # batch sizes a captured CUDA graph points into: never evicted
+        self.max_resident_batches = 2   # activation sets kept resident (train + eval / last partial batch)
+        self.acts_epoch = 0             # bumped whenever an activation set is dropped or rebuilt
         self._saved = None
         self.grad_ready_hook = None     # callable(lo, hi): flat-gradient range [lo, hi) is final (data-parallel overlap)
         self.launches = 0
@@ -143,7 +146,10 @@ class Engine:
         self.W16 = torch.empty(self.n_gemm + (0 if self.rec_active else _align(rec.numel, 8)), device=device, dtype=BF16)
         self._rec16_off = rec.off if self.rec_active else self.n_gemm
         self._p16_version = None
+        self.tail_table = None
         self._acts = {}
+        self._pinned = set()
+        self.acts_epoch += 1
         self._build_norm_table()
         self.scratch = torch.zeros(8, device=device, dtype=F32)   # [0] recon loss, [1:4] map pair-loss sums, [4] smoothness
         # weights of the auxiliary losses times the incoming gradient: [0] reconstruction, [1] consistency,
@@ -226,9 +232,16 @@ class Engine:
         self.G32.zero_()
 
     def refresh_operands(self, force=False):
-        """autocast's weight casts: fp32 master -> bf16 GEMM operands, one launch for region A, one for the recon head."""
+        """autocast's weight casts: fp32 master -> bf16 GEMM operands, one launch for region A, one for the recon head.
+
+        The bf16 operands are rebuilt on EVERY forward except the first one after the engine itself produced them
+        together with the current fp32 values: only `fused_tail` (the Trainer's optimizer step, which writes fp32 and
+        bf16 in the same pass) marks them current, and the mark is spent by the next forward.  Writes the engine cannot see - an external optimizer, the reference's normalize_matrices going
+        through `W.data.copy_` (train.py:474-480; `.data` writes do not bump the tensor version) - are therefore always
+        picked up by the next forward; the cost is two streaming launches (~0.2 ms at B/16)."""
         ver = tuple(s.param._version for s in self.slots.values())
-        if not force and ver == self._p16_version:
+        if not force and self._p16_version is not None and ver == self._p16_version:
+            self._p16_version = None      # the mark covers exactly one forward: the one right after the fused tail
             return
         ops.cast_bf16(self.P32[:self.n_gemm], self.W16[:self.n_gemm])
         self.launches += 1
@@ -236,12 +249,68 @@ class Engine:
             rec = self.slots["reconstruction_head.0.weight"]
             ops.cast_bf16(self.P32[rec.off:rec.off + rec.numel], self.W16[self._rec16_off:self._rec16_off + rec.numel])
             self.launches += 1
-        self._p16_version = ver
+        self._p16_version = None          # valid for this forward only
+
+    def invalidate_operands(self):
+        """Force the next forward to rebuild the bf16 operands (call after writing weights behind the Trainer's back)."""
+        self._p16_version = None
+
+    # ------------------------------------------------------------------------------------------ fused optimizer tail
+    def _build_tail_table(self):
+        """Segment table of nvit_adamw_norm_fused: one entry per trained tensor, the column-normalised matrices first
+        (their units move ~20x the bytes of a row unit), then the row-normalised ones, then everything else."""
+        cfg = self.cfg
+        normed = {}
+        if cfg.use_nvit:
+            for i in range(cfg.n_layer):
+                b = f"transformer.h.{i}."
+                for nm, axis in (("query", 1), ("key", 1), ("value", 1), ("att_c_proj", 0), ("c_fc", 1), ("mlp_c_proj", 0)):
+                    normed[b + nm + ".weight"] = axis
+        segs = {2: [], 1: [], 0: []}
+        for n in self.order:
+            s = self.slots[n]
+            if s.off >= self.n_active:
+                continue
+            decay = 1 if s.off < self.n_decay else 0
+            w16_off = s.off if s.off < self.n_gemm else -1
+            if n in normed:
+                r, c = s.shape
+                kind = 1 if normed[n] == 1 else 2
+                units = (r + 7) // 8 if kind == 1 else (c + 127) // 128
+                segs[kind].append([s.off, r, c, kind, w16_off, decay, units])
+            else:
+                segs[0].append([s.off, 1, s.numel, 0, w16_off, decay, (s.numel + 2047) // 2048])
+        rows, first = [], 0
+        for kind in (2, 1, 0):
+            for off, r, c, k, w16, decay, units in segs[kind]:
+                rows.append([off, r, c, k, w16, decay, first, 0])
+                first += units
+        self.tail_table = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        self.tail_units = first
+
+    def fused_tail(self, m, v, lr, betas, eps, wd, step, counter, gnorm_sq=None, max_norm=0.0, dev_lr_step=None):
+        """clip scale + AdamW + normalize_matrices + bf16 operand emit + zero_grad, one launch (train.py:935-946, 461-480)."""
+        if getattr(self, "tail_table", None) is None:
+            self._build_tail_table()
+        ops.adamw_norm_fused(self.P32, self.G32, m, v, self.W16, self.tail_table, self.tail_table.shape[0], self.tail_units,
+                             lr, betas[0], betas[1], eps, wd, step, counter, gnorm_sq=gnorm_sq, max_norm=max_norm,
+                             dev_lr_step=dev_lr_step, zero_grad=True)
+        self.launches += 1
+        # fp32 and bf16 were written together: the operands are current until somebody bumps a parameter version
+        self._p16_version = tuple(s.param._version for s in self.slots.values())
 
     # ------------------------------------------------------------------------------------------ activations
     def _buffers(self, B):
         if B in self._acts:
+            self._acts[B] = self._acts.pop(B)       # most recently used last
             return self._acts[B]
+        # make room BEFORE allocating (an activation set is tens of GB): drop the least recently used unpinned sets
+        while len(self._acts) >= max(1, self.max_resident_batches):
+            victim = next((b for b in self._acts if b not in self._pinned), None)
+            if victim is None:
+                break
+            del self._acts[victim]
+            self.acts_epoch += 1
         cfg, dev = self.cfg, self.device
         C, L, P, G = cfg.n_embd, cfg.n_layer, cfg.local_patch_size, cfg.global_patch_size
         T = (cfg.image_size // P) ** 2
@@ -283,7 +352,7 @@ class Engine:
                       "k32a": e(M, C, dtype=F32), "k32b": e(M, C, dtype=F32), "dpred": e(M, Kl)})
         for k, v in a["ca"][0].items():      # the original-ViT branch addresses its single cross-attention call by these names
             a["ca_" + k] = v
-        self._acts = {B: a}      # keep one batch size resident
+        self._acts[B] = a
         return a
 
     def _wgrad(self, dy, x, gw):
@@ -297,22 +366,31 @@ class Engine:
         # uint8 [B, S, S, channels] (HWC, as the data loader holds images before ToTensor): normalised on the fly by the
         # im2col kernels with input_mean / input_std (Normalize(0.5, 0.5) of train.py:1081-1092 by default)
         self._u8 = img.dtype == torch.uint8
+        S = cfg.image_size
         if self._u8:
             if img.dim() != 4 or img.shape[-1] != cfg.channels:
                 raise ValueError("uint8 input must be [B, S, S, channels] (HWC)")
-        elif img.dtype != F32:
-            img = img.float()
+            if tuple(img.shape[1:3]) != (S, S):
+                raise ValueError("uint8 input must be [B, S, S, channels] with S = image_size")
+        else:
+            # the activation buffers are sized from the config: any other image shape would write past them (the
+            # reference fails at the position-embedding add, model.py:411-412)
+            if img.dim() != 4 or tuple(img.shape[1:]) != (cfg.channels, S, S):
+                raise ValueError(f"input must be [B, {cfg.channels}, {S}, {S}] (config channels / image_size), got {tuple(img.shape)}")
+            if img.dtype != F32:
+                img = img.float()
+        if img.shape[0] < 1:
+            raise ValueError("empty batch")
         img = img.contiguous()
         self._check_alias(img.device)
         self.refresh_operands()
         B = img.shape[0]
-        if self._u8 and img.shape[1] != cfg.image_size:
-            raise ValueError("uint8 input must be [B, S, S, channels] with S = image_size")
         if not cfg.use_nvit:
             return self._forward_orig(img, save)
         C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
         T = (cfg.image_size // P) ** 2
         a = self._buffers(B)
+        self._cur_B = B
         bias = cfg.bias
         p, w16 = self.p, self.w16
         amul = 0.05 / cfg.base_scale
@@ -366,8 +444,7 @@ class Engine:
         # ---- classifier head (model.py:455-456, 466-468) and reconstruction loss (model.py:459-464)
         ops.pool_ln_fwd(a["h32"][L], p("mlp_head.0.weight"), p("mlp_head.0.bias"), 1e-5, a["y16"], a["xhat"], a["rstd"], B, T, C)
         ops.linear_fwd(a["y16"], w16("mlp_head.1.weight"), a["raw"], bias=p("mlp_head.1.bias"))
-        ops.linear_fwd(a["y16"], w16("mlp_head.1.weight"), a["logits"], bias=p("mlp_head.1.bias"), colscale=p("sz"),
-                       colscale_mul=cfg.sz_init_value / cfg.sz_init_scaling)
+        ops.head_scale_fwd(a["raw"], p("sz"), cfg.sz_init_value / cfg.sz_init_scaling, a["logits"])
         ops.linear_fwd(a["h16"][L], w16("reconstruction_head.0.weight"), a["pred"], bias=p("reconstruction_head.0.bias"))
         self.scratch[0:1].zero_()
         ops.tanh_mse(a["pred"], a["A_l"], self.scratch[0:1])
@@ -452,7 +529,7 @@ class Engine:
         """The four Kohonen losses (model.py:437-442) as device scalars; smoothness sees the UPDATED nodes."""
         cfg = self.cfg
         C = cfg.n_embd
-        a = self._acts[next(iter(self._acts))]
+        a = self._acts[self._cur_B]
         som = a["som"]
         side = int(math.sqrt(cfg.kohonen_nodes // 2))
         if side * side != cfg.kohonen_nodes // 2:
@@ -679,6 +756,7 @@ class Engine:
         C, L, H, P, G = cfg.n_embd, cfg.n_layer, cfg.n_head, cfg.local_patch_size, cfg.global_patch_size
         T = (cfg.image_size // P) ** 2
         a = self._buffers(B)
+        self._cur_B = B
         bias = cfg.bias
         p, w16 = self.p, self.w16
         att_scale = 1.0 / float(C // H) ** 0.5
@@ -855,7 +933,7 @@ class NViTFunction(torch.autograd.Function):
             drec, dcons, dsmooth, dlq, dgq = ((d if d is not None else eng.aux_w.new_zeros(())) for d in daux)
             eng.aux_w[:5].copy_(torch.stack([drec, dcons, dlq, dgq, dsmooth]).to(F32))
         if dlogits is None:
-            dlogits = torch.zeros_like(eng._acts[next(iter(eng._acts))]["logits"])
+            dlogits = torch.zeros_like(eng._acts[eng._cur_B]["logits"])
         eng.backward(dlogits)
         grads = []
         for n in eng.order:

@@ -186,7 +186,17 @@ def head_scale_bwd(dlogits, raw, sz, sz_mul, draw, dsz):
 
 
 def cross_entropy(logits, target, loss, dlogits, gscale=1.0):
+    """Mean softmax cross-entropy (train.py:906).  Targets are int64 class indices; a target outside [0, N) is treated like
+    F.cross_entropy's ignore_index: no loss, zero gradient row (the mean still divides by B)."""
     B, N = logits.shape
+    _chk(logits, F32, "cross_entropy: logits")
+    _chk(target, torch.int64, "cross_entropy: target")
+    if target.shape != (B,):
+        raise ValueError(f"cross_entropy: target must have shape ({B},), got {tuple(target.shape)}")
+    if dlogits is not None:
+        _chk(dlogits, F32, "cross_entropy: dlogits")
+        if dlogits.shape != logits.shape:
+            raise ValueError("cross_entropy: dlogits must match logits")
     _lib.call("nvit_cross_entropy", _p(logits), _p(target), _p(loss), _p(dlogits), float(gscale), B, N, _stream())
 
 
@@ -242,3 +252,16 @@ def adamw_flat(p, g, m, v, n_decay, lr, beta1, beta2, eps, weight_decay, step, g
 
 def weight_norm_multi(table, n_tensors, total_units):
     _lib.call("nvit_weight_norm_multi", _p(table), n_tensors, total_units, _stream())
+
+
+def adamw_norm_fused(p, g, m, v, w16, table, n_segments, total_units, lr, beta1, beta2, eps, weight_decay, step, counter,
+                     gnorm_sq=None, max_norm=0.0, dev_lr_step=None, zero_grad=True):
+    """clip + AdamW + weight normalisation + bf16 operand emit + zero_grad in one pass (nvit_adamw_norm_fused)."""
+    _lib.call("nvit_adamw_norm_fused", _p(p), _p(g), _p(m), _p(v), _p(w16), _p(table), n_segments, total_units, float(lr), float(beta1),
+              float(beta2), float(eps), float(weight_decay), step, _p(gnorm_sq), float(max_norm), _p(dev_lr_step), _p(counter),
+              int(zero_grad), _stream())
+
+
+def head_scale_fwd(raw, sz, sz_mul, logits):
+    B, N = raw.shape
+    _lib.call("nvit_head_scale_fwd", _p(raw), _p(sz), float(sz_mul), _p(logits), B, N, _stream())

@@ -155,8 +155,8 @@ class Trainer:
 
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
                  eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
-                 cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = True, sm_budget: int = 0,
-                 bucket_blocks: int = 1,
+                 cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = False, sm_budget: int = 0,
+                 bucket_blocks: int = 1, fused_tail: bool = True,
                  consistency_weight: float = 0.1, smoothness_weight: float = 0.1):
         import torch.distributed as dist
         self.model = model
@@ -175,19 +175,28 @@ class Trainer:
         self._state_for = None
         self.reducer = None
         self.launches = 0
-        self.overlap = overlap_allreduce      # bucketed all-reduce behind the backward pass vs one all-reduce after it
+        # Data parallel: ONE all-reduce of the flat gradient buffer after the backward pass by default.  MEASURED at N = 8
+        # (profiles/r01_summary.md): bucketed collectives overlapped with backward are SLOWER (53.0 vs 51.7 ms/step),
+        # because NCCL's CTAs cannot share an SM with the persistent 227 KB GEMM CTAs and every bucket costs the GEMM
+        # running beside it a wave; overlap_allreduce=True keeps the bucketed form available.
+        self.overlap = overlap_allreduce
         self.bucket_blocks = max(1, bucket_blocks)   # transformer blocks per overlapped bucket
+        # clip + AdamW + normalize_matrices + bf16 operand emit + zero_grad as one launch (nvit_adamw_norm_fused);
+        # False keeps the separate kernels (sumsq, adamw_flat, weight_norm_multi, cast, memset)
+        self.fused_tail = fused_tail
         if self.dp and sm_budget:
             from . import _lib
             _lib.call("nvit_set_sm_budget", int(sm_budget))
-        # CUDA-graph replay of the whole step (single rank): the ~275 launches, their tensor-map encodes and the Python
-        # between them are captured once; learning rate and step count then live in device memory (self.hyper)
-        # (the Kohonen learning-rate schedule is host-side state, so that mode runs eagerly)
-        self.use_graph = bool(cuda_graph) and not self.dp and not model.config.use_kohonen
+        # CUDA-graph replay of the whole step - forward, backward, the NCCL all-reduce (data parallel) and the optimizer
+        # tail: the ~270 launches, their tensor-map encodes and the Python between them are captured once; learning rate
+        # and step count then live in device memory (self.hyper).  The Kohonen learning-rate schedule is host-side state,
+        # so that mode runs eagerly.
+        self.use_graph = bool(cuda_graph) and not model.config.use_kohonen
         self.graph_warmup_steps = max(1, graph_warmup_steps)
         self._graph = None
         self._graph_inputs = None
         self._graph_launches = 0
+        self._graph_B = None
         self.replays = 0
 
     # ---- optimizer state lives beside the flat parameter buffer
@@ -197,11 +206,14 @@ class Trainer:
         if self._state_for is not eng.P32:
             self.m = torch.zeros_like(eng.P32)
             self.v = torch.zeros_like(eng.P32)
-            self.gnorm = torch.zeros(1, device=eng.P32.device, dtype=F32)
+            # [0] sum of squared gradients (clip), [1] unit counter of the fused tail (uint32 bits); zeroed together
+            self.tail_scratch = torch.zeros(4, device=eng.P32.device, dtype=F32)
+            self.gnorm = self.tail_scratch[0:1]
+            self.unit_counter = self.tail_scratch[1:2].view(torch.int32)
             self.loss_buf = torch.zeros(1, device=eng.P32.device, dtype=F32)
             self.hyper = torch.tensor([self.lr, float(self.opt_step)], device=eng.P32.device, dtype=F32)   # {lr, step}
             self._state_for = eng.P32
-            self._graph = None
+            self._drop_graph()
             cfg = self.model.config
             if cfg.use_kohonen:
                 k = 1.0 / (self.grad_accum * self.world)
@@ -214,10 +226,16 @@ class Trainer:
                                            bucket_elems=(hi - lo) * self.bucket_blocks if self.bucket_blocks > 1 else 0)
                 self._broadcast_params()
 
+    def _drop_graph(self):
+        if self._graph is not None and self._graph_B is not None:
+            self.engine._pinned.discard(self._graph_B)
+        self._graph = None
+        self._graph_B = None
+
     def _broadcast_params(self):
         import torch.distributed as dist
         dist.broadcast(self.engine.P32, src=0, group=self.group)
-        self.engine._p16_version = None
+        self.engine.invalidate_operands()
 
     def normalize_matrices(self):
         """Trainer.normalize_matrices (train.py:461-480): one multi-tensor launch."""
@@ -228,6 +246,10 @@ class Trainer:
         """forward + loss + backward of one micro-batch; gradients accumulate in the flat buffer (train.py:898-933)."""
         eng = self.engine
         self._ensure_state()
+        if y.dim() != 1 or y.shape[0] != X.shape[0]:
+            raise ValueError(f"labels must have shape ({X.shape[0]},), got {tuple(y.shape)}")
+        if y.dtype != torch.int64 or not y.is_contiguous():
+            y = y.long().contiguous()             # the kernel reads int64 class indices (F.cross_entropy's target type)
         if self.model.training:
             self.model.step += 1               # ViT.forward's own counter (model.py:404-405): drives the Kohonen schedule
         logits, recon = eng.forward(X, save=True)
@@ -242,28 +264,42 @@ class Trainer:
         self.last_aux = eng.last_aux
         return logits
 
+    def _all_reduce_grads(self):
+        """Mean of the gradients over the data-parallel ranks (the 1/N is folded into the loss scale): what DDP is meant
+        to do at train.py:434-446, 899-902."""
+        eng = self.engine
+        if self.overlap:
+            self.reducer.finish()             # the buckets went out behind the backward pass; flush the rest and wait
+            return
+        import torch.distributed as dist
+        # one collective over the whole flat buffer on the compute stream's order (capturable in a CUDA graph)
+        dist.all_reduce(eng.G32[:eng.n_active], op=dist.ReduceOp.SUM, group=self.group)
+        self.reducer.reduced_elems += eng.n_active
+
     def optimizer_step(self):
         """clip -> AdamW -> zero_grad -> normalize_matrices (train.py:935-946, 989-990)."""
         eng = self.engine
         if self.dp:
-            if not self.overlap:
-                self.reducer.ready(0, eng.n_active)
-            self.reducer.finish()
+            self._all_reduce_grads()
         self.opt_step += 1
         self.hyper[1:2].add_(1.0)          # device-side step count (what a replayed graph advances)
         na = eng.n_active
         gn = None
+        self.tail_scratch.zero_()
         if self.clip and self.clip > 0:
-            self.gnorm.zero_()
             ops.sumsq(eng.G32[:na], self.gnorm)
             gn = self.gnorm
             self.launches += 1
-        ops.adamw_flat(eng.P32[:na], eng.G32[:na], self.m[:na], self.v[:na], eng.n_decay, self.lr, self.betas[0], self.betas[1],
-                       self.eps, self.wd, self.opt_step, gn, self.clip or 0.0, dev_lr_step=self.hyper)
-        self.launches += 1
-        eng._p16_version = None
-        eng.zero_grad()
-        self.normalize_matrices()
+        if self.fused_tail:
+            eng.fused_tail(self.m, self.v, self.lr, self.betas, self.eps, self.wd, self.opt_step, self.unit_counter, gnorm_sq=gn,
+                           max_norm=self.clip or 0.0, dev_lr_step=self.hyper)
+        else:
+            ops.adamw_flat(eng.P32[:na], eng.G32[:na], self.m[:na], self.v[:na], eng.n_decay, self.lr, self.betas[0], self.betas[1],
+                           self.eps, self.wd, self.opt_step, gn, self.clip or 0.0, dev_lr_step=self.hyper)
+            self.launches += 1
+            eng.invalidate_operands()
+            eng.zero_grad()
+            self.normalize_matrices()
         if self.dp and self.model.config.use_kohonen:
             # the in-forward map update (kohonen.py:121-165) saw different images on every rank: average the node tables so
             # that the replicas stay identical (the reference's DDP would leave them diverged; SURVEY.md 2.3 #3)
@@ -290,10 +326,11 @@ class Trainer:
 
     def input_buffers(self, like_X: torch.Tensor, like_y: torch.Tensor):
         """Static device buffers the captured graph reads; fill them in place (e.g. H2D copies) to avoid a staging copy."""
-        if self._graph_inputs is None or self._graph_inputs[0].shape != like_X.shape or self._graph_inputs[0].dtype != like_X.dtype:
+        if (self._graph_inputs is None or self._graph_inputs[0].shape != like_X.shape or self._graph_inputs[0].dtype != like_X.dtype
+                or self._graph_inputs[1].dtype != like_y.dtype):
             self._graph_inputs = (torch.empty_like(like_X, device=self.engine.P32.device),
                                   torch.empty_like(like_y, device=self.engine.P32.device))
-            self._graph = None
+            self._drop_graph()
         return self._graph_inputs
 
     def step(self, X: torch.Tensor, y: torch.Tensor):
@@ -307,20 +344,44 @@ class Trainer:
             Xs.copy_(X, non_blocking=True)
             ys.copy_(y, non_blocking=True)
         if self._graph is None:
+            eng = self.engine
             before = self.total_launches
             host_step = self.opt_step
+            # The graph holds raw pointers into this batch size's activation set: pin it, so that forwards at other batch
+            # sizes between replays (an eval loader, a partial last batch) can never hand its memory back to the allocator.
+            B = X.shape[0]
+            eng._buffers(B)
+            eng._pinned.add(B)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_eager(Xs, ys)
+            try:
+                with torch.cuda.graph(g):
+                    self._step_eager(Xs, ys)
+            except Exception as e:           # e.g. a collective that cannot be captured: keep training, eagerly, and say so
+                import warnings
+                warnings.warn(f"nvit_b200.Trainer: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); running eagerly")
+                eng._pinned.discard(B)
+                self.use_graph = False
+                self.opt_step = host_step
+                self.hyper[1:2].fill_(float(host_step))
+                self.launches -= self.total_launches - before
+                eng.zero_grad()
+                eng.invalidate_operands()
+                return self._step_eager(X, y)
             self.opt_step = host_step           # capture does not execute; the replay below is the real step
             self.hyper[1:2].fill_(float(host_step))
             self._graph_launches = self.total_launches - before
             self.launches -= self._graph_launches   # count launches when they run, i.e. per replay
             self._graph = g
+            self._graph_B = B
+            # the capture recorded the operand-refresh decision of ITS first forward; replays always find the operands the
+            # previous replay's fused tail wrote, but the first replay may not: refresh them by hand once
+            eng.refresh_operands(force=True)
         self._graph.replay()
         self.opt_step += 1
         self.replays += 1
         self.launches += self._graph_launches
+        # what the replay left behind: operands written by the fused tail of the captured step (when it is in use)
+        self.engine._p16_version = (tuple(s.param._version for s in self.engine.slots.values()) if self.fused_tail else None)
         return self.loss_buf
 
     # ---- checkpoint interchange (train.py:629-655 saves {"model", "optimizer", "model_args", "iter_num", ...})

@@ -4,6 +4,8 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import os as _os  # measurement hooks live in the -DNVIT_BENCH_HOOKS build (python -m nvit_b200.build --hooks)
+_os.environ.setdefault("NVIT_LIB_PATH", _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "nvit_b200", "libnvit_b200_hooks.so"))
 from nvit_b200 import ops, _lib
 
 B, H, T, C = 256, 12, 196, 768

@@ -7,11 +7,14 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "nvit_b200.h")
+TUNING_HEADER = os.path.join(ROOT, "include", "nvit_b200_tuning.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+def declared_functions(path=HEADER, with_hooks=False):
+    text = open(path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    if not with_hooks:       # the -DNVIT_BENCH_HOOKS section is not part of the product library
+        text = re.sub(r"#ifdef NVIT_BENCH_HOOKS.*?#endif", "", text, flags=re.S)
     out = {}
     for m in re.finditer(r"\b(?:int|const char\*)\s+(nvit_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(2).strip()
@@ -42,8 +45,20 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         if name in _lib.SIGNATURES:
             assert len(_lib.SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding has {len(_lib.SIGNATURES[name])}"
+    tuning = declared_functions(TUNING_HEADER)
+    for name, nargs in tuning.items():
+        assert hasattr(lib, name), f"{name} declared in the tuning header but not exported"
+        assert len(_lib.SIGNATURES[name]) == nargs
     for name in _lib.SIGNATURES:
-        assert name in fns, f"{name} bound but not declared in the header"
+        assert name in fns or name in tuning, f"{name} bound but not declared in a header"
+    # wrong-output measurement hooks are compiled out of the product library
+    hooks = set(declared_functions(TUNING_HEADER, with_hooks=True)) - set(tuning)
+    assert hooks == set(_lib.HOOK_SIGNATURES) and hooks
+    for name in hooks:
+        assert not hasattr(lib, name), f"{name} must exist only in -DNVIT_BENCH_HOOKS builds"
+    # and the boundary header itself declares no process-wide variant switches
+    for name in tuning:
+        assert name not in fns
 
 
 def test_library_calls_without_gpu(lib):

@@ -1,5 +1,5 @@
 """bench.py's host-side contract, checked without a GPU: the algorithmic FLOP figures of SURVEY.md 8(d), and the
-`--impl reference` arm (the reference algorithm = oracle port on the host cores): one JSON line with the agreed keys on
+`--impl reference` arm (the unmodified reference model from baseline/_ref on the host cores; oracle port only if unstaged): one JSON line with the agreed keys on
 rank 0, silence on the other ranks."""
 import json
 import os
@@ -41,7 +41,9 @@ def test_reference_arm_prints_one_json_line_with_the_agreed_keys():
         assert key in d, key
     assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    if os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "nvit", "model.py")):
+        assert cb["kind"] == "reference"        # the unmodified reference model is staged: the arm must run it, not the port
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -151,19 +151,35 @@ def total_loss(cfg, logits, aux, y):
         + cfg.reconstruction_weight * aux["reconstruction"]
 
 
-def check_units(cfg, p, X, got):
-    """The CUDA path's units vs the oracle's own: equal, or argmins up to the bf16 rounding of the patch embeddings."""
+def check_units(cfg, p, X, got, engine):
+    """The CUDA path's best-matching units vs the oracle's own.  A discrete choice cannot be "within a tolerance", but it
+    has an exact analytic criterion: the CUDA path picks argmin_g |x' - n_g| for ITS patch embedding x' (bf16 tensor-core
+    GEMM), the oracle for its fp32 x.  With eps = |x' - x| (measured per token from the engine's own fp32 embedding
+    buffer), the triangle inequality gives  d(x, n_mine) <= d(x', n_mine) + eps <= d(x', n_ref) + eps <= d(x, n_ref) + 2 eps,
+    so every unit must satisfy  d_ref(mine) <= best + 2 eps  (+ 1e-5 relative for the fp32 distance arithmetic); a unit
+    that differs from the oracle's although this margin rules it out is a bug.  The mismatch rate is printed."""
     with torch.no_grad():
         local, glob = O.patch_embed(p, cfg, X)
+    B = X.shape[0]
+    acts = engine._acts[B]
     forced = []
     for tag, x in (("local", local), ("global", glob)):
-        d = torch.cdist(x.detach(), p[tag + "_kohonen.nodes"].detach())
+        nodes = p[tag + "_kohonen.nodes"].detach()
+        d = torch.cdist(x.detach(), nodes)
         best, ref = d.min(dim=-1)
         mine = got[tag + "_indices"]
         assert mine.shape == ref.shape and mine.dtype == torch.int64
-        assert float((mine == ref).float().mean()) >= 0.98, (tag, float((mine == ref).float().mean()))
-        excess = d.gather(-1, mine[..., None])[..., 0] / best - 1.0
-        assert float(excess.max()) <= 2e-2, (tag, float(excess.max()))
+        x_gpu = acts[tag + "32"].view_as(x)
+        eps = (x_gpu - x.detach()).norm(dim=-1)
+        d_mine = d.gather(-1, mine[..., None])[..., 0]
+        slack = 2.0 * eps + 1e-5 * best
+        bad = d_mine > best + slack
+        mismatch = float((mine != ref).float().mean())
+        print(f"[kohonen units] {tag}: mismatch rate {mismatch:.4%}, max eps/best {float((eps / best).max()):.3e}, "
+              f"max excess/best {float(((d_mine - best) / best).max()):.3e}")
+        assert not bool(bad.any()), (tag, int(bad.sum()), float(((d_mine - best - slack)[bad]).max()))
+        # and the bf16 input rounding bounds eps itself: |x' - x| <= 2^-7 |x| would already be a broken GEMM
+        assert float((eps / x.detach().norm(dim=-1)).max()) <= 2.0 ** -7, float((eps / x.detach().norm(dim=-1)).max())
         forced.append(mine)
     return tuple(forced)
 
@@ -203,7 +219,7 @@ def test_kohonen_forward_backward_matches_oracle(name, over, batch, seed, node_s
     got = model.engine.last_aux
 
     p = {k: v.detach().to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
-    forced = check_units(cfg, p, X, got)
+    forced = check_units(cfg, p, X, got, model.engine)
     ref_logits, ref_aux = O.vit_forward(p, cfg, X, training=True, step=1, force_indices=forced)
     total_loss(cfg, ref_logits, ref_aux, y).backward()
     formula = isinstance(seed, str)
@@ -265,7 +281,7 @@ def test_kohonen_eval_mode_has_no_update_and_no_grad_path():
     assert torch.equal(before, model.local_kohonen.nodes.detach())
     assert torch.equal(l1, l2) and model.step == 0
     p = {k: v.detach().to(DEV).clone() for k, v in sd.items()}
-    forced = check_units(cfg, p, X, model.engine.last_aux)
+    forced = check_units(cfg, p, X, model.engine.last_aux, model.engine)
     with torch.no_grad():
         rl, ra = O.vit_forward(p, cfg, X, training=False, force_indices=forced)
     assert rel(l1, rl) <= 1e-2
@@ -281,7 +297,7 @@ def test_kohonen_trainer_steps_match_oracle():
     ot = O.OracleTrainer({k: v.to(DEV) for k, v in sd.items()}, cfg, lr=1e-3)
     for it in range(2):
         loss = tr.step(X, y)
-        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, tr.last_aux)
+        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, tr.last_aux, model.engine)
         oloss, _, oaux = ot.step(X, y, force_indices=forced)
         for k in ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization"):
             assert abs(float(tr.last_aux[k]) - float(oaux[k])) <= 1e-2 * abs(float(oaux[k])) + 1e-6, (it, k)
@@ -299,7 +315,7 @@ def test_kohonen_trainer_steps_match_oracle():
     model.eval()
     with torch.no_grad():
         l1, _ = model(X)
-        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, model.engine.last_aux)
+        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, model.engine.last_aux, model.engine)
         l2, _ = O.vit_forward(ot.sd, cfg, X, training=False, force_indices=forced)
     assert rel(l1, l2) <= 2e-2
 

@@ -406,3 +406,153 @@ def test_l16_shapes_match_oracle():
     assert rel(logits.detach(), ref_logits) <= 1e-2, rel(logits.detach(), ref_logits)
     assert abs(float(aux["reconstruction"]) - float(ref_recon)) <= 1e-2 * float(ref_recon)
     check_grads(model, ref_grads)
+
+
+def _steps(trainer, X, y, n):
+    return [float(trainer.step(X, y)) for _ in range(n)]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_cuda_graph_replay_equals_eager_steps(fused):
+    """The bench's timed path: k steps of Trainer(cuda_graph=True) (2 eager warm-up steps, then capture + replays, learning
+    rate and step count in device memory) == the same k eager steps from the same state: losses and every parameter,
+    including a set_lr between replays and an optimizer-state reload (which drops the captured graph)."""
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 13)
+    g = torch.Generator().manual_seed(77)
+    X = torch.randn(16, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (16,), generator=g).to(DEV)
+    me, mg = build(cfg, sd), build(cfg, sd)
+    te = Trainer(me, learning_rate=1e-3, fused_tail=fused)
+    tg = Trainer(mg, learning_rate=1e-3, fused_tail=fused, cuda_graph=True, graph_warmup_steps=2)
+    le, lg = _steps(te, X, y, 5), _steps(tg, X, y, 5)            # 2 eager + capture + 3 replays
+    assert tg.replays == 3 and tg._graph is not None
+    te.set_lr(3e-4)
+    tg.set_lr(3e-4)
+    le += _steps(te, X, y, 2)
+    lg += _steps(tg, X, y, 2)
+    assert tg.replays == 5
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-6 * abs(a), (le, lg)
+    for (n, a), (_, b) in zip(me.named_parameters(), mg.named_parameters()):
+        assert rel(b.detach(), a.detach()) <= 1e-6, (n, rel(b.detach(), a.detach()))
+    assert te.opt_step == tg.opt_step == 7 and float(tg.hyper[1]) == 7.0
+    # a forward at another batch size between replays must not disturb the captured activation set (it is pinned)
+    mg.eval()
+    with torch.no_grad():
+        mg(X[:5])
+        mg(X[:7])
+        mg(X[:3])
+    mg.train()
+    assert 16 in mg.engine._acts and 16 in mg.engine._pinned
+    me.eval()
+    with torch.no_grad():
+        me(X[:5])
+    me.train()
+    le2, lg2 = _steps(te, X, y, 2), _steps(tg, X, y, 2)
+    for a, b in zip(le2, lg2):
+        assert abs(a - b) <= 1e-6 * abs(a), (le2, lg2)
+    # optimizer-state reload: the graph is dropped, re-captured, and the run continues identically
+    state = te.optimizer_state_dict()
+    tg.load_optimizer_state_dict(state)
+    te.load_optimizer_state_dict(state)
+    assert tg._graph is None
+    le3, lg3 = _steps(te, X, y, 3), _steps(tg, X, y, 3)
+    for a, b in zip(le3, lg3):
+        assert abs(a - b) <= 1e-6 * abs(a), (le3, lg3)
+    for (n, a), (_, b) in zip(me.named_parameters(), mg.named_parameters()):
+        assert rel(b.detach(), a.detach()) <= 1e-6, (n, rel(b.detach(), a.detach()))
+
+
+def test_fused_optimizer_tail_equals_separate_kernels():
+    """nvit_adamw_norm_fused (clip + AdamW + normalize_matrices + bf16 operands + zero_grad, one pass) against
+    the separate sumsq / adamw_flat / weight_norm_multi / cast kernels: parameters, moments, bf16 operands, zeroed
+    gradients and unit-norm rows / columns; also in the original-ViT branch (no normalisation) and with bias tensors."""
+    for name, over in (("tiny", dict()), ("mini", dict(bias=True)), ("tiny", dict(use_nvit=False))):
+        cfg = O.named_config(name, **over)
+        sd = O.init_state_dict(cfg, 5)
+        g = torch.Generator().manual_seed(3)
+        X = torch.randn(8, 3, cfg.image_size, cfg.image_size, generator=g).to(DEV)
+        y = torch.randint(0, cfg.num_classes, (8,), generator=g).to(DEV)
+        ma, mb = build(cfg, sd), build(cfg, sd)
+        ta, tb = Trainer(ma, fused_tail=True), Trainer(mb, fused_tail=False)
+        for it in range(3):
+            la, lb = float(ta.step(X, y)), float(tb.step(X, y))
+            assert abs(la - lb) <= 1e-6 * abs(lb), (name, it, la, lb)
+        ea, eb = ma.engine, mb.engine
+        na = ea.n_active
+        assert rel(ea.P32[:na], eb.P32[:na]) <= 1e-6
+        assert rel(ta.m[:na], tb.m[:na]) <= 1e-6 and rel(ta.v[:na], tb.v[:na]) <= 1e-6
+        assert float(ea.G32[:na].abs().max()) == 0.0                      # zero_grad is part of the pass
+        # the bf16 operands the fused pass wrote are exactly the rounding of its fp32 values
+        assert torch.equal(ea.W16[:ea.n_gemm], ea.P32[:ea.n_gemm].to(torch.bfloat16))
+        if cfg.use_nvit:
+            params = dict(ma.named_parameters())
+            for i in range(cfg.n_layer):
+                for nm, dim in O.NORMALIZED:
+                    w = params[f"transformer.h.{i}.{nm}.weight"].detach()
+                    assert float((w.norm(dim=dim) - 1).abs().max()) <= 1e-5, (i, nm)
+        # untrained (grad-less) tensors are not touched by the tail
+        assert torch.equal(dict(ma.named_parameters())["reconstruction_head.0.weight"].detach().cpu(), sd["reconstruction_head.0.weight"])
+
+
+def test_weights_written_behind_the_engines_back_are_seen():
+    """The reference's normalize_matrices writes through `W.data.copy_` (train.py:474-480), which does not bump the tensor
+    version: the next forward must still use the new weights (the bf16 operands are rebuilt on every forward that does
+    not directly follow the Trainer's own fused tail)."""
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 9)
+    g = torch.Generator().manual_seed(21)
+    X = torch.randn(4, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (4,), generator=g).to(DEV)
+    model = build(cfg, sd)
+    tr = Trainer(model)
+    tr.step(X, y)
+    model.eval()
+    with torch.no_grad():
+        l0, _ = model(X)
+        w = dict(model.named_parameters())["transformer.h.0.c_fc.weight"]
+        v0 = w._version
+        new = torch.randn(w.shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+        new = new / new.norm(dim=1, keepdim=True)
+        w.data.copy_(new)                                # exactly what the reference's normalize_matrices does
+        assert w._version == v0                          # ... and it is invisible to version counters
+        l1, _ = model(X)
+        ref = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        lo, _ = O.vit_forward(ref, cfg, X)
+    assert rel(l1, l0) > 1e-3                            # the new weights were used
+    assert rel(l1, lo) <= 1e-2                           # and the result is the oracle's for the new weights
+    # the same between two Trainer steps, announced through invalidate_operands()
+    model.train()
+    w.data.copy_(sd["transformer.h.0.c_fc.weight"].to(DEV))
+    model.engine.invalidate_operands()
+    l2 = float(tr.step(X, y))
+    assert np.isfinite(l2)
+
+
+def test_input_shape_and_label_validation():
+    """a wrongly sized image or label tensor must raise instead of writing past the activation buffers / reading
+    out-of-range classes; int32 labels are converted; an out-of-range label is ignored (zero loss / gradient row)."""
+    from nvit_b200 import ops
+    cfg = O.named_config("tiny")
+    model = build(cfg, O.init_state_dict(cfg, 1))
+    with pytest.raises(ValueError, match="input must be"):
+        model(torch.zeros(2, 3, 40, 40, device=DEV))
+    with pytest.raises(ValueError, match="input must be"):
+        model(torch.zeros(2, 1, 32, 32, device=DEV))
+    tr = Trainer(model)
+    X = torch.randn(4, 3, 32, 32, device=DEV)
+    with pytest.raises(ValueError, match="labels"):
+        tr.step(X, torch.zeros(3, dtype=torch.int64, device=DEV))
+    l32 = float(tr.step(X, torch.tensor([1, 2, 3, 4], dtype=torch.int32, device=DEV)))
+    assert np.isfinite(l32)
+    logits = torch.randn(4, 10, device=DEV)
+    tgt = torch.tensor([1, -100, 3, 12], device=DEV)
+    loss = torch.zeros(1, device=DEV)
+    dl = torch.empty_like(logits)
+    ops.cross_entropy(logits, tgt, loss, dl)
+    ref = (F.cross_entropy(logits[[0, 2]], tgt[[0, 2]], reduction="sum") / 4)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert float(dl[1].abs().max()) == 0.0 and float(dl[3].abs().max()) == 0.0
+    with pytest.raises(TypeError):
+        ops.cross_entropy(logits, tgt.int(), loss, dl)
