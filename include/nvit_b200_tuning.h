@@ -25,6 +25,10 @@ int nvit_gemm_raster_group(int group);
  * gate-backward GEMM; 22 or 24 its number of epilogue groups. */
 int nvit_gemm_swiglu_cta_group(int mode);
 
+/* Attention backward kernel: 2 = warp-specialised (16 compute warps + one MMA / TMA warp, products of the next item in
+ * flight under the passes of the current one; default), 1 = the single-role kernel of round 1. */
+int nvit_attention_bwd_variant(int variant);
+
 /* ---- 2. measurement only, -DNVIT_BENCH_HOOKS builds (outputs are WRONG while active) -------------------------------- */
 #ifdef NVIT_BENCH_HOOKS
 /* 1 = the GEMM epilogue returns the accumulator without reading it (main-loop-only time), 2 = it reads and converts but

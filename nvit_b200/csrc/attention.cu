@@ -737,6 +737,368 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, v2
+// Warp-specialised form of the kernel above (same arithmetic, same tiles): 16 compute warps + ONE dedicated MMA / TMA
+// warp, the work of a head cut into items (kv tile j, q tile c) whose matmuls run on the tensor pipe WHILE the compute
+// warps are in the exponential / dS passes of the neighbouring items:
+//   MMA warp, per item:   wait P^T(i) -> dV_j += P^T dO_c ; S^T(i+1) = K_j' Q_c'^T            (behind dV, same TMEM columns)
+//                         wait dS^T(i) -> dK_j += dS^T Q_c ; dQ_c += dS K_j ; dP^T(i+1) = V_j' dO_c'^T
+//   compute warps:        wait S^T(i) -> P^T = exp2(...) -> TMEM (bf16 pairs over the dead score columns: the A operand of
+//                         dV comes from tensor memory, as in the forward kernel) -> wait dP^T(i) -> dS^T -> shared
+//                         (double-buffered, 2 x 32 KB) -> per kv tile the dV_j / dK_j rows, at the end the dQ rows.
+// v1 kept S^T and dP^T in the SAME 256 TMEM columns and issued every product from a warp that also ran the passes, so
+// each product's issue + latency (17 - 33 single-thread MMA issues, 2 - 3.6 k cycles) sat between two passes: 46 % of
+// the head's 37 k cycles were MMA waits.  Here S^T and dP^T have their own 128 columns (q tiles of 128 instead of the
+// whole row), so both products of item i+1 are in flight while item i is being processed:
+//   TMEM: S^T / P^T [0,128)  dP^T [128,256)  dV_j [256,320)  dK_j [320,384)  dQ [384,512)
+//   smem: Q, K, V, dO tiles (4 x 32 KB, outputs staged in place as before) + two dS^T buffers (O parks in the second one
+//         until delta = rowsum(dO * O) has been taken).
+constexpr int ATT2_CW = 16;                        // compute warps: four threads per TMEM lane
+constexpr int ATT2_COMPUTE = ATT2_CW * 32;
+constexpr int ATT2_THREADS = ATT2_COMPUTE + 32;    // + the MMA / TMA warp
+constexpr int ATT_DS_BYTES = 2 * 16384;            // one dS^T buffer: [128 kv rows][2 k-blocks x 64 q columns]
+constexpr int ATT2_SMEM = 4 * ATT_TILE_BYTES + 2 * ATT_DS_BYTES + 1024 /*align*/ + (4 * 256 + 192 + 1024) * 4 + 128;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attn_bwd_ws_kernel(const __grid_constant__ AttnParams p) {
+  pdl_enter();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_TILE_BYTES;
+  uint8_t* sDO = sV + ATT_TILE_BYTES;
+  uint8_t* sDS = sDO + ATT_TILE_BYTES;                          // two dS^T buffers
+  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);  // [256]  (already times log2e)
+  float* s_delta = s_lse + 256;                                // [256]
+  float* s_invq = s_delta + 256;                               // [256]
+  float* s_invk = s_invq + 256;                                // [256]
+  float* s_scale = s_invk + 256;                               // [64]
+  float* s_dsqk = s_scale + 64;                                // [64]
+  float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
+  float* s_dot = s_rscale + 64;                                // [2][4][128] partial row dots of the normalisation backward
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dot + 1024);
+  uint64_t* bar_qk = bars + 0;      // TMA: q, k tiles
+  uint64_t* bar_vdo = bars + 1;     // TMA: v, dO, O tiles
+  uint64_t* bar_S = bars + 2;       // MMA -> compute: S^T(i) complete
+  uint64_t* bar_dP = bars + 3;      // MMA -> compute: dP^T(i) complete
+  uint64_t* bar_P = bars + 4;       // compute -> MMA: P^T(i) is in tensor memory (16 warp arrivals)
+  uint64_t* bar_dS = bars + 5;      // compute -> MMA: dS^T(i) is in shared memory (16 warp arrivals)
+  uint64_t* bar_free = bars + 6;    // [2] MMA -> compute: the products reading dS^T buffer b have completed
+  uint64_t* bar_acc = bars + 8;     // MMA -> compute: dV_j, dK_j (and every dQ contribution so far) complete
+  uint64_t* bar_norm = bars + 9;    // compute -> MMA: q / k normalised in place (only when they arrive raw)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T, TP = p.TP;
+  const bool has_norm = p.sqk != nullptr;
+  const bool qk_ready = !has_norm || p.inv_q != nullptr;
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+  if (tid == ATT2_COMPUTE) {
+    // the loads go out first (q, k on their own barrier: the first score product needs only those)
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_vdo, 1);
+    mbar_init(bar_S, 1);
+    mbar_init(bar_dP, 1);
+    mbar_init(bar_P, ATT2_CW);
+    mbar_init(bar_dS, ATT2_CW);
+    mbar_init(bar_free + 0, 1);
+    mbar_init(bar_free + 1, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_norm, ATT2_CW);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_qk, 2 * ATT_TILE_BYTES);
+    tma_load_3d(&p.tq, bar_qk, sQ, h * 64, 0, b);
+    tma_load_3d(&p.tk, bar_qk, sK, h * 64, 0, b);
+    mbar_arrive_expect_tx(bar_vdo, 3 * ATT_TILE_BYTES);
+    tma_load_3d(&p.tv, bar_vdo, sV, h * 64, 0, b);
+    tma_load_3d(&p.tdo, bar_vdo, sDO, h * 64, 0, b);
+    tma_load_3d(&p.to, bar_vdo, sDS + ATT_DS_BYTES, h * 64, 0, b);   // O parks in dS^T buffer 1 for the delta pass
+  }
+  if (warp == ATT2_CW) {
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (tid < 64) {
+    const float sc = has_norm ? p.sqk[h * 64 + tid] * p.sqk_mul : 1.f;
+    s_scale[tid] = sc;
+    s_rscale[tid] = sc != 0.f ? 1.f / sc : 0.f;
+    s_dsqk[tid] = 0.f;
+  }
+  if (tid >= 256 && tid < 512) {
+    const int r = tid - 256;  // one thread per (padded) token row
+    s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(b) * p.H + h) * T + r] * LOG2E : 0.f;
+    const bool pre = p.inv_q != nullptr && r < T;
+    s_invq[r] = pre ? p.inv_q[(static_cast<long long>(b) * T + r) * p.ld_inv_q + h] : 0.f;
+    s_invk[r] = pre ? p.inv_k[(static_cast<long long>(b) * T + r) * p.ld_inv_k + h] : 0.f;
+    s_delta[r] = 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
+  const int nQ = p.nQ, nK = p.nK, nItems = nQ * nK;
+
+  if (warp == ATT2_CW) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (see gemm_tcgen05.cu) =====
+    auto ncol_of = [&](int c) { return min(128, TP - 128 * c); };
+    auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
+      mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + j * 16384, 16, 1024), 2, umma_smem_desc(sQ_a + c * 16384, 16, 1024), 2,
+              idesc_kk_n(ncol_of(c)), 4, false);
+      mma_commit(bar_S);
+    };
+    auto issue_dP = [&](int j, int c) {      // dP^T(j,c) = V_j dO_c^T
+      mma_seq(tmem_base + TM_DP, umma_smem_desc(sV_a + j * 16384, 16, 1024), 2, umma_smem_desc(sDO_a + c * 16384, 16, 1024), 2,
+              idesc_kk_n(ncol_of(c)), 4, false);
+      mma_commit(bar_dP);
+    };
+    mbar_wait(bar_qk, 0);
+    if (!qk_ready) mbar_wait(bar_norm, 0);
+    tc_fence_after_sync();
+    issue_S(0, 0);
+    mbar_wait(bar_vdo, 0);
+    tc_fence_after_sync();
+    issue_dP(0, 0);
+    int i = 0;
+    for (int j = 0; j < nK; ++j) {
+      const int kv_steps = min(8, (TP - j * 128) >> 4);
+      for (int c = 0; c < nQ; ++c, ++i) {
+        const int nks = ncol_of(c) >> 4;
+        const int jn = (c + 1 < nQ) ? j : j + 1, cn = (c + 1 < nQ) ? c + 1 : 0;
+        const bool has_next = i + 1 < nItems;
+        const uint32_t buf_a = sDS_a + (i & 1) * ATT_DS_BYTES;
+        // ---- dV_j += P^T(i) dO_c   (A = P^T from tensor memory: 8 columns per k-step)
+        mbar_wait(bar_P, i & 1);
+        tc_fence_after_sync();
+        {
+          uint64_t dd = umma_smem_desc(sDO_a + c * 16384, 8192, 1024);
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            if (elect_one()) umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S + ks * 8, dd, IDESC_KM(64), (c > 0 || ks > 0) ? 1u : 0u);
+            dd += 128;
+          }
+        }
+        // the next score tile rides behind dV (the tensor pipe runs in issue order: it overwrites P^T only after dV read it)
+        if (has_next) issue_S(jn, cn);
+        // ---- dK_j += dS^T(i) Qh_c ; dQ_c += dS(i) Kh_j
+        mbar_wait(bar_dS, i & 1);
+        tc_fence_after_sync();
+        {
+          const uint64_t dp = umma_smem_desc(buf_a, 16, 1024);
+          uint64_t dq = umma_smem_desc(sQ_a + c * 16384, 8192, 1024);
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t da = dp + static_cast<uint64_t>((ks >> 2) * 1024 + (ks & 3) * 2);
+            if (elect_one()) umma_bf16_ss(tmem_base + TM_DK, da, dq, IDESC_KM(64), (c > 0 || ks > 0) ? 1u : 0u);
+            dq += 128;
+          }
+        }
+        mma_seq(tmem_base + TM_DQ + 64 * c, umma_smem_desc(buf_a, 16384, 1024), 128, umma_smem_desc(sK_a + j * 16384, 8192, 1024), 128,
+                IDESC_MM(64), kv_steps, j > 0);
+        mma_commit(bar_free + (i & 1));
+        if (c == nQ - 1) mma_commit(bar_acc);
+        if (has_next) issue_dP(jn, cn);
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int wq = warp & 3;       // TMEM lane quarter this warp may access
+    const int part = warp >> 2;    // which quarter of the columns / channels of a row
+    const int row = wq * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    // dL/d(sqk) partials are reduced into s_dsqk right where they arise (three short-lived 16-float arrays instead of one
+    // that would live across the whole item loop: 96 registers per thread with 17 warps resident)
+    if (!qk_ready) {
+      mbar_wait(bar_qk, 0);
+      for (int r = tid; r < 2 * T; r += ATT2_COMPUTE) {
+        if (r < T) s_invq[r] = normalize_row(sQ, r, s_scale);
+        else s_invk[r - T] = normalize_row(sK, r - T, s_scale);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_norm);
+    }
+    int i = 0;
+    for (int j = 0; j < nK; ++j) {
+      const int kv = j * 128 + row;
+      const bool kv_ok = kv < T;
+      for (int c = 0; c < nQ; ++c, ++i) {
+        const int nch = min(128, TP - 128 * c) >> 4;          // 16-column chunks of this item (<= 8)
+        const int c_begin = (part * nch) / 4, c_end = ((part + 1) * nch) / 4;   // this thread's chunks: at most two
+        const int q0 = c * 128;
+        uint8_t* const buf = sDS + (i & 1) * ATT_DS_BYTES;
+        uint32_t pk[2][8];
+        // ---- P^T = exp2(scale log2e S^T - lse log2e), kept as bf16 pairs
+        mbar_wait(bar_S, i & 1);
+        tc_fence_after_sync();
+        {
+          uint32_t r[2][16];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+            if (c_begin + cc < c_end) tmem_ld_32x32b_x16(t_lane + TM_S + (c_begin + cc) * 16, r[cc]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int ch = c_begin + cc;
+            if (ch < c_end) {
+              float pv[16];
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
+                pv[4 * e4 + 0] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 0]), sl2, -l4.x));
+                pv[4 * e4 + 1] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 1]), sl2, -l4.y));
+                pv[4 * e4 + 2] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 2]), sl2, -l4.z));
+                pv[4 * e4 + 3] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 3]), sl2, -l4.w));
+              }
+              if (!kv_ok) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+              } else if (q0 + ch * 16 + 16 > T) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (q0 + ch * 16 + e >= T) pv[e] = 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
+            }
+          }
+        }
+        tc_fence_before_sync();
+        named_bar_sync(1, ATT2_COMPUTE);        // every score column of this item has been read: P^T may overwrite them
+        tc_fence_after_sync();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+          if (c_begin + cc < c_end) tmem_st_32x32b_x8(t_lane + TM_S + (c_begin + cc) * 8, pk[cc]);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_P);
+        if (i == 0) {
+          // delta = rowsum(dO * O) from the shared tiles (O parks in dS^T buffer 1), under the first dV / S^T products
+          mbar_wait(bar_vdo, 0);
+          for (int r = tid; r < T; r += ATT2_COMPUTE) {
+            float d = 0.f;
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              float a[8], g[8];
+              unpack8(*reinterpret_cast<const uint4*>(sDS + ATT_DS_BYTES + sw128(r, k8)), a);
+              unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, k8)), g);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) d += a[e] * g[e];
+            }
+            s_delta[r] = d;
+          }
+          named_bar_sync(1, ATT2_COMPUTE);
+        }
+        // ---- dS^T = P^T (dP^T - delta) scale -> shared memory (K-major [128 kv][ncol q], 64-column k-blocks)
+        mbar_wait(bar_dP, i & 1);
+        tc_fence_after_sync();
+        if (i >= 2) mbar_wait(bar_free + (i & 1), ((i >> 1) - 1) & 1);   // the products of item i-2 have let go of this buffer
+        {
+          uint32_t r[2][16];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+            if (c_begin + cc < c_end) tmem_ld_32x32b_x16(t_lane + TM_DP + (c_begin + cc) * 16, r[cc]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int ch = c_begin + cc;
+            if (ch < c_end) {
+              float pv[16];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { pv[2 * e] = bf16lo(pk[cc][e]); pv[2 * e + 1] = bf16hi(pk[cc][e]); }
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 d4 = *reinterpret_cast<const float4*>(s_delta + q0 + ch * 16 + 4 * e4);
+                pv[4 * e4 + 0] *= (__uint_as_float(r[cc][4 * e4 + 0]) - d4.x) * p.scale;
+                pv[4 * e4 + 1] *= (__uint_as_float(r[cc][4 * e4 + 1]) - d4.y) * p.scale;
+                pv[4 * e4 + 2] *= (__uint_as_float(r[cc][4 * e4 + 2]) - d4.z) * p.scale;
+                pv[4 * e4 + 3] *= (__uint_as_float(r[cc][4 * e4 + 3]) - d4.w) * p.scale;
+              }
+              uint8_t* blk = buf + (ch >> 2) * 16384;
+              const int k2 = (ch & 3) * 2;
+              *reinterpret_cast<uint4*>(blk + sw128(row, k2)) = pack8(pv);
+              *reinterpret_cast<uint4*>(blk + sw128(row, k2 + 1)) = pack8(pv + 8);
+            }
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dS);
+
+        if (c == nQ - 1) {
+          // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both; staged in the (dead) V_j / K_j rows
+          mbar_wait(bar_acc, j & 1);
+          tc_fence_after_sync();
+          tmem_row16_to_tile(t_lane + TM_DV + part * 16, sV + j * 16384, row, part);
+          if (has_norm) {
+            float g[16], n[16], dacc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) dacc[e] = 0.f;
+            s_dot[part * 128 + row] = norm_bwd_load(t_lane + TM_DK + part * 16, sK, kv_ok ? kv : 0, part, s_scale, s_rscale, g, n, dacc, kv_ok);
+            reduce16_to_smem(dacc, s_dsqk + part * 16, lane);
+            named_bar_sync(1, ATT2_COMPUTE);
+            const float dot = (s_dot[row] + s_dot[128 + row]) + (s_dot[256 + row] + s_dot[384 + row]);
+            if (kv_ok) norm_bwd_store(g, n, dot, s_invk[kv], sK, kv, part);
+          } else {
+            tmem_row16_to_tile(t_lane + TM_DK + part * 16, sK + j * 16384, row, part);
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          named_bar_sync(1, ATT2_COMPUTE);
+          if (tid == 0) {
+            tma_store_3d(&p.tdv, sV + j * 16384, h * 64, j * 128, b);
+            tma_store_3d(&p.tdk, sK + j * 16384, h * 64, j * 128, b);
+            bulk_commit_group();
+          }
+        }
+      }
+    }
+    // ---- dQ rows (complete with the last bar_acc), one 128-row q tile at a time (register budget: 96 per thread with 17
+    // warps resident), staged in place over Qh
+    if (has_norm) {
+      for (int m = 0; m < nQ; ++m) {
+        const int qi = m * 128 + row;
+        const bool ok = qi < T;
+        float g[16], n[16], dacc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dacc[e] = 0.f;
+        s_dot[m * 512 + part * 128 + row] =
+            norm_bwd_load(t_lane + TM_DQ + 64 * m + part * 16, sQ, ok ? qi : 0, part, s_scale, s_rscale, g, n, dacc, ok);
+        reduce16_to_smem(dacc, s_dsqk + part * 16, lane);
+        named_bar_sync(1, ATT2_COMPUTE);
+        if (ok) {
+          const float* sd = s_dot + m * 512;
+          const float dot = (sd[row] + sd[128 + row]) + (sd[256 + row] + sd[384 + row]);
+          norm_bwd_store(g, n, dot, s_invq[qi], sQ, qi, part);
+        }
+      }
+    } else {
+      for (int m = 0; m < nQ; ++m) tmem_row16_to_tile(t_lane + TM_DQ + 64 * m + part * 16, sQ + m * 16384, row, part);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    named_bar_sync(1, ATT2_COMPUTE);
+    if (tid == 0) {
+      for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
+      bulk_commit_group();
+      bulk_wait_group_read<0>();      // all staged tiles have left shared memory before the CTA retires
+    }
+    if (has_norm && tid < 64) atomicAdd(p.dsqk + h * 64 + tid, s_dsqk[tid] * p.sqk_mul);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == ATT2_CW) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int T, int box_rows = ATT_ROWS) {
   const uint64_t dims[3] = {static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
   const uint64_t strides[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * T};
@@ -756,6 +1118,7 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 using namespace nvit;
 
 static long long* g_att_dbg = nullptr;
+static std::atomic<int> g_bwd_variant{1};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
   g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
@@ -840,9 +1203,19 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   int dev;
   if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
     once.mark(dev);
   }
-  launch(attn_bwd_kernel, (unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), p);
+  if (g_bwd_variant.load(std::memory_order_relaxed) == 1)
+    launch(attn_bwd_kernel, (unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), p);
+  else
+    launch(attn_bwd_ws_kernel, (unsigned)(B * H), ATT2_THREADS, ATT2_SMEM, static_cast<cudaStream_t>(stream), p);
   NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_attention_bwd_variant(int variant) {   // tuning switch (include/nvit_b200_tuning.h): same results
+  NVIT_REQUIRE(variant == 1 || variant == 2, "nvit_attention_bwd_variant: 1 (one role, 512 threads) or 2 (warp-specialised, default)");
+  g_bwd_variant.store(variant, std::memory_order_relaxed);
   return NVIT_OK;
 }

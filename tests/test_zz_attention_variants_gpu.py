@@ -1,0 +1,71 @@
+"""Both attention-backward kernels (include/nvit_b200_tuning.h: nvit_attention_bwd_variant) against the fp32 reference and
+against each other: 1 = the single-role kernel of round 1, 2 = the warp-specialised kernel (16 compute warps + one MMA /
+TMA warp, the products of the next (kv tile, q tile) item in flight under the passes of the current one).  The file sorts
+last on purpose: a fault in a kernel variant must not hide the rest of the suite behind `-x`."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from nvit_b200 import _lib, ops  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("kernels_gpu_cases", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_kernels_gpu.py"))
+K = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(K)
+
+DEFAULT_VARIANT = int(os.environ.get("NVIT_ATTN_BWD_VARIANT", "2"))
+
+
+@pytest.fixture(params=[1, 2], ids=["single_role", "warp_specialised"])
+def variant(request):
+    _lib.call("nvit_attention_bwd_variant", request.param)
+    yield request.param
+    _lib.call("nvit_attention_bwd_variant", DEFAULT_VARIANT)
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 1, 64), (3, 3, 64), (2, 2, 196), (1, 12, 196), (2, 2, 16), (1, 2, 256), (2, 1, 130), (1, 1, 48),
+                                   (2, 1, 128), (1, 2, 144), (40, 12, 196)])
+@pytest.mark.parametrize("normed", [True, False])
+def test_attention_backward_variants_match_reference(variant, B, H, T, normed):
+    K.test_attention_fwd_bwd(B, H, T, normed)
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 2, 196), (3, 1, 64), (1, 2, 256)])
+def test_attention_backward_variants_with_prenormalised_qk(variant, B, H, T):
+    K.test_attention_with_prenormalised_qk(B, H, T)
+
+
+@pytest.mark.parametrize("B,H,T", [(4, 12, 196), (2, 3, 64), (3, 2, 256)])
+def test_attention_backward_variants_agree(B, H, T):
+    """Same tiles, same arithmetic; only the fp32 accumulation order over q tiles differs: outputs agree to bf16 rounding."""
+    C, M = H * 64, B * T
+    qkv = K.randn(M, 3 * C, seed=70, scale=0.5, dtype=torch.bfloat16)
+    sqk = (1.0 + 0.2 * K.randn(C, seed=71)).mul(0.03)
+    gb = K.randn(M, C, seed=72, scale=0.1, dtype=torch.bfloat16)
+    out = torch.zeros(M, C, device=K.DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device=K.DEV)
+    ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.03, 8.0, out, lse, B, H, T)
+    res = {}
+    try:
+        for v in (1, 2):
+            _lib.call("nvit_attention_bwd_variant", v)
+            for rep in range(3):       # repeated launches: no state may leak from one head / launch to the next
+                d = torch.zeros(M, 3 * C, device=K.DEV, dtype=torch.bfloat16)
+                ds = torch.zeros(C, device=K.DEV)
+                ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.03, 8.0, out, gb, lse,
+                                  d[:, :C], d[:, C:2 * C], d[:, 2 * C:], ds, B, H, T)
+                torch.cuda.synchronize()
+                if rep == 0:
+                    res[v] = (d, ds)
+                else:
+                    assert torch.equal(d, res[v][0]), (v, rep)
+    finally:
+        _lib.call("nvit_attention_bwd_variant", DEFAULT_VARIANT)
+    assert K.rel(res[2][0], res[1][0]) <= 5e-3, K.rel(res[2][0], res[1][0])
+    assert K.rel(res[2][1], res[1][1]) <= 5e-3
