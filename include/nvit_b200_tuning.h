@@ -25,8 +25,9 @@ int nvit_gemm_raster_group(int group);
  * gate-backward GEMM; 22 or 24 its number of epilogue groups. */
 int nvit_gemm_swiglu_cta_group(int mode);
 
-/* Attention backward kernel: 2 = warp-specialised (16 compute warps + one MMA / TMA warp, products of the next item in
- * flight under the passes of the current one; default), 1 = the single-role kernel of round 1. */
+/* Attention backward kernel: 2 = persistent and warp-specialised (8 compute warps + one MMA warp per SM, the products of the
+ * next (kv tile, q tile) item in flight under the passes of the current one, the next head's tiles loading meanwhile;
+ * default), 1 = the single-role, one-head-per-CTA kernel of round 1. */
 int nvit_attention_bwd_variant(int variant);
 
 /* ---- 2. measurement only, -DNVIT_BENCH_HOOKS builds (outputs are WRONG while active) -------------------------------- */

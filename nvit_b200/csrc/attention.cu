@@ -105,13 +105,19 @@ struct alignas(64) AttnParams {
   long long ldq, ldk, ldo, lddq, lddk, lddv;
   float sqk_mul, scale;
   int B, H, T, TP, nQ, nK;
+  int dbuf;         // attn_bwd_ws_kernel: two (Q, K) tile pairs in shared memory (the next head's tiles load during this one)
   long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
 };
 
 #ifdef NVIT_BENCH_HOOKS
 #define ATT_MARK(i) do { if (p.dbg && blockIdx.x < 8 && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + (i)] = clock64(); } while (0)
+// v2 kernel: 64 slots per CTA (first 4 CTAs): [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp
+#define ATT2_MARK(i) do { if (p.dbg && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
+#define ATT2_MMARK(i) do { if (p.dbg && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
 #else
 #define ATT_MARK(i) do { } while (0)
+#define ATT2_MARK(i) do { } while (0)
+#define ATT2_MMARK(i) do { } while (0)
 #endif
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
@@ -425,10 +431,11 @@ __device__ __forceinline__ void norm_bwd_store(const float (&g)[16], const float
   *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part)) = pack8(d);
   *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part + 1)) = pack8(d + 8);
 }
-__device__ __forceinline__ void tmem_row16_to_tile(uint32_t taddr, uint8_t* tile, int trow, int part) {
+__device__ __forceinline__ void tmem_row16_to_tile(uint32_t taddr, uint8_t* tile, int trow, int part, bool valid = true) {
   uint32_t r[16];
-  tmem_ld_32x32b_x16(taddr, r);
+  tmem_ld_32x32b_x16(taddr, r);      // warp-collective: every lane loads, `valid` only guards the stores
   tmem_wait_ld();
+  if (!valid) return;
   float g[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) g[e] = __uint_as_float(r[e]);
@@ -737,67 +744,133 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
 }
 
+// Two-phase form of norm_bwd_load / norm_bwd_store for the persistent kernel (32 channels per thread there: holding g, n
+// and the sqk partials of both 16-channel halves across the row-dot exchange spilled): phase 1 returns this thread's partial
+// dot and folds g * n into the shared dL/d(sqk) accumulator at once; phase 2 re-reads the 16 accumulator columns and the
+// normalised row (both on chip) and writes dx.
+__device__ __forceinline__ float norm_bwd_dot16(uint32_t taddr, const uint8_t* tile, int trow, int part16, const float* s_scale,
+                                                const float* s_rscale, float* s_dsqk, int lane, bool valid) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_wait_ld();
+  float n[16], acc[16];
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part16)), n);
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part16 + 1)), n + 8);
+  float dot = 0.f;
+  float sc[16], rs[16];
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) {
+    *reinterpret_cast<float4*>(sc + 4 * e4) = *reinterpret_cast<const float4*>(s_scale + part16 * 16 + 4 * e4);
+    *reinterpret_cast<float4*>(rs + 4 * e4) = *reinterpret_cast<const float4*>(s_rscale + part16 * 16 + 4 * e4);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float g = __uint_as_float(r[e]);
+    const float nn = n[e] * rs[e];
+    acc[e] = valid ? g * nn : 0.f;
+    dot += g * sc[e] * nn;
+  }
+  reduce16_to_smem(acc, s_dsqk + part16 * 16, lane);
+  return dot;
+}
+// (warp-collective: the TMEM load is .sync.aligned, so EVERY lane calls this; `valid` only guards the stores)
+__device__ __forceinline__ void norm_bwd_apply16(uint32_t taddr, uint8_t* tile, int trow, int part16, const float* s_scale,
+                                                 const float* s_rscale, float dot, float inv, bool valid) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_wait_ld();
+  if (!valid) return;
+  float n[16], d[16], sc[16], rs[16];
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part16)), n);
+  unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * part16 + 1)), n + 8);
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) {
+    *reinterpret_cast<float4*>(sc + 4 * e4) = *reinterpret_cast<const float4*>(s_scale + part16 * 16 + 4 * e4);
+    *reinterpret_cast<float4*>(rs + 4 * e4) = *reinterpret_cast<const float4*>(s_rscale + part16 * 16 + 4 * e4);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) d[e] = (__uint_as_float(r[e]) * sc[e] - n[e] * rs[e] * dot) * inv;
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part16)) = pack8(d);
+  *reinterpret_cast<uint4*>(tile + sw128(trow, 2 * part16 + 1)) = pack8(d + 8);
+}
+
 // ------------------------------------------------------------------------------------------------ backward, v2
-// Warp-specialised form of the kernel above (same arithmetic, same tiles): 16 compute warps + ONE dedicated MMA / TMA
-// warp, the work of a head cut into items (kv tile j, q tile c) whose matmuls run on the tensor pipe WHILE the compute
-// warps are in the exponential / dS passes of the neighbouring items:
+// Persistent, warp-specialised form of the kernel above (same arithmetic, same 128-row tiles): one CTA per SM walks over
+// (batch, head) pairs; 8 compute warps (two threads per TMEM lane) + ONE dedicated MMA warp.  The work of a head is cut into
+// items (kv tile j, q tile c) whose matmuls run on the tensor pipe WHILE the compute warps are in the exponential / dS passes
+// of the neighbouring items, and the next head's Q / K tiles are loaded while the current head is being processed:
 //   MMA warp, per item:   wait P^T(i) -> dV_j += P^T dO_c ; S^T(i+1) = K_j' Q_c'^T            (behind dV, same TMEM columns)
 //                         wait dS^T(i) -> dK_j += dS^T Q_c ; dQ_c += dS K_j ; dP^T(i+1) = V_j' dO_c'^T
 //   compute warps:        wait S^T(i) -> P^T = exp2(...) -> TMEM (bf16 pairs over the dead score columns: the A operand of
 //                         dV comes from tensor memory, as in the forward kernel) -> wait dP^T(i) -> dS^T -> shared
 //                         (double-buffered, 2 x 32 KB) -> per kv tile the dV_j / dK_j rows, at the end the dQ rows.
-// v1 kept S^T and dP^T in the SAME 256 TMEM columns and issued every product from a warp that also ran the passes, so
-// each product's issue + latency (17 - 33 single-thread MMA issues, 2 - 3.6 k cycles) sat between two passes: 46 % of
-// the head's 37 k cycles were MMA waits.  Here S^T and dP^T have their own 128 columns (q tiles of 128 instead of the
-// whole row), so both products of item i+1 are in flight while item i is being processed:
+// MEASURED on v1 (scripts/attn_phases.py): of a head's 37 k cycles, 17 k were waits for products issued by a warp that
+// also ran the passes (S^T and dP^T shared 256 TMEM columns, so each product sat between two passes) and 9 k were the
+// set-up of a fresh CTA (barriers, TMEM allocation, the wait for the first tiles) that nothing could overlap at one
+// CTA per SM.  MEASURED on a first warp-specialised version with 16 compute warps (17 warps -> 96 registers per thread):
+// the spills it caused went to L2 (L1 is 28 KB beside 200 KB of shared memory) and made it 1.5x SLOWER than v1; with 8
+// compute warps each thread takes four 16-column chunks of a row at up to 168 registers and nothing spills.
 //   TMEM: S^T / P^T [0,128)  dP^T [128,256)  dV_j [256,320)  dK_j [320,384)  dQ [384,512)
-//   smem: Q, K, V, dO tiles (4 x 32 KB, outputs staged in place as before) + two dS^T buffers (O parks in the second one
-//         until delta = rowsum(dO * O) has been taken).
-constexpr int ATT2_CW = 16;                        // compute warps: four threads per TMEM lane
-constexpr int ATT2_COMPUTE = ATT2_CW * 32;
-constexpr int ATT2_THREADS = ATT2_COMPUTE + 32;    // + the MMA / TMA warp
+//   smem: (Q, K) x 2 when they fit (T <= 208: the other pair receives the next head) + V + dO tiles of exactly TP rows,
+//         two dS^T buffers (O parks in the second one until delta = rowsum(dO * O) has been taken), small per-head arrays.
 constexpr int ATT_DS_BYTES = 2 * 16384;            // one dS^T buffer: [128 kv rows][2 k-blocks x 64 q columns]
-constexpr int ATT2_SMEM = 4 * ATT_TILE_BYTES + 2 * ATT_DS_BYTES + 1024 /*align*/ + (4 * 256 + 192 + 1024) * 4 + 128;
+constexpr int ATT2_MAX_SMEM = 232448;              // 227 KB
 
-__global__ void __launch_bounds__(ATT2_THREADS, 1) attn_bwd_ws_kernel(const __grid_constant__ AttnParams p) {
+// per-head arrays (floats): lse[AL] invq[AL] invk[AL] delta[AL] scale[64] rscale[64] dsqk[64] dot[512]; then the barriers
+__host__ __device__ constexpr int att2_array_bytes(int AL) { return (4 * AL + 3 * 64 + 256) * 4 + 128; }
+
+// MEASURED: the 16-compute-warp instantiation (four threads per lane) needs 17 warps -> 96 registers per thread and spills
+// ~900 bytes; re-splitting the register file with setmaxnreg (640-thread CTA, 112 / 56 registers) neither made ptxas use the
+// larger budget nor ran (the MMA warp timed out on its first barrier), so only ATT2_CW = 8 is instantiated.
+template <int ATT2_CW>
+__global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int ATT2_COMPUTE = ATT2_CW * 32;
+  constexpr int ATT2_THREADS = ATT2_COMPUTE + 32;    // + the MMA warp
+  constexpr int PARTS = ATT2_CW / 4;                 // threads per TMEM lane
+  constexpr int NCC = 8 / PARTS;                     // 16-column chunks per thread and item, at most
+  constexpr int NH2 = 4 / PARTS;                     // 16-channel groups per thread in the epilogues
   pdl_enter();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_TILE_BYTES;
-  uint8_t* sDO = sV + ATT_TILE_BYTES;
-  uint8_t* sDS = sDO + ATT_TILE_BYTES;                          // two dS^T buffers
-  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);  // [256]  (already times log2e)
-  float* s_delta = s_lse + 256;                                // [256]
-  float* s_invq = s_delta + 256;                               // [256]
-  float* s_invk = s_invq + 256;                                // [256]
-  float* s_scale = s_invk + 256;                               // [64]
-  float* s_dsqk = s_scale + 64;                                // [64]
-  float* s_rscale = s_dsqk + 64;                               // [64]  1/s (0 where s == 0)
-  float* s_dot = s_rscale + 64;                                // [2][4][128] partial row dots of the normalisation backward
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dot + 1024);
-  uint64_t* bar_qk = bars + 0;      // TMA: q, k tiles
-  uint64_t* bar_vdo = bars + 1;     // TMA: v, dO, O tiles
-  uint64_t* bar_S = bars + 2;       // MMA -> compute: S^T(i) complete
-  uint64_t* bar_dP = bars + 3;      // MMA -> compute: dP^T(i) complete
-  uint64_t* bar_P = bars + 4;       // compute -> MMA: P^T(i) is in tensor memory (16 warp arrivals)
-  uint64_t* bar_dS = bars + 5;      // compute -> MMA: dS^T(i) is in shared memory (16 warp arrivals)
-  uint64_t* bar_free = bars + 6;    // [2] MMA -> compute: the products reading dS^T buffer b have completed
-  uint64_t* bar_acc = bars + 8;     // MMA -> compute: dV_j, dK_j (and every dQ contribution so far) complete
-  uint64_t* bar_norm = bars + 9;    // compute -> MMA: q / k normalised in place (only when they arrive raw)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();         // 128B-swizzled tiles need a 1024-byte aligned base
+  const int T = p.T, TP = p.TP;
+  const uint32_t R = static_cast<uint32_t>(TP) * 128u;  // bytes of one [TP tokens][64 bf16] tile
+  const int nbuf = p.dbuf ? 2 : 1;
+  uint8_t* sQK = smem;                                  // [nbuf][Q | K]
+  uint8_t* sV = sQK + nbuf * 2 * R;
+  uint8_t* sDO = sV + R;
+  uint8_t* sDS = sDO + R;                               // two dS^T buffers
+  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);
+  float* s_invq = s_lse + TP;
+  float* s_invk = s_invq + TP;
+  float* s_delta = s_invk + TP;
+  float* s_scale = s_delta + TP;                        // [64]
+  float* s_rscale = s_scale + 64;                       // [64]  1/s (0 where s == 0)
+  float* s_dsqk = s_rscale + 64;                        // [64]
+  float* s_dot = s_dsqk + 64;                           // [PARTS][128] partial row dots of the normalisation backward
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dot + PARTS * 128);
+  uint64_t* bar_qk = bars + 0;      // [2] TMA: q, k tiles of buffer pair b
+  uint64_t* bar_vdo = bars + 2;     // TMA: v, dO, O tiles
+  uint64_t* bar_S = bars + 3;       // MMA -> compute: S^T(i) complete
+  uint64_t* bar_dP = bars + 4;      // MMA -> compute: dP^T(i) complete
+  uint64_t* bar_P = bars + 5;       // compute -> MMA: P^T(i) is in tensor memory (one arrival per compute warp)
+  uint64_t* bar_dS = bars + 6;      // compute -> MMA: dS^T(i) is in shared memory
+  uint64_t* bar_free = bars + 7;    // [2] MMA -> compute: the products reading dS^T buffer b have completed
+  uint64_t* bar_acc = bars + 9;     // MMA -> compute: dV_j, dK_j (and every dQ contribution so far) complete
+  uint64_t* bar_norm = bars + 10;   // compute -> MMA: q / k normalised in place (only when they arrive raw)
+  uint64_t* bar_dv = bars + 11;     // MMA -> compute: dV_j complete (its rows are staged while dK_j / dQ still run)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int T = p.T, TP = p.TP;
   const bool has_norm = p.sqk != nullptr;
   const bool qk_ready = !has_norm || p.inv_q != nullptr;
+  const int nQ = p.nQ, nK = p.nK, nItems = nQ * nK;
+  const int nheads = p.B * p.H;
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+  ATT2_MARK(0);
 
-  if (tid == ATT2_COMPUTE) {
-    // the loads go out first (q, k on their own barrier: the first score product needs only those)
-    mbar_init(bar_qk, 1);
+  if (tid == 0) {
+    mbar_init(bar_qk + 0, 1);
+    mbar_init(bar_qk + 1, 1);
     mbar_init(bar_vdo, 1);
     mbar_init(bar_S, 1);
     mbar_init(bar_dP, 1);
@@ -807,290 +880,450 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attn_bwd_ws_kernel(const __gr
     mbar_init(bar_free + 1, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_norm, ATT2_CW);
+    mbar_init(bar_dv, 1);
     fence_barrier_init();
-    mbar_arrive_expect_tx(bar_qk, 2 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tq, bar_qk, sQ, h * 64, 0, b);
-    tma_load_3d(&p.tk, bar_qk, sK, h * 64, 0, b);
-    mbar_arrive_expect_tx(bar_vdo, 3 * ATT_TILE_BYTES);
-    tma_load_3d(&p.tv, bar_vdo, sV, h * 64, 0, b);
-    tma_load_3d(&p.tdo, bar_vdo, sDO, h * 64, 0, b);
-    tma_load_3d(&p.to, bar_vdo, sDS + ATT_DS_BYTES, h * 64, 0, b);   // O parks in dS^T buffer 1 for the delta pass
+    // the first head's tiles go out at once (q, k on their own barrier: the first score product needs only those)
+    const int hd = blockIdx.x, b0 = hd / p.H, h0 = hd % p.H;
+    mbar_arrive_expect_tx(bar_qk, 2 * R);
+    tma_load_3d(&p.tq, bar_qk, sQK, h0 * 64, 0, b0);
+    tma_load_3d(&p.tk, bar_qk, sQK + R, h0 * 64, 0, b0);
+    mbar_arrive_expect_tx(bar_vdo, 3 * R);
+    tma_load_3d(&p.tv, bar_vdo, sV, h0 * 64, 0, b0);
+    tma_load_3d(&p.tdo, bar_vdo, sDO, h0 * 64, 0, b0);
+    tma_load_3d(&p.to, bar_vdo, sDS + ATT_DS_BYTES, h0 * 64, 0, b0);   // O parks in dS^T buffer 1 for the delta pass
   }
   if (warp == ATT2_CW) {
-    __syncwarp();
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
-  if (tid < 64) {
-    const float sc = has_norm ? p.sqk[h * 64 + tid] * p.sqk_mul : 1.f;
-    s_scale[tid] = sc;
-    s_rscale[tid] = sc != 0.f ? 1.f / sc : 0.f;
-    s_dsqk[tid] = 0.f;
-  }
-  if (tid >= 256 && tid < 512) {
-    const int r = tid - 256;  // one thread per (padded) token row
-    s_lse[r] = (r < T) ? p.lse[(static_cast<long long>(b) * p.H + h) * T + r] * LOG2E : 0.f;
-    const bool pre = p.inv_q != nullptr && r < T;
-    s_invq[r] = pre ? p.inv_q[(static_cast<long long>(b) * T + r) * p.ld_inv_q + h] : 0.f;
-    s_invk[r] = pre ? p.inv_k[(static_cast<long long>(b) * T + r) * p.ld_inv_k + h] : 0.f;
+  for (int r = tid; r < TP; r += ATT2_THREADS) {   // rows >= T are never written again and must stay finite
+    s_lse[r] = 0.f;
+    s_invq[r] = 0.f;
+    s_invk[r] = 0.f;
     s_delta[r] = 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
-  const int nQ = p.nQ, nK = p.nK, nItems = nQ * nK;
+  const uint32_t sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
 
   if (warp == ATT2_CW) {
     // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues (see gemm_tcgen05.cu) =====
+    uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_vdo = 0, ph_P = 0, ph_dS = 0, ph_norm = 0;
     auto ncol_of = [&](int c) { return min(128, TP - 128 * c); };
-    auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
-      mma_seq(tmem_base + TM_S, umma_smem_desc(sK_a + j * 16384, 16, 1024), 2, umma_smem_desc(sQ_a + c * 16384, 16, 1024), 2,
-              idesc_kk_n(ncol_of(c)), 4, false);
-      mma_commit(bar_S);
-    };
-    auto issue_dP = [&](int j, int c) {      // dP^T(j,c) = V_j dO_c^T
-      mma_seq(tmem_base + TM_DP, umma_smem_desc(sV_a + j * 16384, 16, 1024), 2, umma_smem_desc(sDO_a + c * 16384, 16, 1024), 2,
-              idesc_kk_n(ncol_of(c)), 4, false);
-      mma_commit(bar_dP);
-    };
-    mbar_wait(bar_qk, 0);
-    if (!qk_ready) mbar_wait(bar_norm, 0);
-    tc_fence_after_sync();
-    issue_S(0, 0);
-    mbar_wait(bar_vdo, 0);
-    tc_fence_after_sync();
-    issue_dP(0, 0);
-    int i = 0;
-    for (int j = 0; j < nK; ++j) {
-      const int kv_steps = min(8, (TP - j * 128) >> 4);
-      for (int c = 0; c < nQ; ++c, ++i) {
-        const int nks = ncol_of(c) >> 4;
-        const int jn = (c + 1 < nQ) ? j : j + 1, cn = (c + 1 < nQ) ? c + 1 : 0;
-        const bool has_next = i + 1 < nItems;
-        const uint32_t buf_a = sDS_a + (i & 1) * ATT_DS_BYTES;
-        // ---- dV_j += P^T(i) dO_c   (A = P^T from tensor memory: 8 columns per k-step)
-        mbar_wait(bar_P, i & 1);
-        tc_fence_after_sync();
-        {
-          uint64_t dd = umma_smem_desc(sDO_a + c * 16384, 8192, 1024);
-#pragma unroll 1
-          for (int ks = 0; ks < nks; ++ks) {
-            if (elect_one()) umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S + ks * 8, dd, IDESC_KM(64), (c > 0 || ks > 0) ? 1u : 0u);
-            dd += 128;
-          }
+    int n = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      const int pb = p.dbuf ? (n & 1) : 0;
+      const uint32_t sQ_a = smem_u32(sQK + pb * 2 * R), sK_a = sQ_a + R;
+      // MEASURED (first persistent version, marks of scripts/attn_bwd_phases_v2.py): issuing through mma_seq (one election
+      // and ~19 dependent instructions per MMA) cost ~125 cycles per MMA - the 32 MMAs of an item took 4 k cycles to ISSUE
+      // against ~1.5 k on the tensor pipe, and the compute warps waited for dP^T / the accumulators.  Here one lane is elected
+      // per product and issues its k-steps back to back from constant offsets.
+      auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
+        const uint64_t da = umma_smem_desc(sK_a + j * 16384, 16, 1024), db = umma_smem_desc(sQ_a + c * 16384, 16, 1024);
+        const uint32_t id = idesc_kk_n(ncol_of(c));
+        if (elect_one()) {
+          umma_bf16_ss(tmem_base + TM_S, da, db, id, 0u);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(tmem_base + TM_S, da + 2 * ks, db + 2 * ks, id);
+          umma_commit(bar_S);
         }
-        // the next score tile rides behind dV (the tensor pipe runs in issue order: it overwrites P^T only after dV read it)
-        if (has_next) issue_S(jn, cn);
-        // ---- dK_j += dS^T(i) Qh_c ; dQ_c += dS(i) Kh_j
-        mbar_wait(bar_dS, i & 1);
-        tc_fence_after_sync();
-        {
-          const uint64_t dp = umma_smem_desc(buf_a, 16, 1024);
-          uint64_t dq = umma_smem_desc(sQ_a + c * 16384, 8192, 1024);
-#pragma unroll 1
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t da = dp + static_cast<uint64_t>((ks >> 2) * 1024 + (ks & 3) * 2);
-            if (elect_one()) umma_bf16_ss(tmem_base + TM_DK, da, dq, IDESC_KM(64), (c > 0 || ks > 0) ? 1u : 0u);
-            dq += 128;
-          }
+        __syncwarp();
+      };
+      auto issue_dP = [&](int j, int c) {      // dP^T(j,c) = V_j dO_c^T
+        const uint64_t da = umma_smem_desc(sV_a + j * 16384, 16, 1024), db = umma_smem_desc(sDO_a + c * 16384, 16, 1024);
+        const uint32_t id = idesc_kk_n(ncol_of(c));
+        if (elect_one()) {
+          umma_bf16_ss(tmem_base + TM_DP, da, db, id, 0u);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(tmem_base + TM_DP, da + 2 * ks, db + 2 * ks, id);
+          umma_commit(bar_dP);
         }
-        mma_seq(tmem_base + TM_DQ + 64 * c, umma_smem_desc(buf_a, 16384, 1024), 128, umma_smem_desc(sK_a + j * 16384, 8192, 1024), 128,
-                IDESC_MM(64), kv_steps, j > 0);
-        mma_commit(bar_free + (i & 1));
-        if (c == nQ - 1) mma_commit(bar_acc);
-        if (has_next) issue_dP(jn, cn);
+        __syncwarp();
+      };
+      ATT2_MMARK(0);
+      if (pb == 0) { mbar_wait(bar_qk, ph_qk0); ph_qk0 ^= 1; }
+      else { mbar_wait(bar_qk + 1, ph_qk1); ph_qk1 ^= 1; }
+      if (!qk_ready) { mbar_wait(bar_norm, ph_norm); ph_norm ^= 1; }
+      tc_fence_after_sync();
+      ATT2_MMARK(1);
+      issue_S(0, 0);
+      mbar_wait(bar_vdo, ph_vdo);
+      ph_vdo ^= 1;
+      tc_fence_after_sync();
+      issue_dP(0, 0);
+      ATT2_MMARK(2);
+      int i = 0;
+      for (int j = 0; j < nK; ++j) {
+        const int kv_steps = min(8, (TP - j * 128) >> 4);
+        for (int c = 0; c < nQ; ++c, ++i) {
+          const int nks = ncol_of(c) >> 4;
+          const int jn = (c + 1 < nQ) ? j : j + 1, cn = (c + 1 < nQ) ? c + 1 : 0;
+          const bool has_next = i + 1 < nItems;
+          const uint32_t buf_a = sDS_a + (i & 1) * ATT_DS_BYTES;
+          // ---- dV_j += P^T(i) dO_c   (A = P^T from tensor memory: 8 columns per k-step)
+          mbar_wait(bar_P, ph_P);
+          ph_P ^= 1;
+          tc_fence_after_sync();
+          ATT2_MMARK(3 + 4 * i);
+          {
+            const uint64_t dd = umma_smem_desc(sDO_a + c * 16384, 8192, 1024);
+            const uint32_t first = c > 0 ? 1u : 0u;
+            if (elect_one()) {
+              umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S, dd, IDESC_KM(64), first);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks)
+                if (ks < nks) umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S + ks * 8, dd + 128 * ks, IDESC_KM(64), 1u);
+              if (c == nQ - 1) umma_commit(bar_dv);
+            }
+            __syncwarp();
+          }
+          // the next score tile rides behind dV (the tensor pipe runs in issue order: it overwrites P^T only after dV read it)
+          if (has_next) issue_S(jn, cn);
+          ATT2_MMARK(4 + 4 * i);
+          mbar_wait(bar_dS, ph_dS);
+          ph_dS ^= 1;
+          tc_fence_after_sync();
+          ATT2_MMARK(5 + 4 * i);
+          // dP^T of the next item first, unless this item completes a kv tile (then the compute warps wait for dV_j / dK_j
+          // next and have a whole epilogue and a P pass before they need dP^T).  Its TMEM columns are free: every compute
+          // warp has read dP^T(i) before it announced dS^T(i).
+          if (has_next && c != nQ - 1) issue_dP(jn, cn);
+          // ---- dK_j += dS^T(i) Qh_c ; dQ_c += dS(i) Kh_j
+          {
+            const uint64_t dp = umma_smem_desc(buf_a, 16, 1024);
+            const uint64_t dq = umma_smem_desc(sQ_a + c * 16384, 8192, 1024);
+            const uint64_t dsm = umma_smem_desc(buf_a, 16384, 1024), dkm = umma_smem_desc(sK_a + j * 16384, 8192, 1024);
+            const uint32_t first_k = c > 0 ? 1u : 0u, first_q = j > 0 ? 1u : 0u;
+            if (elect_one()) {
+              umma_bf16_ss(tmem_base + TM_DK, dp, dq, IDESC_KM(64), first_k);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks)
+                if (ks < nks) umma_bf16_ss_acc(tmem_base + TM_DK, dp + static_cast<uint64_t>((ks >> 2) * 1024 + (ks & 3) * 2), dq + 128 * ks, IDESC_KM(64));
+              umma_bf16_ss(tmem_base + TM_DQ + 64 * c, dsm, dkm, IDESC_MM(64), first_q);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks)
+                if (ks < kv_steps) umma_bf16_ss_acc(tmem_base + TM_DQ + 64 * c, dsm + 128 * ks, dkm + 128 * ks, IDESC_MM(64));
+              umma_commit(bar_free + (i & 1));
+              if (c == nQ - 1) umma_commit(bar_acc);
+            }
+            __syncwarp();
+          }
+          if (has_next && c == nQ - 1) issue_dP(jn, cn);
+          ATT2_MMARK(6 + 4 * i);
+        }
       }
     }
   } else {
     // ===================== compute warps =====================
     const int wq = warp & 3;       // TMEM lane quarter this warp may access
-    const int part = warp >> 2;    // which quarter of the columns / channels of a row
+    const int part = warp >> 2;    // which share of the columns / channels of a row
     const int row = wq * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const float sl2 = p.scale * LOG2E;
-    // dL/d(sqk) partials are reduced into s_dsqk right where they arise (three short-lived 16-float arrays instead of one
-    // that would live across the whole item loop: 96 registers per thread with 17 warps resident)
-    if (!qk_ready) {
-      mbar_wait(bar_qk, 0);
-      for (int r = tid; r < 2 * T; r += ATT2_COMPUTE) {
-        if (r < T) s_invq[r] = normalize_row(sQ, r, s_scale);
-        else s_invk[r - T] = normalize_row(sK, r - T, s_scale);
+    uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_vdo = 0, ph_S = 0, ph_dP = 0, ph_acc = 0, ph_free0 = 0, ph_free1 = 0, ph_dv = 0;
+    bool used0 = false, used1 = false;     // dS^T buffer b has been filled before
+    // per-head scalars of the NEXT head travel in registers from the start of a head to its end (latency fully hidden)
+    float nx_lse = 0.f, nx_invq = 0.f, nx_invk = 0.f, nx_sc = 1.f;
+    auto fetch_head = [&](int hd) {
+      const int b = hd / p.H, h = hd % p.H;
+      if (tid < T) {
+        nx_lse = p.lse[(static_cast<long long>(b) * p.H + h) * T + tid];      // raw: any use here would wait for the load
+        if (p.inv_q != nullptr) {
+          nx_invq = p.inv_q[(static_cast<long long>(b) * T + tid) * p.ld_inv_q + h];
+          nx_invk = p.inv_k[(static_cast<long long>(b) * T + tid) * p.ld_inv_k + h];
+        }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_norm);
-    }
-    int i = 0;
-    for (int j = 0; j < nK; ++j) {
-      const int kv = j * 128 + row;
-      const bool kv_ok = kv < T;
-      for (int c = 0; c < nQ; ++c, ++i) {
-        const int nch = min(128, TP - 128 * c) >> 4;          // 16-column chunks of this item (<= 8)
-        const int c_begin = (part * nch) / 4, c_end = ((part + 1) * nch) / 4;   // this thread's chunks: at most two
-        const int q0 = c * 128;
-        uint8_t* const buf = sDS + (i & 1) * ATT_DS_BYTES;
-        uint32_t pk[2][8];
-        // ---- P^T = exp2(scale log2e S^T - lse log2e), kept as bf16 pairs
-        mbar_wait(bar_S, i & 1);
-        tc_fence_after_sync();
-        {
-          uint32_t r[2][16];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc)
-            if (c_begin + cc < c_end) tmem_ld_32x32b_x16(t_lane + TM_S + (c_begin + cc) * 16, r[cc]);
-          tmem_wait_ld();
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int ch = c_begin + cc;
-            if (ch < c_end) {
-              float pv[16];
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
-                pv[4 * e4 + 0] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 0]), sl2, -l4.x));
-                pv[4 * e4 + 1] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 1]), sl2, -l4.y));
-                pv[4 * e4 + 2] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 2]), sl2, -l4.z));
-                pv[4 * e4 + 3] = ex2_approx(fmaf(__uint_as_float(r[cc][4 * e4 + 3]), sl2, -l4.w));
-              }
-              if (!kv_ok) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) pv[e] = 0.f;
-              } else if (q0 + ch * 16 + 16 > T) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  if (q0 + ch * 16 + e >= T) pv[e] = 0.f;
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
-            }
-          }
+      if (tid < 64 && has_norm) nx_sc = p.sqk[h * 64 + tid];
+    };
+    auto publish_head = [&]() {
+      if (tid < T) {
+        s_lse[tid] = nx_lse * LOG2E;
+        if (p.inv_q != nullptr) { s_invq[tid] = nx_invq; s_invk[tid] = nx_invk; }
+      }
+      if (tid < 64) {
+        const float sc = has_norm ? nx_sc * p.sqk_mul : 1.f;
+        s_scale[tid] = sc;
+        s_rscale[tid] = sc != 0.f ? 1.f / sc : 0.f;
+        s_dsqk[tid] = 0.f;
+      }
+    };
+    fetch_head(blockIdx.x);
+    publish_head();
+    named_bar_sync(1, ATT2_COMPUTE);
+    ATT2_MARK(1);
+
+    int n = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      const int b = hd / p.H, h = hd % p.H;
+      const int pb = p.dbuf ? (n & 1) : 0;
+      uint8_t* const sQ = sQK + pb * 2 * R;
+      uint8_t* const sK = sQ + R;
+      const int hd_next = hd + gridDim.x;
+      const bool more = hd_next < nheads;
+      if (more) fetch_head(hd_next);
+      if (!qk_ready) {
+        if (pb == 0) { mbar_wait(bar_qk, ph_qk0); ph_qk0 ^= 1; }
+        else { mbar_wait(bar_qk + 1, ph_qk1); ph_qk1 ^= 1; }
+        for (int r = tid; r < 2 * T; r += ATT2_COMPUTE) {
+          if (r < T) s_invq[r] = normalize_row(sQ, r, s_scale);
+          else s_invk[r - T] = normalize_row(sK, r - T, s_scale);
         }
-        tc_fence_before_sync();
-        named_bar_sync(1, ATT2_COMPUTE);        // every score column of this item has been read: P^T may overwrite them
-        tc_fence_after_sync();
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-          if (c_begin + cc < c_end) tmem_st_32x32b_x8(t_lane + TM_S + (c_begin + cc) * 8, pk[cc]);
-        tmem_wait_st();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_P);
-        if (i == 0) {
-          // delta = rowsum(dO * O) from the shared tiles (O parks in dS^T buffer 1), under the first dV / S^T products
-          mbar_wait(bar_vdo, 0);
-          for (int r = tid; r < T; r += ATT2_COMPUTE) {
-            float d = 0.f;
-#pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8) {
-              float a[8], g[8];
-              unpack8(*reinterpret_cast<const uint4*>(sDS + ATT_DS_BYTES + sw128(r, k8)), a);
-              unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, k8)), g);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) d += a[e] * g[e];
-            }
-            s_delta[r] = d;
-          }
-          named_bar_sync(1, ATT2_COMPUTE);
-        }
-        // ---- dS^T = P^T (dP^T - delta) scale -> shared memory (K-major [128 kv][ncol q], 64-column k-blocks)
-        mbar_wait(bar_dP, i & 1);
-        tc_fence_after_sync();
-        if (i >= 2) mbar_wait(bar_free + (i & 1), ((i >> 1) - 1) & 1);   // the products of item i-2 have let go of this buffer
-        {
-          uint32_t r[2][16];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc)
-            if (c_begin + cc < c_end) tmem_ld_32x32b_x16(t_lane + TM_DP + (c_begin + cc) * 16, r[cc]);
-          tmem_wait_ld();
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int ch = c_begin + cc;
-            if (ch < c_end) {
-              float pv[16];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { pv[2 * e] = bf16lo(pk[cc][e]); pv[2 * e + 1] = bf16hi(pk[cc][e]); }
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 d4 = *reinterpret_cast<const float4*>(s_delta + q0 + ch * 16 + 4 * e4);
-                pv[4 * e4 + 0] *= (__uint_as_float(r[cc][4 * e4 + 0]) - d4.x) * p.scale;
-                pv[4 * e4 + 1] *= (__uint_as_float(r[cc][4 * e4 + 1]) - d4.y) * p.scale;
-                pv[4 * e4 + 2] *= (__uint_as_float(r[cc][4 * e4 + 2]) - d4.z) * p.scale;
-                pv[4 * e4 + 3] *= (__uint_as_float(r[cc][4 * e4 + 3]) - d4.w) * p.scale;
-              }
-              uint8_t* blk = buf + (ch >> 2) * 16384;
-              const int k2 = (ch & 3) * 2;
-              *reinterpret_cast<uint4*>(blk + sw128(row, k2)) = pack8(pv);
-              *reinterpret_cast<uint4*>(blk + sw128(row, k2 + 1)) = pack8(pv + 8);
-            }
-          }
-        }
-        tc_fence_before_sync();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dS);
-
-        if (c == nQ - 1) {
-          // ---- dV_j and dK_j rows: every thread takes 16 channels of its row of both; staged in the (dead) V_j / K_j rows
-          mbar_wait(bar_acc, j & 1);
+        if (lane == 0) mbar_arrive(bar_norm);
+      }
+      int i = 0;
+      for (int j = 0; j < nK; ++j) {
+        const int kv = j * 128 + row;
+        const bool kv_ok = kv < T;
+        for (int c = 0; c < nQ; ++c, ++i) {
+          const int nch = min(128, TP - 128 * c) >> 4;          // 16-column chunks of this item (<= 8)
+          const int c_begin = (part * nch) / PARTS, c_end = ((part + 1) * nch) / PARTS;   // this thread's chunks: at most NCC
+          const int q0 = c * 128;
+          const int bsel = i & 1;
+          uint8_t* const buf = sDS + bsel * ATT_DS_BYTES;
+          uint32_t pk[NCC][8];
+          // ---- P^T = exp2(scale log2e S^T - lse log2e), kept as bf16 pairs
+          ATT2_MARK(2 + 6 * i);
+          mbar_wait(bar_S, ph_S);
+          ph_S ^= 1;
           tc_fence_after_sync();
-          tmem_row16_to_tile(t_lane + TM_DV + part * 16, sV + j * 16384, row, part);
-          if (has_norm) {
-            float g[16], n[16], dacc[16];
+          ATT2_MARK(3 + 6 * i);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) dacc[e] = 0.f;
-            s_dot[part * 128 + row] = norm_bwd_load(t_lane + TM_DK + part * 16, sK, kv_ok ? kv : 0, part, s_scale, s_rscale, g, n, dacc, kv_ok);
-            reduce16_to_smem(dacc, s_dsqk + part * 16, lane);
+          for (int pr = 0; pr < NCC / 2; ++pr) {       // two chunks per round: 32 accumulator columns in flight per thread
+            uint32_t r[2][16];
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+              if (c_begin + 2 * pr + c2 < c_end) tmem_ld_32x32b_x16(t_lane + TM_S + (c_begin + 2 * pr + c2) * 16, r[c2]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int cc = 2 * pr + c2;
+              const int ch = c_begin + cc;
+              if (ch < c_end) {
+                float pv[16];
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
+                  pv[4 * e4 + 0] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 0]), sl2, -l4.x));
+                  pv[4 * e4 + 1] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 1]), sl2, -l4.y));
+                  pv[4 * e4 + 2] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 2]), sl2, -l4.z));
+                  pv[4 * e4 + 3] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 3]), sl2, -l4.w));
+                }
+                if (!kv_ok) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+                } else if (q0 + ch * 16 + 16 > T) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e)
+                    if (q0 + ch * 16 + e >= T) pv[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
+              }
+            }
+          }
+          tc_fence_before_sync();
+          named_bar_sync(1, ATT2_COMPUTE);        // every score column of this item has been read: P^T may overwrite them
+          tc_fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < NCC; ++cc)
+            if (c_begin + cc < c_end) tmem_st_32x32b_x8(t_lane + TM_S + (c_begin + cc) * 8, pk[cc]);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_P);
+          ATT2_MARK(4 + 6 * i);
+          if (i == 0 && more && p.dbuf && tid == 0) {
+            // The other (Q, K) pair receives the next head's tiles while this head is processed.  Its last readers were the
+            // output stores of the previous head (issued by this thread): they have long drained, the wait is a formality.
+            bulk_wait_group_read<0>();
+            uint8_t* nq = sQK + (pb ^ 1) * 2 * R;
+            const int bn = hd_next / p.H, hn = hd_next % p.H;
+            mbar_arrive_expect_tx(bar_qk + (pb ^ 1), 2 * R);
+            tma_load_3d(&p.tq, bar_qk + (pb ^ 1), nq, hn * 64, 0, bn);
+            tma_load_3d(&p.tk, bar_qk + (pb ^ 1), nq + R, hn * 64, 0, bn);
+          }
+          if (i == 0) {
+            // delta = rowsum(dO * O) from the shared tiles (O parks in dS^T buffer 1), under the first dV / S^T products
+            mbar_wait(bar_vdo, ph_vdo);
+            ph_vdo ^= 1;
+            for (int r = tid; r < T; r += ATT2_COMPUTE) {
+              float d = 0.f;
+#pragma unroll
+              for (int k8 = 0; k8 < 8; ++k8) {
+                float a[8], g[8];
+                unpack8(*reinterpret_cast<const uint4*>(sDS + ATT_DS_BYTES + sw128(r, k8)), a);
+                unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, k8)), g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += a[e] * g[e];
+              }
+              s_delta[r] = d;
+            }
             named_bar_sync(1, ATT2_COMPUTE);
-            const float dot = (s_dot[row] + s_dot[128 + row]) + (s_dot[256 + row] + s_dot[384 + row]);
-            if (kv_ok) norm_bwd_store(g, n, dot, s_invk[kv], sK, kv, part);
+          }
+          // ---- dS^T = P^T (dP^T - delta) scale -> shared memory (K-major [128 kv][ncol q], 64-column k-blocks)
+          mbar_wait(bar_dP, ph_dP);
+          ph_dP ^= 1;
+          tc_fence_after_sync();
+          // the products that read this buffer's previous contents have completed
+          if (bsel == 0) {
+            if (used0) { mbar_wait(bar_free, ph_free0); ph_free0 ^= 1; }
+            used0 = true;
           } else {
-            tmem_row16_to_tile(t_lane + TM_DK + part * 16, sK + j * 16384, row, part);
+            if (used1) { mbar_wait(bar_free + 1, ph_free1); ph_free1 ^= 1; }
+            used1 = true;
+          }
+          ATT2_MARK(5 + 6 * i);
+#pragma unroll
+          for (int pr = 0; pr < NCC / 2; ++pr) {
+            uint32_t r[2][16];
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+              if (c_begin + 2 * pr + c2 < c_end) tmem_ld_32x32b_x16(t_lane + TM_DP + (c_begin + 2 * pr + c2) * 16, r[c2]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int cc = 2 * pr + c2;
+              const int ch = c_begin + cc;
+              if (ch < c_end) {
+                float pv[16];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { pv[2 * e] = bf16lo(pk[cc][e]); pv[2 * e + 1] = bf16hi(pk[cc][e]); }
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 d4 = *reinterpret_cast<const float4*>(s_delta + q0 + ch * 16 + 4 * e4);
+                  pv[4 * e4 + 0] *= (__uint_as_float(r[c2][4 * e4 + 0]) - d4.x) * p.scale;
+                  pv[4 * e4 + 1] *= (__uint_as_float(r[c2][4 * e4 + 1]) - d4.y) * p.scale;
+                  pv[4 * e4 + 2] *= (__uint_as_float(r[c2][4 * e4 + 2]) - d4.z) * p.scale;
+                  pv[4 * e4 + 3] *= (__uint_as_float(r[c2][4 * e4 + 3]) - d4.w) * p.scale;
+                }
+                if (!kv_ok) {       // rows past the sequence: the tiles hold exactly TP rows, what lies behind them is not ours
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+                }
+                uint8_t* blk = buf + (ch >> 2) * 16384;
+                const int k2 = (ch & 3) * 2;
+                *reinterpret_cast<uint4*>(blk + sw128(row, k2)) = pack8(pv);
+                *reinterpret_cast<uint4*>(blk + sw128(row, k2 + 1)) = pack8(pv + 8);
+              }
+            }
           }
           tc_fence_before_sync();
           fence_proxy_async_smem();
-          named_bar_sync(1, ATT2_COMPUTE);
-          if (tid == 0) {
-            tma_store_3d(&p.tdv, sV + j * 16384, h * 64, j * 128, b);
-            tma_store_3d(&p.tdk, sK + j * 16384, h * 64, j * 128, b);
-            bulk_commit_group();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dS);
+          ATT2_MARK(6 + 6 * i);
+
+          if (c == nQ - 1) {
+            // ---- dV_j and dK_j rows: every thread takes 32 channels of its row of both; staged in the (dead) V_j / K_j rows
+            // dV_j was complete long ago (it was issued a whole dS pass before): stage its rows while dK_j / dQ still run
+            mbar_wait(bar_dv, ph_dv);
+            ph_dv ^= 1;
+            tc_fence_after_sync();
+#pragma unroll
+            for (int h2 = 0; h2 < NH2; ++h2)      // tiles hold exactly TP rows: lanes past the last row must not store
+              tmem_row16_to_tile(t_lane + TM_DV + (part * NH2 + h2) * 16, sV + j * 16384, row, part * NH2 + h2, kv < TP);
+            mbar_wait(bar_acc, ph_acc);
+            ph_acc ^= 1;
+            tc_fence_after_sync();
+            ATT2_MARK(7 + 6 * i);
+            if (j == nK - 1 && more && tid == 0) {
+              // every product of this head has completed: dO and the O parking slot are free for the next head's tiles
+              // (V follows once this head's output stores have left its rows)
+              const int bn = hd_next / p.H, hn = hd_next % p.H;
+              mbar_arrive_expect_tx(bar_vdo, 3 * R);
+              tma_load_3d(&p.tdo, bar_vdo, sDO, hn * 64, 0, bn);
+              tma_load_3d(&p.to, bar_vdo, sDS + ATT_DS_BYTES, hn * 64, 0, bn);
+            }
+            if (has_norm) {
+              float pd = 0.f;
+#pragma unroll
+              for (int h2 = 0; h2 < NH2; ++h2)
+                pd += norm_bwd_dot16(t_lane + TM_DK + (part * NH2 + h2) * 16, sK, kv_ok ? kv : 0, part * NH2 + h2, s_scale, s_rscale, s_dsqk, lane, kv_ok);
+              s_dot[part * 128 + row] = pd;
+              named_bar_sync(1, ATT2_COMPUTE);
+              float dot = 0.f;
+#pragma unroll
+              for (int pp = 0; pp < PARTS; ++pp) dot += s_dot[pp * 128 + row];
+#pragma unroll
+              for (int h2 = 0; h2 < NH2; ++h2)
+                norm_bwd_apply16(t_lane + TM_DK + (part * NH2 + h2) * 16, sK, kv_ok ? kv : 0, part * NH2 + h2, s_scale, s_rscale, dot,
+                                 s_invk[kv_ok ? kv : 0], kv_ok);
+              __syncwarp();
+            } else {
+#pragma unroll
+              for (int h2 = 0; h2 < NH2; ++h2)
+                tmem_row16_to_tile(t_lane + TM_DK + (part * NH2 + h2) * 16, sK + j * 16384, row, part * NH2 + h2, kv < TP);
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();
+            named_bar_sync(1, ATT2_COMPUTE);
+            if (tid == 0) {
+              tma_store_3d(&p.tdv, sV + j * 16384, h * 64, j * 128, b);
+              tma_store_3d(&p.tdk, sK + j * 16384, h * 64, j * 128, b);
+              bulk_commit_group();
+            }
           }
         }
       }
-    }
-    // ---- dQ rows (complete with the last bar_acc), one 128-row q tile at a time (register budget: 96 per thread with 17
-    // warps resident), staged in place over Qh
-    if (has_norm) {
+      ATT2_MARK(30);
+      // ---- dQ rows (complete with the last bar_acc), one 128-row q tile at a time, staged in place over Qh
       for (int m = 0; m < nQ; ++m) {
         const int qi = m * 128 + row;
         const bool ok = qi < T;
-        float g[16], n[16], dacc[16];
+        if (has_norm) {
+          float pd = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dacc[e] = 0.f;
-        s_dot[m * 512 + part * 128 + row] =
-            norm_bwd_load(t_lane + TM_DQ + 64 * m + part * 16, sQ, ok ? qi : 0, part, s_scale, s_rscale, g, n, dacc, ok);
-        reduce16_to_smem(dacc, s_dsqk + part * 16, lane);
-        named_bar_sync(1, ATT2_COMPUTE);
-        if (ok) {
-          const float* sd = s_dot + m * 512;
-          const float dot = (sd[row] + sd[128 + row]) + (sd[256 + row] + sd[384 + row]);
-          norm_bwd_store(g, n, dot, s_invq[qi], sQ, qi, part);
+          for (int h2 = 0; h2 < NH2; ++h2)
+            pd += norm_bwd_dot16(t_lane + TM_DQ + 64 * m + (part * NH2 + h2) * 16, sQ, ok ? qi : 0, part * NH2 + h2, s_scale, s_rscale, s_dsqk, lane, ok);
+          named_bar_sync(1, ATT2_COMPUTE);      // the previous exchange through s_dot has been read by everybody
+          s_dot[part * 128 + row] = pd;
+          named_bar_sync(1, ATT2_COMPUTE);
+          float dot = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < PARTS; ++pp) dot += s_dot[pp * 128 + row];
+#pragma unroll
+          for (int h2 = 0; h2 < NH2; ++h2)
+            norm_bwd_apply16(t_lane + TM_DQ + 64 * m + (part * NH2 + h2) * 16, sQ, ok ? qi : 0, part * NH2 + h2, s_scale, s_rscale, dot,
+                             s_invq[ok ? qi : 0], ok);
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int h2 = 0; h2 < NH2; ++h2)
+            tmem_row16_to_tile(t_lane + TM_DQ + 64 * m + (part * NH2 + h2) * 16, sQ + m * 16384, row, part * NH2 + h2, qi < TP);
         }
       }
-    } else {
-      for (int m = 0; m < nQ; ++m) tmem_row16_to_tile(t_lane + TM_DQ + 64 * m + part * 16, sQ + m * 16384, row, part);
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      if (tid == 0 && more) {
+        // V is free once the dV stores of this head have left its rows (the last one was issued a dQ epilogue ago)
+        bulk_wait_group_read<0>();
+        const int bn = hd_next / p.H, hn = hd_next % p.H;
+        tma_load_3d(&p.tv, bar_vdo, sV, hn * 64, 0, bn);
+      }
+      named_bar_sync(1, ATT2_COMPUTE);
+      if (tid == 0) {
+        for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
+        bulk_commit_group();
+        if (more && !p.dbuf) {          // single (Q, K) pair: its rows are free only when these stores have read them
+          bulk_wait_group_read<0>();
+          const int bn = hd_next / p.H, hn = hd_next % p.H;
+          mbar_arrive_expect_tx(bar_qk, 2 * R);
+          tma_load_3d(&p.tq, bar_qk, sQ, hn * 64, 0, bn);
+          tma_load_3d(&p.tk, bar_qk, sK, hn * 64, 0, bn);
+        }
+      }
+      if (has_norm && tid < 64) atomicAdd(p.dsqk + h * 64 + tid, s_dsqk[tid] * p.sqk_mul);
+      // every reader of this head's per-head arrays is past the barrier above: publish the next head's values
+      if (more) publish_head();
+      named_bar_sync(1, ATT2_COMPUTE);
+      ATT2_MARK(31);
     }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    named_bar_sync(1, ATT2_COMPUTE);
-    if (tid == 0) {
-      for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
-      bulk_commit_group();
-      bulk_wait_group_read<0>();      // all staged tiles have left shared memory before the CTA retires
-    }
-    if (has_norm && tid < 64) atomicAdd(p.dsqk + h * 64 + tid, s_dsqk[tid] * p.sqk_mul);
   }
+  if (tid == 0) bulk_wait_group_read<0>();      // the staged output tiles have left shared memory before the CTA retires
   tc_fence_before_sync();
   __syncthreads();
   if (warp == ATT2_CW) {
@@ -1118,7 +1351,7 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 using namespace nvit;
 
 static long long* g_att_dbg = nullptr;
-static std::atomic<int> g_bwd_variant{1};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel
+static std::atomic<int> g_bwd_variant{2};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
   g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
@@ -1179,11 +1412,15 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
                  reinterpret_cast<uintptr_t>(dv)) & 15) == 0, "nvit_attention_bwd: buffers must be 16-byte aligned");
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  if ((rc = make_head_tmap(&p.tq, q, ldq, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.tdo, dout, ldo, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T))) return rc;
+  const int variant = g_bwd_variant.load(std::memory_order_relaxed);
+  const int TP = (int)((T + 15) / 16 * 16);
+  // v1 loads whole 256-row boxes; the persistent kernel keeps tiles of exactly TP rows
+  const int in_rows = variant == 1 ? ATT_ROWS : TP;
+  if ((rc = make_head_tmap(&p.tq, q, ldq, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.tdo, dout, ldo, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T, in_rows))) return rc;
   if ((rc = make_head_tmap(&p.tdq, dq, lddq, (int)B, (int)H, (int)T, 128))) return rc;
   if ((rc = make_head_tmap(&p.tdk, dk, lddk, (int)B, (int)H, (int)T, 128))) return rc;
   if ((rc = make_head_tmap(&p.tdv, dv, lddv, (int)B, (int)H, (int)T, 128))) return rc;
@@ -1195,7 +1432,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   p.sqk_mul = sqk_mul;
   p.scale = scale;
   p.B = (int)B; p.H = (int)H; p.T = (int)T;
-  p.TP = (int)((T + 15) / 16 * 16);
+  p.TP = TP;
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
   p.dbg = g_att_dbg;
@@ -1203,19 +1440,28 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   int dev;
   if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_MAX_SMEM));
     once.mark(dev);
   }
-  if (g_bwd_variant.load(std::memory_order_relaxed) == 1)
+  if (variant == 1) {
     launch(attn_bwd_kernel, (unsigned)(B * H), ATT_THREADS, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream), p);
-  else
-    launch(attn_bwd_ws_kernel, (unsigned)(B * H), ATT2_THREADS, ATT2_SMEM, static_cast<cudaStream_t>(stream), p);
+  } else {
+    // shared memory: (Q, K) x 2 when it fits (the next head's tiles load during the current head), V, dO, two dS^T buffers
+    const long long R = 128ll * TP;
+    const long long fixed = 2 * ATT_DS_BYTES + att2_array_bytes(TP);
+    p.dbuf = (6 * R + fixed <= ATT2_MAX_SMEM) ? 1 : 0;
+    const long long smem = (p.dbuf ? 6 : 4) * R + fixed;
+    NVIT_REQUIRE(smem <= ATT2_MAX_SMEM, "nvit_attention_bwd: shared-memory plan does not fit (T = %lld)", (long long)T);
+    const long long heads = B * H;
+    const int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
+    launch(attn_bwd_ws_kernel<8>, (unsigned)grid, 8 * 32 + 32, (size_t)smem, static_cast<cudaStream_t>(stream), p);
+  }
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
 
 extern "C" int nvit_attention_bwd_variant(int variant) {   // tuning switch (include/nvit_b200_tuning.h): same results
-  NVIT_REQUIRE(variant == 1 || variant == 2, "nvit_attention_bwd_variant: 1 (one role, 512 threads) or 2 (warp-specialised, default)");
+  NVIT_REQUIRE(variant == 1 || variant == 2, "nvit_attention_bwd_variant: 1 (one role, one head per CTA) or 2 (persistent, warp-specialised; default)");
   g_bwd_variant.store(variant, std::memory_order_relaxed);
   return NVIT_OK;
 }

@@ -151,7 +151,7 @@ def total_loss(cfg, logits, aux, y):
         + cfg.reconstruction_weight * aux["reconstruction"]
 
 
-def check_units(cfg, p, X, got, engine):
+def check_units(cfg, p, X, got, engine, same_weights=True):
     """The CUDA path's best-matching units vs the oracle's own.  A discrete choice cannot be "within a tolerance", but it
     has an exact analytic criterion: the CUDA path picks argmin_g |x' - n_g| for ITS patch embedding x' (bf16 tensor-core
     GEMM), the oracle for its fp32 x.  With eps = |x' - x| (measured per token from the engine's own fp32 embedding
@@ -178,8 +178,16 @@ def check_units(cfg, p, X, got, engine):
         print(f"[kohonen units] {tag}: mismatch rate {mismatch:.4%}, max eps/best {float((eps / best).max()):.3e}, "
               f"max excess/best {float(((d_mine - best) / best).max()):.3e}")
         assert not bool(bad.any()), (tag, int(bad.sum()), float(((d_mine - best - slack)[bad]).max()))
-        # and the bf16 input rounding bounds eps itself: |x' - x| <= 2^-7 |x| would already be a broken GEMM
-        assert float((eps / x.detach().norm(dim=-1)).max()) <= 2.0 ** -7, float((eps / x.detach().norm(dim=-1)).max())
+        # and the bf16 rounding of the GEMM operands bounds eps itself: every product term carries at most 2^-8 relative error
+        # (two operands rounded to 8 significant bits), so |x' - x|_inf <= 2^-8 * (|img| . |W|) per channel (+ fp32 summation)
+        # (only meaningful while the oracle holds the SAME weights as the model: not after separately taken optimizer steps)
+        if not same_weights:
+            forced.append(mine)
+            continue
+        A, W = (acts["A_l"], "local_patch_embed.weight") if tag == "local" else (acts["A_g"], "global_patch_embed.1.weight")
+        bound = (A.float().abs() @ p[W].detach().reshape(p[W].shape[0], -1).abs().t()) * 2.0 ** -8 + 1e-6
+        err = (x_gpu - x.detach()).reshape(bound.shape).abs()
+        assert bool((err <= bound).all()), (tag, float((err / bound).max()))
         forced.append(mine)
     return tuple(forced)
 
@@ -297,7 +305,7 @@ def test_kohonen_trainer_steps_match_oracle():
     ot = O.OracleTrainer({k: v.to(DEV) for k, v in sd.items()}, cfg, lr=1e-3)
     for it in range(2):
         loss = tr.step(X, y)
-        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, tr.last_aux, model.engine)
+        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, tr.last_aux, model.engine, same_weights=(it == 0))
         oloss, _, oaux = ot.step(X, y, force_indices=forced)
         for k in ("kohonen_consistency", "kohonen_smoothness", "local_quantization", "global_quantization"):
             assert abs(float(tr.last_aux[k]) - float(oaux[k])) <= 1e-2 * abs(float(oaux[k])) + 1e-6, (it, k)
@@ -315,7 +323,7 @@ def test_kohonen_trainer_steps_match_oracle():
     model.eval()
     with torch.no_grad():
         l1, _ = model(X)
-        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, model.engine.last_aux, model.engine)
+        forced = check_units(cfg, {k: v.detach() for k, v in ot.sd.items()}, X, model.engine.last_aux, model.engine, same_weights=False)
         l2, _ = O.vit_forward(ot.sd, cfg, X, training=False, force_indices=forced)
     assert rel(l1, l2) <= 2e-2
 
