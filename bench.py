@@ -524,7 +524,7 @@ def main():
             "step_tensor_frac": {"flop_per_image": fpi, "achieved_tflops_per_gpu": fpi * value / world / 1e12,
                                  "frac_of_sustained_peak": fpi * value / world / 1e12 / peak},
             "roofline": dominant,
-            "kernel_groups": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table[:8]],
+            "kernel_groups": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table[:16]],
             "probed_ms_per_step": probed_ms,
         }
         if dp_parity is not None:

@@ -226,7 +226,7 @@ int nvit_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int
  * is L2-normalised before it is written back as fp32 and as the bf16 GEMM operand; g is zeroed if zero_grad != 0.
  * p, g, m, v are the flat buffers (same layout); w16 the flat bf16 operand buffer.  table_dev: n_segments entries of
  * 8 x int64 {element offset, rows, cols, kind, bf16 element offset or -1, weight-decay flag, first_unit, 0}; kind 0 = plain
- * (unit = 2048 elements), 1 = normalise every row over cols (unit = 8 rows), 2 = normalise every column over rows (unit =
+ * (unit = 8192 elements), 1 = normalise every row over cols (unit = 32 rows), 2 = normalise every column over rows (unit =
  * 128 columns); first_unit = running sum of units.  unit_counter_zeroed: device uint32 that must be 0 at launch (units
  * are claimed dynamically).  The other arguments are those of nvit_adamw_flat. */
 int nvit_adamw_norm_fused(float* p, float* g, float* m, float* v, void* w16_bf16, const int64_t* table_dev, int64_t n_segments,

@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
     const int part = warp >> 2;    // which share of the columns / channels of a row
     const int row = wq * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const float sl2 = p.scale * LOG2E;
+    const f32x2 sl2x2 = pack2(p.scale * LOG2E, p.scale * LOG2E), scx2 = pack2(p.scale, p.scale);
     uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_vdo = 0, ph_S = 0, ph_dP = 0, ph_acc = 0, ph_free0 = 0, ph_free1 = 0, ph_dv = 0;
     bool used0 = false, used1 = false;     // dS^T buffer b has been filled before
     // per-head scalars of the NEXT head travel in registers from the start of a head to its end (latency fully hidden)
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
     };
     auto publish_head = [&]() {
       if (tid < T) {
-        s_lse[tid] = nx_lse * LOG2E;
+        s_lse[tid] = -nx_lse * LOG2E;       // stored negated: the P pass adds it inside one FFMA2
         if (p.inv_q != nullptr) { s_invq[tid] = nx_invq; s_invk[tid] = nx_invk; }
       }
       if (tid < 64) {
@@ -1105,12 +1105,15 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
               if (ch < c_end) {
                 float pv[16];
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
+                for (int e4 = 0; e4 < 4; ++e4) {     // exponent = s * scale log2e + (-lse log2e), two columns per FFMA2
                   const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
-                  pv[4 * e4 + 0] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 0]), sl2, -l4.x));
-                  pv[4 * e4 + 1] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 1]), sl2, -l4.y));
-                  pv[4 * e4 + 2] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 2]), sl2, -l4.z));
-                  pv[4 * e4 + 3] = ex2_approx(fmaf(__uint_as_float(r[c2][4 * e4 + 3]), sl2, -l4.w));
+                  float a0, a1, a2, a3;
+                  unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 0]), __uint_as_float(r[c2][4 * e4 + 1])), sl2x2, pack2(l4.x, l4.y)), a0, a1);
+                  unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 2]), __uint_as_float(r[c2][4 * e4 + 3])), sl2x2, pack2(l4.z, l4.w)), a2, a3);
+                  pv[4 * e4 + 0] = ex2_approx(a0);
+                  pv[4 * e4 + 1] = ex2_approx(a1);
+                  pv[4 * e4 + 2] = ex2_approx(a2);
+                  pv[4 * e4 + 3] = ex2_approx(a3);
                 }
                 if (!kv_ok) {
 #pragma unroll
@@ -1160,7 +1163,7 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
 #pragma unroll
                 for (int e = 0; e < 8; ++e) d += a[e] * g[e];
               }
-              s_delta[r] = d;
+              s_delta[r] = -d * p.scale;      // stored as -delta * scale: the dS pass adds it inside one FFMA2
             }
             named_bar_sync(1, ATT2_COMPUTE);
           }
@@ -1191,14 +1194,12 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
               if (ch < c_end) {
                 float pv[16];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { pv[2 * e] = bf16lo(pk[cc][e]); pv[2 * e + 1] = bf16hi(pk[cc][e]); }
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
+                for (int e4 = 0; e4 < 4; ++e4) {     // dS = P * (dP scale + (-delta scale)), two columns per FFMA2
                   const float4 d4 = *reinterpret_cast<const float4*>(s_delta + q0 + ch * 16 + 4 * e4);
-                  pv[4 * e4 + 0] *= (__uint_as_float(r[c2][4 * e4 + 0]) - d4.x) * p.scale;
-                  pv[4 * e4 + 1] *= (__uint_as_float(r[c2][4 * e4 + 1]) - d4.y) * p.scale;
-                  pv[4 * e4 + 2] *= (__uint_as_float(r[c2][4 * e4 + 2]) - d4.z) * p.scale;
-                  pv[4 * e4 + 3] *= (__uint_as_float(r[c2][4 * e4 + 3]) - d4.w) * p.scale;
+                  const f32x2 t0 = fma2(pack2(__uint_as_float(r[c2][4 * e4 + 0]), __uint_as_float(r[c2][4 * e4 + 1])), scx2, pack2(d4.x, d4.y));
+                  const f32x2 t1 = fma2(pack2(__uint_as_float(r[c2][4 * e4 + 2]), __uint_as_float(r[c2][4 * e4 + 3])), scx2, pack2(d4.z, d4.w));
+                  unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4]), t0), pv[4 * e4 + 0], pv[4 * e4 + 1]);
+                  unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4 + 1]), t1), pv[4 * e4 + 2], pv[4 * e4 + 3]);
                 }
                 if (!kv_ok) {       // rows past the sequence: the tiles hold exactly TP rows, what lies behind them is not ours
 #pragma unroll

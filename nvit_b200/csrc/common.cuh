@@ -340,6 +340,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ----------------------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2)
+// Blackwell issues fp32 FMA / MUL / ADD on register PAIRS (fma.rn.f32x2 -> SASS FFMA2): half the issue slots for the
+// elementwise epilogues whose cost is instruction count (the SiLU-gate forward / backward epilogues of the GEMM).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// both halves of a packed bf16 pair as an fp32 pair
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) { return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) { float lo, hi; unpack2(v, lo, hi); return pack_bf16(lo, hi); }
+
 // ----------------------------------------------------------------------------- host: per-device once-flags
 // cudaFuncSetAttribute is per device and entry points are called from several host threads (the main thread, the
 // autograd engine's backward thread): one bit per device, set after the attribute call succeeded.  Two threads racing

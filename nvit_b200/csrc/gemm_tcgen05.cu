@@ -507,31 +507,30 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
                   }
                   const uint32_t uc[4] = {u8.x, u8.y, u8.z, u8.w}, vc[4] = {v8.x, v8.y, v8.z, v8.w};
                   uint32_t ou[4], ov[4];
+                  // Two gate columns at a time on packed fp32 pairs (FFMA2): the epilogue's cost is its instruction count
+                  // (MEASURED in round 1: 15 % of the warp samples issuing, everything else waiting on dependent results),
+                  // and the pair form halves the fp32 instructions per element (13 -> 6.5).
+                  const f32x2 half2 = pack2(0.5f, 0.5f), one2 = pack2(1.f, 1.f), neg2 = pack2(-1.f, -1.f);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int cc = c * 64 + hh * 32 + 8 * j + 2 * e;      // column within the tile
-                    float2 su = make_float2(1.f, 1.f), sv = su;
+                    f32x2 su = one2, sv = one2;
                     if (use_vec) {
-                      su = *reinterpret_cast<const float2*>(s_vec + cc);
-                      sv = *reinterpret_cast<const float2*>(s_vec + 256 + cc);
+                      const float2 a = *reinterpret_cast<const float2*>(s_vec + cc), b = *reinterpret_cast<const float2*>(s_vec + 256 + cc);
+                      su = pack2(a.x, a.y);
+                      sv = pack2(b.x, b.y);
                     }
-                    float du2[2], dv2[2];
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
-                      const float ur = hl ? bf16hi(uc[e]) : bf16lo(uc[e]);
-                      const float vr = hl ? bf16hi(vc[e]) : bf16lo(vc[e]);
-                      const float g = __uint_as_float(r[8 * j + 2 * e + hl]);
-                      const float s_u = hl ? su.y : su.x, s_v = hl ? sv.y : sv.x;
-                      const float uh = ur * s_u, vh = vr * s_v;
-                      const float sg = fmaf(0.5f, tanh_approx_(0.5f * vh), 0.5f);
-                      const float sl = vh * sg;                               // silu(vh)
-                      const float gu = g * sl;                                // dL/d(u scaled)
-                      const float gv = g * uh * fmaf(sl, 1.f - sg, sg);       // dL/d(v scaled): silu' = sg + silu (1 - sg)
-                      du2[hl] = gu * s_u;
-                      dv2[hl] = gv * s_v;
-                    }
-                    ou[e] = pack_bf16(du2[0], du2[1]);
-                    ov[e] = pack_bf16(dv2[0], dv2[1]);
+                    const f32x2 g = pack2(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+                    const f32x2 uh = mul2(bf16x2_to_f32x2(uc[e]), su), vh = mul2(bf16x2_to_f32x2(vc[e]), sv);
+                    float h0, h1;
+                    unpack2(mul2(vh, half2), h0, h1);
+                    const f32x2 sg = fma2(pack2(tanh_approx_(h0), tanh_approx_(h1)), half2, half2);   // sigmoid(vh)
+                    const f32x2 sl = mul2(vh, sg);                                               // silu(vh)
+                    const f32x2 gu = mul2(g, sl);                                                // dL/d(u scaled)
+                    const f32x2 dsl = fma2(sl, fma2(sg, neg2, one2), sg);                        // silu' = sg + silu (1 - sg)
+                    const f32x2 gv = mul2(mul2(g, uh), dsl);                                     // dL/d(v scaled)
+                    ou[e] = f32x2_to_bf16x2(mul2(gu, su));
+                    ov[e] = f32x2_to_bf16x2(mul2(gv, sv));
                   }
                   *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
                   *reinterpret_cast<uint4*>(sbuf + 16384 + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
@@ -580,16 +579,23 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
           const int n0 = n_blk * 128 + eg * 64;
           if (n0 < p.N) {  // uniform over the group
             uint32_t xo[32];
+            // x = (u su) * silu(v sv) on packed fp32 pairs, sigmoid through tanh.approx (one MUFU op per element instead of
+            // ex2 + rcp, as in the backward epilogue): ~6 instructions per element instead of ~10
+            const f32x2 half2 = pack2(0.5f, 0.5f);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float4 su = make_float4(1.f, 1.f, 1.f, 1.f), sv = su;
+            for (int i = 0; i < 32; ++i) {
+              f32x2 su = pack2(1.f, 1.f), sv = su;
               if (p.colscale) {
-                su = *reinterpret_cast<const float4*>(s_vec + eg * 64 + 2 * i);
-                sv = *reinterpret_cast<const float4*>(s_vec + 128 + eg * 64 + 2 * i);
+                const float2 a = *reinterpret_cast<const float2*>(s_vec + eg * 64 + 2 * i);
+                const float2 b = *reinterpret_cast<const float2*>(s_vec + 128 + eg * 64 + 2 * i);
+                su = pack2(a.x, a.y);
+                sv = pack2(b.x, b.y);
               }
-              xo[i] = pack_bf16(silu_mul(bf16lo(uo[i]) * su.x, bf16lo(vo[i]) * sv.x), silu_mul(bf16hi(uo[i]) * su.y, bf16hi(vo[i]) * sv.y));
-              xo[i + 1] = pack_bf16(silu_mul(bf16lo(uo[i + 1]) * su.z, bf16lo(vo[i + 1]) * sv.z),
-                                    silu_mul(bf16hi(uo[i + 1]) * su.w, bf16hi(vo[i + 1]) * sv.w));
+              const f32x2 uh = mul2(bf16x2_to_f32x2(uo[i]), su), vh = mul2(bf16x2_to_f32x2(vo[i]), sv);
+              float h0, h1;
+              unpack2(mul2(vh, half2), h0, h1);
+              const f32x2 sg = fma2(pack2(tanh_approx_(h0), tanh_approx_(h1)), half2, half2);
+              xo[i] = f32x2_to_bf16x2(mul2(mul2(uh, vh), sg));
             }
             stage_store(xo, &p.tma_c, n0, false);
             if (p.C2) {

@@ -5,8 +5,8 @@
 // autocast's weight casts of the next forward (train.py:905) and optimizer.zero_grad (train.py:946).
 //
 // Work is cut into units listed in a device table of segments (one per parameter tensor):
-//   kind 0  plain        unit = 2048 consecutive elements: AdamW (+ bf16 copy for GEMM weights)
-//   kind 1  row-normed   unit = 8 rows, one warp per row: the row's p, g, m, v pass through registers once, the updated
+//   kind 0  plain        unit = 8192 consecutive elements: AdamW (+ bf16 copy for GEMM weights)
+//   kind 1  row-normed   unit = 32 rows, one warp per row: the row's p, g, m, v pass through registers once, the updated
 //                        row is L2-normalised in registers and written as fp32 + bf16 (query/key/value/c_fc: norm over n_embd = dim 1)
 //   kind 2  col-normed   unit = 128 columns x all rows: pass 1 updates and accumulates the column sums of squares, pass 2
 //                        re-reads the (L2-resident) slab, scales it and writes fp32 + bf16 (att_c_proj / mlp_c_proj: dim 0)
@@ -43,7 +43,8 @@ __device__ __forceinline__ float4 adamw_vec(float4 p, const float4 g, float4& m,
 }
 
 constexpr int TAIL_FIELDS = 8;      // {offset, rows, cols, kind, w16 offset or -1, decay, first_unit, reserved}
-constexpr int PLAIN_UNIT = 2048;    // elements per kind-0 unit (256 threads x 2 float4)
+constexpr int PLAIN_UNIT = 8192;    // elements per kind-0 unit (256 threads x 8 float4)
+constexpr int ROW_UNIT = 32;        // rows per kind-1 unit (8 warps x 4 rows)
 
 __global__ void __launch_bounds__(256, 2)
 adamw_norm_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __restrict__ Mo, float* __restrict__ Vo,
@@ -53,7 +54,7 @@ adamw_norm_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __r
   pdl_enter();
   __shared__ float4 s_part[8][32];
   __shared__ float4 s_inv[32];
-  __shared__ long long s_unit;
+  __shared__ long long s_unit[2];
   if (dev_lr_step) {   // CUDA-graph friendly: learning rate and 1-based step count live in device memory
     h.lr = dev_lr_step[0];
     const float t = dev_lr_step[1];
@@ -69,12 +70,13 @@ adamw_norm_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __r
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (;;) {
-    __syncthreads();                       // everybody has read s_unit / s_inv of the previous unit
-    if (threadIdx.x == 0) s_unit = (long long)atomicAdd(counter, 1u);
-    __syncthreads();
-    const long long unit = s_unit;
+  // Units are claimed one ahead: the atomic's round trip to L2 (~1 us) runs under the current unit's streaming.
+  if (threadIdx.x == 0) s_unit[0] = (long long)atomicAdd(counter, 1u);
+  for (int it = 0;; ++it) {
+    __syncthreads();                       // s_unit[it & 1] is published; everybody is done with the previous unit
+    const long long unit = s_unit[it & 1];
     if (unit >= total_units) break;
+    if (threadIdx.x == 0) s_unit[(it + 1) & 1] = (long long)atomicAdd(counter, 1u);
     int lo = 0, hi = n_seg - 1;            // last segment with first_unit <= unit
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -97,32 +99,45 @@ adamw_norm_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __r
       const long long n = 1ll * rows * cols;
       const long long base = u * PLAIN_UNIT;
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const long long i = base + (it * 256 + threadIdx.x) * 4;
-        if (i + 4 <= n) {
-          float4 pp = *reinterpret_cast<const float4*>(p + i);
-          const float4 gg = *reinterpret_cast<const float4*>(g + i);
-          float4 mm = *reinterpret_cast<const float4*>(m + i);
-          float4 vv = *reinterpret_cast<const float4*>(v + i);
-          pp = adamw_vec(pp, gg, mm, vv, k, decay);
-          *reinterpret_cast<float4*>(p + i) = pp;
-          *reinterpret_cast<float4*>(m + i) = mm;
-          *reinterpret_cast<float4*>(v + i) = vv;
-          if (zero_grad) *reinterpret_cast<float4*>(g + i) = zero4;
-          if (w16) *reinterpret_cast<uint2*>(w16 + i) = make_uint2(pack_bf16(pp.x, pp.y), pack_bf16(pp.z, pp.w));
-        } else {
-          for (long long t = i; t < n && t < i + 4; ++t) {
-            float me = m[t], ve = v[t];
-            const float pe = adamw_elem(p[t], g[t], me, ve, k, decay);
-            p[t] = pe; m[t] = me; v[t] = ve;
-            if (zero_grad) g[t] = 0.f;
-            if (w16) w16[t] = __float2bfloat16(pe);
+      for (int half = 0; half < 2; ++half) {       // 2 x (4 float4 of each stream in flight per thread)
+        float4 pp[4], gg[4], mm[4], vv[4];
+        long long idx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          idx[q] = base + ((half * 4 + q) * 256 + threadIdx.x) * 4;
+          if (idx[q] + 4 <= n) {
+            pp[q] = *reinterpret_cast<const float4*>(p + idx[q]);
+            gg[q] = *reinterpret_cast<const float4*>(g + idx[q]);
+            mm[q] = *reinterpret_cast<const float4*>(m + idx[q]);
+            vv[q] = *reinterpret_cast<const float4*>(v + idx[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long long i = idx[q];
+          if (i + 4 <= n) {
+            pp[q] = adamw_vec(pp[q], gg[q], mm[q], vv[q], k, decay);
+            *reinterpret_cast<float4*>(p + i) = pp[q];
+            *reinterpret_cast<float4*>(m + i) = mm[q];
+            *reinterpret_cast<float4*>(v + i) = vv[q];
+            if (zero_grad) *reinterpret_cast<float4*>(g + i) = zero4;
+            if (w16) *reinterpret_cast<uint2*>(w16 + i) = make_uint2(pack_bf16(pp[q].x, pp[q].y), pack_bf16(pp[q].z, pp[q].w));
+          } else {
+            for (long long t = i; t < n && t < i + 4; ++t) {
+              float me = m[t], ve = v[t];
+              const float pe = adamw_elem(p[t], g[t], me, ve, k, decay);
+              p[t] = pe; m[t] = me; v[t] = ve;
+              if (zero_grad) g[t] = 0.f;
+              if (w16) w16[t] = __float2bfloat16(pe);
+            }
           }
         }
       }
     } else if (kind == 1) {
       // ---------------------------------------------------------------- one warp per row, the row stays in registers
-      const int r = (int)u * 8 + wy;
+#pragma unroll 1
+      for (int rr = 0; rr < ROW_UNIT / 8; ++rr) {
+      const int r = (int)u * ROW_UNIT + rr * 8 + wy;
       if (r < rows) {
         const long long ro = 1ll * r * cols;
         if ((cols & 3) == 0 && cols <= 1024) {
@@ -173,6 +188,7 @@ adamw_norm_fused_kernel(float* __restrict__ P, float* __restrict__ G, float* __r
             if (w16) w16[ro + c] = __float2bfloat16(x);
           }
         }
+      }
       }
     } else {
       // ---------------------------------------------------------------- 128 columns x all rows, two passes

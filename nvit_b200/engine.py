@@ -276,10 +276,10 @@ class Engine:
             if n in normed:
                 r, c = s.shape
                 kind = 1 if normed[n] == 1 else 2
-                units = (r + 7) // 8 if kind == 1 else (c + 127) // 128
+                units = (r + 31) // 32 if kind == 1 else (c + 127) // 128
                 segs[kind].append([s.off, r, c, kind, w16_off, decay, units])
             else:
-                segs[0].append([s.off, 1, s.numel, 0, w16_off, decay, (s.numel + 2047) // 2048])
+                segs[0].append([s.off, 1, s.numel, 0, w16_off, decay, (s.numel + 8191) // 8192])
         rows, first = [], 0
         for kind in (2, 1, 0):
             for off, r, c, k, w16, decay, units in segs[kind]:

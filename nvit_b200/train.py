@@ -425,7 +425,7 @@ class Trainer:
         self.lr, self.betas, self.eps = group["lr"], tuple(group["betas"]), group["eps"]
         self.opt_step = step
         self.hyper.copy_(torch.tensor([self.lr, float(step)], dtype=F32))
-        self._graph = None
+        self._drop_graph()
 
     @property
     def total_launches(self) -> int:

@@ -412,31 +412,56 @@ def _steps(trainer, X, y, n):
     return [float(trainer.step(X, y)) for _ in range(n)]
 
 
+def _param_dist(ma, mb):
+    worst = 0.0
+    for (n, a), (_, b) in zip(ma.named_parameters(), mb.named_parameters()):
+        worst = max(worst, rel(b.detach(), a.detach()))
+    return worst
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_cuda_graph_replay_equals_eager_steps(fused):
     """The bench's timed path: k steps of Trainer(cuda_graph=True) (2 eager warm-up steps, then capture + replays, learning
-    rate and step count in device memory) == the same k eager steps from the same state: losses and every parameter,
-    including a set_lr between replays and an optimizer-state reload (which drops the captured graph)."""
+    rate and step count in device memory) against the same k eager steps from the same state, including a set_lr between
+    replays, forwards at other batch sizes between replays (the captured activation set is pinned) and an optimizer-state
+    reload (which drops and re-captures the graph).
+
+    Two EAGER runs of the same steps are not bit-identical either (fp32 atomics: split-K reduce-adds, per-channel alpha / sqk
+    / bias sums; AdamW's first steps turn that noise into +-lr on near-zero gradients), so the criterion is calibrated in
+    place: a second eager trainer gives the noise floor (itself a noisy number: a handful of steps), and graph-vs-eager must
+    stay within 10x of it and under absolute caps (loss 2e-3, parameters 2e-2) that a missed launch, a stale learning rate
+    or a wrong step count break by an order of magnitude (MEASURED: deviations 3e-5 ... 4e-4 against floors 2e-5 ... 3e-4)."""
     cfg = O.named_config("tiny")
     sd = O.init_state_dict(cfg, 13)
     g = torch.Generator().manual_seed(77)
     X = torch.randn(16, 3, 32, 32, generator=g).to(DEV)
     y = torch.randint(0, 10, (16,), generator=g).to(DEV)
-    me, mg = build(cfg, sd), build(cfg, sd)
+    me, m2, mg = build(cfg, sd), build(cfg, sd), build(cfg, sd)
     te = Trainer(me, learning_rate=1e-3, fused_tail=fused)
+    t2 = Trainer(m2, learning_rate=1e-3, fused_tail=fused)
     tg = Trainer(mg, learning_rate=1e-3, fused_tail=fused, cuda_graph=True, graph_warmup_steps=2)
-    le, lg = _steps(te, X, y, 5), _steps(tg, X, y, 5)            # 2 eager + capture + 3 replays
+    trainers = (te, t2, tg)
+
+    def run(n):
+        return [_steps(t, X, y, n) for t in trainers]
+
+    def check(tag, losses):
+        le, l2, lg = losses
+        floor = max(abs(a - b) / abs(a) for a, b in zip(le, l2))
+        dev = max(abs(a - b) / abs(a) for a, b in zip(le, lg))
+        pfloor, pdev = _param_dist(me, m2), _param_dist(me, mg)
+        print(f"[graph vs eager, {tag}] loss deviation {dev:.2e} (eager-vs-eager floor {floor:.2e}); "
+              f"worst parameter rel-L2 {pdev:.2e} (floor {pfloor:.2e})")
+        assert dev <= 10 * floor + 1e-5 and dev <= 2e-3, (tag, dev, floor, le, lg)
+        assert pdev <= 10 * pfloor + 1e-5 and pdev <= 2e-2, (tag, pdev, pfloor)
+
+    check("2 eager + capture + 3 replays", run(5))
     assert tg.replays == 3 and tg._graph is not None
-    te.set_lr(3e-4)
-    tg.set_lr(3e-4)
-    le += _steps(te, X, y, 2)
-    lg += _steps(tg, X, y, 2)
+    for t in trainers:
+        t.set_lr(3e-4)
+    check("set_lr between replays", run(2))
     assert tg.replays == 5
-    for a, b in zip(le, lg):
-        assert abs(a - b) <= 1e-6 * abs(a), (le, lg)
-    for (n, a), (_, b) in zip(me.named_parameters(), mg.named_parameters()):
-        assert rel(b.detach(), a.detach()) <= 1e-6, (n, rel(b.detach(), a.detach()))
-    assert te.opt_step == tg.opt_step == 7 and float(tg.hyper[1]) == 7.0
+    assert te.opt_step == tg.opt_step == 7 and float(tg.hyper[1]) == 7.0 and abs(float(tg.hyper[0]) - 3e-4) < 1e-9
     # a forward at another batch size between replays must not disturb the captured activation set (it is pinned)
     mg.eval()
     with torch.no_grad():
@@ -445,29 +470,25 @@ def test_cuda_graph_replay_equals_eager_steps(fused):
         mg(X[:3])
     mg.train()
     assert 16 in mg.engine._acts and 16 in mg.engine._pinned
-    me.eval()
-    with torch.no_grad():
-        me(X[:5])
-    me.train()
-    le2, lg2 = _steps(te, X, y, 2), _steps(tg, X, y, 2)
-    for a, b in zip(le2, lg2):
-        assert abs(a - b) <= 1e-6 * abs(a), (le2, lg2)
-    # optimizer-state reload: the graph is dropped, re-captured, and the run continues identically
+    check("after forwards at other batch sizes", run(2))
+    assert tg.replays == 7
+    # optimizer-state reload: the graph is dropped, re-captured, and the run continues like the eager ones
     state = te.optimizer_state_dict()
-    tg.load_optimizer_state_dict(state)
-    te.load_optimizer_state_dict(state)
+    msd = {k: v.detach().clone() for k, v in me.state_dict().items()}
+    for m, t in ((me, te), (m2, t2), (mg, tg)):
+        m.load_state_dict(msd)
+        t.load_optimizer_state_dict(state)
     assert tg._graph is None
-    le3, lg3 = _steps(te, X, y, 3), _steps(tg, X, y, 3)
-    for a, b in zip(le3, lg3):
-        assert abs(a - b) <= 1e-6 * abs(a), (le3, lg3)
-    for (n, a), (_, b) in zip(me.named_parameters(), mg.named_parameters()):
-        assert rel(b.detach(), a.detach()) <= 1e-6, (n, rel(b.detach(), a.detach()))
+    check("after an optimizer-state reload", run(3))
+    assert tg._graph is not None
 
 
 def test_fused_optimizer_tail_equals_separate_kernels():
     """nvit_adamw_norm_fused (clip + AdamW + normalize_matrices + bf16 operands + zero_grad, one pass) against
-    the separate sumsq / adamw_flat / weight_norm_multi / cast kernels: parameters, moments, bf16 operands, zeroed
-    gradients and unit-norm rows / columns; also in the original-ViT branch (no normalisation) and with bias tensors."""
+    the separate sumsq / adamw_flat / weight_norm_multi / cast kernels ON IDENTICAL GRADIENTS AND STATE (two backward passes
+    of the same batch differ in the last bits through fp32 atomics, which AdamW's first steps amplify): parameters,
+    moments, bf16 operands, zeroed gradients and unit-norm rows / columns; also in the original-ViT branch (no
+    normalisation) and with bias tensors."""
     for name, over in (("tiny", dict()), ("mini", dict(bias=True)), ("tiny", dict(use_nvit=False))):
         cfg = O.named_config(name, **over)
         sd = O.init_state_dict(cfg, 5)
@@ -476,16 +497,27 @@ def test_fused_optimizer_tail_equals_separate_kernels():
         y = torch.randint(0, cfg.num_classes, (8,), generator=g).to(DEV)
         ma, mb = build(cfg, sd), build(cfg, sd)
         ta, tb = Trainer(ma, fused_tail=True), Trainer(mb, fused_tail=False)
-        for it in range(3):
-            la, lb = float(ta.step(X, y)), float(tb.step(X, y))
-            assert abs(la - lb) <= 1e-6 * abs(lb), (name, it, la, lb)
         ea, eb = ma.engine, mb.engine
-        na = ea.n_active
-        assert rel(ea.P32[:na], eb.P32[:na]) <= 1e-6
-        assert rel(ta.m[:na], tb.m[:na]) <= 1e-6 and rel(ta.v[:na], tb.v[:na]) <= 1e-6
-        assert float(ea.G32[:na].abs().max()) == 0.0                      # zero_grad is part of the pass
-        # the bf16 operands the fused pass wrote are exactly the rounding of its fp32 values
-        assert torch.equal(ea.W16[:ea.n_gemm], ea.P32[:ea.n_gemm].to(torch.bfloat16))
+        for it in range(3):
+            ta._ensure_state()
+            tb._ensure_state()
+            # same parameters, moments and gradients on both sides, then one optimizer tail each
+            eb.P32.copy_(ea.P32)
+            tb.m.copy_(ta.m)
+            tb.v.copy_(ta.v)
+            ta.loss_buf.zero_()
+            ta.micro_step(X, y)
+            eb.G32.copy_(ea.G32)
+            ta.optimizer_step()
+            tb.optimizer_step()
+            torch.cuda.synchronize()
+            na = ea.n_active
+            assert rel(ea.P32[:na], eb.P32[:na]) <= 1e-6, (name, it, rel(ea.P32[:na], eb.P32[:na]))
+            assert rel(ta.m[:na], tb.m[:na]) <= 1e-6 and rel(ta.v[:na], tb.v[:na]) <= 1e-6, (name, it)
+            assert float(ea.G32[:na].abs().max()) == 0.0 and float(eb.G32[:na].abs().max()) == 0.0      # zero_grad is part of the pass
+            # the bf16 operands the fused pass wrote are exactly the rounding of its fp32 values
+            assert torch.equal(ea.W16[:ea.n_gemm], ea.P32[:ea.n_gemm].to(torch.bfloat16)), (name, it)
+            assert ta.opt_step == tb.opt_step == it + 1
         if cfg.use_nvit:
             params = dict(ma.named_parameters())
             for i in range(cfg.n_layer):
@@ -494,6 +526,9 @@ def test_fused_optimizer_tail_equals_separate_kernels():
                     assert float((w.norm(dim=dim) - 1).abs().max()) <= 1e-5, (i, nm)
         # untrained (grad-less) tensors are not touched by the tail
         assert torch.equal(dict(ma.named_parameters())["reconstruction_head.0.weight"].detach().cpu(), sd["reconstruction_head.0.weight"])
+        # and whole steps of the two trainers stay together (up to the atomics noise of two separate backward passes)
+        la, lb = float(ta.step(X, y)), float(tb.step(X, y))
+        assert abs(la - lb) <= 2e-3 * abs(lb), (name, la, lb)
 
 
 def test_weights_written_behind_the_engines_back_are_seen():
