@@ -60,6 +60,10 @@ int nvit_gemm_bf16(const void* A, const void* B, void* C, void* C2_bf16, int64_t
 int nvit_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 /* out[0] += sum(x^2): global gradient norm of clip_grad_norm_ (train.py:938) */
 int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void* stream);
+/* The same with a run-to-run and rank-to-rank reproducible result (no floating-point atomics): data-parallel replicas then
+ * derive bit-identical clip coefficients from their bit-identical all-reduced gradients.  workspace: workspace_floats >= 2
+ * device floats, workspace[0] zero before the FIRST use (the kernel leaves it zero); at most workspace_floats - 1 CTAs run. */
+int nvit_sumsq_f32_det(const float* x, int64_t n, float* out_accum, float* workspace, int64_t workspace_floats, void* stream);
 /* out[N] += column sums of a bf16 [M,N] matrix (bias gradients of nn.Linear when config.bias) */
 int nvit_colsum_bf16(const void* x_bf16, int64_t M, int64_t N, int64_t ldx, float* out_accum, void* stream);
 /* dpos[T,C] += sum_b dx[b,t,c]; dbias[C] += sum_{b,t} dx  (autograd of `+ pos_embed` and conv bias, model.py:407-415) */

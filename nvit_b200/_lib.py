@@ -26,6 +26,7 @@ SIGNATURES = {
     "nvit_residual_bwd_staged": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
+    "nvit_sumsq_f32_det": [P, I64, P, P, I64, P],
     "nvit_colsum_bf16": [P, I64, I64, I64, P, P],
     "nvit_pos_bias_grad": [P, I64, I64, I64, P, P, P],
     "nvit_residual_fwd": [P, P, P, F32, P, P, P, P, I64, I64, P],

@@ -79,6 +79,48 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   if (threadIdx.x == 0) atomicAdd(out, tot);
 }
 
+// Deterministic form (data-parallel replicas must compute bit-identical clip coefficients from bit-identical gradients, or
+// they drift apart by an ulp per step): every CTA stores its partial sum at workspace[1 + blockIdx.x]; the CTA that arrives
+// last (ticket counter in workspace[0], reset for the next launch) adds the partials IN INDEX ORDER and accumulates into out.
+__global__ void __launch_bounds__(256) sumsq_det_kernel(const float* __restrict__ x, long long n, float* __restrict__ out,
+                                                        float* __restrict__ ws) {
+  pdl_enter();
+  __shared__ float red[32];
+  __shared__ bool s_last;
+  const long long stride = 1ll * gridDim.x * blockDim.x;
+  float acc = 0.f;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  long long i = 1ll * blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    const long long n4 = n >> 2;
+    for (; i < n4; i += stride) {
+      const float4 a = ldg_f4_stream(x + i * 4);
+      acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    for (long long t = n4 * 4 + 1ll * blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc += x[t] * x[t];
+  } else {
+    for (; i < n; i += stride) acc += x[i] * x[i];
+  }
+  const float tot = block_sum(acc, red);      // fixed tree: a CTA's partial does not depend on timing
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+  if (threadIdx.x == 0) {
+    ws[1 + blockIdx.x] = tot;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float part = 0.f;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) part += __ldcg(ws + 1 + b);   // fixed assignment b -> thread
+    const float total = block_sum(part, red);
+    if (threadIdx.x == 0) {
+      out[0] += total;
+      *ticket = 0u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums (bias grads)
 // grid.x over 256-column chunks (thread = column), grid.y over row slabs.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ldx,
@@ -640,6 +682,17 @@ extern "C" int nvit_sumsq_f32(const float* x, int64_t n, float* out_accum, void*
   NVIT_REQUIRE(n >= 0 && out_accum && (n == 0 || x), "nvit_sumsq_f32: bad arguments");
   if (n == 0) return NVIT_OK;
   launch(sumsq_kernel, stream_grid(n / 4 + 1, 256, 4), 256, 0, ST(stream), x, n, out_accum);
+  NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_sumsq_f32_det(const float* x, int64_t n, float* out_accum, float* workspace, int64_t workspace_floats, void* stream) {
+  NVIT_REQUIRE(n >= 0 && out_accum && workspace && (n == 0 || x), "nvit_sumsq_f32_det: bad arguments");
+  if (n == 0) return NVIT_OK;
+  int grid = stream_grid(n / 4 + 1, 256, 4);
+  if (grid > workspace_floats - 1) grid = (int)(workspace_floats - 1);
+  NVIT_REQUIRE(grid >= 1, "nvit_sumsq_f32_det: workspace too small");
+  launch(sumsq_det_kernel, grid, 256, 0, ST(stream), x, n, out_accum, workspace);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }

@@ -95,6 +95,11 @@ def sumsq(x, out):
     _lib.call("nvit_sumsq_f32", _p(x), x.numel(), _p(out), _stream())
 
 
+def sumsq_det(x, out, workspace):
+    """out[0] += sum(x^2), reproducible to the bit (nvit_sumsq_f32_det); workspace: fp32 scratch, [0] zero before first use."""
+    _lib.call("nvit_sumsq_f32_det", _p(x), x.numel(), _p(out), _p(workspace), workspace.numel(), _stream())
+
+
 def colsum(x, out):
     _lib.call("nvit_colsum_bf16", _p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream())
 

@@ -210,6 +210,7 @@ class Trainer:
             self.tail_scratch = torch.zeros(4, device=eng.P32.device, dtype=F32)
             self.gnorm = self.tail_scratch[0:1]
             self.unit_counter = self.tail_scratch[1:2].view(torch.int32)
+            self.sumsq_ws = torch.zeros(1024, device=eng.P32.device, dtype=F32)     # nvit_sumsq_f32_det scratch ([0] = ticket)
             self.loss_buf = torch.zeros(1, device=eng.P32.device, dtype=F32)
             self.hyper = torch.tensor([self.lr, float(self.opt_step)], device=eng.P32.device, dtype=F32)   # {lr, step}
             self._state_for = eng.P32
@@ -287,7 +288,8 @@ class Trainer:
         gn = None
         self.tail_scratch.zero_()
         if self.clip and self.clip > 0:
-            ops.sumsq(eng.G32[:na], self.gnorm)
+            # reproducible sum: replicas must derive the SAME clip coefficient from their identical all-reduced gradients
+            ops.sumsq_det(eng.G32[:na], self.gnorm, self.sumsq_ws)
             gn = self.gnorm
             self.launches += 1
         if self.fused_tail:

@@ -6,13 +6,13 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from nvit_b200 import ViT, ViTConfig, Trainer
-from oracle import nvit_oracle as O
+import bench
 
 name = sys.argv[1] if len(sys.argv) > 1 else "b16"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 variant = sys.argv[4] if len(sys.argv) > 4 else "nvit"
-cfg = ViTConfig(**O.named_config(name, use_nvit=(variant != "orig"), use_kohonen=(variant == "kohonen")).as_dict())
+cfg = ViTConfig(**bench.config_dict(name, variant))
 torch.manual_seed(0)
 model = ViT(cfg).cuda().train()
 tr = Trainer(model)

@@ -575,3 +575,25 @@ def test_weight_norm_multi_rows_and_columns():
     torch.cuda.synchronize()
     for w, b in zip(ws, before):
         assert float((w - b).abs().max()) < 1e-6
+
+
+def test_sumsq_deterministic_form():
+    """nvit_sumsq_f32_det: the value of nvit_sumsq_f32 (and torch), accumulated into out, bit-identical from run to run and
+    self-cleaning (the ticket word is zero again after every launch)."""
+    for n in (1, 1023, 1 << 20, 30_000_001):
+        x = randn(n, seed=90)
+        ref = float((x.double() ** 2).sum())
+        ws = torch.zeros(1024, device=DEV)
+        outs = []
+        for rep in range(4):
+            out = torch.full((1,), 2.0, device=DEV)
+            ops.sumsq_det(x, out, ws)
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+            assert float(ws[0]) == 0.0
+        assert abs(float(outs[0]) - 2.0 - ref) <= 1e-5 * ref + 1e-6, (n, float(outs[0]), ref)
+        assert all(torch.equal(o, outs[0]) for o in outs), n
+        # a small workspace limits the grid, not the result
+        out2 = torch.zeros(1, device=DEV)
+        ops.sumsq_det(x, out2, torch.zeros(9, device=DEV))
+        assert abs(float(out2) - ref) <= 1e-5 * ref + 1e-6
