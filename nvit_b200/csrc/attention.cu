@@ -112,8 +112,9 @@ struct alignas(64) AttnParams {
 #ifdef NVIT_BENCH_HOOKS
 #define ATT_MARK(i) do { if (p.dbg && blockIdx.x < 8 && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + (i)] = clock64(); } while (0)
 // v2 kernel: 64 slots per CTA (first 4 CTAs): [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp
-#define ATT2_MARK(i) do { if (p.dbg && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
-#define ATT2_MMARK(i) do { if (p.dbg && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
+// (marks are taken during the SECOND head a CTA processes: steady state, with a head before and a head after it)
+#define ATT2_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
+#define ATT2_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
 #else
 #define ATT_MARK(i) do { } while (0)
 #define ATT2_MARK(i) do { } while (0)
@@ -866,7 +867,6 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
   const int nQ = p.nQ, nK = p.nK, nItems = nQ * nK;
   const int nheads = p.B * p.H;
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
-  ATT2_MARK(0);
 
   if (tid == 0) {
     mbar_init(bar_qk + 0, 1);
@@ -1024,7 +1024,14 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
     const f32x2 sl2x2 = pack2(p.scale * LOG2E, p.scale * LOG2E), scx2 = pack2(p.scale, p.scale);
     uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_vdo = 0, ph_S = 0, ph_dP = 0, ph_acc = 0, ph_free0 = 0, ph_free1 = 0, ph_dv = 0;
     bool used0 = false, used1 = false;     // dS^T buffer b has been filled before
-    // per-head scalars of the NEXT head travel in registers from the start of a head to its end (latency fully hidden)
+    // per-head scalars of the NEXT head travel in registers from the start of a head to its end.
+    // MEASURED (same box, scripts/attn_bwd_time.py, v1 = 455 us as the reference point): this form 386-388 us.  The phase
+    // marks show a 2.9 k-cycle stall at the start of each head (the fetched values are spilled, and the spill store waits
+    // for the load), yet every attempt to remove it was slower: 4-byte cp.async copies into shared memory (lse
+    // double-buffered) 408-412 us; the same plus taking dL/d(sqk) from the dQ rows only (it equals the dK-row sum, both are
+    // sum dS[q,r] Qh[q,c] Kh[r,c]) 394-396 us; that identity alone 408 us; fetching right before the dQ epilogue 420 us.
+    // At 168 registers and 2 warps per scheduler the kernel is latency-bound (ncu: issue slots 37 % busy, 0.5 eligible
+    // warps per scheduler) and reacts to any change of the instruction schedule by +-5 %.
     float nx_lse = 0.f, nx_invq = 0.f, nx_invk = 0.f, nx_sc = 1.f;
     auto fetch_head = [&](int hd) {
       const int b = hd / p.H, h = hd % p.H;
@@ -1052,10 +1059,10 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
     fetch_head(blockIdx.x);
     publish_head();
     named_bar_sync(1, ATT2_COMPUTE);
-    ATT2_MARK(1);
 
     int n = 0;
     for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      ATT2_MARK(0);
       const int b = hd / p.H, h = hd % p.H;
       const int pb = p.dbuf ? (n & 1) : 0;
       uint8_t* const sQ = sQK + pb * 2 * R;

@@ -10,7 +10,7 @@ Memory layout (HBM):
   * ``P32``  one flat fp32 buffer holding every parameter; ``model.parameters()`` are views into it.  Order:
     [GEMM weights in GEMM-operand order | other weight-decayed params | no-decay params || params that never get a
     gradient].  AdamW, the gradient norm and the data-parallel all-reduce stream over contiguous ranges of it.
-  * ``G32``  the gradients in the same layout (``p.grad`` views).
+  * ``G32``  the gradients in the same layout (the autograd path hands out clones of its slices as ``p.grad``).
   * ``W16``  bf16 GEMM operands, one cast launch from the head of ``P32`` (q/k/v concatenated to [3C, C], etc).
   * per-layer activations saved for backward (bf16 GEMM operands, fp32 residual stream), allocated once per batch size.
 """
@@ -921,13 +921,19 @@ class NViTFunction(torch.autograd.Function):
         ctx.engine = engine
         ctx.n_params = len(params)
         if not engine.cfg.use_kohonen:
-            ctx.mark_non_differentiable(recon)      # not in the objective without the maps (train.py:909-926)
+            # Not in the reference's objective without the maps (train.py:909-926), so its backward is not scheduled
+            # (reconstruction_head.* stay grad-less, as in the reference's loop).  The output stays differentiable on
+            # purpose: a loop that DOES put it into its loss gets an error from backward() instead of silent zeros.
             return logits, recon
         return (logits, recon, *(engine.last_aux[k] for k in NViTFunction.AUX))
 
     @staticmethod
     def backward(ctx, dlogits, *daux):
         eng = ctx.engine
+        if not eng.cfg.use_kohonen and daux and daux[0] is not None and bool((daux[0] != 0).any()):
+            raise RuntimeError("nvit_b200: a gradient arrived for aux_losses['reconstruction'], but without Kohonen maps the "
+                               "reconstruction loss is not part of the reference's objective (train.py:909-926) and its "
+                               "backward pass is not built in this mode; use use_kohonen=True or keep it out of the loss")
         eng.zero_grad()
         if eng.cfg.use_kohonen:
             drec, dcons, dsmooth, dlq, dgq = ((d if d is not None else eng.aux_w.new_zeros(())) for d in daux)

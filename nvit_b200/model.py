@@ -255,8 +255,12 @@ class ViT(nn.Module):
         return self._engine
 
     def _apply(self, fn, *args, **kwargs):
+        # model.to(dev) / .cuda() / .float() re-create parameter storage: the engine's flat buffers must be rebuilt then - but
+        # only then (a no-op .to() must not throw the flat buffers, and the Trainer's optimizer state keyed on them, away)
+        before = [(p.data_ptr(), p.device, p.dtype) for p in self.parameters()]
         out = super()._apply(fn, *args, **kwargs)
-        if getattr(self, "_engine", None) is not None:
+        after = [(p.data_ptr(), p.device, p.dtype) for p in self.parameters()]
+        if getattr(self, "_engine", None) is not None and before != after:
             self._engine.invalidate()
         return out
 

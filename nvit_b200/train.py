@@ -204,8 +204,19 @@ class Trainer:
         eng = self.engine
         eng.param_list()
         if self._state_for is not eng.P32:
+            old_m, old_v = getattr(self, "m", None), getattr(self, "v", None)
             self.m = torch.zeros_like(eng.P32)
             self.v = torch.zeros_like(eng.P32)
+            if old_m is not None and self.opt_step > 0:
+                # the engine re-materialised its flat buffers (model.to(...) with a real move / cast): the moments follow
+                # when the layout is the same, otherwise say so instead of silently restarting AdamW at step opt_step
+                if old_m.numel() == self.m.numel():
+                    self.m.copy_(old_m)
+                    self.v.copy_(old_v)
+                else:
+                    import warnings
+                    warnings.warn("nvit_b200.Trainer: the parameter layout changed under a running optimizer; AdamW moments "
+                                  "were reset (load_optimizer_state_dict restores them)")
             # [0] sum of squared gradients (clip), [1] unit counter of the fused tail (uint32 bits); zeroed together
             self.tail_scratch = torch.zeros(4, device=eng.P32.device, dtype=F32)
             self.gnorm = self.tail_scratch[0:1]

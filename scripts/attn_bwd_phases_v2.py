@@ -39,6 +39,6 @@ for cta in range(2):
     row = m[cta]
     t0 = int(row[0])
     print(f"CTA {cta} compute marks (cycles since kernel entry):")
-    print("   ", {i: int(row[i]) - t0 for i in range(32) if int(row[i]) != 0})
+    print("   ", {i: int(row[i]) - t0 for i in range(32) if int(row[i]) != 0 or i == 0})
     print(f"CTA {cta} MMA-warp marks:")
     print("   ", {i: int(row[32 + i]) - t0 for i in range(32) if int(row[32 + i]) != 0})

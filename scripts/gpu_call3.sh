@@ -1,3 +1,4 @@
 #!/bin/bash
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t3.log 2>&1; echo "all tests rc=$?"; tail -3 gpurun_out/r2_t3.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench3.log 2>&1; echo "bench rc=$?"
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t3.log 2>&1; echo "all tests rc=$?"; tail -3 gpurun_out/r2_t3.log
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2_smoke.log
+timeout 90 python scripts/attn_bwd_time.py > gpurun_out/r2_attn_time.log 2>&1; grep variant gpurun_out/r2_attn_time.log

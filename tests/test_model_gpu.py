@@ -591,3 +591,30 @@ def test_input_shape_and_label_validation():
     assert float(dl[1].abs().max()) == 0.0 and float(dl[3].abs().max()) == 0.0
     with pytest.raises(TypeError):
         ops.cross_entropy(logits, tgt.int(), loss, dl)
+
+
+def test_reconstruction_gradient_request_fails_loudly_and_state_survives_a_noop_move():
+    """without Kohonen maps the reconstruction loss has no backward here - asking for one must raise, not
+    return zeros; and a no-op model.to(device) must not reset the engine or the Trainer's AdamW moments."""
+    cfg = O.named_config("tiny")
+    sd = O.init_state_dict(cfg, 2)
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(4, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (4,), generator=g).to(DEV)
+    model = build(cfg, sd)
+    logits, aux = model(X)
+    with pytest.raises(RuntimeError, match="reconstruction"):
+        (F.cross_entropy(logits, y) + 0.1 * aux["reconstruction"]).backward()
+    model.zero_grad(set_to_none=True)
+    logits, aux = model(X)
+    F.cross_entropy(logits, y).backward()                  # the supported objective still works
+    assert dict(model.named_parameters())["transformer.h.0.c_fc.weight"].grad is not None
+    model.zero_grad(set_to_none=True)
+    tr = Trainer(model)
+    tr.step(X, y)
+    tr.step(X, y)
+    P32, m_before = model.engine.P32, tr.m.clone()
+    model.to(DEV)                                          # no parameter moves: nothing may be rebuilt
+    assert model.engine.P32 is P32
+    tr.step(X, y)
+    assert tr._state_for is P32 and float((tr.m - m_before).abs().max()) > 0 and tr.opt_step == 3
