@@ -494,14 +494,19 @@ def main():
         top = next((r for r in table if "frac" in r), None)
         dominant = {"kernel": top["group"] if top else None, "bound": top["bound"] if top else None,
                     "achieved": top.get("achieved") if top else None, "peak": (peak if top and top["bound"] == "tensor" else float(peaks["hbm_gbs"])),
-                    "unit": top.get("unit") if top else None, "frac": top.get("frac") if top else None, "traffic": None,
+                    "unit": top.get("unit") if top else None, "frac": top.get("frac") if top else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the group's largest launch (c_fc wgrad, 6144 x 768 x 50176)
+                    # from one ncu --set full capture: 717.2 MB against 713 MB algorithmic (dY 617 + X 77 + fp32 dW 19)
+                    "traffic": (717.2e6 if (top and top["group"].startswith("gemm wgrad") and args.config == "b16" and B == 256) else None),
+                    "traffic_source": "profiles/r02_ncu_full_wgrad_gemm_raw.csv (the c_fc weight-gradient launch of the group; bytes per launch)",
                     "peak_source": f"MEASURED_PEAKS.json ({how}): bf16_tflops_sustained for tensor-bound groups, hbm_gbs for HBM-bound ones",
                     "share_of_step": top.get("share") if top else None, "ms_per_step": top.get("ms_per_step") if top else None,
                     "how": f"the kernel group with the largest share of the step; CUDA events around every launch over {probe_steps} eager "
                            f"steps of the same workload"
                            + (" (the timed region replays a CUDA graph, where events cannot be timed)" if trainer.use_graph else "")
-                           + "; algorithmic FLOPs / bytes from the call arguments; see kernel_groups for the rest and "
-                             "profiles/ for the ncu launch list and --set full captures"}
+                           + "; algorithmic FLOPs / bytes from the call arguments.  Event brackets over-state launches shorter than "
+                             "~60 us (the eager host cannot keep the queue full between two recorded events); profiles/"
+                             "r02_launch_summary.txt is the ncu launch list of the same step"}
         line = {
             "metric": METRIC if (args.config == "b16" and args.variant == "nvit") else
                       f"{VARIANT_NAME[args.variant]}-{args.config.upper()} train images/sec",
