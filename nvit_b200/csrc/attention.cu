@@ -279,8 +279,19 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
   for (int i = 0; i < p.nQ; ++i) {
     if (t.warp == 0) {
       tc_fence_after_sync();
-      mma_seq(tmem_base, umma_smem_desc(sQ_a + i * 16384, 16, 1024), 2, umma_smem_desc(sK_a, 16, 1024), 2, idesc_kk_n(TP), 4, false);
-      mma_commit(bar_mma);
+      // one election per product, its k-steps issued back to back from constant offsets (MEASURED in the backward kernel: a
+      // per-MMA election loop costs ~125 cycles per MMA, which here sat on the head's critical path: 4 + 13 MMAs per q tile)
+      {
+        const uint64_t da = umma_smem_desc(sQ_a + i * 16384, 16, 1024), db = umma_smem_desc(sK_a, 16, 1024);
+        const uint32_t id = idesc_kk_n(TP);
+        if (elect_one()) {
+          umma_bf16_ss(tmem_base, da, db, id, 0u);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(tmem_base, da + 2 * ks, db + 2 * ks, id);
+          umma_commit(bar_mma);
+        }
+        __syncwarp();
+      }
     }
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -345,14 +356,16 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
     if (t.warp == 0) {
       if (i == 0) mbar_wait(bar_tmav, 0);
       tc_fence_after_sync();
-      uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
+      const uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
       const int nks = TP >> 4;
-#pragma unroll 1
-      for (int ks = 0; ks < nks; ++ks) {
-        if (elect_one()) umma_bf16_ts(tmem_base + TMF_O, tmem_base + ks * 8, dv, IDESC_KM(64), ks > 0 ? 1u : 0u);
-        dv += 128;
+      if (elect_one()) {
+        umma_bf16_ts(tmem_base + TMF_O, tmem_base, dv, IDESC_KM(64), 0u);
+#pragma unroll
+        for (int ks = 1; ks < 16; ++ks)
+          if (ks < nks) umma_bf16_ts(tmem_base + TMF_O, tmem_base + ks * 8, dv + 128 * ks, IDESC_KM(64), 1u);
+        umma_commit(bar_mma);
       }
-      mma_commit(bar_mma);
+      __syncwarp();
     }
     const float total = s_part[t.row] + s_part[128 + t.row];
     mbar_wait(bar_mma, mma_phase);
