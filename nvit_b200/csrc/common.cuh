@@ -340,6 +340,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ----------------------------------------------------------------------------- cp.async (LDGSTS): global -> shared, no registers
+// 16 bytes per thread; src_bytes = 0 zero-fills the destination (out-of-range rows / columns)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2)
 // Blackwell issues fp32 FMA / MUL / ADD on register PAIRS (fma.rn.f32x2 -> SASS FFMA2): half the issue slots for the
 // elementwise epilogues whose cost is instruction count (the SiLU-gate forward / backward epilogues of the GEMM).

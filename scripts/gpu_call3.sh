@@ -1,3 +1,4 @@
 #!/bin/bash
-timeout 200 python -m pytest tests/test_zz_attention_variants_gpu.py tests/test_kernels_gpu.py -m gpu -x -q -k "attention" > gpurun_out/r2_t3b.log 2>&1; echo "attention tests rc=$?"; tail -2 gpurun_out/r2_t3b.log
-timeout 90 python scripts/attn_bwd_time.py > gpurun_out/r2_attn_time.log 2>&1; cat gpurun_out/r2_attn_time.log
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t3.log 2>&1; echo "all tests rc=$?"; tail -3 gpurun_out/r2_t3.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench3.log 2>&1; echo "bench rc=$?"
+python bench.py --steps 10 --warmup 3 --config l16 --no-cpu-baseline > gpurun_out/r2_bench_l16.log 2>&1; echo "l16 rc=$?"

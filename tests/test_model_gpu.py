@@ -428,9 +428,10 @@ def test_cuda_graph_replay_equals_eager_steps(fused):
 
     Two EAGER runs of the same steps are not bit-identical either (fp32 atomics: split-K reduce-adds, per-channel alpha / sqk
     / bias sums; AdamW's first steps turn that noise into +-lr on near-zero gradients), so the criterion is calibrated in
-    place: a second eager trainer gives the noise floor (itself a noisy number: a handful of steps), and graph-vs-eager must
-    stay within 10x of it and under absolute caps (loss 2e-3, parameters 2e-2) that a missed launch, a stale learning rate
-    or a wrong step count break by an order of magnitude (MEASURED: deviations 3e-5 ... 4e-4 against floors 2e-5 ... 3e-4)."""
+    place: a second eager trainer gives the noise floor (itself a noisy number: a handful of steps, measured between 1e-7 and
+    3e-4), and graph-vs-eager must stay within max(10x floor, 5e-4 on losses / 5e-3 on parameters) and under absolute caps
+    (loss 2e-3, parameters 2e-2) that a missed launch, a stale learning rate or a wrong step count break by an order of
+    magnitude (MEASURED: deviations 2e-5 ... 4e-4)."""
     cfg = O.named_config("tiny")
     sd = O.init_state_dict(cfg, 13)
     g = torch.Generator().manual_seed(77)
@@ -452,8 +453,8 @@ def test_cuda_graph_replay_equals_eager_steps(fused):
         pfloor, pdev = _param_dist(me, m2), _param_dist(me, mg)
         print(f"[graph vs eager, {tag}] loss deviation {dev:.2e} (eager-vs-eager floor {floor:.2e}); "
               f"worst parameter rel-L2 {pdev:.2e} (floor {pfloor:.2e})")
-        assert dev <= 10 * floor + 1e-5 and dev <= 2e-3, (tag, dev, floor, le, lg)
-        assert pdev <= 10 * pfloor + 1e-5 and pdev <= 2e-2, (tag, pdev, pfloor)
+        assert dev <= max(10 * floor, 5e-4) and dev <= 2e-3, (tag, dev, floor, le, lg)
+        assert pdev <= max(10 * pfloor, 5e-3) and pdev <= 2e-2, (tag, pdev, pfloor)
 
     check("2 eager + capture + 3 replays", run(5))
     assert tg.replays == 3 and tg._graph is not None
