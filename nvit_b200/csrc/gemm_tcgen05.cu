@@ -382,6 +382,10 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
     const int vec_col = NG == 4 ? eg * 64 + (et & 63) : et;       // column of the 256-wide tile
     float gate_su = 1.f, gate_sv = 1.f;
     if constexpr (GATEB) {
+      if (!use_vec) {      // no scale vector (cross-attention gate): the epilogue multiplies by ones
+        for (int i = et; i < 512; i += 128 * NG) s_vec[i] = 1.f;
+        named_bar_sync(3, 128 * NG);
+      }
       if (unit0 < total_units && NVIT_DBG(p) != 1) {
         int mt0, nb0;
         tile_coords(p, unit0 / p.splits, mt0, nb0);
@@ -545,23 +549,20 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int cc = c * 64 + hh * 32 + 8 * j + 2 * e;      // column within the tile
-                    f32x2 su = one2, sv = one2;
-                    if (use_vec) {
-                      const float2 a = *reinterpret_cast<const float2*>(s_vec + cc), b = *reinterpret_cast<const float2*>(s_vec + 256 + cc);
-                      su = pack2(a.x, a.y);
-                      sv = pack2(b.x, b.y);
-                    }
+                    // (s_vec holds ones when there is no scale vector: no select inside this loop)
+                    const float2 a = *reinterpret_cast<const float2*>(s_vec + cc), b = *reinterpret_cast<const float2*>(s_vec + 256 + cc);
+                    const f32x2 su = pack2(a.x, a.y), sv = pack2(b.x, b.y);
                     const f32x2 g = pack2(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
-                    const f32x2 uh = mul2(bf16x2_to_f32x2(uc[e]), su), vh = mul2(bf16x2_to_f32x2(vc[e]), sv);
+                    const f32x2 vh = mul2(bf16x2_to_f32x2(vc[e]), sv);
                     float h0, h1;
                     unpack2(mul2(vh, half2), h0, h1);
                     const f32x2 sg = fma2(pack2(tanh_approx_(h0), tanh_approx_(h1)), half2, half2);   // sigmoid(vh)
                     const f32x2 sl = mul2(vh, sg);                                               // silu(vh)
-                    const f32x2 gu = mul2(g, sl);                                                // dL/d(u scaled)
                     const f32x2 dsl = fma2(sl, fma2(sg, neg2, one2), sg);                        // silu' = sg + silu (1 - sg)
-                    const f32x2 gv = mul2(mul2(g, uh), dsl);                                     // dL/d(v scaled)
-                    ou[e] = f32x2_to_bf16x2(mul2(gu, su));
-                    ov[e] = f32x2_to_bf16x2(mul2(gv, sv));
+                    const f32x2 gs = mul2(g, su);                                                // g su
+                    // dL/du_raw = g silu(vh) su ;  dL/dv_raw = g (u su) silu'(vh) sv
+                    ou[e] = f32x2_to_bf16x2(mul2(gs, sl));
+                    ov[e] = f32x2_to_bf16x2(mul2(mul2(gs, bf16x2_to_f32x2(uc[e])), mul2(dsl, sv)));
                   }
                   *reinterpret_cast<uint4*>(sbuf + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
                   *reinterpret_cast<uint4*>(sbuf + 16384 + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);

@@ -1,4 +1,5 @@
 #!/bin/bash
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t3.log 2>&1; echo "all tests rc=$?"; tail -3 gpurun_out/r2_t3.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench3.log 2>&1; echo "bench rc=$?"
-python bench.py --steps 10 --warmup 3 --config l16 --no-cpu-baseline > gpurun_out/r2_bench_l16.log 2>&1; echo "l16 rc=$?"
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "gate or swiglu" > gpurun_out/r2_t3b.log 2>&1; echo "gate tests rc=$?"; tail -2 gpurun_out/r2_t3b.log
+timeout 100 python scripts/one_gemm.py "dgrad+gate" 2>&1 | tail -1
+timeout 100 python scripts/one_gemm.py "c_fc swiglu" 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_model_gpu.py tests/test_kohonen_gpu.py -m gpu -x -q > gpurun_out/r2_t3c.log 2>&1; echo "model tests rc=$?"; tail -2 gpurun_out/r2_t3c.log
