@@ -833,9 +833,11 @@ constexpr int ATT2_MAX_SMEM = 232448;              // 227 KB
 // per-head arrays (floats): lse[AL] invq[AL] invk[AL] delta[AL] scale[64] rscale[64] dsqk[64] dot[512]; then the barriers
 __host__ __device__ constexpr int att2_array_bytes(int AL) { return (4 * AL + 3 * 64 + 256) * 4 + 128; }
 
-// MEASURED: the 16-compute-warp instantiation (four threads per lane) needs 17 warps -> 96 registers per thread and spills
-// ~900 bytes; re-splitting the register file with setmaxnreg (640-thread CTA, 112 / 56 registers) neither made ptxas use the
-// larger budget nor ran (the MMA warp timed out on its first barrier), so only ATT2_CW = 8 is instantiated.
+// MEASURED: the 16-compute-warp instantiation (four threads per lane) needs 17 warps -> 96 registers per thread (warps are
+// allocated in groups of four: 20 x 32 x 96) and spills ~900 bytes.  Re-splitting the CTA's own allocation with setmaxnreg
+// (640-thread CTA; 512 x 112 + 128 x 32 = 640 x 96 - a first attempt with 112 / 56 asked for more than the CTA owns and
+// blocked forever) runs, and ptxas does use R0..R109 in the compute branch, but 441 spill instructions remain there and 56
+// in the 32-register MMA branch: 689 us against 386 us for 8 compute warps at 168 registers.  Only ATT2_CW = 8 is built.
 template <int ATT2_CW>
 __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const __grid_constant__ AttnParams p) {
   constexpr int ATT2_COMPUTE = ATT2_CW * 32;
