@@ -27,7 +27,8 @@ int nvit_gemm_swiglu_cta_group(int mode);
 
 /* Attention backward kernel: 2 = persistent and warp-specialised (8 compute warps + one MMA warp per SM, the products of the
  * next (kv tile, q tile) item in flight under the passes of the current one, the next head's tiles loading meanwhile;
- * default), 1 = the single-role, one-head-per-CTA kernel of round 1. */
+ * default), 3 = 2 with the dV / dK / dQ epilogues on a warpgroup of their own (one thread per accumulator row; runs as 2 for
+ * raw q / k with sqk and for T > 208), 1 = the single-role, one-head-per-CTA kernel of round 1. */
 int nvit_attention_bwd_variant(int variant);
 
 /* ---- 2. measurement only, -DNVIT_BENCH_HOOKS builds (outputs are WRONG while active) -------------------------------- */

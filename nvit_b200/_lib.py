@@ -109,8 +109,8 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_PDL")                 # programmatic dependent launch of every kernel (see include/nvit_b200.h)
     if mode in ("0", "1"):
         lib.nvit_set_pdl(int(mode))
-    mode = os.environ.get("NVIT_ATTN_BWD_VARIANT")    # 1 = round-1 single-role kernel, 2 = warp-specialised (default)
-    if mode in ("1", "2"):
+    mode = os.environ.get("NVIT_ATTN_BWD_VARIANT")    # 1 = round-1 single-role kernel, 2 = warp-specialised, 3 = 2 + epilogue warpgroup
+    if mode in ("1", "2", "3"):
         lib.nvit_attention_bwd_variant(int(mode))
     mode = os.environ.get("NVIT_GEMM_CTA_GROUP")      # benchmarking hook: pin cta_group::1 or ::2 GEMM tiles
     if mode in ("1", "2"):

@@ -115,10 +115,18 @@ struct alignas(64) AttnParams {
 // (marks are taken during the SECOND head a CTA processes: steady state, with a head before and a head after it)
 #define ATT2_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
 #define ATT2_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
+// v3 kernel: 96 slots per CTA (first 2 CTAs): [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp (thread
+// 384), [64,96) thread 0 of the epilogue warpgroup (thread 256); second head of the CTA, as above
+#define ATT3_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 0) p.dbg[blockIdx.x * 96 + (i)] = clock64(); } while (0)
+#define ATT3_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 384) p.dbg[blockIdx.x * 96 + 32 + (i)] = clock64(); } while (0)
+#define ATT3_EMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 256) p.dbg[blockIdx.x * 96 + 64 + (i)] = clock64(); } while (0)
 #else
 #define ATT_MARK(i) do { } while (0)
 #define ATT2_MARK(i) do { } while (0)
 #define ATT2_MMARK(i) do { } while (0)
+#define ATT3_MARK(i) do { } while (0)
+#define ATT3_MMARK(i) do { } while (0)
+#define ATT3_EMARK(i) do { } while (0)
 #endif
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
@@ -1355,6 +1363,583 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, v3
+// attn_bwd_ws_kernel with the output epilogues moved to a warpgroup of their own.  The phase marks of v2 show a head's
+// ~32 k cycles as: exponential passes 7.7 k, dS passes 4.9 k, the two kv-tile epilogues 6.4 k, dQ epilogue + hand-over 5.7 k,
+// waits ~5 k - all on the same eight warps.  Here
+//   warps 0-7    compute: only the P^T / dS^T passes and delta (two threads per TMEM lane, as in v2);
+//   warps 8-11   epilogue: ONE thread per accumulator row (64 channels), so the row dot of the normalisation backward is
+//                thread-local (no exchange through shared memory, no CTA-wide barrier); it drains dV_j / dK_j / dQ from
+//                tensor memory as soon as their commit barrier fires, frees the columns for the next kv tile / head
+//                (bar_dvfree / bar_dkfree / bar_dqfree), stages the rows in the dead operand tiles, issues every TMA store
+//                and every load of the following heads, and owns the per-head arrays it alone reads (1/||q||, 1/||k||,
+//                the sqk vectors, the dL/d(sqk) accumulator);
+//   warp 12      MMA issuer (as in v2, plus the three "columns are free" waits); warps 13-15 only exist because
+//                setmaxnreg works on whole warpgroups.
+// Registers: 16 warps launch at 128 per thread; the compute warpgroups raise themselves to 144, the MMA warpgroup drops
+// to 96 (2 x 128 x 144 + 128 x 128 + 128 x 96 = 65536; at 64 the MMA loop kept its barrier phases in local memory).
+// Needs the two (Q, K) tile pairs (TP <= 208) and q / k that arrive normalised or without sqk; nvit_attention_bwd falls
+// back to v2 otherwise.
+constexpr int ATT3_THREADS = 512;
+constexpr int ATT3_COMPUTE = 256;
+constexpr int ATT3_EPI = 128;
+template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// 64 accumulator columns of this thread's TMEM lane -> registers
+__device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, uint32_t (&r)[64]) {
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_32x32b_x32(taddr + 32, r + 32);
+  tmem_wait_ld();
+}
+// plain rows (dV, or dK / dQ without normalisation): fp32 -> bf16 into the swizzled tile
+__device__ __forceinline__ void row64_to_tile(const uint32_t (&r)[64], uint8_t* tile, int trow) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(r[8 * c + e]);
+    *reinterpret_cast<uint4*>(tile + sw128(trow, c)) = pack8(g);
+  }
+}
+// backward of y = s * x/||x|| for the whole row held by one thread (see norm_bwd_load): dL/dy in r[], the unit vector is
+// recovered from the normalised bf16 row in the tile, dx overwrites that row; g * n goes to the dL/d(sqk) accumulator.
+// Warp-collective (shuffles inside): `valid` only guards the contribution and the stores.
+__device__ __forceinline__ void norm_bwd_row64(const uint32_t (&r)[64], uint8_t* tile, int trow, const float* s_scale,
+                                               const float* s_rscale, float* s_dsqk, float inv, int lane, bool valid) {
+  float dot = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float n[16], acc[16];
+    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * q)), n);
+    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * q + 1)), n + 8);
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + q * 16 + 4 * e4);
+      const float4 rs = *reinterpret_cast<const float4*>(s_rscale + q * 16 + 4 * e4);
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float g = __uint_as_float(r[q * 16 + 4 * e4 + e]);
+        const float nn = n[4 * e4 + e] * rsv[e];
+        acc[4 * e4 + e] = valid ? g * nn : 0.f;
+        dot += g * scv[e] * nn;
+      }
+    }
+    reduce16_to_smem(acc, s_dsqk + q * 16, lane);
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float n[8], d[8];
+    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, c)), n);
+    const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c * 8), sc1 = *reinterpret_cast<const float4*>(s_scale + c * 8 + 4);
+    const float4 rs0 = *reinterpret_cast<const float4*>(s_rscale + c * 8), rs1 = *reinterpret_cast<const float4*>(s_rscale + c * 8 + 4);
+    const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+    const float rsv[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = (__uint_as_float(r[8 * c + e]) * scv[e] - n[e] * rsv[e] * dot) * inv;
+    *reinterpret_cast<uint4*>(tile + sw128(trow, c)) = pack8(d);
+  }
+}
+
+__global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int PARTS = 2, NCC = 4;
+  pdl_enter();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int T = p.T, TP = p.TP;
+  const uint32_t R = static_cast<uint32_t>(TP) * 128u;
+  uint8_t* sQK = smem;                                  // [2][Q | K]
+  uint8_t* sV = sQK + 4 * R;
+  uint8_t* sDO = sV + R;
+  uint8_t* sDS = sDO + R;                               // two dS^T buffers (O parks in the second one until delta is taken)
+  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);   // compute warps
+  float* s_delta = s_lse + TP;                                       // compute warps
+  float* s_invq = s_delta + TP;                                      // epilogue warps (and everything below)
+  float* s_invk = s_invq + TP;
+  float* s_scale = s_invk + TP;
+  float* s_rscale = s_scale + 64;
+  float* s_dsqk = s_rscale + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dsqk + 64);
+  uint64_t* bar_qk = bars + 0;       // [2] TMA: q, k tiles of pair b
+  uint64_t* bar_do = bars + 2;       // TMA: dO, O
+  uint64_t* bar_v = bars + 3;        // TMA: V
+  uint64_t* bar_S = bars + 4;        // MMA -> compute
+  uint64_t* bar_dP = bars + 5;       // MMA -> compute
+  uint64_t* bar_P = bars + 6;        // compute -> MMA (one arrival per compute warp)
+  uint64_t* bar_dS = bars + 7;       // compute -> MMA
+  uint64_t* bar_free = bars + 8;     // [2] MMA -> compute: the products reading dS^T buffer b have completed
+  uint64_t* bar_acc = bars + 10;     // MMA -> epilogue: dK_j (and every dQ contribution so far) complete
+  uint64_t* bar_dv = bars + 11;      // MMA -> epilogue: dV_j complete
+  uint64_t* bar_dvfree = bars + 12;  // epilogue -> MMA: dV_j has left tensor memory (one arrival per epilogue warp)
+  uint64_t* bar_dkfree = bars + 13;  // epilogue -> MMA: dK_j has left tensor memory
+  uint64_t* bar_dqfree = bars + 14;  // epilogue -> MMA: dQ of the head has left tensor memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_norm = p.sqk != nullptr;
+  const int nQ = p.nQ, nK = p.nK, nItems = nQ * nK;
+  const int nheads = p.B * p.H;
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+  if (tid == 0) {
+    mbar_init(bar_qk + 0, 1);
+    mbar_init(bar_qk + 1, 1);
+    mbar_init(bar_do, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_S, 1);
+    mbar_init(bar_dP, 1);
+    mbar_init(bar_P, ATT3_COMPUTE / 32);
+    mbar_init(bar_dS, ATT3_COMPUTE / 32);
+    mbar_init(bar_free + 0, 1);
+    mbar_init(bar_free + 1, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_dv, 1);
+    mbar_init(bar_dvfree, ATT3_EPI / 32);
+    mbar_init(bar_dkfree, ATT3_EPI / 32);
+    mbar_init(bar_dqfree, ATT3_EPI / 32);
+    fence_barrier_init();
+    // the first head's tiles, and the second head's q / k into the other pair
+    const int hd = blockIdx.x, b0 = hd / p.H, h0 = hd % p.H;
+    mbar_arrive_expect_tx(bar_qk, 2 * R);
+    tma_load_3d(&p.tq, bar_qk, sQK, h0 * 64, 0, b0);
+    tma_load_3d(&p.tk, bar_qk, sQK + R, h0 * 64, 0, b0);
+    mbar_arrive_expect_tx(bar_do, 2 * R);
+    tma_load_3d(&p.tdo, bar_do, sDO, h0 * 64, 0, b0);
+    tma_load_3d(&p.to, bar_do, sDS + ATT_DS_BYTES, h0 * 64, 0, b0);
+    mbar_arrive_expect_tx(bar_v, R);
+    tma_load_3d(&p.tv, bar_v, sV, h0 * 64, 0, b0);
+    const int hd1 = hd + gridDim.x;
+    if (hd1 < nheads) {
+      const int b1 = hd1 / p.H, h1 = hd1 % p.H;
+      mbar_arrive_expect_tx(bar_qk + 1, 2 * R);
+      tma_load_3d(&p.tq, bar_qk + 1, sQK + 2 * R, h1 * 64, 0, b1);
+      tma_load_3d(&p.tk, bar_qk + 1, sQK + 3 * R, h1 * 64, 0, b1);
+    }
+  }
+  if (warp == 12) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int r = tid; r < TP; r += ATT3_THREADS) {   // rows >= T are never written again and must stay finite
+    s_lse[r] = 0.f;
+    s_invq[r] = 0.f;
+    s_invk[r] = 0.f;
+    s_delta[r] = 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
+
+  if (warp >= 12) {
+    setmaxnreg_dec<96>();
+    if (warp == 12) {
+      // ===================== MMA issuer =====================
+      uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_do = 0, ph_v = 0, ph_P = 0, ph_dS = 0, ph_dvf = 0, ph_dkf = 0, ph_dqf = 0;
+      auto ncol_of = [&](int c) { return min(128, TP - 128 * c); };
+      int n = 0;
+      bool tile_before = false;          // a kv tile of this CTA has been processed before: its accumulators must have been drained
+      for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+        const int pb = n & 1;
+        const uint32_t sQ_a = smem_u32(sQK + pb * 2 * R), sK_a = sQ_a + R;
+        auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
+          const uint64_t da = umma_smem_desc(sK_a + j * 16384, 16, 1024), db = umma_smem_desc(sQ_a + c * 16384, 16, 1024);
+          const uint32_t id = idesc_kk_n(ncol_of(c));
+          if (elect_one()) {
+            umma_bf16_ss(tmem_base + TM_S, da, db, id, 0u);
+#pragma unroll
+            for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(tmem_base + TM_S, da + 2 * ks, db + 2 * ks, id);
+            umma_commit(bar_S);
+          }
+          __syncwarp();
+        };
+        auto issue_dP = [&](int j, int c) {      // dP^T(j,c) = V_j dO_c^T
+          const uint64_t da = umma_smem_desc(sV_a + j * 16384, 16, 1024), db = umma_smem_desc(sDO_a + c * 16384, 16, 1024);
+          const uint32_t id = idesc_kk_n(ncol_of(c));
+          if (elect_one()) {
+            umma_bf16_ss(tmem_base + TM_DP, da, db, id, 0u);
+#pragma unroll
+            for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(tmem_base + TM_DP, da + 2 * ks, db + 2 * ks, id);
+            umma_commit(bar_dP);
+          }
+          __syncwarp();
+        };
+        ATT3_MMARK(0);
+        if (pb == 0) { mbar_wait(bar_qk, ph_qk0); ph_qk0 ^= 1; }
+        else { mbar_wait(bar_qk + 1, ph_qk1); ph_qk1 ^= 1; }
+        tc_fence_after_sync();
+        ATT3_MMARK(1);
+        issue_S(0, 0);
+        mbar_wait(bar_do, ph_do);
+        ph_do ^= 1;
+        mbar_wait(bar_v, ph_v);
+        ph_v ^= 1;
+        tc_fence_after_sync();
+        issue_dP(0, 0);
+        ATT3_MMARK(2);
+        int i = 0;
+        for (int j = 0; j < nK; ++j) {
+          const int kv_steps = min(8, (TP - j * 128) >> 4);
+          for (int c = 0; c < nQ; ++c, ++i) {
+            const int nks = ncol_of(c) >> 4;
+            const int jn = (c + 1 < nQ) ? j : j + 1, cn = (c + 1 < nQ) ? c + 1 : 0;
+            const bool has_next = i + 1 < nItems;
+            const uint32_t buf_a = sDS_a + (i & 1) * ATT_DS_BYTES;
+            // ---- dV_j += P^T(i) dO_c   (A = P^T from tensor memory)
+            mbar_wait(bar_P, ph_P);
+            ph_P ^= 1;
+            if (c == 0 && tile_before) { mbar_wait(bar_dvfree, ph_dvf); ph_dvf ^= 1; }   // the previous tile's dV rows are out
+            tc_fence_after_sync();
+            ATT3_MMARK(3 + 4 * i);
+            {
+              const uint64_t dd = umma_smem_desc(sDO_a + c * 16384, 8192, 1024);
+              const uint32_t first = c > 0 ? 1u : 0u;
+              if (elect_one()) {
+                umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S, dd, IDESC_KM(64), first);
+#pragma unroll
+                for (int ks = 1; ks < 8; ++ks)
+                  if (ks < nks) umma_bf16_ts(tmem_base + TM_DV, tmem_base + TM_S + ks * 8, dd + 128 * ks, IDESC_KM(64), 1u);
+                if (c == nQ - 1) umma_commit(bar_dv);
+              }
+              __syncwarp();
+            }
+            if (has_next) issue_S(jn, cn);
+            ATT3_MMARK(4 + 4 * i);
+            mbar_wait(bar_dS, ph_dS);
+            ph_dS ^= 1;
+            tc_fence_after_sync();
+            ATT3_MMARK(5 + 4 * i);
+            if (has_next && c != nQ - 1) issue_dP(jn, cn);
+            if (c == 0 && tile_before) { mbar_wait(bar_dkfree, ph_dkf); ph_dkf ^= 1; }
+            if (i == 0 && n > 0) { mbar_wait(bar_dqfree, ph_dqf); ph_dqf ^= 1; }
+            tc_fence_after_sync();
+            // ---- dK_j += dS^T(i) Qh_c ; dQ_c += dS(i) Kh_j
+            {
+              const uint64_t dp = umma_smem_desc(buf_a, 16, 1024);
+              const uint64_t dq = umma_smem_desc(sQ_a + c * 16384, 8192, 1024);
+              const uint64_t dsm = umma_smem_desc(buf_a, 16384, 1024), dkm = umma_smem_desc(sK_a + j * 16384, 8192, 1024);
+              const uint32_t first_k = c > 0 ? 1u : 0u, first_q = j > 0 ? 1u : 0u;
+              if (elect_one()) {
+                umma_bf16_ss(tmem_base + TM_DK, dp, dq, IDESC_KM(64), first_k);
+#pragma unroll
+                for (int ks = 1; ks < 8; ++ks)
+                  if (ks < nks) umma_bf16_ss_acc(tmem_base + TM_DK, dp + static_cast<uint64_t>((ks >> 2) * 1024 + (ks & 3) * 2), dq + 128 * ks, IDESC_KM(64));
+                umma_bf16_ss(tmem_base + TM_DQ + 64 * c, dsm, dkm, IDESC_MM(64), first_q);
+#pragma unroll
+                for (int ks = 1; ks < 8; ++ks)
+                  if (ks < kv_steps) umma_bf16_ss_acc(tmem_base + TM_DQ + 64 * c, dsm + 128 * ks, dkm + 128 * ks, IDESC_MM(64));
+                umma_commit(bar_free + (i & 1));
+                if (c == nQ - 1) umma_commit(bar_acc);
+              }
+              __syncwarp();
+            }
+            if (has_next && c == nQ - 1) issue_dP(jn, cn);
+            if (c == nQ - 1) tile_before = true;
+            ATT3_MMARK(6 + 4 * i);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    setmaxnreg_inc<144>();
+    // ===================== compute warps: the two passes of every item, delta once per head =====================
+    const int wq = warp & 3;
+    const int part = warp >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const f32x2 sl2x2 = pack2(p.scale * LOG2E, p.scale * LOG2E), scx2 = pack2(p.scale, p.scale);
+    uint32_t ph_do = 0, ph_S = 0, ph_dP = 0, ph_free0 = 0, ph_free1 = 0;
+    bool used0 = false, used1 = false;
+    if (tid < T) s_lse[tid] = -p.lse[static_cast<long long>(blockIdx.x) * T + tid] * LOG2E;   // (b * H + h) * T = head * T
+    named_bar_sync(1, ATT3_COMPUTE);
+
+    int n = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      ATT3_MARK(0);
+      const int hd_next = hd + gridDim.x;
+      const bool more = hd_next < nheads;
+      float nx_lse = 0.f;
+      if (more && tid < T) nx_lse = p.lse[static_cast<long long>(hd_next) * T + tid];   // used only at the end of the head
+      int i = 0;
+      for (int j = 0; j < nK; ++j) {
+        const int kv = j * 128 + row;
+        const bool kv_ok = kv < T;
+        for (int c = 0; c < nQ; ++c, ++i) {
+          const int nch = min(128, TP - 128 * c) >> 4;
+          const int c_begin = (part * nch) / PARTS, c_end = ((part + 1) * nch) / PARTS;
+          const int q0 = c * 128;
+          const int bsel = i & 1;
+          uint8_t* const buf = sDS + bsel * ATT_DS_BYTES;
+          uint32_t pk[NCC][8];
+          // ---- P^T = exp2(scale log2e S^T - lse log2e), kept as bf16 pairs
+          ATT3_MARK(2 + 6 * i);
+          mbar_wait(bar_S, ph_S);
+          ph_S ^= 1;
+          tc_fence_after_sync();
+          ATT3_MARK(3 + 6 * i);
+#pragma unroll
+          for (int pr = 0; pr < NCC / 2; ++pr) {
+            uint32_t r[2][16];
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+              if (c_begin + 2 * pr + c2 < c_end) tmem_ld_32x32b_x16(t_lane + TM_S + (c_begin + 2 * pr + c2) * 16, r[c2]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int cc = 2 * pr + c2;
+              const int ch = c_begin + cc;
+              if (ch < c_end) {
+                float pv[16];
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
+                  float a0, a1, a2, a3;
+                  unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 0]), __uint_as_float(r[c2][4 * e4 + 1])), sl2x2, pack2(l4.x, l4.y)), a0, a1);
+                  unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 2]), __uint_as_float(r[c2][4 * e4 + 3])), sl2x2, pack2(l4.z, l4.w)), a2, a3);
+                  pv[4 * e4 + 0] = ex2_approx(a0);
+                  pv[4 * e4 + 1] = ex2_approx(a1);
+                  pv[4 * e4 + 2] = ex2_approx(a2);
+                  pv[4 * e4 + 3] = ex2_approx(a3);
+                }
+                if (!kv_ok) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+                } else if (q0 + ch * 16 + 16 > T) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e)
+                    if (q0 + ch * 16 + e >= T) pv[e] = 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
+              }
+            }
+          }
+          tc_fence_before_sync();
+          named_bar_sync(1, ATT3_COMPUTE);        // every score column of this item has been read: P^T may overwrite them
+          tc_fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < NCC; ++cc)
+            if (c_begin + cc < c_end) tmem_st_32x32b_x8(t_lane + TM_S + (c_begin + cc) * 8, pk[cc]);
+          tmem_wait_st();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_P);
+          ATT3_MARK(4 + 6 * i);
+          if (i == 0) {
+            // delta = rowsum(dO * O) from the shared tiles (O parks in dS^T buffer 1), under the first dV / S^T products
+            mbar_wait(bar_do, ph_do);
+            ph_do ^= 1;
+            for (int r = tid; r < T; r += ATT3_COMPUTE) {
+              float d = 0.f;
+#pragma unroll
+              for (int k8 = 0; k8 < 8; ++k8) {
+                float a[8], g[8];
+                unpack8(*reinterpret_cast<const uint4*>(sDS + ATT_DS_BYTES + sw128(r, k8)), a);
+                unpack8(*reinterpret_cast<const uint4*>(sDO + sw128(r, k8)), g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += a[e] * g[e];
+              }
+              s_delta[r] = -d * p.scale;
+            }
+            named_bar_sync(1, ATT3_COMPUTE);
+          }
+          // ---- dS^T = P^T (dP^T - delta) scale -> shared memory
+          mbar_wait(bar_dP, ph_dP);
+          ph_dP ^= 1;
+          tc_fence_after_sync();
+          if (bsel == 0) {
+            if (used0) { mbar_wait(bar_free, ph_free0); ph_free0 ^= 1; }
+            used0 = true;
+          } else {
+            if (used1) { mbar_wait(bar_free + 1, ph_free1); ph_free1 ^= 1; }
+            used1 = true;
+          }
+          ATT3_MARK(5 + 6 * i);
+#pragma unroll
+          for (int pr = 0; pr < NCC / 2; ++pr) {
+            uint32_t r[2][16];
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+              if (c_begin + 2 * pr + c2 < c_end) tmem_ld_32x32b_x16(t_lane + TM_DP + (c_begin + 2 * pr + c2) * 16, r[c2]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int cc = 2 * pr + c2;
+              const int ch = c_begin + cc;
+              if (ch < c_end) {
+                float pv[16];
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                  const float4 d4 = *reinterpret_cast<const float4*>(s_delta + q0 + ch * 16 + 4 * e4);
+                  const f32x2 t0 = fma2(pack2(__uint_as_float(r[c2][4 * e4 + 0]), __uint_as_float(r[c2][4 * e4 + 1])), scx2, pack2(d4.x, d4.y));
+                  const f32x2 t1 = fma2(pack2(__uint_as_float(r[c2][4 * e4 + 2]), __uint_as_float(r[c2][4 * e4 + 3])), scx2, pack2(d4.z, d4.w));
+                  unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4]), t0), pv[4 * e4 + 0], pv[4 * e4 + 1]);
+                  unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4 + 1]), t1), pv[4 * e4 + 2], pv[4 * e4 + 3]);
+                }
+                if (!kv_ok) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+                }
+                uint8_t* blk = buf + (ch >> 2) * 16384;
+                const int k2 = (ch & 3) * 2;
+                *reinterpret_cast<uint4*>(blk + sw128(row, k2)) = pack8(pv);
+                *reinterpret_cast<uint4*>(blk + sw128(row, k2 + 1)) = pack8(pv + 8);
+              }
+            }
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dS);
+          ATT3_MARK(6 + 6 * i);
+        }
+      }
+      ATT3_MARK(30);
+      // every P pass of this head lies behind a CTA-wide barrier of the compute warps: s_lse may take the next head's values
+      if (more && tid < T) s_lse[tid] = -nx_lse * LOG2E;
+      named_bar_sync(1, ATT3_COMPUTE);
+      ATT3_MARK(31);
+    }
+  } else {
+    // ===================== epilogue warpgroup: one thread per accumulator row =====================
+    const int ew = warp - 8;                 // = warp & 3: the TMEM lane quarter this warp may access
+    const int et = tid - ATT3_COMPUTE;       // 0 .. 127
+    const int row = ew * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    uint32_t ph_dv = 0, ph_acc = 0;
+    int n = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      const int b = hd / p.H, h = hd % p.H;
+      const int pb = n & 1;
+      uint8_t* const sQ = sQK + pb * 2 * R;
+      uint8_t* const sK = sQ + R;
+      const int hd_next = hd + gridDim.x, hd_next2 = hd + 2 * gridDim.x;
+      const bool more = hd_next < nheads;
+      // per-head arrays of this warpgroup (its previous readers are behind the barrier that ends the loop body)
+      if (has_norm) {
+        if (p.inv_q != nullptr) {
+          for (int r = et; r < T; r += ATT3_EPI) {
+            s_invq[r] = p.inv_q[(static_cast<long long>(b) * T + r) * p.ld_inv_q + h];
+            s_invk[r] = p.inv_k[(static_cast<long long>(b) * T + r) * p.ld_inv_k + h];
+          }
+        }
+        if (et < 64) {
+          const float sc = p.sqk[h * 64 + et] * p.sqk_mul;
+          s_scale[et] = sc;
+          s_rscale[et] = sc != 0.f ? 1.f / sc : 0.f;
+          s_dsqk[et] = 0.f;
+        }
+      }
+      named_bar_sync(2, ATT3_EPI);
+      ATT3_EMARK(0);
+      for (int j = 0; j < nK; ++j) {
+        const int kv = j * 128 + row;
+        const bool kv_ok = kv < T;
+        uint32_t r[64];
+        // ---- dV_j
+        ATT3_EMARK(1 + 6 * j);
+        mbar_wait(bar_dv, ph_dv);
+        ph_dv ^= 1;
+        tc_fence_after_sync();
+        ATT3_EMARK(2 + 6 * j);
+        __syncwarp();
+        tmem_ld_row64(t_lane + TM_DV, r);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dvfree);
+        if (kv < TP) row64_to_tile(r, sV + j * 16384, row);      // tiles hold exactly TP rows: lanes past the last row must not store
+        fence_proxy_async_smem();
+        named_bar_sync(2, ATT3_EPI);
+        if (et == 0) {
+          tma_store_3d(&p.tdv, sV + j * 16384, h * 64, j * 128, b);
+          bulk_commit_group();
+        }
+        // ---- dK_j
+        ATT3_EMARK(3 + 6 * j);
+        mbar_wait(bar_acc, ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after_sync();
+        ATT3_EMARK(4 + 6 * j);
+        if (j == nK - 1 && more && et == 0) {
+          // every product of this head has completed: dO and the O parking slot are free, and V once the dV stores have read
+          // its rows (the last one was issued a dS pass ago)
+          const int bn = hd_next / p.H, hn = hd_next % p.H;
+          mbar_arrive_expect_tx(bar_do, 2 * R);
+          tma_load_3d(&p.tdo, bar_do, sDO, hn * 64, 0, bn);
+          tma_load_3d(&p.to, bar_do, sDS + ATT_DS_BYTES, hn * 64, 0, bn);
+          bulk_wait_group_read<0>();
+          mbar_arrive_expect_tx(bar_v, R);
+          tma_load_3d(&p.tv, bar_v, sV, hn * 64, 0, bn);
+        }
+        __syncwarp();
+        tmem_ld_row64(t_lane + TM_DK, r);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkfree);
+        if (has_norm) {
+          norm_bwd_row64(r, sK, kv_ok ? kv : 0, s_scale, s_rscale, s_dsqk, s_invk[kv_ok ? kv : 0], lane, kv_ok);
+        } else if (kv < TP) {
+          row64_to_tile(r, sK + j * 16384, row);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, ATT3_EPI);
+        if (et == 0) {
+          tma_store_3d(&p.tdk, sK + j * 16384, h * 64, j * 128, b);
+          bulk_commit_group();
+        }
+        __syncwarp();
+        ATT3_EMARK(5 + 6 * j);
+      }
+      // ---- dQ rows (complete with the last bar_acc), one 128-row q tile at a time, staged in place over Qh
+      for (int m = 0; m < nQ; ++m) {
+        const int qi = m * 128 + row;
+        const bool ok = qi < T;
+        uint32_t r[64];
+        __syncwarp();
+        tmem_ld_row64(t_lane + TM_DQ + 64 * m, r);
+        if (m == nQ - 1) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dqfree);
+        }
+        if (has_norm) {
+          norm_bwd_row64(r, sQ, ok ? qi : 0, s_scale, s_rscale, s_dsqk, s_invq[ok ? qi : 0], lane, ok);
+        } else if (qi < TP) {
+          row64_to_tile(r, sQ + m * 16384, row);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, ATT3_EPI);
+      ATT3_EMARK(30);
+      if (et == 0) {
+        for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
+        bulk_commit_group();
+        if (hd_next2 < nheads) {
+          // this (Q, K) pair receives the tiles of the head after the next one as soon as the output stores have read its rows
+          bulk_wait_group_read<0>();
+          const int b2 = hd_next2 / p.H, h2 = hd_next2 % p.H;
+          mbar_arrive_expect_tx(bar_qk + pb, 2 * R);
+          tma_load_3d(&p.tq, bar_qk + pb, sQ, h2 * 64, 0, b2);
+          tma_load_3d(&p.tk, bar_qk + pb, sK, h2 * 64, 0, b2);
+        }
+      }
+      if (has_norm && et < 64) atomicAdd(p.dsqk + h * 64 + et, s_dsqk[et] * p.sqk_mul);
+      named_bar_sync(2, ATT3_EPI);
+      ATT3_EMARK(31);
+    }
+    if (et == 0) bulk_wait_group_read<0>();      // the staged output tiles have left shared memory before the CTA retires
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int make_head_tmap(CUtensorMap* m, const void* base, long long ld, int B, int H, int T, int box_rows = ATT_ROWS) {
   const uint64_t dims[3] = {static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
   const uint64_t strides[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * T};
@@ -1374,7 +1959,7 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 using namespace nvit;
 
 static long long* g_att_dbg = nullptr;
-static std::atomic<int> g_bwd_variant{2};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel
+static std::atomic<int> g_bwd_variant{2};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel, 3 = attn_bwd_ws3_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
   g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
@@ -1464,6 +2049,7 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_MAX_SMEM));
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_ws3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_MAX_SMEM));
     once.mark(dev);
   }
   if (variant == 1) {
@@ -1477,14 +2063,18 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
     NVIT_REQUIRE(smem <= ATT2_MAX_SMEM, "nvit_attention_bwd: shared-memory plan does not fit (T = %lld)", (long long)T);
     const long long heads = B * H;
     const int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
-    launch(attn_bwd_ws_kernel<8>, (unsigned)grid, 8 * 32 + 32, (size_t)smem, static_cast<cudaStream_t>(stream), p);
+    // v3 (epilogue warpgroup) needs both (Q, K) pairs and q / k that are not normalised in place; otherwise v2 runs
+    if (variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr))
+      launch(attn_bwd_ws3_kernel, (unsigned)grid, ATT3_THREADS, (size_t)smem, static_cast<cudaStream_t>(stream), p);
+    else
+      launch(attn_bwd_ws_kernel<8>, (unsigned)grid, 8 * 32 + 32, (size_t)smem, static_cast<cudaStream_t>(stream), p);
   }
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
 
 extern "C" int nvit_attention_bwd_variant(int variant) {   // tuning switch (include/nvit_b200_tuning.h): same results
-  NVIT_REQUIRE(variant == 1 || variant == 2, "nvit_attention_bwd_variant: 1 (one role, one head per CTA) or 2 (persistent, warp-specialised; default)");
+  NVIT_REQUIRE(variant >= 1 && variant <= 3, "nvit_attention_bwd_variant: 1 (one role, one head per CTA), 2 (persistent, warp-specialised; default) or 3 (2 + epilogue warpgroup)");
   g_bwd_variant.store(variant, std::memory_order_relaxed);
   return NVIT_OK;
 }

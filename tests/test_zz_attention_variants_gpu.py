@@ -1,7 +1,8 @@
-"""Both attention-backward kernels (include/nvit_b200_tuning.h: nvit_attention_bwd_variant) against the fp32 reference and
+"""The attention-backward kernels (include/nvit_b200_tuning.h: nvit_attention_bwd_variant) against the fp32 reference and
 against each other: 1 = the single-role kernel of round 1 (one head per CTA), 2 = the persistent warp-specialised kernel
 (8 compute warps + one MMA warp, the products of the next (kv tile, q tile) item in flight under the passes of the current
-one, the next head's tiles loading meanwhile).  The file sorts
+one, the next head's tiles loading meanwhile), 3 = 2 with the dV / dK / dQ epilogues on a warpgroup of their own (one thread
+per accumulator row; falls back to 2 for raw q / k with sqk and for T > 208).  The file sorts
 last on purpose: a fault in a kernel variant must not hide the rest of the suite behind `-x`."""
 import importlib.util
 import os
@@ -23,7 +24,7 @@ _spec.loader.exec_module(K)
 DEFAULT_VARIANT = int(os.environ.get("NVIT_ATTN_BWD_VARIANT", "2"))
 
 
-@pytest.fixture(params=[1, 2], ids=["single_role", "persistent"])
+@pytest.fixture(params=[1, 2, 3], ids=["single_role", "persistent", "persistent_epilogue_wg"])
 def variant(request):
     _lib.call("nvit_attention_bwd_variant", request.param)
     yield request.param
@@ -54,7 +55,7 @@ def test_attention_backward_variants_agree(B, H, T):
     ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.03, 8.0, out, lse, B, H, T)
     res = {}
     try:
-        for v in (1, 2):
+        for v in (1, 2, 3):
             _lib.call("nvit_attention_bwd_variant", v)
             for rep in range(3):       # repeated launches: no state may leak from one head / launch to the next
                 d = torch.zeros(M, 3 * C, device=K.DEV, dtype=torch.bfloat16)
@@ -68,6 +69,6 @@ def test_attention_backward_variants_agree(B, H, T):
                     assert torch.equal(d, res[v][0]), (v, rep)
     finally:
         _lib.call("nvit_attention_bwd_variant", DEFAULT_VARIANT)
-    for v in (2,):
+    for v in (2, 3):
         assert K.rel(res[v][0], res[1][0]) <= 5e-3, (v, K.rel(res[v][0], res[1][0]))
         assert K.rel(res[v][1], res[1][1]) <= 5e-3
