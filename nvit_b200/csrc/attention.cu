@@ -46,6 +46,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 prefetch of a [rows x 64] head tile: the box travels HBM -> L2 now, the real load (same map and coordinates) later
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -106,7 +111,9 @@ struct alignas(64) AttnParams {
   float sqk_mul, scale;
   int B, H, T, TP, nQ, nK;
   int dbuf;         // attn_bwd_ws_kernel: two (Q, K) tile pairs in shared memory (the next head's tiles load during this one)
+  int* work;        // attn_bwd_ws3_kernel: {next unclaimed head - 2 gridDim.x, CTAs that have finished}; both return to 0 by themselves
   long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
+  int no_prefetch;  // A/B aid: v3 without the L2 prefetch of the next head's V / dO / O
 };
 
 #ifdef NVIT_BENCH_HOOKS
@@ -115,11 +122,16 @@ struct alignas(64) AttnParams {
 // (marks are taken during the SECOND head a CTA processes: steady state, with a head before and a head after it)
 #define ATT2_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
 #define ATT2_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
-// v3 kernel: 96 slots per CTA (first 2 CTAs): [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp (thread
-// 384), [64,96) thread 0 of the epilogue warpgroup (thread 256); second head of the CTA, as above
-#define ATT3_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 0) p.dbg[blockIdx.x * 96 + (i)] = clock64(); } while (0)
-#define ATT3_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 384) p.dbg[blockIdx.x * 96 + 32 + (i)] = clock64(); } while (0)
-#define ATT3_EMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 2 && threadIdx.x == 256) p.dbg[blockIdx.x * 96 + 64 + (i)] = clock64(); } while (0)
+// v3 kernel (buffer of 16384 int64): 96 slots per CTA from [1024 + 96 cta]: [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp (thread
+// 384), [64,96) thread 0 of the epilogue warpgroup (thread 256); FOURTH head of CTAs 0 and 100 (steady state; slots 0 and 1)
+#define ATT3_MARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 0) p.dbg[1024 + blockIdx.x * 96 + (i)] = clock64(); } while (0)
+#define ATT3_MMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 384) p.dbg[1024 + blockIdx.x * 96 + 32 + (i)] = clock64(); } while (0)
+#define ATT3_EMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 256) p.dbg[1024 + blockIdx.x * 96 + 64 + (i)] = clock64(); } while (0)
+// [512 + 2 cta + k]: globaltimer when CTA `cta` entered (k = 0) and left (k = 1) the kernel (buffer of 1024 int64)
+#define ATT3_CTAMARK(k) do { if (p.dbg && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.dbg[512 + blockIdx.x * 2 + (k)] = gt; \
+    if ((k) == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[512 + 296 + blockIdx.x] = sm; } } } while (0)
+// [192 + 32 cta + n]: when the compute warps of the first two CTAs entered their n-th head (n < 31), [.. + 31]: when they left the last
+#define ATT3_HEADMARK(n) do { } while (0)
 #else
 #define ATT_MARK(i) do { } while (0)
 #define ATT2_MARK(i) do { } while (0)
@@ -127,6 +139,8 @@ struct alignas(64) AttnParams {
 #define ATT3_MARK(i) do { } while (0)
 #define ATT3_MMARK(i) do { } while (0)
 #define ATT3_EMARK(i) do { } while (0)
+#define ATT3_HEADMARK(n) do { } while (0)
+#define ATT3_CTAMARK(k) do { } while (0)
 #endif
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
@@ -854,6 +868,7 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
   constexpr int NCC = 8 / PARTS;                     // 16-column chunks per thread and item, at most
   constexpr int NH2 = 4 / PARTS;                     // 16-channel groups per thread in the epilogues
   pdl_enter();
+  ATT3_CTAMARK(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();         // 128B-swizzled tiles need a 1024-byte aligned base
   const int T = p.T, TP = p.TP;
@@ -1357,6 +1372,7 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
   if (tid == 0) bulk_wait_group_read<0>();      // the staged output tiles have left shared memory before the CTA retires
   tc_fence_before_sync();
   __syncthreads();
+  ATT3_CTAMARK(1);
   if (warp == ATT2_CW) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -1374,17 +1390,33 @@ __global__ void __launch_bounds__(ATT2_CW * 32 + 32, 1) attn_bwd_ws_kernel(const
 //                (bar_dvfree / bar_dkfree / bar_dqfree), stages the rows in the dead operand tiles, issues every TMA store
 //                and every load of the following heads, and owns the per-head arrays it alone reads (1/||q||, 1/||k||,
 //                the sqk vectors, the dL/d(sqk) accumulator);
-//   warp 12      MMA issuer (as in v2, plus the three "columns are free" waits); warps 13-15 only exist because
-//                setmaxnreg works on whole warpgroups.
-// Registers: 16 warps launch at 128 per thread; the compute warpgroups raise themselves to 144, the MMA warpgroup drops
-// to 96 (2 x 128 x 144 + 128 x 128 + 128 x 96 = 65536; at 64 the MMA loop kept its barrier phases in local memory).
+//   warp 12      MMA issuer (as in v2, plus the "columns are free" waits).
+// Registers: 13 warps -> 152 per thread for every role, no setmaxnreg.  (MEASURED: a first form with 16 warps at 128 and
+// setmaxnreg - compute 144, epilogue 128, MMA warpgroup 96 - kept loop state of the MMA warp and two chunk registers of
+// the exponential pass in local memory; with 224 KB of shared memory the L1 holds next to nothing, so every reload was an
+// L2 round trip on the critical path, and the CTAs of one launch took 270 ... 410 us depending on how loaded the memory
+// system looked from their SM - with 74 or 32 CTAs in flight every one of them ran at the fast rate.)
 // Needs the two (Q, K) tile pairs (TP <= 208) and q / k that arrive normalised or without sqk; nvit_attention_bwd falls
 // back to v2 otherwise.
-constexpr int ATT3_THREADS = 512;
+constexpr int ATT3_THREADS = 512;   // 8 compute warps + 4 epilogue warps + the MMA warp (+ 3 idle warps: setmaxnreg works on warpgroups)
 constexpr int ATT3_COMPUTE = 256;
+#ifndef ATT3_REG_COMPUTE
+#define ATT3_REG_COMPUTE 144
+#define ATT3_REG_EPI 128
+#define ATT3_REG_MMA 96
+#endif
+static_assert(256 * ATT3_REG_COMPUTE + 128 * ATT3_REG_EPI + 128 * ATT3_REG_MMA <= 65536, "register split of attn_bwd_ws3_kernel");
 constexpr int ATT3_EPI = 128;
 template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// barrier parities of a role live as bits of ONE register (MEASURED: ten separate phase variables put the MMA warp's loop
+// state into local memory, and with 224 KB of shared memory the L1 holds next to nothing: every such reload is an L2 round
+// trip on the path that issues the products)
+__device__ __forceinline__ void mbar_wait_flip(uint64_t* bar, uint32_t& phases, int bit) {
+  mbar_wait(bar, (phases >> bit) & 1u);
+  phases ^= 1u << bit;
+}
 
 // 64 accumulator columns of this thread's TMEM lane -> registers
 __device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, uint32_t (&r)[64]) {
@@ -1402,50 +1434,73 @@ __device__ __forceinline__ void row64_to_tile(const uint32_t (&r)[64], uint8_t* 
     *reinterpret_cast<uint4*>(tile + sw128(trow, c)) = pack8(g);
   }
 }
-// backward of y = s * x/||x|| for the whole row held by one thread (see norm_bwd_load): dL/dy in r[], the unit vector is
-// recovered from the normalised bf16 row in the tile, dx overwrites that row; g * n goes to the dL/d(sqk) accumulator.
-// Warp-collective (shuffles inside): `valid` only guards the contribution and the stores.
-__device__ __forceinline__ void norm_bwd_row64(const uint32_t (&r)[64], uint8_t* tile, int trow, const float* s_scale,
-                                               const float* s_rscale, float* s_dsqk, float inv, int lane, bool valid) {
-  float dot = 0.f;
+// backward of y = s * x/||x|| for the whole row held by one thread: dL/dy in r[], the normalised bf16 row yh = s * n still
+// sits in the tile, dx overwrites it.  With yh instead of n nothing needs 1/s in the first pass:
+//   dot = sum_c g_c s_c n_c = sum_c g_c yh_c ;  dx_c = (g_c s_c - yh_c / s_c * dot) / ||x|| ;  dL/ds_c = sum_rows g_c yh_c / s_c
+// (the 1/s_c of dL/ds is applied once per head by the caller).  Packed fp32 pairs throughout: 2 (+1 with DSQK) instructions
+// per pair in the first pass, 6 in the second (MEASURED on the scalar form with n = yh / s recomputed per element and both
+// the q and the k rows feeding dL/ds: 6.2 k cycles per 128-row tile against 0.55 k for the plain dV rows - the epilogue
+// warpgroup, not the compute warps, set the pace of the kernel).
+// q and k share the scale vector, so sum over q rows of g n equals the sum over k rows (both are
+// sum_ij dS_ij s_c nq_ic nk_jc): only the dQ rows feed the accumulator (DSQK) and the caller doubles it.
+// Rows that do not exist (`valid` false) read `zero_row` instead of the tile: their g is finite garbage, g * 0 adds nothing.
+// Warp-collective with DSQK (shuffles inside).
+template <bool DSQK>
+__device__ __forceinline__ void norm_bwd_row64(const uint32_t (&r)[64], uint8_t* tile, int trow, const uint8_t* zero_row,
+                                               const float* s_scale, const float* s_rscale, float* s_dsqk, float inv, int lane,
+                                               bool valid) {
+  const uint8_t* const src = valid ? tile + trow * 128 : zero_row;
+  const int sw = valid ? (trow & 7) : 0;
+  f32x2 dot2 = pack2(0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float n[16], acc[16];
-    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * q)), n);
-    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, 2 * q + 1)), n + 8);
+    const uint4 y0 = *reinterpret_cast<const uint4*>(src + (((2 * q) ^ sw) << 4));
+    const uint4 y1 = *reinterpret_cast<const uint4*>(src + (((2 * q + 1) ^ sw) << 4));
+    const uint32_t yw[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    float acc[16];
 #pragma unroll
-    for (int e4 = 0; e4 < 4; ++e4) {
-      const float4 sc = *reinterpret_cast<const float4*>(s_scale + q * 16 + 4 * e4);
-      const float4 rs = *reinterpret_cast<const float4*>(s_rscale + q * 16 + 4 * e4);
-      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float g = __uint_as_float(r[q * 16 + 4 * e4 + e]);
-        const float nn = n[4 * e4 + e] * rsv[e];
-        acc[4 * e4 + e] = valid ? g * nn : 0.f;
-        dot += g * scv[e] * nn;
+    for (int e = 0; e < 8; ++e) {
+      const f32x2 g2 = pack2(__uint_as_float(r[q * 16 + 2 * e]), __uint_as_float(r[q * 16 + 2 * e + 1]));
+      const f32x2 y2 = bf16x2_to_f32x2(yw[e]);
+      if constexpr (DSQK) {
+        const f32x2 t2 = mul2(g2, y2);
+        dot2 = add2(dot2, t2);
+        unpack2(t2, acc[2 * e], acc[2 * e + 1]);
+      } else {
+        dot2 = fma2(g2, y2, dot2);
       }
     }
-    reduce16_to_smem(acc, s_dsqk + q * 16, lane);
+    if constexpr (DSQK) reduce16_to_smem(acc, s_dsqk + q * 16, lane);
   }
   if (!valid) return;
+  float d0, d1;
+  unpack2(dot2, d0, d1);
+  const float nb = -(d0 + d1) * inv;
+  const f32x2 a2 = pack2(inv, inv), nb2 = pack2(nb, nb);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float n[8], d[8];
-    unpack8(*reinterpret_cast<const uint4*>(tile + sw128(trow, c)), n);
+    const uint4 y = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+    const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
     const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c * 8), sc1 = *reinterpret_cast<const float4*>(s_scale + c * 8 + 4);
     const float4 rs0 = *reinterpret_cast<const float4*>(s_rscale + c * 8), rs1 = *reinterpret_cast<const float4*>(s_rscale + c * 8 + 4);
-    const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-    const float rsv[8] = {rs0.x, rs0.y, rs0.z, rs0.w, rs1.x, rs1.y, rs1.z, rs1.w};
+    const f32x2 s2[4] = {pack2(sc0.x, sc0.y), pack2(sc0.z, sc0.w), pack2(sc1.x, sc1.y), pack2(sc1.z, sc1.w)};
+    const f32x2 q2[4] = {pack2(rs0.x, rs0.y), pack2(rs0.z, rs0.w), pack2(rs1.x, rs1.y), pack2(rs1.z, rs1.w)};
+    uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = (__uint_as_float(r[8 * c + e]) * scv[e] - n[e] * rsv[e] * dot) * inv;
-    *reinterpret_cast<uint4*>(tile + sw128(trow, c)) = pack8(d);
+    for (int e = 0; e < 4; ++e) {
+      const f32x2 g2 = pack2(__uint_as_float(r[8 * c + 2 * e]), __uint_as_float(r[8 * c + 2 * e + 1]));
+      const f32x2 x1 = mul2(g2, s2[e]);                              // g s
+      const f32x2 x2 = mul2(bf16x2_to_f32x2(yw[e]), q2[e]);          // yh / s = n
+      o[e] = f32x2_to_bf16x2(fma2(x1, a2, mul2(x2, nb2)));           // (g s - n dot) / ||x||
+    }
+    *reinterpret_cast<uint4*>(tile + trow * 128 + ((c ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __grid_constant__ AttnParams p) {
   constexpr int PARTS = 2, NCC = 4;
   pdl_enter();
+  ATT3_CTAMARK(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int T = p.T, TP = p.TP;
@@ -1454,8 +1509,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
   uint8_t* sV = sQK + 4 * R;
   uint8_t* sDO = sV + R;
   uint8_t* sDS = sDO + R;                               // two dS^T buffers (O parks in the second one until delta is taken)
-  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);   // compute warps
-  float* s_delta = s_lse + TP;                                       // compute warps
+  float* s_lse = reinterpret_cast<float*>(sDS + 2 * ATT_DS_BYTES);   // [2][TP]: written by the epilogue warps a head ahead, read by the compute warps
+  float* s_delta = s_lse + 2 * TP;                                   // compute warps
   float* s_invq = s_delta + TP;                                      // epilogue warps (and everything below)
   float* s_invk = s_invq + TP;
   float* s_scale = s_invk + TP;
@@ -1474,8 +1529,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
   uint64_t* bar_dv = bars + 11;      // MMA -> epilogue: dV_j complete
   uint64_t* bar_dvfree = bars + 12;  // epilogue -> MMA: dV_j has left tensor memory (one arrival per epilogue warp)
   uint64_t* bar_dkfree = bars + 13;  // epilogue -> MMA: dK_j has left tensor memory
-  uint64_t* bar_dqfree = bars + 14;  // epilogue -> MMA: dQ of the head has left tensor memory
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* bar_dqfree = bars + 14;  // [2] epilogue -> MMA: q tile m of the head's dQ has left tensor memory
+  uint64_t* bar_next = bars + 16;    // [2] epilogue -> compute, MMA: s_head[(n + 1) & 3] and s_lse[(n + 1) & 1] are written (bar n & 1)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  int* const s_head = reinterpret_cast<int*>(bars + 19);            // [4] head of iteration n at [n & 3]; -1: the CTA is done
+  uint8_t* const s_zero = reinterpret_cast<uint8_t*>(bars) + 256;   // one all-zero tile row (stands in for rows that do not exist)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_norm = p.sqk != nullptr;
@@ -1498,7 +1556,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
     mbar_init(bar_dv, 1);
     mbar_init(bar_dvfree, ATT3_EPI / 32);
     mbar_init(bar_dkfree, ATT3_EPI / 32);
-    mbar_init(bar_dqfree, ATT3_EPI / 32);
+    mbar_init(bar_dqfree + 0, ATT3_EPI / 32);
+    mbar_init(bar_dqfree + 1, ATT3_EPI / 32);
+    mbar_init(bar_next + 0, ATT3_EPI / 32);
+    mbar_init(bar_next + 1, ATT3_EPI / 32);
+    s_head[0] = static_cast<int>(blockIdx.x);
     fence_barrier_init();
     // the first head's tiles, and the second head's q / k into the other pair
     const int hd = blockIdx.x, b0 = hd / p.H, h0 = hd % p.H;
@@ -1522,8 +1584,15 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
+  // The dS^T buffers start out all zero (except where the first head's O tile is landing): accumulator lanes past the last
+  // row are fed from parts of them that no pass writes, and norm_bwd_row64 relies on those lanes holding FINITE garbage.
+  for (uint32_t o = tid * 16u; o < 2u * ATT_DS_BYTES; o += ATT3_THREADS * 16u)
+    if (o < static_cast<uint32_t>(ATT_DS_BYTES) || o >= ATT_DS_BYTES + R) *reinterpret_cast<uint4*>(sDS + o) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 8) reinterpret_cast<uint4*>(s_zero)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   for (int r = tid; r < TP; r += ATT3_THREADS) {   // rows >= T are never written again and must stay finite
     s_lse[r] = 0.f;
+    s_lse[TP + r] = 0.f;
     s_invq[r] = 0.f;
     s_invk[r] = 0.f;
     s_delta[r] = 0.f;
@@ -1535,14 +1604,18 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
   const uint32_t sV_a = smem_u32(sV), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
 
   if (warp >= 12) {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<ATT3_REG_MMA>();
     if (warp == 12) {
       // ===================== MMA issuer =====================
-      uint32_t ph_qk0 = 0, ph_qk1 = 0, ph_do = 0, ph_v = 0, ph_P = 0, ph_dS = 0, ph_dvf = 0, ph_dkf = 0, ph_dqf = 0;
+      uint32_t ph = 0;   // bits: 0/1 qk pair, 2 do, 3 v, 4 P, 5 dS, 6 dvfree, 7 dkfree, 8/9 dqfree, 10/11 next
       auto ncol_of = [&](int c) { return min(128, TP - 128 * c); };
       int n = 0;
       bool tile_before = false;          // a kv tile of this CTA has been processed before: its accumulators must have been drained
-      for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+      for (;; ++n) {
+        if (n > 0) {     // is there another head?  (published by the epilogue warpgroup during its iteration n - 1)
+          mbar_wait_flip(bar_next + ((n - 1) & 1), ph, 10 + ((n - 1) & 1));
+          if (s_head[n & 3] < 0) break;
+        }
         const int pb = n & 1;
         const uint32_t sQ_a = smem_u32(sQK + pb * 2 * R), sK_a = sQ_a + R;
         auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
@@ -1568,15 +1641,12 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           __syncwarp();
         };
         ATT3_MMARK(0);
-        if (pb == 0) { mbar_wait(bar_qk, ph_qk0); ph_qk0 ^= 1; }
-        else { mbar_wait(bar_qk + 1, ph_qk1); ph_qk1 ^= 1; }
+        mbar_wait_flip(bar_qk + pb, ph, pb);
         tc_fence_after_sync();
         ATT3_MMARK(1);
         issue_S(0, 0);
-        mbar_wait(bar_do, ph_do);
-        ph_do ^= 1;
-        mbar_wait(bar_v, ph_v);
-        ph_v ^= 1;
+        mbar_wait_flip(bar_do, ph, 2);
+        mbar_wait_flip(bar_v, ph, 3);
         tc_fence_after_sync();
         issue_dP(0, 0);
         ATT3_MMARK(2);
@@ -1589,9 +1659,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
             const bool has_next = i + 1 < nItems;
             const uint32_t buf_a = sDS_a + (i & 1) * ATT_DS_BYTES;
             // ---- dV_j += P^T(i) dO_c   (A = P^T from tensor memory)
-            mbar_wait(bar_P, ph_P);
-            ph_P ^= 1;
-            if (c == 0 && tile_before) { mbar_wait(bar_dvfree, ph_dvf); ph_dvf ^= 1; }   // the previous tile's dV rows are out
+            mbar_wait_flip(bar_P, ph, 4);
+            if (c == 0 && tile_before) mbar_wait_flip(bar_dvfree, ph, 6);   // the previous tile's dV rows are out
             tc_fence_after_sync();
             ATT3_MMARK(3 + 4 * i);
             {
@@ -1608,13 +1677,14 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
             }
             if (has_next) issue_S(jn, cn);
             ATT3_MMARK(4 + 4 * i);
-            mbar_wait(bar_dS, ph_dS);
-            ph_dS ^= 1;
+            mbar_wait_flip(bar_dS, ph, 5);
             tc_fence_after_sync();
             ATT3_MMARK(5 + 4 * i);
             if (has_next && c != nQ - 1) issue_dP(jn, cn);
-            if (c == 0 && tile_before) { mbar_wait(bar_dkfree, ph_dkf); ph_dkf ^= 1; }
-            if (i == 0 && n > 0) { mbar_wait(bar_dqfree, ph_dqf); ph_dqf ^= 1; }
+            if (c == 0 && tile_before) mbar_wait_flip(bar_dkfree, ph, 7);
+            if (j == 0 && n > 0) {       // first contribution to dQ_c of this head: the previous head's rows must have left
+              mbar_wait_flip(bar_dqfree + c, ph, 8 + c);
+            }
             tc_fence_after_sync();
             // ---- dK_j += dS^T(i) Qh_c ; dQ_c += dS(i) Kh_j
             {
@@ -1644,25 +1714,26 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       }
     }
   } else if (warp < 8) {
-    setmaxnreg_inc<144>();
+    setmaxnreg_inc<ATT3_REG_COMPUTE>();
     // ===================== compute warps: the two passes of every item, delta once per head =====================
     const int wq = warp & 3;
     const int part = warp >> 2;
     const int row = wq * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const f32x2 sl2x2 = pack2(p.scale * LOG2E, p.scale * LOG2E), scx2 = pack2(p.scale, p.scale);
-    uint32_t ph_do = 0, ph_S = 0, ph_dP = 0, ph_free0 = 0, ph_free1 = 0;
-    bool used0 = false, used1 = false;
+    uint32_t ph = 0;   // bits: 0 do, 1 S, 2 dP, 3/4 free, 5/6 dS^T buffer used before, 7/8 next
     if (tid < T) s_lse[tid] = -p.lse[static_cast<long long>(blockIdx.x) * T + tid] * LOG2E;   // (b * H + h) * T = head * T
     named_bar_sync(1, ATT3_COMPUTE);
 
     int n = 0;
-    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+    for (;; ++n) {
+      if (n > 0) {       // the epilogue warpgroup has published the next head (or the end) and its log-sum-exp row
+        mbar_wait_flip(bar_next + ((n - 1) & 1), ph, 7 + ((n - 1) & 1));
+        if (s_head[n & 3] < 0) break;
+      }
+      const float* const lse_n = s_lse + (n & 1) * TP;
       ATT3_MARK(0);
-      const int hd_next = hd + gridDim.x;
-      const bool more = hd_next < nheads;
-      float nx_lse = 0.f;
-      if (more && tid < T) nx_lse = p.lse[static_cast<long long>(hd_next) * T + tid];   // used only at the end of the head
+      ATT3_HEADMARK(n);
       int i = 0;
       for (int j = 0; j < nK; ++j) {
         const int kv = j * 128 + row;
@@ -1676,8 +1747,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           uint32_t pk[NCC][8];
           // ---- P^T = exp2(scale log2e S^T - lse log2e), kept as bf16 pairs
           ATT3_MARK(2 + 6 * i);
-          mbar_wait(bar_S, ph_S);
-          ph_S ^= 1;
+          mbar_wait_flip(bar_S, ph, 1);
           tc_fence_after_sync();
           ATT3_MARK(3 + 6 * i);
 #pragma unroll
@@ -1695,7 +1765,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
                 float pv[16];
 #pragma unroll
                 for (int e4 = 0; e4 < 4; ++e4) {
-                  const float4 l4 = *reinterpret_cast<const float4*>(s_lse + q0 + ch * 16 + 4 * e4);
+                  const float4 l4 = *reinterpret_cast<const float4*>(lse_n + q0 + ch * 16 + 4 * e4);
                   float a0, a1, a2, a3;
                   unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 0]), __uint_as_float(r[c2][4 * e4 + 1])), sl2x2, pack2(l4.x, l4.y)), a0, a1);
                   unpack2(fma2(pack2(__uint_as_float(r[c2][4 * e4 + 2]), __uint_as_float(r[c2][4 * e4 + 3])), sl2x2, pack2(l4.z, l4.w)), a2, a3);
@@ -1730,8 +1800,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           ATT3_MARK(4 + 6 * i);
           if (i == 0) {
             // delta = rowsum(dO * O) from the shared tiles (O parks in dS^T buffer 1), under the first dV / S^T products
-            mbar_wait(bar_do, ph_do);
-            ph_do ^= 1;
+            mbar_wait_flip(bar_do, ph, 0);
             for (int r = tid; r < T; r += ATT3_COMPUTE) {
               float d = 0.f;
 #pragma unroll
@@ -1747,16 +1816,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
             named_bar_sync(1, ATT3_COMPUTE);
           }
           // ---- dS^T = P^T (dP^T - delta) scale -> shared memory
-          mbar_wait(bar_dP, ph_dP);
-          ph_dP ^= 1;
+          mbar_wait_flip(bar_dP, ph, 2);
           tc_fence_after_sync();
-          if (bsel == 0) {
-            if (used0) { mbar_wait(bar_free, ph_free0); ph_free0 ^= 1; }
-            used0 = true;
-          } else {
-            if (used1) { mbar_wait(bar_free + 1, ph_free1); ph_free1 ^= 1; }
-            used1 = true;
-          }
+          if ((ph >> (5 + bsel)) & 1u) mbar_wait_flip(bar_free + bsel, ph, 3 + bsel);
+          ph |= 1u << (5 + bsel);
           ATT3_MARK(5 + 6 * i);
 #pragma unroll
           for (int pr = 0; pr < NCC / 2; ++pr) {
@@ -1797,43 +1860,92 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           ATT3_MARK(6 + 6 * i);
         }
       }
-      ATT3_MARK(30);
-      // every P pass of this head lies behind a CTA-wide barrier of the compute warps: s_lse may take the next head's values
-      if (more && tid < T) s_lse[tid] = -nx_lse * LOG2E;
-      named_bar_sync(1, ATT3_COMPUTE);
       ATT3_MARK(31);
     }
+    ATT3_HEADMARK(31);
   } else {
     // ===================== epilogue warpgroup: one thread per accumulator row =====================
+    setmaxnreg_dec<ATT3_REG_EPI>();
     const int ew = warp - 8;                 // = warp & 3: the TMEM lane quarter this warp may access
     const int et = tid - ATT3_COMPUTE;       // 0 .. 127
     const int row = ew * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    uint32_t ph_dv = 0, ph_acc = 0;
+    uint32_t ph = 0;   // bits: 0 dv, 1 acc
+    // This warpgroup also owns the head sequence.  Heads 0 and 1 of a CTA are blockIdx.x and blockIdx.x + gridDim.x (their
+    // tiles are requested at kernel entry); every further head is claimed from a device-wide counter, so an SM that runs
+    // slowly takes fewer heads (MEASURED with the static stride: the CTAs of one launch took 251 ... 303 us, one SM pair
+    // 360 us - and the launch lasts as long as its slowest CTA).  Thread 0 claims head n + 2 at the top of iteration n,
+    // publishes it at the top of iteration n + 1 in s_head[], and the compute warps and the MMA warp learn through
+    // bar_next - together with the next head's log-sum-exp row, which this warpgroup fetches for them - whether another
+    // head follows.
+    float nx_iq[2] = {0.f, 0.f}, nx_ik[2] = {0.f, 0.f}, nx_lse[2] = {0.f, 0.f}, nx_sc = 0.f;
+    auto fetch_head_arrays = [&](int head) {       // per-head vectors of `head`, into registers (consumed an iteration later)
+      const int bb = head / p.H, hh = head % p.H;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = et + k * ATT3_EPI;
+        if (r < T) {
+          nx_lse[k] = p.lse[static_cast<long long>(head) * T + r];
+          if (has_norm && p.inv_q != nullptr) {
+            nx_iq[k] = p.inv_q[(static_cast<long long>(bb) * T + r) * p.ld_inv_q + hh];
+            nx_ik[k] = p.inv_k[(static_cast<long long>(bb) * T + r) * p.ld_inv_k + hh];
+          }
+        }
+      }
+      if (has_norm && et < 64) nx_sc = p.sqk[hh * 64 + et];
+    };
+    fetch_head_arrays(blockIdx.x);
+    int claimed = static_cast<int>(blockIdx.x + gridDim.x);     // thread 0: the head of iteration n + 1
+    if (claimed >= nheads) claimed = -1;
     int n = 0;
-    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++n) {
+    for (;; ++n) {
+      const int hd = s_head[n & 3];                // published an iteration ago (n = 0: at kernel entry)
+      if (hd < 0) break;
       const int b = hd / p.H, h = hd % p.H;
       const int pb = n & 1;
       uint8_t* const sQ = sQK + pb * 2 * R;
       uint8_t* const sK = sQ + R;
-      const int hd_next = hd + gridDim.x, hd_next2 = hd + 2 * gridDim.x;
-      const bool more = hd_next < nheads;
+      ATT3_EMARK(12);
       // per-head arrays of this warpgroup (its previous readers are behind the barrier that ends the loop body)
       if (has_norm) {
         if (p.inv_q != nullptr) {
-          for (int r = et; r < T; r += ATT3_EPI) {
-            s_invq[r] = p.inv_q[(static_cast<long long>(b) * T + r) * p.ld_inv_q + h];
-            s_invk[r] = p.inv_k[(static_cast<long long>(b) * T + r) * p.ld_inv_k + h];
-          }
+          // 1/||q||, 1/||k|| of this head were fetched a head ahead (TP <= 208: two rows per thread)
+          if (et < T) { s_invq[et] = nx_iq[0]; s_invk[et] = nx_ik[0]; }
+          if (et + ATT3_EPI < T) { s_invq[et + ATT3_EPI] = nx_iq[1]; s_invk[et + ATT3_EPI] = nx_ik[1]; }
         }
         if (et < 64) {
-          const float sc = p.sqk[h * 64 + et] * p.sqk_mul;
+          const float sc = nx_sc * p.sqk_mul;
           s_scale[et] = sc;
           s_rscale[et] = sc != 0.f ? 1.f / sc : 0.f;
           s_dsqk[et] = 0.f;
         }
       }
+      if (et == 0) s_head[(n + 1) & 3] = claimed;
       named_bar_sync(2, ATT3_EPI);
+      const int hd_next = s_head[(n + 1) & 3];
+      const bool more = hd_next >= 0;
+      ATT3_EMARK(13);
+      if (et == 0) {
+        if (n > 0 && more) {
+          // The OTHER (Q, K) pair - the previous head's - receives the tiles of the next head now: its dQ / dK stores were
+          // issued at the end of the previous iteration and have had the barrier above to read their rows (waiting for them
+          // right there cost the whole warpgroup ~1 k cycles per head; the tiles are not needed before the next head starts).
+          bulk_wait_group_read<0>();
+          const int b2 = hd_next / p.H, h2 = hd_next % p.H;
+          uint8_t* const sQo = sQK + (pb ^ 1) * 2 * R;
+          mbar_arrive_expect_tx(bar_qk + (pb ^ 1), 2 * R);
+          tma_load_3d(&p.tq, bar_qk + (pb ^ 1), sQo, h2 * 64, 0, b2);
+          tma_load_3d(&p.tk, bar_qk + (pb ^ 1), sQo + R, h2 * 64, 0, b2);
+        }
+        // the head of iteration n + 2 (the result is not looked at before the top of the next iteration)
+        if (more) {
+          const int c = atomicAdd(p.work, 1) + 2 * static_cast<int>(gridDim.x);
+          claimed = c < nheads ? c : -1;
+        } else {
+          claimed = -1;
+        }
+      }
+      if (more) fetch_head_arrays(hd_next);
       ATT3_EMARK(0);
       for (int j = 0; j < nK; ++j) {
         const int kv = j * 128 + row;
@@ -1841,8 +1953,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
         uint32_t r[64];
         // ---- dV_j
         ATT3_EMARK(1 + 6 * j);
-        mbar_wait(bar_dv, ph_dv);
-        ph_dv ^= 1;
+        mbar_wait_flip(bar_dv, ph, 0);
         tc_fence_after_sync();
         ATT3_EMARK(2 + 6 * j);
         __syncwarp();
@@ -1857,10 +1968,20 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           tma_store_3d(&p.tdv, sV + j * 16384, h * 64, j * 128, b);
           bulk_commit_group();
         }
+        if (j == 0) {
+          // the next head's log-sum-exp row (requested at the top of the iteration) goes to the buffer the compute warps read
+          // during head n + 1; they finished head n - 1, its last reader, before this iteration could start
+          if (more) {
+            float* const lse_w = s_lse + ((n + 1) & 1) * TP;
+            if (et < T) lse_w[et] = -nx_lse[0] * LOG2E;
+            if (et + ATT3_EPI < T) lse_w[et + ATT3_EPI] = -nx_lse[1] * LOG2E;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_next + (n & 1));
+        }
         // ---- dK_j
         ATT3_EMARK(3 + 6 * j);
-        mbar_wait(bar_acc, ph_acc);
-        ph_acc ^= 1;
+        mbar_wait_flip(bar_acc, ph, 1);
         tc_fence_after_sync();
         ATT3_EMARK(4 + 6 * j);
         if (j == nK - 1 && more && et == 0) {
@@ -1880,7 +2001,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dkfree);
         if (has_norm) {
-          norm_bwd_row64(r, sK, kv_ok ? kv : 0, s_scale, s_rscale, s_dsqk, s_invk[kv_ok ? kv : 0], lane, kv_ok);
+          norm_bwd_row64<false>(r, sK, kv_ok ? kv : 0, s_zero, s_scale, s_rscale, s_dsqk, s_invk[kv_ok ? kv : 0], lane, kv_ok);
         } else if (kv < TP) {
           row64_to_tile(r, sK + j * 16384, row);
         }
@@ -1900,16 +2021,15 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
         uint32_t r[64];
         __syncwarp();
         tmem_ld_row64(t_lane + TM_DQ + 64 * m, r);
-        if (m == nQ - 1) {
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_dqfree);
-        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dqfree + m);
         if (has_norm) {
-          norm_bwd_row64(r, sQ, ok ? qi : 0, s_scale, s_rscale, s_dsqk, s_invq[ok ? qi : 0], lane, ok);
+          norm_bwd_row64<true>(r, sQ, ok ? qi : 0, s_zero, s_scale, s_rscale, s_dsqk, s_invq[ok ? qi : 0], lane, ok);
         } else if (qi < TP) {
           row64_to_tile(r, sQ + m * 16384, row);
         }
+        ATT3_EMARK(20 + m);
       }
       fence_proxy_async_smem();
       named_bar_sync(2, ATT3_EPI);
@@ -1917,16 +2037,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       if (et == 0) {
         for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
         bulk_commit_group();
-        if (hd_next2 < nheads) {
-          // this (Q, K) pair receives the tiles of the head after the next one as soon as the output stores have read its rows
-          bulk_wait_group_read<0>();
-          const int b2 = hd_next2 / p.H, h2 = hd_next2 % p.H;
-          mbar_arrive_expect_tx(bar_qk + pb, 2 * R);
-          tma_load_3d(&p.tq, bar_qk + pb, sQ, h2 * 64, 0, b2);
-          tma_load_3d(&p.tk, bar_qk + pb, sK, h2 * 64, 0, b2);
-        }
       }
-      if (has_norm && et < 64) atomicAdd(p.dsqk + h * 64 + et, s_dsqk[et] * p.sqk_mul);
+      // s_dsqk holds sum over the q rows of g * yh: times 1/s for g * n, times two for the k rows (see norm_bwd_row64)
+      if (has_norm && et < 64) atomicAdd(p.dsqk + h * 64 + et, s_dsqk[et] * s_rscale[et] * (2.f * p.sqk_mul));
       named_bar_sync(2, ATT3_EPI);
       ATT3_EMARK(31);
     }
@@ -1934,6 +2047,15 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
   }
   tc_fence_before_sync();
   __syncthreads();
+  ATT3_CTAMARK(1);
+  if (tid == 0) {
+    // the last CTA to get here puts the head counter back to zero for the next launch (every claim precedes the claimer's count)
+    __threadfence();
+    if (atomicInc(reinterpret_cast<unsigned*>(p.work) + 1, gridDim.x - 1) == gridDim.x - 1) {
+      __threadfence();
+      atomicExch(p.work, 0);
+    }
+  }
   if (warp == 12) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -1959,6 +2081,10 @@ static int attn_check(const char* who, int64_t B, int64_t H, int64_t T, int64_t 
 using namespace nvit;
 
 static long long* g_att_dbg = nullptr;
+// head counters of attn_bwd_ws3_kernel: 64 {claim, done} pairs used round-robin by the launches (zero at module load, and every
+// launch leaves its pair at zero), so launches on different streams do not share one and graph replays reuse their own
+__device__ int g_att_work[2 * 64];
+static std::atomic<unsigned> g_att_work_slot{0};
 static std::atomic<int> g_bwd_variant{2};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel, 3 = attn_bwd_ws3_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
@@ -1993,6 +2119,7 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
   p.dbg = g_att_dbg;
+  { static const int np = getenv("NVIT_ATTN_NO_PREFETCH") ? atoi(getenv("NVIT_ATTN_NO_PREFETCH")) : 0; p.no_prefetch = np; }
   static DeviceOnce once;
   int dev;
   if (once.needed(&dev)) {
@@ -2057,13 +2184,19 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
   } else {
     // shared memory: (Q, K) x 2 when it fits (the next head's tiles load during the current head), V, dO, two dS^T buffers
     const long long R = 128ll * TP;
-    const long long fixed = 2 * ATT_DS_BYTES + att2_array_bytes(TP);
+    const long long fixed = 2 * ATT_DS_BYTES + att2_array_bytes(TP) + (variant == 3 ? 4 * TP : 0);   // v3: second log-sum-exp row
     p.dbuf = (6 * R + fixed <= ATT2_MAX_SMEM) ? 1 : 0;
     const long long smem = (p.dbuf ? 6 : 4) * R + fixed;
     NVIT_REQUIRE(smem <= ATT2_MAX_SMEM, "nvit_attention_bwd: shared-memory plan does not fit (T = %lld)", (long long)T);
     const long long heads = B * H;
-    const int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
+    int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
+    { static const int ge = getenv("NVIT_ATTN_GRID") ? atoi(getenv("NVIT_ATTN_GRID")) : 0; if (ge > 0 && ge < grid) grid = ge; }   // A/B aid
     // v3 (epilogue warpgroup) needs both (Q, K) pairs and q / k that are not normalised in place; otherwise v2 runs
+    if (variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr)) {
+      int* work_base = nullptr;
+      NVIT_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&work_base), g_att_work));
+      p.work = work_base + 2 * (g_att_work_slot.fetch_add(1, std::memory_order_relaxed) % 64u);
+    }
     if (variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr))
       launch(attn_bwd_ws3_kernel, (unsigned)grid, ATT3_THREADS, (size_t)smem, static_cast<cudaStream_t>(stream), p);
     else

@@ -94,15 +94,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the GPU.  The trap path makes no
+// call: a printf here (a call site with the ABI's register conventions) made ptxas keep loop state of the waiting warps -
+// the barrier parities of the attention kernels' MMA warp - in local memory, i.e. behind an L2 round trip per wait.
+__device__ __forceinline__ void mbar_timeout_trap() {
+  asm volatile("trap;");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("nvit_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > (1ll << 31)) mbar_timeout_trap();
   }
 }
 
@@ -250,10 +252,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
   if (mbar_try_wait_a(bar_addr, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_a(bar_addr, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("nvit_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > (1ll << 31)) mbar_timeout_trap();
   }
 }
 __device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {

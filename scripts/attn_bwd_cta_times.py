@@ -1,4 +1,5 @@
-"""Phase timing of the warp-specialised attention backward (clock64 marks, hooks build): compute thread 0 and the MMA warp."""
+"""Per-CTA wall time of the persistent attention-backward kernels (hooks build: globaltimer at kernel entry / exit of every CTA,
+%smid of the SM it ran on).  Usage: python scripts/attn_bwd_cta_times.py [variant ...]"""
 import os
 import sys
 
@@ -26,19 +27,27 @@ kw = dict(inv_q=inv[:, :H], inv_k=inv[:, H:])
 ops.attention_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.036, 8.0, out, lse, B, H, T, **kw)
 bwd = lambda: ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk, 1 / 0.036, 8.0, out, do, lse,
                                 dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dsqk, B, H, T, **kw)
-_lib.call("nvit_attention_bwd_variant", 2)
-for _ in range(3):
+for v in [int(a) for a in sys.argv[1:]] or [2, 3]:
+    _lib.call("nvit_attention_bwd_variant", v)
+    for _ in range(3):
+        bwd()
+    buf = torch.zeros(16384, dtype=torch.int64, device=dev)
+    _lib.call("nvit_attention_debug", buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     bwd()
-buf = torch.zeros(16384, dtype=torch.int64, device=dev)
-_lib.call("nvit_attention_debug", buf.data_ptr())
-bwd()
-torch.cuda.synchronize()
-_lib.call("nvit_attention_debug", None)
-m = buf.cpu().view(8, 64)
-for cta in range(2):
-    row = m[cta]
-    t0 = int(row[0])
-    print(f"CTA {cta} compute marks (cycles since kernel entry):")
-    print("   ", {i: int(row[i]) - t0 for i in range(32) if int(row[i]) != 0 or i == 0})
-    print(f"CTA {cta} MMA-warp marks:")
-    print("   ", {i: int(row[32 + i]) - t0 for i in range(32) if int(row[32 + i]) != 0})
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.call("nvit_attention_debug", None)
+    h = buf.cpu()
+    G = int(os.environ.get("NVIT_ATTN_GRID", 148))
+    ct = h[512:512 + 2 * G].view(G, 2)
+    sm = h[808:808 + G].tolist()
+    t0 = int(ct[:, 0].min())
+    dur = ((ct[:, 1] - ct[:, 0]).float() / 1e3).tolist()
+    print(f"variant {v}: launch {e0.elapsed_time(e1) * 1e3:.1f} us; last exit {(int(ct[:, 1].max()) - t0) / 1e3:.1f} us after the first entry")
+    print("  duration (us) by SM id:")
+    by_sm = sorted(zip(sm, dur, range(G)))
+    for i in range(0, G, 16):
+        print("   ", " ".join(f"{s}:{d:.0f}" for s, d, _ in by_sm[i:i + 16]))
+    print("  CTA -> SM:", " ".join(str(s) for s in sm[:32]), "...")

@@ -30,15 +30,25 @@ bwd = lambda: ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sqk
 _lib.call("nvit_attention_bwd_variant", 3)
 for _ in range(3):
     bwd()
-buf = torch.zeros(512, dtype=torch.int64, device=dev)
+buf = torch.zeros(16384, dtype=torch.int64, device=dev)
 _lib.call("nvit_attention_debug", buf.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 bwd()
+e1.record()
 torch.cuda.synchronize()
+print(f"marked launch: {e0.elapsed_time(e1) * 1e3:.1f} us")
 _lib.call("nvit_attention_debug", None)
-m = buf.cpu()[:192].view(2, 96)
-for cta in range(2):
-    row = m[cta]
+h = buf.cpu()
+ct = h[512:512 + 296].view(148, 2)
+sm = h[808:808 + 148].tolist()
+dur = ((ct[:, 1] - ct[:, 0]).float() / 1e3).tolist()
+full = [i for i in range(148) if i + 20 * 148 < B * H]          # CTAs that process 21 heads
+order = sorted(full, key=lambda i: dur[i])
+print("durations (us) of the 21-head CTAs, sorted:", " ".join(f"{dur[i]:.0f}" for i in order))
+for tag, cta in (("fastest", order[0]), ("median", order[len(order) // 2]), ("slowest", order[-1])):
+    row = h[1024 + cta * 96:1024 + cta * 96 + 96]
     t0 = int(row[0])
+    print(f"--- {tag} CTA {cta} (SM {sm[cta]}, {dur[cta]:.0f} us); marks of its 4th head, cycles since the compute warps entered it")
     for name, off in (("compute", 0), ("MMA warp", 32), ("epilogue", 64)):
-        print(f"CTA {cta} {name} marks (cycles since the compute warps entered the head):")
-        print("   ", {i: int(row[off + i]) - t0 for i in range(32) if int(row[off + i]) != 0 or (off == 0 and i == 0)})
+        print(f"  {name}:", {i: int(row[off + i]) - t0 for i in range(32) if int(row[off + i]) != 0 or (off == 0 and i == 0)})

@@ -43,6 +43,7 @@ def timeit(f, n=20):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
+    print('   ', ' '.join(f'{t:.0f}' for t in ts))
     ts.sort()
     return ts[len(ts) // 2], ts[0]
 
