@@ -111,6 +111,8 @@ struct alignas(64) AttnParams {
   float sqk_mul, scale;
   int B, H, T, TP, nQ, nK;
   int dbuf;         // attn_bwd_ws_kernel: two (Q, K) tile pairs in shared memory (the next head's tiles load during this one)
+  unsigned h_magic; // attn_bwd_ws3_kernel: 2^32 / H rounded up: head / H = umulhi(head, h_magic) for head * H < 2^32 (a runtime division
+                    // is ~40 dependent instructions, and the per-head set-up of its roles sits on the critical path)
   int* work;        // attn_bwd_ws3_kernel: {next unclaimed head - 2 gridDim.x, CTAs that have finished}; both return to 0 by themselves
   long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
   int no_prefetch;  // A/B aid: v3 without the L2 prefetch of the next head's V / dO / O
@@ -1531,8 +1533,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
   uint64_t* bar_dkfree = bars + 13;  // epilogue -> MMA: dK_j has left tensor memory
   uint64_t* bar_dqfree = bars + 14;  // [2] epilogue -> MMA: q tile m of the head's dQ has left tensor memory
   uint64_t* bar_next = bars + 16;    // [2] epilogue -> compute, MMA: s_head[(n + 1) & 3] and s_lse[(n + 1) & 1] are written (bar n & 1)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
-  int* const s_head = reinterpret_cast<int*>(bars + 19);            // [4] head of iteration n at [n & 3]; -1: the CTA is done
+  uint64_t* bar_dqst = bars + 18;    // epilogue -> store warp: the head's dQ rows are staged over Qh
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
+  int* const s_head = reinterpret_cast<int*>(bars + 20);            // [4] head of iteration n at [n & 3]; -1: the CTA is done
   uint8_t* const s_zero = reinterpret_cast<uint8_t*>(bars) + 256;   // one all-zero tile row (stands in for rows that do not exist)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1560,6 +1563,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
     mbar_init(bar_dqfree + 1, ATT3_EPI / 32);
     mbar_init(bar_next + 0, ATT3_EPI / 32);
     mbar_init(bar_next + 1, ATT3_EPI / 32);
+    mbar_init(bar_dqst, 1);
     s_head[0] = static_cast<int>(blockIdx.x);
     fence_barrier_init();
     // the first head's tiles, and the second head's q / k into the other pair
@@ -1610,16 +1614,15 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       uint32_t ph = 0;   // bits: 0/1 qk pair, 2 do, 3 v, 4 P, 5 dS, 6 dvfree, 7 dkfree, 8/9 dqfree, 10/11 next
       auto ncol_of = [&](int c) { return min(128, TP - 128 * c); };
       int n = 0;
+      bool more_heads = false;
       bool tile_before = false;          // a kv tile of this CTA has been processed before: its accumulators must have been drained
       for (;; ++n) {
-        if (n > 0) {     // is there another head?  (published by the epilogue warpgroup during its iteration n - 1)
-          mbar_wait_flip(bar_next + ((n - 1) & 1), ph, 10 + ((n - 1) & 1));
-          if (s_head[n & 3] < 0) break;
-        }
+        // (whether head n exists was settled during the last item of head n - 1, see below)
         const int pb = n & 1;
         const uint32_t sQ_a = smem_u32(sQK + pb * 2 * R), sK_a = sQ_a + R;
-        auto issue_S = [&](int j, int c) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]
-          const uint64_t da = umma_smem_desc(sK_a + j * 16384, 16, 1024), db = umma_smem_desc(sQ_a + c * 16384, 16, 1024);
+        auto issue_S = [&](int j, int c, uint32_t swap = 0u) {       // S^T(j,c) = Kh_j Qh_c^T  [128 kv x ncol]; swap: the OTHER (Q, K) pair
+          const uint32_t q_a = smem_u32(sQK + (pb ^ swap) * 2 * R);
+          const uint64_t da = umma_smem_desc(q_a + R + j * 16384, 16, 1024), db = umma_smem_desc(q_a + c * 16384, 16, 1024);
           const uint32_t id = idesc_kk_n(ncol_of(c));
           if (elect_one()) {
             umma_bf16_ss(tmem_base + TM_S, da, db, id, 0u);
@@ -1641,10 +1644,12 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           __syncwarp();
         };
         ATT3_MMARK(0);
-        mbar_wait_flip(bar_qk + pb, ph, pb);
-        tc_fence_after_sync();
+        if (n == 0) {      // later heads: their first S^T product was issued behind the last dV product of the head before
+          mbar_wait_flip(bar_qk + pb, ph, pb);
+          tc_fence_after_sync();
+          issue_S(0, 0);
+        }
         ATT3_MMARK(1);
-        issue_S(0, 0);
         mbar_wait_flip(bar_do, ph, 2);
         mbar_wait_flip(bar_v, ph, 3);
         tc_fence_after_sync();
@@ -1675,7 +1680,21 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
               }
               __syncwarp();
             }
-            if (has_next) issue_S(jn, cn);
+            if (has_next) {
+              issue_S(jn, cn);
+            } else {
+              // Last item of the head.  Is there another head?  (Published by the epilogue warpgroup during its iteration n,
+              // thousands of cycles ago.)  If so its first S^T product goes out now, behind this head's last dV product: it
+              // runs under the last dS pass, and the compute warps find it finished when they enter the head
+              // (MEASURED: issued at the top of the head it reached them ~1.8 k cycles after they had entered it).
+              mbar_wait_flip(bar_next + (n & 1), ph, 10 + (n & 1));
+              more_heads = s_head[(n + 1) & 3] >= 0;
+              if (more_heads) {
+                mbar_wait_flip(bar_qk + (pb ^ 1), ph, pb ^ 1);
+                tc_fence_after_sync();
+                issue_S(0, 0, 1u);
+              }
+            }
             ATT3_MMARK(4 + 4 * i);
             mbar_wait_flip(bar_dS, ph, 5);
             tc_fence_after_sync();
@@ -1711,7 +1730,38 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
             ATT3_MMARK(6 + 4 * i);
           }
         }
+        if (!more_heads) break;
       }
+    }
+    else if (warp == 13 && lane == 0) {
+      // ===================== store warp (one thread): the head's dQ tiles out, the head after next's Q / K in =====================
+      // The stores of dQ are queued behind the next head's dO / O / V loads in the SM's bulk-copy pipeline, so waiting for them
+      // to have read their rows takes ~4 k cycles (MEASURED when thread 0 of the epilogue warpgroup did this at the top of its
+      // iteration: the whole warpgroup waited with it at its next barrier, and the MMA warp for the dV columns behind that).
+      // This thread has nothing else to do.
+      uint32_t ph = 0;   // bits: 0 dqst, 1/2 next
+      mbar_wait_flip(bar_next + 0, ph, 1);          // iteration 0's publication (head 1) is not needed here, only consumed
+      for (int n = 0;; ++n) {
+        const int hd = s_head[n & 3];                // visible: kernel entry (n = 0) or the wait on bar_dqst of iteration n - 1
+        if (hd < 0) break;
+        const int b = static_cast<int>(__umulhi(static_cast<unsigned>(hd), p.h_magic)), h = hd - b * p.H;
+        const int pb = n & 1;
+        uint8_t* const sQ = sQK + pb * 2 * R;
+        mbar_wait_flip(bar_dqst, ph, 0);
+        for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
+        bulk_commit_group();
+        if (s_head[(n + 1) & 3] < 0) break;          // no iteration n + 1: nothing publishes a head n + 2
+        mbar_wait_flip(bar_next + ((n + 1) & 1), ph, 1 + ((n + 1) & 1));
+        const int hd2 = s_head[(n + 2) & 3];
+        if (hd2 >= 0) {
+          bulk_wait_group_read<0>();                 // the dQ stores have read pair pb (its dK stores: see the epilogue warpgroup)
+          const int b2 = static_cast<int>(__umulhi(static_cast<unsigned>(hd2), p.h_magic)), h2 = hd2 - b2 * p.H;
+          mbar_arrive_expect_tx(bar_qk + pb, 2 * R);
+          tma_load_3d(&p.tq, bar_qk + pb, sQ, h2 * 64, 0, b2);
+          tma_load_3d(&p.tk, bar_qk + pb, sQ + R, h2 * 64, 0, b2);
+        }
+      }
+      bulk_wait_group_read<0>();                     // the staged tiles have left shared memory before the CTA retires
     }
   } else if (warp < 8) {
     setmaxnreg_inc<ATT3_REG_COMPUTE>();
@@ -1774,14 +1824,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
                   pv[4 * e4 + 2] = ex2_approx(a2);
                   pv[4 * e4 + 3] = ex2_approx(a3);
                 }
-                if (!kv_ok) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
-                } else if (q0 + ch * 16 + 16 > T) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e)
-                    if (q0 + ch * 16 + e >= T) pv[e] = 0.f;
-                }
+                // No masking of rows / columns >= T: q, k, v and dO arrive with those rows zero-filled and lse, delta hold zeros
+                // there, so such entries of P^T and dS^T are finite and only ever multiply zeros (dV: dO rows; dK: Qh rows;
+                // dQ: Kh rows) or land in output rows the stores clip.  (The per-element selects were 40 % of this pass.)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) pk[cc][e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
               }
@@ -1842,10 +1887,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
                   unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4]), t0), pv[4 * e4 + 0], pv[4 * e4 + 1]);
                   unpack2(mul2(bf16x2_to_f32x2(pk[cc][2 * e4 + 1]), t1), pv[4 * e4 + 2], pv[4 * e4 + 3]);
                 }
-                if (!kv_ok) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) pv[e] = 0.f;
-                }
                 uint8_t* blk = buf + (ch >> 2) * 16384;
                 const int k2 = (ch & 3) * 2;
                 *reinterpret_cast<uint4*>(blk + sw128(row, k2)) = pack8(pv);
@@ -1880,7 +1921,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
     // head follows.
     float nx_iq[2] = {0.f, 0.f}, nx_ik[2] = {0.f, 0.f}, nx_lse[2] = {0.f, 0.f}, nx_sc = 0.f;
     auto fetch_head_arrays = [&](int head) {       // per-head vectors of `head`, into registers (consumed an iteration later)
-      const int bb = head / p.H, hh = head % p.H;
+      const int bb = static_cast<int>(__umulhi(static_cast<unsigned>(head), p.h_magic)), hh = head - bb * p.H;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int r = et + k * ATT3_EPI;
@@ -1895,13 +1936,14 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       if (has_norm && et < 64) nx_sc = p.sqk[hh * 64 + et];
     };
     fetch_head_arrays(blockIdx.x);
-    int claimed = static_cast<int>(blockIdx.x + gridDim.x);     // thread 0: the head of iteration n + 1
-    if (claimed >= nheads) claimed = -1;
+    // thread 0: the head of iteration n + 1 is claim_base + claim_raw (>= nheads: none); claim_raw is the counter's answer, which
+    // nothing may touch before the top of the next iteration (148 CTAs hit one address: the answer takes up to ~4 k cycles)
+    int claim_raw = 0, claim_base = static_cast<int>(blockIdx.x + gridDim.x);
     int n = 0;
     for (;; ++n) {
       const int hd = s_head[n & 3];                // published an iteration ago (n = 0: at kernel entry)
       if (hd < 0) break;
-      const int b = hd / p.H, h = hd % p.H;
+      const int b = static_cast<int>(__umulhi(static_cast<unsigned>(hd), p.h_magic)), h = hd - b * p.H;
       const int pb = n & 1;
       uint8_t* const sQ = sQK + pb * 2 * R;
       uint8_t* const sK = sQ + R;
@@ -1920,31 +1962,23 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
           s_dsqk[et] = 0.f;
         }
       }
-      if (et == 0) s_head[(n + 1) & 3] = claimed;
+      if (et == 0) {
+        const int claimed = claim_base + claim_raw;          // first use of the counter value fetched an iteration ago
+        s_head[(n + 1) & 3] = claimed < nheads ? claimed : -1;
+      }
       named_bar_sync(2, ATT3_EPI);
       const int hd_next = s_head[(n + 1) & 3];
       const bool more = hd_next >= 0;
       ATT3_EMARK(13);
       if (et == 0) {
-        if (n > 0 && more) {
-          // The OTHER (Q, K) pair - the previous head's - receives the tiles of the next head now: its dQ / dK stores were
-          // issued at the end of the previous iteration and have had the barrier above to read their rows (waiting for them
-          // right there cost the whole warpgroup ~1 k cycles per head; the tiles are not needed before the next head starts).
-          bulk_wait_group_read<0>();
-          const int b2 = hd_next / p.H, h2 = hd_next % p.H;
-          uint8_t* const sQo = sQK + (pb ^ 1) * 2 * R;
-          mbar_arrive_expect_tx(bar_qk + (pb ^ 1), 2 * R);
-          tma_load_3d(&p.tq, bar_qk + (pb ^ 1), sQo, h2 * 64, 0, b2);
-          tma_load_3d(&p.tk, bar_qk + (pb ^ 1), sQo + R, h2 * 64, 0, b2);
-        }
-        // the head of iteration n + 2 (the result is not looked at before the top of the next iteration)
-        if (more) {
-          const int c = atomicAdd(p.work, 1) + 2 * static_cast<int>(gridDim.x);
-          claimed = c < nheads ? c : -1;
-        } else {
-          claimed = -1;
-        }
+        // the head of iteration n + 2 (MEASURED: using the counter's answer right here - even just adding to it - kept this
+        // thread, and at the next barrier its warpgroup, waiting 3 - 5 k cycles)
+        claim_base = more ? 2 * static_cast<int>(gridDim.x) : nheads;
+        if (more) claim_raw = atomicAdd(p.work, 1);
+        // (MEASURED: L2 prefetches (cp.async.bulk.prefetch.tensor) of the next head's V / dO / O issued here, a head ahead of
+        // their exposed loads, made the launch slower, 263 -> 285 us: this thread sat ~3 k cycles in their issue.)
       }
+      ATT3_EMARK(14);
       if (more) fetch_head_arrays(hd_next);
       ATT3_EMARK(0);
       for (int j = 0; j < nK; ++j) {
@@ -1987,7 +2021,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
         if (j == nK - 1 && more && et == 0) {
           // every product of this head has completed: dO and the O parking slot are free, and V once the dV stores have read
           // its rows (the last one was issued a dS pass ago)
-          const int bn = hd_next / p.H, hn = hd_next % p.H;
+          const int bn = static_cast<int>(__umulhi(static_cast<unsigned>(hd_next), p.h_magic)), hn = hd_next - bn * p.H;
           mbar_arrive_expect_tx(bar_do, 2 * R);
           tma_load_3d(&p.tdo, bar_do, sDO, hn * 64, 0, bn);
           tma_load_3d(&p.to, bar_do, sDS + ATT_DS_BYTES, hn * 64, 0, bn);
@@ -2032,15 +2066,14 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
         ATT3_EMARK(20 + m);
       }
       fence_proxy_async_smem();
-      named_bar_sync(2, ATT3_EPI);
+      named_bar_sync(2, ATT3_EPI);        // the only barrier at the end of an iteration: every reader of the per-head arrays is behind it
       ATT3_EMARK(30);
       if (et == 0) {
-        for (int m = 0; m < nQ; ++m) tma_store_3d(&p.tdq, sQ + m * 16384, h * 64, m * 128, b);
-        bulk_commit_group();
+        bulk_wait_group_read<0>();        // this thread's dV / dK stores (issued thousands of cycles ago) have read their rows:
+        mbar_arrive(bar_dqst);            // the store warp may send dQ out and, after it, refill this (Q, K) pair
       }
       // s_dsqk holds sum over the q rows of g * yh: times 1/s for g * n, times two for the k rows (see norm_bwd_row64)
       if (has_norm && et < 64) atomicAdd(p.dsqk + h * 64 + et, s_dsqk[et] * s_rscale[et] * (2.f * p.sqk_mul));
-      named_bar_sync(2, ATT3_EPI);
       ATT3_EMARK(31);
     }
     if (et == 0) bulk_wait_group_read<0>();      // the staged output tiles have left shared memory before the CTA retires
@@ -2085,7 +2118,7 @@ static long long* g_att_dbg = nullptr;
 // launch leaves its pair at zero), so launches on different streams do not share one and graph replays reuse their own
 __device__ int g_att_work[2 * 64];
 static std::atomic<unsigned> g_att_work_slot{0};
-static std::atomic<int> g_bwd_variant{2};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel, 3 = attn_bwd_ws3_kernel
+static std::atomic<int> g_bwd_variant{3};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel, 3 = attn_bwd_ws3_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
   g_att_dbg = static_cast<long long*>(dev_buf_256_int64);
@@ -2192,12 +2225,14 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
     int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
     { static const int ge = getenv("NVIT_ATTN_GRID") ? atoi(getenv("NVIT_ATTN_GRID")) : 0; if (ge > 0 && ge < grid) grid = ge; }   // A/B aid
     // v3 (epilogue warpgroup) needs both (Q, K) pairs and q / k that are not normalised in place; otherwise v2 runs
-    if (variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr)) {
+    const bool v3 = variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr) && H >= 2 && heads * H < (1ll << 32);   // (h_magic)
+    if (v3) {
+      p.h_magic = static_cast<unsigned>((1ull << 32) / static_cast<unsigned long long>(H) + 1ull);
       int* work_base = nullptr;
       NVIT_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&work_base), g_att_work));
       p.work = work_base + 2 * (g_att_work_slot.fetch_add(1, std::memory_order_relaxed) % 64u);
     }
-    if (variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr))
+    if (v3)
       launch(attn_bwd_ws3_kernel, (unsigned)grid, ATT3_THREADS, (size_t)smem, static_cast<cudaStream_t>(stream), p);
     else
       launch(attn_bwd_ws_kernel<8>, (unsigned)grid, 8 * 32 + 32, (size_t)smem, static_cast<cudaStream_t>(stream), p);

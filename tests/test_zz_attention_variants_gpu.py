@@ -21,7 +21,7 @@ _spec = importlib.util.spec_from_file_location("kernels_gpu_cases", os.path.join
 K = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(K)
 
-DEFAULT_VARIANT = int(os.environ.get("NVIT_ATTN_BWD_VARIANT", "2"))
+DEFAULT_VARIANT = int(os.environ.get("NVIT_ATTN_BWD_VARIANT", "3"))
 
 
 @pytest.fixture(params=[1, 2, 3], ids=["single_role", "persistent", "persistent_epilogue_wg"])
