@@ -59,7 +59,16 @@ struct alignas(64) GemmParams {
   float colscale_mul;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
   int group_n;         // tile order: 0 = n fastest over the whole width, G > 0 = bands of G tiles along n (tile_coords)
+  // x / tiles_n and x / splits as umulhi(x, magic) (magic = 2^32 / d rounded up; exact while x * d < 2^32; 0 = divide).
+  // A runtime integer division is ~40 dependent instructions (I2F, MUFU.RCP, F2I, fix-ups): the roles of this kernel
+  // did up to ten of them per tile, the epilogue warps of the gate-backward GEMM on their critical path.
+  unsigned magic_tiles_n, magic_splits;
 };
+
+__device__ __forceinline__ int fast_div(int x, int d, unsigned magic) {
+  if (magic) return static_cast<int>(__umulhi(static_cast<unsigned>(x), magic));
+  return d == 1 ? x : x / d;
+}
 
 // Tile index -> (m tile, n tile).  The persistent CTAs (or pairs) take consecutive indices, so the order decides which
 // operand panels the ~74 / 148 tiles in flight share.  n fastest: the tiles in flight span few A row-panels and the whole
@@ -67,8 +76,8 @@ struct alignas(64) GemmParams {
 // fastest, then m) make the set in flight ~74/G x G: 9 + 8 panels for G = 8, i.e. fewer distinct bytes pulled through L2.
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_tile, int& n_blk) {
   if (p.group_n <= 0) {
-    n_blk = t % p.tiles_n;
-    m_tile = t / p.tiles_n;
+    m_tile = fast_div(t, p.tiles_n, p.magic_tiles_n);
+    n_blk = t - m_tile * p.tiles_n;
     return;
   }
   const int band_tiles = p.tiles_m * p.group_n;
@@ -211,8 +220,8 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
       uint32_t phase = 0;
       const uint32_t full0 = smem_u32(full_bar);
       for (int u = unit0; u < total_units; u += unit_stride) {
-        const int split = u % p.splits;
-        const int t = u / p.splits;
+        const int t = fast_div(u, p.splits, p.magic_splits);
+        const int split = u - t * p.splits;
         int m_tile, n_blk;
         tile_coords(p, t, m_tile, n_blk);
         const int m_blk = m_tile * (CG2 ? 2 : 1) + (int)cta_rank;   // this CTA's 128-row block
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int u = unit0; u < total_units; u += unit_stride) {
-        const int split = u % p.splits;
+        const int split = u - fast_div(u, p.splits, p.magic_splits) * p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
@@ -388,20 +397,20 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
       }
       if (unit0 < total_units && NVIT_DBG(p) != 1) {
         int mt0, nb0;
-        tile_coords(p, unit0 / p.splits, mt0, nb0);
+        tile_coords(p, fast_div(unit0, p.splits, p.magic_splits), mt0, nb0);
         if constexpr (NG == 2) gate_fetch(mt0 * (CG2 ? 2 : 1) + (int)cta_rank, nb0, 0);
         else gate_prefetch(mt0 * (CG2 ? 2 : 1) + (int)cta_rank, nb0);
       }
       if (unit0 < total_units && use_vec && vec_thread) {
         int mt0, nb0;
-        tile_coords(p, unit0 / p.splits, mt0, nb0);
+        tile_coords(p, fast_div(unit0, p.splits, p.magic_splits), mt0, nb0);
         const int j0 = min(nb0 * TILE_N + vec_col, p.N - 1);
         gate_su = __ldg(p.colscale + j0) * p.colscale_mul;
         gate_sv = __ldg(p.colscale + p.swiglu_half + j0) * p.colscale_mul;
       }
     }
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int t = u / p.splits;
+      const int t = fast_div(u, p.splits, p.magic_splits);
       int m_tile, n_blk;
       tile_coords(p, t, m_tile, n_blk);
       const int m_blk = m_tile * (CG2 ? 2 : 1) + (int)cta_rank;
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
             s_vec[256 + vec_col] = gate_sv;
             if (u + unit_stride < total_units) {
               int mtn, nbn;
-              tile_coords(p, (u + unit_stride) / p.splits, mtn, nbn);
+              tile_coords(p, fast_div(u + unit_stride, p.splits, p.magic_splits), mtn, nbn);
               const int jn = min(nbn * TILE_N + vec_col, p.N - 1);
               gate_su = __ldg(p.colscale + jn) * p.colscale_mul;
               gate_sv = __ldg(p.colscale + p.swiglu_half + jn) * p.colscale_mul;
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
                 gate_fetch(m_blk, n_blk, 1);
               } else if (u + unit_stride < total_units) {
                 int mt2, nb2;
-                tile_coords(p, (u + unit_stride) / p.splits, mt2, nb2);
+                tile_coords(p, fast_div(u + unit_stride, p.splits, p.magic_splits), mt2, nb2);
                 gate_fetch(mt2 * (CG2 ? 2 : 1) + (int)cta_rank, nb2, 0);
               }
             }
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
                 if (lane == 0) bulk_wait_group_read<0>();
                 __syncwarp();
                 int mt2, nb2;
-                tile_coords(p, (u + unit_stride) / p.splits, mt2, nb2);
+                tile_coords(p, fast_div(u + unit_stride, p.splits, p.magic_splits), mt2, nb2);
                 gate_prefetch(mt2 * (CG2 ? 2 : 1) + (int)cta_rank, nb2);
               }
             }
@@ -1040,6 +1049,14 @@ static int launch_gemm(GemmParams& p, const void* A, const void* B, long long ld
     once.mark(dev);
   }
   const long long units = 1ll * p.tiles_m * p.tiles_n * p.splits;
+  {
+    auto magic = [&](int d) -> unsigned {      // see GemmParams::magic_*: dividends are unit / tile indices below `units` (+ one grid stride)
+      const long long xmax = units + 2 * nvit_num_sms();
+      return (d >= 2 && xmax * d < (1ll << 32)) ? static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(d) + 1ull) : 0u;
+    };
+    p.magic_tiles_n = magic(p.tiles_n);
+    p.magic_splits = magic(p.splits);
+  }
   const int nwork = (int)(units < workers ? units : workers);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
