@@ -25,6 +25,12 @@ int nvit_gemm_raster_group(int group);
  * gate-backward GEMM; 22 or 24 its number of epilogue groups. */
 int nvit_gemm_swiglu_cta_group(int mode);
 
+/* Attention forward kernel: 2 = persistent and warp-specialised (one CTA per SM claims heads from a device-wide counter; two
+ * softmax warpgroups, one per 128-row q tile, one thread per score row; an MMA warp; one thread for every tile load and store;
+ * two (Q, K, V) buffer sets; default; runs as 1 for q / k that are normalised inside the kernel), 1 = one head per CTA, two
+ * CTAs per SM (round 1). */
+int nvit_attention_fwd_variant(int variant);
+
 /* Attention backward kernel: 2 = persistent and warp-specialised (8 compute warps + one MMA warp per SM, the products of the
  * next (kv tile, q tile) item in flight under the passes of the current one, the next head's tiles loading meanwhile;
  * default), 3 = 2 with the dV / dK / dQ epilogues on a warpgroup of their own (one thread per accumulator row; runs as 2 for

@@ -21,6 +21,7 @@ SIGNATURES = {
     "nvit_gemm_raster_group": [I32],
     "nvit_gemm_swiglu_cta_group": [I32],
     "nvit_attention_bwd_variant": [I32],
+    "nvit_attention_fwd_variant": [I32],
     "nvit_set_sm_budget": [I32],
     "nvit_set_pdl": [I32],
     "nvit_residual_bwd_staged": [I32],
@@ -112,6 +113,9 @@ def load() -> ctypes.CDLL:
     mode = os.environ.get("NVIT_ATTN_BWD_VARIANT")    # 1 = round-1 single-role kernel, 2 = warp-specialised, 3 = 2 + epilogue warpgroup
     if mode in ("1", "2", "3"):
         lib.nvit_attention_bwd_variant(int(mode))
+    mode = os.environ.get("NVIT_ATTN_FWD_VARIANT")    # 1 = one head per CTA (round 1), 2 = persistent warp-specialised kernel
+    if mode in ("1", "2"):
+        lib.nvit_attention_fwd_variant(int(mode))
     mode = os.environ.get("NVIT_GEMM_CTA_GROUP")      # benchmarking hook: pin cta_group::1 or ::2 GEMM tiles
     if mode in ("1", "2"):
         lib.nvit_gemm_force_cta_group(int(mode))

@@ -51,6 +51,14 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int32_t c0
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// barrier parities of a role live as bits of ONE register (MEASURED: ten separate phase variables put the MMA warp's loop
+// state into local memory, and with 224 KB of shared memory the L1 holds next to nothing: every such reload is an L2 round
+// trip on the path that issues the products)
+__device__ __forceinline__ void mbar_wait_flip(uint64_t* bar, uint32_t& phases, int bit) {
+  mbar_wait(bar, (phases >> bit) & 1u);
+  phases ^= 1u << bit;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -426,6 +434,292 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
   if (t.warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ forward, persistent
+// attn_fwd_kernel spends a head as a serial chain (S^T product -> exponentials -> P back to tensor memory -> PV product -> O
+// rows out) and gets its overlap from a second resident CTA; every head pays the set-up of a CTA (barriers, TMEM allocation,
+// exposed tile loads).  Here ONE persistent CTA per SM walks over heads it claims from a device-wide counter (as
+// attn_bwd_ws3_kernel does):
+//   warps 0-3 / 4-7  two softmax warpgroups, one per 128-row q tile of the head, ONE thread per score row: the row sum is
+//                    thread-local, and P goes back over the row's own dead score columns chunk by chunk (P chunk c lands in
+//                    columns the thread has already read), so there is no barrier between reading S and writing P and no P
+//                    held in registers; afterwards the warpgroup normalises its O rows into the dead Qh rows;
+//   warp 8           MMA issuer: S_0, S_1 back to back, O_r = P_r V when warpgroup r has written P_r; the next head's S_r goes
+//                    out as soon as warpgroup r has drained O_r, i.e. while the other warpgroup may still be in this head;
+//   warp 9 (1 lane)  head sequence, every tile load (two (Q, K, V) buffer sets: the head after next loads while the next one
+//                    is processed) and the O stores.
+// Tensor memory: q tile r owns columns [256 r, 256 r + 256): S in [0, TP), P over [0, TP / 2), O in [128, 192).
+// Handles pre-normalised q / k (inv_q given) and plain attention (sqk == NULL); nvit_attention_fwd keeps the round-1 kernel for
+// q / k that are normalised in shared memory.
+constexpr int ATTF_THREADS = 320;
+__global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __grid_constant__ AttnParams p) {
+  pdl_enter();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int T = p.T, TP = p.TP, nQ = p.nQ;
+  const uint32_t R = static_cast<uint32_t>(TP) * 128u;       // one [TP tokens][64 bf16] tile
+  // (the S^T products and the O stores address whole 128-row q tiles: for short sequences that reaches past the six tiles)
+  const uint32_t tiles_end = max(6u * R, 3u * R + static_cast<uint32_t>(nQ) * 16384u);
+  float* s_bound = reinterpret_cast<float*>(smem + tiles_end);   // [256] per head of a token: scale * max_c s_c^2 (bound of the logits)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bound + 256);
+  uint64_t* bar_qk = bars + 0;     // [2] agent -> MMA, softmax: Q, K of buffer set b have landed (or: no further head)
+  uint64_t* bar_v = bars + 2;      // [2] agent -> MMA: V of buffer set b
+  uint64_t* bar_S = bars + 4;      // [2] MMA -> softmax warpgroup r
+  uint64_t* bar_P = bars + 6;      // [2] softmax r -> MMA (one arrival per warp)
+  uint64_t* bar_O = bars + 8;      // [2] MMA -> softmax r
+  uint64_t* bar_free = bars + 10;  // [2] softmax r -> MMA: O_r has left tensor memory
+  uint64_t* bar_ost = bars + 12;   // [2] softmax r -> agent: the O rows of q tile r are staged
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  int* const s_head = reinterpret_cast<int*>(bars + 15);      // [4] head of iteration n at [n & 3]; -1: none
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_norm = p.sqk != nullptr;
+  const int nheads = p.B * p.H;
+  auto split_head = [&](int hd, int& b, int& h) {
+    b = p.h_magic ? static_cast<int>(__umulhi(static_cast<unsigned>(hd), p.h_magic)) : hd / p.H;
+    h = hd - b * p.H;
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);          // qk, v
+    for (int i = 4; i < 6; ++i) mbar_init(bars + i, 1);          // S
+    for (int i = 6; i < 8; ++i) mbar_init(bars + i, 4);          // P
+    for (int i = 8; i < 10; ++i) mbar_init(bars + i, 1);         // O
+    for (int i = 10; i < 14; ++i) mbar_init(bars + i, 4);        // free, ost
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  // per-head bound of the logits: |scale * qh.kh| <= scale * max_c s_c^2 (unit-norm q / k), one warp per head
+  for (int h = warp; h < p.H; h += ATTF_THREADS / 32) {
+    float mx = 0.f;
+    if (has_norm) {
+      const float s0 = p.sqk[h * 64 + lane] * p.sqk_mul, s1 = p.sqk[h * 64 + 32 + lane] * p.sqk_mul;
+      mx = warp_max(fmaxf(s0 * s0, s1 * s1));
+    }
+    if (lane == 0) s_bound[h] = p.scale * mx;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const float sl2 = p.scale * LOG2E;
+
+  if (warp < 8) {
+    // ===================== softmax warpgroups =====================
+    const int wg = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + wg * 256;
+    const int nch = TP >> 4;
+    const int qtok = wg * 128 + row;
+    uint32_t ph = 0;   // bits: 0/1 qk, 2 S, 3 O
+    for (int n = 0;; ++n) {
+      const int bs = n & 1;
+      mbar_wait_flip(bar_qk + bs, ph, bs);
+      const int hd = s_head[n & 3];
+      if (hd < 0) break;
+      if (wg >= nQ) continue;                    // T <= 128: the second warpgroup has no q tile
+      int b, h;
+      split_head(hd, b, h);
+      const float bound = s_bound[h];
+      const bool two_pass = !has_norm || !(bound <= 60.f);
+      uint8_t* const sQ = smem + bs * 3 * R;
+      mbar_wait_flip(bar_S + wg, ph, 2);
+      tc_fence_after_sync();
+      float m2 = bound * LOG2E;                  // log2-domain offset subtracted before exp2
+      if (two_pass) {
+        float mx = -INFINITY;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_lane + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c * 16 + e < T) mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+        m2 = mx * sl2;
+      }
+      // ---- P = exp2(scale log2e S - m2): chunk c of P (8 columns of bf16 pairs) goes over score columns this thread has read
+      const f32x2 sl2x2 = pack2(sl2, sl2), nm2 = pack2(-m2, -m2);
+      f32x2 sum2 = pack2(0.f, 0.f);
+      for (int c0 = 0; c0 < nch; c0 += 2) {
+        uint32_t r[2][16];
+        tmem_ld_32x32b_x16(t_lane + c0 * 16, r[0]);
+        if (c0 + 1 < nch) tmem_ld_32x32b_x16(t_lane + c0 * 16 + 16, r[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = c0 + k;
+          if (c < nch) {
+            uint32_t pk[8];
+            if (c * 16 + 16 <= T) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float a0, a1;
+                unpack2(fma2(pack2(__uint_as_float(r[k][2 * e]), __uint_as_float(r[k][2 * e + 1])), sl2x2, nm2), a0, a1);
+                const f32x2 pv = pack2(ex2_approx(a0), ex2_approx(a1));
+                sum2 = add2(sum2, pv);
+                pk[e] = f32x2_to_bf16x2(pv);
+              }
+            } else {                               // the chunk that holds column T: columns >= T contribute nothing
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float a0, a1;
+                unpack2(fma2(pack2(__uint_as_float(r[k][2 * e]), __uint_as_float(r[k][2 * e + 1])), sl2x2, nm2), a0, a1);
+                const float p0 = c * 16 + 2 * e < T ? ex2_approx(a0) : 0.f, p1 = c * 16 + 2 * e + 1 < T ? ex2_approx(a1) : 0.f;
+                const f32x2 pv = pack2(p0, p1);
+                sum2 = add2(sum2, pv);
+                pk[e] = f32x2_to_bf16x2(pv);
+              }
+            }
+            tmem_st_32x32b_x8(t_lane + c * 8, pk);
+          }
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_P + wg);
+      float t0, t1;
+      unpack2(sum2, t0, t1);
+      const float total = t0 + t1;
+      // ---- O rows: normalise, stage over the (dead) Qh rows of this q tile, hand the tile to the agent's TMA store
+      mbar_wait_flip(bar_O + wg, ph, 3);
+      tc_fence_after_sync();
+      uint32_t o[64];
+      tmem_ld_32x32b_x32(t_lane + 128, o);
+      tmem_ld_32x32b_x32(t_lane + 160, o + 32);
+      tmem_wait_ld();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + wg);
+      if (qtok < T) {
+        const float inv = 1.f / total;
+        const f32x2 inv2 = pack2(inv, inv);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = f32x2_to_bf16x2(mul2(pack2(__uint_as_float(o[8 * c + 2 * e]), __uint_as_float(o[8 * c + 2 * e + 1])), inv2));
+          *reinterpret_cast<uint4*>(sQ + sw128(qtok, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        p.lse[static_cast<long long>(hd) * T + qtok] = (m2 + log2f(total)) * LN2;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ost + wg);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    uint32_t ph = 0;   // bits: 0/1 qk, 2/3 v, 4/5 P, 6/7 free
+    const uint32_t id_s = idesc_kk_n(TP);
+    const int nks = TP >> 4;
+    for (int n = 0;; ++n) {
+      const int bs = n & 1;
+      mbar_wait_flip(bar_qk + bs, ph, bs);
+      if (s_head[n & 3] < 0) break;
+      tc_fence_after_sync();
+      const uint32_t sQ_a = smem_u32(smem + bs * 3 * R), sK_a = sQ_a + R, sV_a = sK_a + R;
+      for (int r = 0; r < nQ; ++r) {
+        if (n > 0) {
+          mbar_wait_flip(bar_free + r, ph, 6 + r);     // the previous head's O_r has left these columns
+          tc_fence_after_sync();
+        }
+        const uint64_t da = umma_smem_desc(sQ_a + r * 16384, 16, 1024), db = umma_smem_desc(sK_a, 16, 1024);
+        const uint32_t td = tmem_base + r * 256;
+        if (elect_one()) {
+          umma_bf16_ss(td, da, db, id_s, 0u);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(td, da + 2 * ks, db + 2 * ks, id_s);
+          umma_commit(bar_S + r);
+        }
+        __syncwarp();
+      }
+      mbar_wait_flip(bar_v + bs, ph, 2 + bs);
+      for (int r = 0; r < nQ; ++r) {
+        mbar_wait_flip(bar_P + r, ph, 4 + r);
+        tc_fence_after_sync();
+        const uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
+        const uint32_t td = tmem_base + r * 256;
+        if (elect_one()) {
+          umma_bf16_ts(td + 128, td, dv, IDESC_KM(64), 0u);
+#pragma unroll
+          for (int ks = 1; ks < 16; ++ks)
+            if (ks < nks) umma_bf16_ts(td + 128, td + ks * 8, dv + 128 * ks, IDESC_KM(64), 1u);
+          umma_commit(bar_O + r);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== agent (one thread): head sequence, tile loads, O stores =====================
+    auto load_head = [&](int hd, int bs) {
+      int b, h;
+      split_head(hd, b, h);
+      uint8_t* const sQ = smem + bs * 3 * R;
+      mbar_arrive_expect_tx(bar_qk + bs, 2 * R);
+      tma_load_3d(&p.tq, bar_qk + bs, sQ, h * 64, 0, b);
+      tma_load_3d(&p.tk, bar_qk + bs, sQ + R, h * 64, 0, b);
+      mbar_arrive_expect_tx(bar_v + bs, R);
+      tma_load_3d(&p.tv, bar_v + bs, sQ + 2 * R, h * 64, 0, b);
+    };
+    auto no_head = [&](int bs) {       // the waiters of this buffer set find s_head = -1
+      mbar_arrive(bar_qk + bs);
+      mbar_arrive(bar_v + bs);
+    };
+    // heads 0 and 1 of the CTA are fixed, every further one is claimed from the device-wide counter two heads ahead; the
+    // counter's answer is first looked at an iteration after the request (148 CTAs hit one address)
+    const int id0 = static_cast<int>(blockIdx.x), id1 = static_cast<int>(blockIdx.x + gridDim.x);
+    s_head[0] = id0;
+    load_head(id0, 0);
+    s_head[1] = id1 < nheads ? id1 : -1;
+    if (id1 < nheads) load_head(id1, 1); else no_head(1);
+    int claim_raw = id1 < nheads ? atomicAdd(p.work, 1) : nheads;
+    uint32_t ph = 0;   // bits: 0/1 ost
+    for (int n = 0;; ++n) {
+      const int hd = s_head[n & 3];
+      if (hd < 0) break;
+      const int bs = n & 1;
+      int b, h;
+      split_head(hd, b, h);
+      uint8_t* const sQ = smem + bs * 3 * R;
+      for (int r = 0; r < nQ; ++r) {
+        mbar_wait_flip(bar_ost + r, ph, r);
+        tma_store_3d(&p.to, sQ + r * 16384, h * 64, r * 128, b);
+      }
+      bulk_commit_group();
+      // buffer set bs is free (every product of head n has completed before its O rows were staged): head n + 2 goes there
+      const int nxt = claim_raw + 2 * static_cast<int>(gridDim.x);
+      const bool valid = nxt < nheads;
+      s_head[(n + 2) & 3] = valid ? nxt : -1;
+      if (valid) {
+        bulk_wait_group_read<0>();           // the O stores have read the Qh rows
+        load_head(nxt, bs);
+        claim_raw = atomicAdd(p.work, 1);
+      } else {
+        no_head(bs);
+        claim_raw = nheads;
+      }
+    }
+    bulk_wait_group_read<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicInc(reinterpret_cast<unsigned*>(p.work) + 1, gridDim.x - 1) == gridDim.x - 1) {
+      __threadfence();
+      atomicExch(p.work, 0);
+    }
+  }
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1412,14 +1706,6 @@ constexpr int ATT3_EPI = 128;
 template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
-// barrier parities of a role live as bits of ONE register (MEASURED: ten separate phase variables put the MMA warp's loop
-// state into local memory, and with 224 KB of shared memory the L1 holds next to nothing: every such reload is an L2 round
-// trip on the path that issues the products)
-__device__ __forceinline__ void mbar_wait_flip(uint64_t* bar, uint32_t& phases, int bit) {
-  mbar_wait(bar, (phases >> bit) & 1u);
-  phases ^= 1u << bit;
-}
-
 // 64 accumulator columns of this thread's TMEM lane -> registers
 __device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, uint32_t (&r)[64]) {
   tmem_ld_32x32b_x32(taddr, r);
@@ -2118,6 +2404,7 @@ static long long* g_att_dbg = nullptr;
 // launch leaves its pair at zero), so launches on different streams do not share one and graph replays reuse their own
 __device__ int g_att_work[2 * 64];
 static std::atomic<unsigned> g_att_work_slot{0};
+static std::atomic<int> g_fwd_variant{2};   // nvit_attention_fwd_variant: 1 = attn_fwd_kernel (one head per CTA, two CTAs per SM), 2 = attn_fwd_ws_kernel
 static std::atomic<int> g_bwd_variant{3};   // nvit_attention_bwd_variant: 1 = attn_bwd_kernel, 2 = attn_bwd_ws_kernel, 3 = attn_bwd_ws3_kernel
 #ifdef NVIT_BENCH_HOOKS
 extern "C" int nvit_attention_debug(void* dev_buf_256_int64) {   // measurement aid: phase timestamps, see ATT_MARK
@@ -2137,9 +2424,14 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   NVIT_REQUIRE((ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "nvit_attention_fwd: out must be 16-byte aligned rows");
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  if ((rc = make_head_tmap(&p.tq, q, ldq, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T))) return rc;
-  if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T))) return rc;
+  const int TPf = (int)((T + 15) / 16 * 16);
+  // the persistent kernel takes q / k that need no work in shared memory (pre-normalised, or plain attention) and keeps tiles
+  // of exactly TP rows; q / k normalised in place go to the one-head-per-CTA kernel with its 256-row tiles
+  const bool ws = g_fwd_variant.load(std::memory_order_relaxed) == 2 && !(sqk != nullptr && inv_q == nullptr) && H <= 256;
+  const int in_rows = ws ? TPf : ATT_ROWS;
+  if ((rc = make_head_tmap(&p.tq, q, ldq, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.tk, k, ldk, (int)B, (int)H, (int)T, in_rows))) return rc;
+  if ((rc = make_head_tmap(&p.tv, v, ldv, (int)B, (int)H, (int)T, in_rows))) return rc;
   if ((rc = make_head_tmap(&p.to, out, ldo, (int)B, (int)H, (int)T, 128))) return rc;
   p.ldo = ldo;
   p.lse = lse;
@@ -2157,9 +2449,23 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   int dev;
   if (once.needed(&dev)) {
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    NVIT_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_MAX_SMEM));
     once.mark(dev);
   }
-  launch(attn_fwd_kernel, (unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), p);
+  if (ws) {
+    const long long heads = B * H;
+    p.h_magic = (H >= 2 && heads * H < (1ll << 32)) ? static_cast<unsigned>((1ull << 32) / static_cast<unsigned long long>(H) + 1ull) : 0u;
+    int* work_base = nullptr;
+    NVIT_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&work_base), g_att_work));
+    p.work = work_base + 2 * (g_att_work_slot.fetch_add(1, std::memory_order_relaxed) % 64u);
+    const size_t tile = 128ull * TPf;
+    const size_t tiles_end = std::max<size_t>(6 * tile, 3 * tile + 16384ull * p.nQ);
+    const size_t smem = tiles_end + 256 * 4 + 256;            // two (Q, K, V) sets, the per-head bounds, barriers
+    const int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
+    launch(attn_fwd_ws_kernel, (unsigned)grid, ATTF_THREADS, smem, static_cast<cudaStream_t>(stream), p);
+  } else {
+    launch(attn_fwd_kernel, (unsigned)(B * H), ATT_FWD_THREADS, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream), p);
+  }
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
 }
@@ -2238,6 +2544,12 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
       launch(attn_bwd_ws_kernel<8>, (unsigned)grid, 8 * 32 + 32, (size_t)smem, static_cast<cudaStream_t>(stream), p);
   }
   NVIT_CUDA_CHECK(cudaGetLastError());
+  return NVIT_OK;
+}
+
+extern "C" int nvit_attention_fwd_variant(int variant) {   // tuning switch (include/nvit_b200_tuning.h): same results
+  NVIT_REQUIRE(variant == 1 || variant == 2, "nvit_attention_fwd_variant: 1 (one head per CTA, two CTAs per SM) or 2 (persistent, warp-specialised; default)");
+  g_fwd_variant.store(variant, std::memory_order_relaxed);
   return NVIT_OK;
 }
 

@@ -49,7 +49,10 @@ def timeit(f, n=20):
 
 
 fwd()
-print(f"attention fwd: median {timeit(fwd)[0]:.1f} us   ({4.0 * B * H * T * T * 64 / 1e12:.4f} TFLOP)")
+for v in (1, 2):
+    _lib.call("nvit_attention_fwd_variant", v)
+    med, best = timeit(fwd)
+    print(f"attention fwd variant {v}: median {med:.1f} us, best {best:.1f} us   ({4.0 * B * H * T * T * 64 / 1e12:.4f} TFLOP)")
 for v in (1, 2, 3):
     _lib.call("nvit_attention_bwd_variant", v)
     med, best = timeit(bwd)
