@@ -356,6 +356,10 @@ def main():
     ap.add_argument("--unfused-tail", action="store_true", help="separate sumsq / AdamW / normalize / cast kernels (A/B)")
     ap.add_argument("--bucket-blocks", type=int, default=1, help="data parallel: transformer blocks per overlapped all-reduce bucket")
     ap.add_argument("--sm-budget", type=int, default=0, help="data parallel: SMs the persistent kernels may use (0 = all)")
+    ap.add_argument("--overlap-reserve-sms", type=int, default=0, help="with --overlap: SMs the kernel launches right after a bucket's "
+                                                                        "all-reduce leave to NCCL (0 = none)")
+    ap.add_argument("--overlap-reserve-calls", type=int, default=4, help="with --overlap-reserve-sms: how many launches after each bucket")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="data parallel: NCCL_MAX_CTAS for the process group (0 = NCCL's default)")
     ap.add_argument("--no-dp-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -373,12 +377,15 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        if args.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     cfg = ViTConfig(**config_dict(args.config, args.variant))
     trainer_kwargs = dict(learning_rate=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, cuda_graph=not args.no_graph,
                           overlap_allreduce=args.overlap, sm_budget=args.sm_budget, bucket_blocks=args.bucket_blocks,
+                          overlap_reserve_sms=args.overlap_reserve_sms, overlap_reserve_calls=args.overlap_reserve_calls,
                           fused_tail=not args.unfused_tail)
 
     dp_parity = None

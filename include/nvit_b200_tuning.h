@@ -42,9 +42,10 @@ int nvit_attention_bwd_variant(int variant);
 /* 1 = the GEMM epilogue returns the accumulator without reading it (main-loop-only time), 2 = it reads and converts but
  * neither stages nor stores, 3 / 4 = finer cuts of the gate-backward epilogue. */
 int nvit_gemm_debug(int mode);
-/* device buffer of 256 int64 receiving clock64() phase marks of the first 8 CTAs of the next attention launches
- * (NULL switches it off) */
-int nvit_attention_debug(void* dev_buf_256_int64);
+/* device buffer of 16384 int64 receiving clock64() / globaltimer marks of the next attention launches (NULL switches it off):
+ * phase marks of the roles of every CTA of the persistent backward kernel (4th head), entry / exit time and SM id of every CTA;
+ * scripts/attn_bwd_phases_v3.py and scripts/attn_bwd_cta_times.py decode it */
+int nvit_attention_debug(void* dev_buf_16384_int64);
 #endif
 
 #ifdef __cplusplus

@@ -133,8 +133,22 @@ def last_error() -> str:
 PROBE = None
 
 
+# Data-parallel overlap (train.GradReducer): after a bucket's all-reduce has been put on the side stream, the next `n` entry-point
+# calls size their persistent grids for `budget` SMs, so that NCCL's CTAs find free SMs beside them; then all SMs again.
+_WINDOW = [0]
+
+
+def sm_budget_window(n_calls: int, budget: int) -> None:
+    load().nvit_set_sm_budget(int(budget))
+    _WINDOW[0] = int(n_calls)
+
+
 def call(name: str, *args) -> None:
     """Call an entry point; a non-zero status becomes a RuntimeError carrying nvit_last_error()."""
+    if _WINDOW[0] > 0:
+        _WINDOW[0] -= 1
+        if _WINDOW[0] == 0:
+            load().nvit_set_sm_budget(0)
     if PROBE is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

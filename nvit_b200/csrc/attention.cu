@@ -46,11 +46,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// L2 prefetch of a [rows x 64] head tile: the box travels HBM -> L2 now, the real load (same map and coordinates) later
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 // barrier parities of a role live as bits of ONE register (MEASURED: ten separate phase variables put the MMA warp's loop
 // state into local memory, and with 224 KB of shared memory the L1 holds next to nothing: every such reload is an L2 round
 // trip on the path that issues the products)
@@ -123,7 +118,6 @@ struct alignas(64) AttnParams {
                     // is ~40 dependent instructions, and the per-head set-up of its roles sits on the critical path)
   int* work;        // attn_bwd_ws3_kernel: {next unclaimed head - 2 gridDim.x, CTAs that have finished}; both return to 0 by themselves
   long long* dbg;   // measurement aid (nvit_attention_debug): clock64 marks of thread 0 of the first 8 CTAs, 32 slots each
-  int no_prefetch;  // A/B aid: v3 without the L2 prefetch of the next head's V / dO / O
 };
 
 #ifdef NVIT_BENCH_HOOKS
@@ -133,15 +127,13 @@ struct alignas(64) AttnParams {
 #define ATT2_MARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == 0) p.dbg[blockIdx.x * 64 + (i)] = clock64(); } while (0)
 #define ATT2_MMARK(i) do { if (p.dbg && n == 1 && blockIdx.x < 4 && threadIdx.x == ATT2_COMPUTE) p.dbg[blockIdx.x * 64 + 32 + (i)] = clock64(); } while (0)
 // v3 kernel (buffer of 16384 int64): 96 slots per CTA from [1024 + 96 cta]: [0,32) thread 0 of the compute warps, [32,64) lane 0 of the MMA warp (thread
-// 384), [64,96) thread 0 of the epilogue warpgroup (thread 256); FOURTH head of CTAs 0 and 100 (steady state; slots 0 and 1)
+// 384), [64,96) thread 0 of the epilogue warpgroup (thread 256); FOURTH head of every CTA (steady state)
 #define ATT3_MARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 0) p.dbg[1024 + blockIdx.x * 96 + (i)] = clock64(); } while (0)
 #define ATT3_MMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 384) p.dbg[1024 + blockIdx.x * 96 + 32 + (i)] = clock64(); } while (0)
 #define ATT3_EMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 256) p.dbg[1024 + blockIdx.x * 96 + 64 + (i)] = clock64(); } while (0)
 // [512 + 2 cta + k]: globaltimer when CTA `cta` entered (k = 0) and left (k = 1) the kernel (buffer of 1024 int64)
 #define ATT3_CTAMARK(k) do { if (p.dbg && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.dbg[512 + blockIdx.x * 2 + (k)] = gt; \
     if ((k) == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[512 + 296 + blockIdx.x] = sm; } } } while (0)
-// [192 + 32 cta + n]: when the compute warps of the first two CTAs entered their n-th head (n < 31), [.. + 31]: when they left the last
-#define ATT3_HEADMARK(n) do { } while (0)
 #else
 #define ATT_MARK(i) do { } while (0)
 #define ATT2_MARK(i) do { } while (0)
@@ -149,7 +141,6 @@ struct alignas(64) AttnParams {
 #define ATT3_MARK(i) do { } while (0)
 #define ATT3_MMARK(i) do { } while (0)
 #define ATT3_EMARK(i) do { } while (0)
-#define ATT3_HEADMARK(n) do { } while (0)
 #define ATT3_CTAMARK(k) do { } while (0)
 #endif
 
@@ -2069,7 +2060,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       }
       const float* const lse_n = s_lse + (n & 1) * TP;
       ATT3_MARK(0);
-      ATT3_HEADMARK(n);
       int i = 0;
       for (int j = 0; j < nK; ++j) {
         const int kv = j * 128 + row;
@@ -2189,7 +2179,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attn_bwd_ws3_kernel(const __g
       }
       ATT3_MARK(31);
     }
-    ATT3_HEADMARK(31);
   } else {
     // ===================== epilogue warpgroup: one thread per accumulator row =====================
     setmaxnreg_dec<ATT3_REG_EPI>();
@@ -2444,7 +2433,6 @@ extern "C" int nvit_attention_fwd(const void* q, const void* k, const void* v, i
   p.nQ = (int)((T + 127) / 128);
   p.nK = p.nQ;
   p.dbg = g_att_dbg;
-  { static const int np = getenv("NVIT_ATTN_NO_PREFETCH") ? atoi(getenv("NVIT_ATTN_NO_PREFETCH")) : 0; p.no_prefetch = np; }
   static DeviceOnce once;
   int dev;
   if (once.needed(&dev)) {
@@ -2529,7 +2517,9 @@ extern "C" int nvit_attention_bwd(const void* q, const void* k, const void* v, i
     NVIT_REQUIRE(smem <= ATT2_MAX_SMEM, "nvit_attention_bwd: shared-memory plan does not fit (T = %lld)", (long long)T);
     const long long heads = B * H;
     int grid = (int)(heads < nvit_num_sms() ? heads : nvit_num_sms());
-    { static const int ge = getenv("NVIT_ATTN_GRID") ? atoi(getenv("NVIT_ATTN_GRID")) : 0; if (ge > 0 && ge < grid) grid = ge; }   // A/B aid
+#ifdef NVIT_BENCH_HOOKS
+    { static const int ge = getenv("NVIT_ATTN_GRID") ? atoi(getenv("NVIT_ATTN_GRID")) : 0; if (ge > 0 && ge < grid) grid = ge; }   // scripts/attn_bwd_cta_times.py
+#endif
     // v3 (epilogue warpgroup) needs both (Q, K) pairs and q / k that are not normalised in place; otherwise v2 runs
     const bool v3 = variant == 3 && p.dbuf && (sqk == nullptr || inv_q != nullptr) && H >= 2 && heads * H < (1ll << 32);   // (h_magic)
     if (v3) {

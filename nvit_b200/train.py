@@ -29,7 +29,8 @@ class GradReducer:
     flushed at `finish()`.
     """
 
-    def __init__(self, flat: torch.Tensor, group=None, min_bucket: int = 1 << 20, bucket_elems: int = 0):
+    def __init__(self, flat: torch.Tensor, group=None, min_bucket: int = 1 << 20, bucket_elems: int = 0,
+                 reserve_sms: int = 0, reserve_calls: int = 0):
         """`bucket_elems` > 0 merges adjacent large ranges (consecutive transformer blocks arrive back to front) until a
         bucket holds at least that many elements: fewer, longer collectives beside the backward pass."""
         import torch.distributed as dist
@@ -44,6 +45,11 @@ class GradReducer:
         self.small: list[tuple[int, int]] = []
         self.comm_stream = torch.cuda.Stream() if flat.is_cuda else None
         self.reduced_elems = 0
+        # `reserve_sms` > 0: the `reserve_calls` kernel launches that follow a bucket's all-reduce leave that many SMs free
+        # (nvit_set_sm_budget for a window of launches): NCCL's CTAs cannot share an SM with a 227 KB persistent CTA, and a
+        # collective that has to wait for SMs costs the kernel beside it a wave
+        self.reserve_sms, self.reserve_calls = reserve_sms, reserve_calls
+        self.total_sms = torch.cuda.get_device_properties(flat.device).multi_processor_count if flat.is_cuda else 0
 
     def _issue(self, lo: int, hi: int):
         if hi <= lo or self.world == 1:
@@ -56,6 +62,9 @@ class GradReducer:
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
                 self.pending.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self.reserve_sms > 0 and self.reserve_calls > 0:
+                from . import _lib
+                _lib.sm_budget_window(self.reserve_calls, self.total_sms - self.reserve_sms)
         else:
             self.pending.append(self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -156,6 +165,7 @@ class Trainer:
     def __init__(self, model, learning_rate: float = 1e-3, betas=(0.9, 0.95), weight_decay: float = 0.1, grad_clip: float = 1.0,
                  eps: float = 1e-8, gradient_accumulation_steps: int = 1, process_group=None, data_parallel: bool | None = None,
                  cuda_graph: bool = False, graph_warmup_steps: int = 2, overlap_allreduce: bool = False, sm_budget: int = 0,
+                 overlap_reserve_sms: int = 0, overlap_reserve_calls: int = 0,
                  bucket_blocks: int = 1, fused_tail: bool = True,
                  consistency_weight: float = 0.1, smoothness_weight: float = 0.1):
         import torch.distributed as dist
@@ -180,6 +190,7 @@ class Trainer:
         # because NCCL's CTAs cannot share an SM with the persistent 227 KB GEMM CTAs and every bucket costs the GEMM
         # running beside it a wave; overlap_allreduce=True keeps the bucketed form available.
         self.overlap = overlap_allreduce
+        self.overlap_reserve = (int(overlap_reserve_sms), int(overlap_reserve_calls))
         self.bucket_blocks = max(1, bucket_blocks)   # transformer blocks per overlapped bucket
         # clip + AdamW + normalize_matrices + bf16 operand emit + zero_grad as one launch (nvit_adamw_norm_fused);
         # False keeps the separate kernels (sumsq, adamw_flat, weight_norm_multi, cast, memset)
@@ -235,7 +246,9 @@ class Trainer:
             if self.dp:
                 lo, hi = eng.block_grad_range(0)
                 self.reducer = GradReducer(eng.G32, self.group,
-                                           bucket_elems=(hi - lo) * self.bucket_blocks if self.bucket_blocks > 1 else 0)
+                                           bucket_elems=(hi - lo) * self.bucket_blocks if self.bucket_blocks > 1 else 0,
+                                           reserve_sms=self.overlap_reserve[0] if self.overlap else 0,
+                                           reserve_calls=self.overlap_reserve[1] if self.overlap else 0)
                 self._broadcast_params()
 
     def _drop_graph(self):

@@ -82,3 +82,23 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnvit_b200.so")
     with pytest.raises(RuntimeError, match="no fallback"):
         _lib.load()
+
+
+def test_sm_budget_window_counts_entry_point_calls():
+    """Data-parallel overlap: after a bucket's all-reduce the next n entry-point calls size their grids for fewer SMs, then all
+    SMs again (nvit_b200._lib.sm_budget_window; no kernel runs here)."""
+    from nvit_b200 import _lib
+    lib = _lib.load()
+    total = lib.nvit_sm_count()
+    try:
+        _lib.sm_budget_window(3, total - 8)
+        assert lib.nvit_sm_count() == total - 8
+        _lib.call("nvit_set_pdl", 0)
+        _lib.call("nvit_set_pdl", 0)
+        assert lib.nvit_sm_count() == total - 8
+        _lib.call("nvit_set_pdl", 0)
+        assert lib.nvit_sm_count() == total
+        _lib.call("nvit_set_pdl", 0)
+        assert lib.nvit_sm_count() == total
+    finally:
+        lib.nvit_set_sm_budget(0)
