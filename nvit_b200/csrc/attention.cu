@@ -64,7 +64,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // the O tile + the delta jobs) made the backward 460 -> 587 us: the set-up phase grew from 2.7 k to 19 k cycles.
 // MEASURED: moving every 2nd / 3rd / 4th exponential of the softmax passes from the SFU to a degree-4 polynomial on the
 // FMA pipe (the FlashAttention-4 trade) made both kernels slower (fwd 150 -> 166 / 159 / 157 us, bwd 490 -> 505 / 494 /
-// 496 us): these passes are bound by issue slots and latency, not by ex2 throughput.
+// 496 us): these passes are bound by issue slots and latency, not by ex2 throughput.  Round 2, persistent forward (whose
+// exponential pass, 4.4 k cycles per q tile for the 53 k exponentials of the two warpgroups, sits at 75 % of the SFU rate): every
+// other PAIR through a cubic in packed fp32 (FFMA2, 7.5e-5 relative error): 93.1 us against 91 us, the pass still 4.47 k cycles
+// (scripts/attn_fwd_phases.py): at one half the packed-pair FMA pipe is the new limit (per 16-column chunk 40 FFMA2 / FADD2 at
+// two issue cycles each + 8 MUFU + 8 F2FP + 16 integer against 16 + 16 MUFU before), and the balance point near one quarter
+// would return ~0.9 k of a head's 7.1 k cycles = 0.14 ms per step before the power cap takes its share.  Not pursued.
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a 128B-swizzled tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
@@ -132,6 +137,8 @@ struct alignas(64) AttnParams {
 #define ATT3_MMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 384) p.dbg[1024 + blockIdx.x * 96 + 32 + (i)] = clock64(); } while (0)
 #define ATT3_EMARK(i) do { if (p.dbg && n == 3 && threadIdx.x == 256) p.dbg[1024 + blockIdx.x * 96 + 64 + (i)] = clock64(); } while (0)
 // [512 + 2 cta + k]: globaltimer when CTA `cta` entered (k = 0) and left (k = 1) the kernel (buffer of 1024 int64)
+// persistent forward: [1024 + 96 cta + 32 role + i], roles: thread 0 (softmax warpgroup 0), thread 128 (warpgroup 1), thread 256 (MMA warp); 4th head
+#define ATTF_MARK(role, i) do { if (p.dbg && n == 3 && threadIdx.x == (role) * 128) p.dbg[1024 + blockIdx.x * 96 + (role) * 32 + (i)] = clock64(); } while (0)
 #define ATT3_CTAMARK(k) do { if (p.dbg && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.dbg[512 + blockIdx.x * 2 + (k)] = gt; \
     if ((k) == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[512 + 296 + blockIdx.x] = sm; } } } while (0)
 #else
@@ -142,6 +149,7 @@ struct alignas(64) AttnParams {
 #define ATT3_MMARK(i) do { } while (0)
 #define ATT3_EMARK(i) do { } while (0)
 #define ATT3_CTAMARK(k) do { } while (0)
+#define ATTF_MARK(role, i) do { } while (0)
 #endif
 
 __host__ __device__ constexpr uint32_t IDESC_KM(int N) { return umma_idesc_bf16(128, N, 0, 1); }  // A K-major, B MN-major
@@ -448,6 +456,7 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
 constexpr int ATTF_THREADS = 320;
 __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __grid_constant__ AttnParams p) {
   pdl_enter();
+  ATT3_CTAMARK(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int T = p.T, TP = p.TP, nQ = p.nQ;
@@ -510,6 +519,7 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
     uint32_t ph = 0;   // bits: 0/1 qk, 2 S, 3 O
     for (int n = 0;; ++n) {
       const int bs = n & 1;
+      ATTF_MARK(wg, 0);
       mbar_wait_flip(bar_qk + bs, ph, bs);
       const int hd = s_head[n & 3];
       if (hd < 0) break;
@@ -519,8 +529,10 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
       const float bound = s_bound[h];
       const bool two_pass = !has_norm || !(bound <= 60.f);
       uint8_t* const sQ = smem + bs * 3 * R;
+      ATTF_MARK(wg, 1);
       mbar_wait_flip(bar_S + wg, ph, 2);
       tc_fence_after_sync();
+      ATTF_MARK(wg, 2);
       float m2 = bound * LOG2E;                  // log2-domain offset subtracted before exp2
       if (two_pass) {
         float mx = -INFINITY;
@@ -575,12 +587,14 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_P + wg);
+      ATTF_MARK(wg, 3);
       float t0, t1;
       unpack2(sum2, t0, t1);
       const float total = t0 + t1;
       // ---- O rows: normalise, stage over the (dead) Qh rows of this q tile, hand the tile to the agent's TMA store
       mbar_wait_flip(bar_O + wg, ph, 3);
       tc_fence_after_sync();
+      ATTF_MARK(wg, 4);
       uint32_t o[64];
       tmem_ld_32x32b_x32(t_lane + 128, o);
       tmem_ld_32x32b_x32(t_lane + 160, o + 32);
@@ -604,6 +618,7 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ost + wg);
+      ATTF_MARK(wg, 5);
     }
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
@@ -615,9 +630,11 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
     const int nks = TP >> 4;
     for (int n = 0;; ++n) {
       const int bs = n & 1;
+      ATTF_MARK(2, 0);
       mbar_wait_flip(bar_qk + bs, ph, bs);
       if (s_head[n & 3] < 0) break;
       tc_fence_after_sync();
+      ATTF_MARK(2, 1);
       const uint32_t sQ_a = smem_u32(smem + bs * 3 * R), sK_a = sQ_a + R, sV_a = sK_a + R;
       for (int r = 0; r < nQ; ++r) {
         if (n > 0) {
@@ -633,8 +650,10 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
           umma_commit(bar_S + r);
         }
         __syncwarp();
+        ATTF_MARK(2, 2 + r);
       }
       mbar_wait_flip(bar_v + bs, ph, 2 + bs);
+      ATTF_MARK(2, 4);
       for (int r = 0; r < nQ; ++r) {
         mbar_wait_flip(bar_P + r, ph, 4 + r);
         tc_fence_after_sync();
@@ -648,6 +667,7 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
           umma_commit(bar_O + r);
         }
         __syncwarp();
+        ATTF_MARK(2, 5 + r);
       }
     }
   } else if (lane == 0) {
@@ -704,6 +724,7 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
   }
   tc_fence_before_sync();
   __syncthreads();
+  ATT3_CTAMARK(1);
   if (tid == 0) {
     __threadfence();
     if (atomicInc(reinterpret_cast<unsigned*>(p.work) + 1, gridDim.x - 1) == gridDim.x - 1) {
