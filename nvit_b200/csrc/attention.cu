@@ -547,6 +547,8 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
         m2 = mx * sl2;
       }
       // ---- P = exp2(scale log2e S - m2): chunk c of P (8 columns of bf16 pairs) goes over score columns this thread has read
+      // (MEASURED: fetching the chunk pair after this one from tensor memory while this one is worked on - two register sets, 167
+      // registers - leaves the pass at 4.47 k cycles and the kernel at 93.1 us: the pass does not wait on tcgen05.ld latency.)
       const f32x2 sl2x2 = pack2(sl2, sl2), nm2 = pack2(-m2, -m2);
       f32x2 sum2 = pack2(0.f, 0.f);
       for (int c0 = 0; c0 < nch; c0 += 2) {

@@ -10,6 +10,7 @@
 //   bwd : read g, h, x [, h0], write dh, dx [, dh0]; per-channel dalpha and scalar dskip reduced in-CTA then atomically.
 // No epsilon anywhere, as in the reference (a zero row gives NaN there too).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nvit {
 
@@ -432,18 +433,27 @@ extern "C" int nvit_residual_bwd(const float* g, const float* h, const void* x_b
   // least two stages per warp; one persistent CTA per SM with as many warps (8, 6 or 4) and stages (<= 4) as 227 KB hold.
   const uintptr_t align_all = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(x_bf16) |
                               reinterpret_cast<uintptr_t>(h0) | reinterpret_cast<uintptr_t>(dh);
-  // MEASURED (scripts/hbm_kernels_bench.py, M = 50 176, registers -> staged): C = 768: plain 129 -> 114 us, += 140 -> 137,
-  // skip 168 -> 175, skip and += 302 -> 200; C = 1024: 177 -> 147, 245 -> 183, 238 -> 238, 404 -> 262.  The skip form
-  // without += is the one case the ring does not help (two stages only, the longest arithmetic chain per row), so the
-  // automatic mode keeps it in registers; small widths (tiny models, microsecond launches) stay on the register form too.
-  const bool want_staged = g_bwd_staged == 1 || (g_bwd_staged == 2 && C >= 512 && !(h0 && !dh_accumulate));
+  // MEASURED (scripts/hbm_kernels_bench.py, M = 50 176, registers -> staged with eight warps): C = 768: plain 129 -> 114 us,
+  // += 140 -> 137, skip 168 -> 175, skip and += 302 -> 200; C = 1024: 177 -> 147, 245 -> 183, 238 -> 238, 404 -> 262.  The skip
+  // form without += has the longest arithmetic chain per row and the largest stage: with eight warps only two stages fit and the
+  // ring does not help.  MEASURED (scripts/residual_w_sweep.py, C = 768, us): skip form 6 warps x 3 stages 157, 4 x 4 183
+  // (registers 168); += form 8 warps 134, 6 warps 136; plain form 113 / 130.  So the skip form alone starts at six warps and takes
+  // the ring only where three stages fit (C <= 832), else it stays in registers; small widths (tiny models, microsecond
+  // launches) stay on the register form too.
+  const bool skip_only = h0 && !dh_accumulate;
+  const size_t stage = static_cast<size_t>(C) * 4 * (2 + (h0 ? 1 : 0) + (dh_accumulate ? 1 : 0)) + static_cast<size_t>(C) * 2;
+  auto ring_bytes = [&](int W, int ns) { return ((smem + 8u * W * ns + 127u) & ~size_t(127)) + static_cast<size_t>(W) * ns * stage; };
+  const bool want_staged = g_bwd_staged == 1 || (g_bwd_staged == 2 && C >= 512 && (!skip_only || ring_bytes(6, 3) <= kStagedSmemMax));
   if (want_staged && (C % 8) == 0 && (align_all & 15) == 0) {
-    const size_t stage = static_cast<size_t>(C) * 4 * (2 + (h0 ? 1 : 0) + (dh_accumulate ? 1 : 0)) + static_cast<size_t>(C) * 2;
-    for (int W = 8; W >= 4; W -= 2) {
+    int W0 = skip_only ? 6 : 8;
+#ifdef NVIT_BENCH_HOOKS
+    if (const char* e = getenv("NVIT_RES_W")) W0 = atoi(e);   // measurement only: first warp count tried
+#endif
+    for (int W = W0; W >= 4; W -= 2) {
       int ns = 4;
       size_t total = 0;
       for (; ns >= 2; --ns) {
-        total = ((smem + 8u * W * ns + 127u) & ~size_t(127)) + static_cast<size_t>(W) * ns * stage;
+        total = ring_bytes(W, ns);
         if (total <= kStagedSmemMax) break;
       }
       if (ns < 2) continue;

@@ -1,0 +1,87 @@
+// Probe: tensor-memory read rate of tcgen05.ld (32x32b, x16 / x32 per instruction) per SM, with 4 / 8 / 16 warps reading
+// their own lane quarter back to back, and the same with 16 ex2.approx per 16 columns in between (the softmax pass of the
+// attention forward kernel: is it the SFU or the TMEM read path that takes 4.4 k cycles per 128 x 208 tile pair?).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -I nvit_b200/csrc -o gpurun_out/tmem_read_bw scripts/probes/tmem_read_bw.cu
+#include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+namespace nvit { int nvit_num_sms() { return 148; } void nvit_set_error(const char*, ...) {} }
+using namespace nvit;
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// mode 0: x16 loads only; 1: x32 loads only; 2: x16 loads + 16 ex2 each; 3: 16 ex2 per step without loads
+template <int MODE>
+__global__ void __launch_bounds__(512) probe(long long* out, float* sink, int iters) {
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(&tptr, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = tptr + ((uint32_t)((warp & 3) * 32) << 16);
+  float acc = 0.f, ac[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const float fb = -(float)(it & 63);
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {                    // 13 x 16 = 208 columns: one row of scores
+      uint32_t r[32];
+      if (MODE == 0 || MODE == 2) {
+        tmem_ld_32x32b_x16(base + c * 16, r);
+        tmem_wait_ld();
+      } else if (MODE == 1) {
+        tmem_ld_32x32b_x32(base + (c & 7) * 32, r);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(fb - (float)(c * 16 + e) * 0.25f);
+      }
+      if (MODE >= 2) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ac[e & 3] += ex2a(__uint_as_float(r[e]));
+      } else {
+        acc += __uint_as_float(r[0]) + __uint_as_float(r[MODE == 1 ? 31 : 15]);
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  acc += ac[0] + ac[1] + ac[2] + ac[3];
+  if (acc == 12345.678f) sink[0] = acc;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tptr, 512);
+}
+
+template <int MODE>
+static void run(const char* what, int warps, int iters, long long* d_out, float* d_sink) {
+  probe<MODE><<<148, warps * 32>>>(d_out, d_sink, iters);
+  probe<MODE><<<148, warps * 32>>>(d_out, d_sink, iters);
+  cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < 148; ++i) avg += h[i];
+  avg /= 148;
+  const double cols = 13.0 * (MODE == 1 ? 32 : 16);
+  const double bytes = (double)warps * iters * cols * 32 * 4;
+  printf("%-28s warps %2d: %9.0f cycles, %6.1f B/cycle/SM, %5.2f cycles per warp per 16 columns (%s)\n", what, warps, avg, bytes / avg,
+         avg / (iters * cols / 16.0), cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+  long long* d_out;
+  float* d_sink;
+  cudaMalloc(&d_out, 148 * sizeof(long long));
+  cudaMalloc(&d_sink, 4);
+  const int iters = 200;
+  for (int w : {4, 8, 16}) run<0>("ld x16, wait each", w, iters, d_out, d_sink);
+  for (int w : {4, 8, 16}) run<1>("ld x32, wait each", w, iters, d_out, d_sink);
+  for (int w : {4, 8, 16}) run<2>("ld x16 + 16 ex2", w, iters, d_out, d_sink);
+  for (int w : {4, 8, 16}) run<3>("16 ex2 only (bytes nominal)", w, iters, d_out, d_sink);
+  return 0;
+}
