@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 2) attn_fwd_kernel(const __gr
 //                    thread-local, and P goes back over the row's own dead score columns chunk by chunk (P chunk c lands in
 //                    columns the thread has already read), so there is no barrier between reading S and writing P and no P
 //                    held in registers; afterwards the warpgroup normalises its O rows into the dead Qh rows;
-//   warp 8           MMA issuer: S_0, S_1 back to back, O_r = P_r V when warpgroup r has written P_r; the next head's S_r goes
-//                    out as soon as warpgroup r has drained O_r, i.e. while the other warpgroup may still be in this head;
+//   warp 8           MMA issuer: the q tiles alternate - S_0(n), O_1(n - 1), S_1(n), O_0(n) with O_r = P_r V - so the next head's S_r
+//                    goes out as soon as warpgroup r has drained O_r, while the other warpgroup is still in its pass;
 //   warp 9 (1 lane)  head sequence, every tile load (two (Q, K, V) buffer sets: the head after next loads while the next one
 //                    is processed) and the O stores.
 // Tensor memory: q tile r owns columns [256 r, 256 r + 256): S in [0, TP), P over [0, TP / 2), O in [128, 192).
@@ -630,47 +630,64 @@ __global__ void __launch_bounds__(ATTF_THREADS, 1) attn_fwd_ws_kernel(const __gr
     uint32_t ph = 0;   // bits: 0/1 qk, 2/3 v, 4/5 P, 6/7 free
     const uint32_t id_s = idesc_kk_n(TP);
     const int nks = TP >> 4;
+    // Product order: S_0(n), O_1(n - 1), S_1(n), O_0(n) - the two q tiles ALTERNATE, so neither warpgroup's next S waits behind
+    // the other's pass: 93.1 -> 88.8 us (MEASURED; with S_0, S_1, O_0, O_1 per head warpgroup 0 idled from its O rows until
+    // warpgroup 1 had written P_1).  Warpgroup 1 settles ~1.5 k cycles behind warpgroup 0.  MEASURED on top of this order:
+    // forcing a half-pass lag (warpgroup 0 signals the middle of its first pass, S_1 of the first head goes out then) with the
+    // score chunks fetched a pair ahead: 93.0 us, the pass itself 4.3 k -> 4.8 k cycles - a warpgroup that has the SFU to itself
+    // is no faster, so the pass is bound by the warp's own chain (scripts/probes/tmem_read_bw.cu runs the same chain at 190
+    // cycles per 16 columns with one warp per scheduler, 283 with two; the kernel needs ~340).
+    auto issue_s = [&](int n, int r) {
+      const int bs = n & 1;
+      if (n > 0) {
+        mbar_wait_flip(bar_free + r, ph, 6 + r);       // the previous head's O_r has left these columns
+        tc_fence_after_sync();
+      }
+      const uint32_t sQ_a = smem_u32(smem + bs * 3 * R), sK_a = sQ_a + R;
+      const uint64_t da = umma_smem_desc(sQ_a + r * 16384, 16, 1024), db = umma_smem_desc(sK_a, 16, 1024);
+      const uint32_t td = tmem_base + r * 256;
+      if (elect_one()) {
+        umma_bf16_ss(td, da, db, id_s, 0u);
+#pragma unroll
+        for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(td, da + 2 * ks, db + 2 * ks, id_s);
+        umma_commit(bar_S + r);
+      }
+      __syncwarp();
+    };
+    auto issue_o = [&](int n, int r) {
+      const int bs = n & 1;
+      mbar_wait_flip(bar_P + r, ph, 4 + r);
+      tc_fence_after_sync();
+      const uint32_t sV_a = smem_u32(smem + bs * 3 * R) + 2 * R;
+      const uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
+      const uint32_t td = tmem_base + r * 256;
+      if (elect_one()) {
+        umma_bf16_ts(td + 128, td, dv, IDESC_KM(64), 0u);
+#pragma unroll
+        for (int ks = 1; ks < 16; ++ks)
+          if (ks < nks) umma_bf16_ts(td + 128, td + ks * 8, dv + 128 * ks, IDESC_KM(64), 1u);
+        umma_commit(bar_O + r);
+      }
+      __syncwarp();
+    };
     for (int n = 0;; ++n) {
       const int bs = n & 1;
       ATTF_MARK(2, 0);
       mbar_wait_flip(bar_qk + bs, ph, bs);
-      if (s_head[n & 3] < 0) break;
+      const bool more = s_head[n & 3] >= 0;
       tc_fence_after_sync();
       ATTF_MARK(2, 1);
-      const uint32_t sQ_a = smem_u32(smem + bs * 3 * R), sK_a = sQ_a + R, sV_a = sK_a + R;
-      for (int r = 0; r < nQ; ++r) {
-        if (n > 0) {
-          mbar_wait_flip(bar_free + r, ph, 6 + r);     // the previous head's O_r has left these columns
-          tc_fence_after_sync();
-        }
-        const uint64_t da = umma_smem_desc(sQ_a + r * 16384, 16, 1024), db = umma_smem_desc(sK_a, 16, 1024);
-        const uint32_t td = tmem_base + r * 256;
-        if (elect_one()) {
-          umma_bf16_ss(td, da, db, id_s, 0u);
-#pragma unroll
-          for (int ks = 1; ks < 4; ++ks) umma_bf16_ss_acc(td, da + 2 * ks, db + 2 * ks, id_s);
-          umma_commit(bar_S + r);
-        }
-        __syncwarp();
-        ATTF_MARK(2, 2 + r);
-      }
+      if (more) issue_s(n, 0);
+      ATTF_MARK(2, 2);
+      if (nQ > 1 && n > 0) issue_o(n - 1, 1);          // (V of head n - 1 landed an iteration ago)
+      ATTF_MARK(2, 6);
+      if (!more) break;
+      if (nQ > 1) issue_s(n, 1);
+      ATTF_MARK(2, 3);
       mbar_wait_flip(bar_v + bs, ph, 2 + bs);
       ATTF_MARK(2, 4);
-      for (int r = 0; r < nQ; ++r) {
-        mbar_wait_flip(bar_P + r, ph, 4 + r);
-        tc_fence_after_sync();
-        const uint64_t dv = umma_smem_desc(sV_a, 8192, 1024);
-        const uint32_t td = tmem_base + r * 256;
-        if (elect_one()) {
-          umma_bf16_ts(td + 128, td, dv, IDESC_KM(64), 0u);
-#pragma unroll
-          for (int ks = 1; ks < 16; ++ks)
-            if (ks < nks) umma_bf16_ts(td + 128, td + ks * 8, dv + 128 * ks, IDESC_KM(64), 1u);
-          umma_commit(bar_O + r);
-        }
-        __syncwarp();
-        ATTF_MARK(2, 5 + r);
-      }
+      issue_o(n, 0);
+      ATTF_MARK(2, 5);
     }
   } else if (lane == 0) {
     // ===================== agent (one thread): head sequence, tile loads, O stores =====================
