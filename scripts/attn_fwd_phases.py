@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from nvit_b200 import ops, _lib
 
-B, H, T = 256, 12, 196
+B, H, T = int(os.environ.get("B", 256)), int(os.environ.get("H", 12)), int(os.environ.get("T", 196))
 C = H * 64
 M = B * T
 dev = "cuda"

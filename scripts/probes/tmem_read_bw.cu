@@ -138,6 +138,169 @@ static void run(const char* what, int warps, int iters, long long* d_out, float*
          avg / (iters * cols / 16.0), cudaGetErrorString(cudaGetLastError()));
 }
 
+// The kernel's pass (mode 6) on `wc` warps while `blockDim.x / 32 - wc` further warps poll an mbarrier that has not fired, the way
+// the MMA warp, the agent and the other warpgroup wait inside attn_fwd_ws_kernel (mbar_wait: try_wait + clock64 time-out check).
+__global__ void __launch_bounds__(512) probe_spin(long long* out, float* sink, int iters, int wc) {
+  __shared__ uint32_t tptr;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tptr, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = tptr + ((uint32_t)((warp & 3) * 32) << 16);
+  float acc = 0.f;
+  if (warp >= wc) {
+    mbar_wait(&bar, 0);
+  } else {
+    named_bar_sync(1, wc * 32);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const float fb = -(float)(it & 63);
+      const f32x2 sl2x2 = pack2(1.25f, 1.25f), nm2 = pack2(fb, fb);
+      f32x2 sum2 = pack2(0.f, 0.f);
+      for (int c0 = 0; c0 < 13; c0 += 2) {
+        uint32_t r[2][16];
+        tmem_ld_32x32b_x16(base + c0 * 16, r[0]);
+        if (c0 + 1 < 13) tmem_ld_32x32b_x16(base + c0 * 16 + 16, r[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = c0 + k;
+          if (c < 13) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float a0, a1;
+              unpack2(fma2(pack2(__uint_as_float(r[k][2 * e]), __uint_as_float(r[k][2 * e + 1])), sl2x2, nm2), a0, a1);
+              const f32x2 pv = pack2(ex2a(a0), ex2a(a1));
+              sum2 = add2(sum2, pv);
+              pk[e] = f32x2_to_bf16x2(pv);
+            }
+            st8(base + c * 8, pk);
+          }
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      float t0f, t1f;
+      unpack2(sum2, t0f, t1f);
+      acc += t0f + t1f;
+    }
+    named_bar_sync(1, wc * 32);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) { out[blockIdx.x] = t1 - t0; mbar_arrive(&bar); }
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tptr, 512);
+}
+
+static void run_spin(int wc, int spinners, int iters, long long* d_out, float* d_sink) {
+  for (int rep = 0; rep < 2; ++rep) probe_spin<<<148, (wc + spinners) * 32>>>(d_out, d_sink, iters, wc);
+  cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < 148; ++i) avg += h[i];
+  avg /= 148;
+  printf("kernel's pass, %d warps + %d polling warps: %9.0f cycles, %6.2f cycles per warp per 16 columns (%s)\n", wc, spinners, avg,
+         avg / (iters * 13.0), cudaGetErrorString(cudaGetLastError()));
+}
+
+// Variants of the pass with a ROLLED loop (the kernel's chunk count is a run-time value):
+//  0: as the kernel has it: ld pair, wait, work + st per chunk
+//  1: the next pair's loads issued BEFORE this pair's stores (two register sets), stores at the end of the iteration
+//  2: as 0 with "#pragma unroll 1" lifted (the compiler may pipeline across the 7 iterations)
+template <int V>
+__global__ void __launch_bounds__(512) probe_pass(long long* out, float* sink, int iters, int nch) {
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(&tptr, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t base = tptr + ((uint32_t)((warp & 3) * 32) << 16);
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const float fb = -(float)(it & 63);
+    const f32x2 sl2x2 = pack2(1.25f, 1.25f), nm2 = pack2(fb, fb);
+    f32x2 sum2 = pack2(0.f, 0.f);
+    auto work1 = [&](const uint32_t (&r)[16], uint32_t (&pk)[8]) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a0, a1;
+        unpack2(fma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sl2x2, nm2), a0, a1);
+        const f32x2 pv = pack2(ex2a(a0), ex2a(a1));
+        sum2 = add2(sum2, pv);
+        pk[e] = f32x2_to_bf16x2(pv);
+      }
+    };
+    if (V == 0 || V == 2) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < nch; c0 += 2) {
+        uint32_t r[2][16], pk[8];
+        tmem_ld_32x32b_x16(base + c0 * 16, r[0]);
+        if (c0 + 1 < nch) tmem_ld_32x32b_x16(base + c0 * 16 + 16, r[1]);
+        tmem_wait_ld();
+        work1(r[0], pk);
+        st8(base + c0 * 8, pk);
+        if (c0 + 1 < nch) { work1(r[1], pk); st8(base + c0 * 8 + 8, pk); }
+      }
+    } else {
+      uint32_t ra[2][16], rb[2][16], pa[8], pb[8];
+      tmem_ld_32x32b_x16(base, ra[0]);
+      tmem_ld_32x32b_x16(base + 16, ra[1]);
+#pragma unroll 1
+      for (int c0 = 0; c0 < nch; c0 += 4) {
+        tmem_wait_ld();
+        if (c0 + 2 < nch) tmem_ld_32x32b_x16(base + (c0 + 2) * 16, rb[0]);       // next pair: before this pair's stores
+        if (c0 + 3 < nch) tmem_ld_32x32b_x16(base + (c0 + 3) * 16, rb[1]);
+        work1(ra[0], pa);
+        if (c0 + 1 < nch) work1(ra[1], pb);
+        st8(base + c0 * 8, pa);
+        if (c0 + 1 < nch) st8(base + c0 * 8 + 8, pb);
+        if (c0 + 2 < nch) {
+          tmem_wait_ld();
+          if (c0 + 4 < nch) tmem_ld_32x32b_x16(base + (c0 + 4) * 16, ra[0]);
+          if (c0 + 5 < nch) tmem_ld_32x32b_x16(base + (c0 + 5) * 16, ra[1]);
+          work1(rb[0], pa);
+          if (c0 + 3 < nch) work1(rb[1], pb);
+          st8(base + (c0 + 2) * 8, pa);
+          if (c0 + 3 < nch) st8(base + (c0 + 3) * 8, pb);
+        }
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    float t0f, t1f;
+    unpack2(sum2, t0f, t1f);
+    acc += t0f + t1f;
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  if (acc == 12345.678f) sink[0] = acc;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tptr, 512);
+}
+
+template <int V>
+static void run_pass(const char* what, int warps, int iters, long long* d_out, float* d_sink) {
+  for (int rep = 0; rep < 2; ++rep) probe_pass<V><<<148, warps * 32>>>(d_out, d_sink, iters, 13);
+  cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < 148; ++i) avg += h[i];
+  avg /= 148;
+  printf("%-44s warps %d: %9.0f cycles, %6.2f cycles per warp per 16 columns (%s)\n", what, warps, avg, avg / (iters * 13.0),
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 int main() {
   long long* d_out;
   float* d_sink;
@@ -151,5 +314,9 @@ int main() {
   for (int w : {4, 8}) run<4>("ld x16 + 16 ex2 + cvt + st x8", w, iters, d_out, d_sink);
   for (int w : {4, 8}) run<5>("same, stores 4 chunks at a time", w, iters, d_out, d_sink);
   for (int w : {4, 8}) run<6>("the kernel's pass, verbatim", w, iters, d_out, d_sink);
+  for (int w : {4, 8}) run_pass<0>("rolled loop, ld - wait - work - st", w, iters, d_out, d_sink);
+  for (int w : {4, 8}) run_pass<1>("rolled loop, next loads before the stores", w, iters, d_out, d_sink);
+  for (int sp : {0, 2, 6}) run_spin(4, sp, iters, d_out, d_sink);
+  for (int sp : {0, 2}) run_spin(8, sp, iters, d_out, d_sink);
   return 0;
 }
