@@ -203,7 +203,16 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  What the barrier orders here are tensor-memory reads (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync in front of it), not generic memory, so the arrive needs no cluster-scope release:
+// MEASURED (ncu source view of the gate GEMM, round 2): `mbarrier.arrive.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR
+// + CGAERRBAR in front of the SYNCS.ARRIVE, and those instructions held 16.5 % of all warp samples of the kernel.  The relaxed
+// form: gate forward GEMM 385 -> 374 us, the other pair-mode GEMMs unchanged, but the fused gate-BACKWARD GEMM 300 - 313 ->
+// 330 - 342 us (same box, alternating libraries, scripts/gpu_call20.sh) - that kernel keeps the release form.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completion bytes are signalled on the mbarrier at cluster address `bar`

@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) gemm_tcgen05_kernel(const __
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // the issuing CTA's barrier
+          if constexpr (CG2 && GATEB) mbar_arrive_cluster_release(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // (see common.cuh)
+          else if constexpr (CG2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // the issuing CTA's barrier
           else mbar_arrive(&tmem_empty[acc]);
         }
       };
