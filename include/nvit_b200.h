@@ -36,6 +36,10 @@ int nvit_set_sm_budget(int n);
  * griddepcontrol.wait before its first global-memory access, so results are those of plain stream order.  Process-wide;
  * takes effect for launches (and graph captures) made after the call.  Default off. */
 int nvit_set_pdl(int on);
+/* TMA tensor maps are encoded once per distinct (base, type, shape, pitch, box) and kept in a process-wide table (the
+ * engine's buffers are static, so a training step encodes none after its first run).  Counters since load: maps encoded
+ * by the driver / maps served from the table.  Host pointers; either may be NULL. */
+int nvit_tmap_cache_stats(int64_t* encodes, int64_t* hits);
 
 /* ---- GEMM: nn.Linear / nn.Conv2d-as-GEMM forward, dgrad and wgrad (model.py:99-101,130,148,155,226-228,259,262,
  *      286-304,329-332,341-344 and their autograd backward) ------------------------------------------------------

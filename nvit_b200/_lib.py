@@ -24,6 +24,7 @@ SIGNATURES = {
     "nvit_attention_fwd_variant": [I32],
     "nvit_set_sm_budget": [I32],
     "nvit_set_pdl": [I32],
+    "nvit_tmap_cache_stats": [P, P],
     "nvit_residual_bwd_staged": [I32],
     "nvit_cast_f32_to_bf16": [P, P, I64, P],
     "nvit_sumsq_f32": [P, I64, P, P],
@@ -160,3 +161,10 @@ def call(name: str, *args) -> None:
         rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")
+
+
+def tmap_cache_stats() -> tuple[int, int]:
+    """(maps encoded by the driver, maps served from the table) since the library was loaded."""
+    enc, hit = c_int64(0), c_int64(0)
+    load().nvit_tmap_cache_stats(ctypes.byref(enc), ctypes.byref(hit))
+    return int(enc.value), int(hit.value)

@@ -20,6 +20,8 @@
 // emits x = (u*su) * silu(v*sv) directly (plus, optionally, the raw bf16 u|v for the backward pass).
 #include "common.cuh"
 #include <string.h>
+#include <mutex>
+#include <unordered_map>
 
 namespace nvit {
 
@@ -893,6 +895,26 @@ static PFN_encodeTiled get_encode_fn() {
   return f;
 }
 
+// Encoded tensor maps are kept: a map is a pure function of (base, type, swizzle, rank, dims, pitches, box) and every buffer of
+// the engine is static, so a step re-encodes nothing (up to five maps per GEMM, ~150 GEMMs and 26 attention launches per
+// step before).  A re-allocated buffer at the same address with the same shape yields the identical map, so entries never
+// go stale; the table is simply emptied when it reaches TMAP_CACHE_MAX entries.
+struct TmapKey {
+  uint64_t w[11];   // base, (dt, sw, rank), dims[3], pitches[2] (bytes), box[3]; unused slots zero
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : k.w) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xFF51AFD7ED558CCDull; }
+    return (size_t)(h ^ (h >> 32));
+  }
+};
+static constexpr size_t TMAP_CACHE_MAX = 8192;
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::atomic<long long> g_tmap_encodes{0}, g_tmap_hits{0};
+
 // Tensor map of rank 2 or 3 (dims innermost first, strides in elements for dims 1..rank-1).
 static int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int esize, CUtensorMapSwizzle sw, int rank,
                      const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
@@ -915,12 +937,33 @@ static int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, i
       return NVIT_ERR_ARG;
     }
   }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.w[0] = reinterpret_cast<uintptr_t>(base);
+  key.w[1] = ((uint64_t)dt << 32) | ((uint64_t)sw << 8) | (uint64_t)rank;
+  for (int i = 0; i < rank; ++i) { key.w[2 + i] = d[i]; key.w[7 + i] = b[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.w[5 + i] = s[i];
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *m = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return NVIT_OK;
+    }
+  }
+  g_tmap_encodes.fetch_add(1, std::memory_order_relaxed);
   CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     nvit_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
                    (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return NVIT_ERR_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *m);
   }
   return NVIT_OK;
 }
@@ -1228,6 +1271,13 @@ extern "C" int nvit_gemm_swiglu_cta_group(int mode) {   // benchmarking hook: 1 
   if (mode > 20) g_gateb_groups = mode - 20;
   else if (mode > 10) g_gateb_cg = mode - 10;
   else g_swiglu_cg = mode;
+  return NVIT_OK;
+}
+
+// Tensor-map table counters (encodes = maps built by the driver call, hits = maps taken from the table), process-wide.
+extern "C" int nvit_tmap_cache_stats(int64_t* encodes, int64_t* hits) {
+  if (encodes) *encodes = nvit::g_tmap_encodes.load(std::memory_order_relaxed);
+  if (hits) *hits = nvit::g_tmap_hits.load(std::memory_order_relaxed);
   return NVIT_OK;
 }
 
