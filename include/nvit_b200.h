@@ -165,6 +165,23 @@ int nvit_im2col_bf16(const float* img, void* out_bf16, int64_t B, int64_t ch, in
  * shift = -mean/std.  One byte per sample crosses PCIe instead of four. */
 int nvit_im2col_u8(const void* img_u8_nhwc, void* out_bf16, int64_t B, int64_t ch, int64_t S, int64_t ksize, int64_t stride,
                    int64_t pad, float scale, float shift, void* stream);
+/* AutoAugment on the device, before the patch gather (replaces kornia.augmentation.auto.AutoAugment(dataset) in the
+ * DataLoader workers, train.py:1081-1092 / 262-273).  src, dst: uint8 [B, S, S, 3], distinct buffers.  Per image b two
+ * operations are applied in order: ops[b*2 + k] with parameters params[(b*2 + k)*8 ..]:
+ *   0 identity
+ *   1 affine      p0..p5 = m00 m01 ox m10 m11 oy: source pixel = M (x - c, y - c) + o, c = (S-1)/2 (already inside o);
+ *                 nearest neighbour (ties to even), zero fill         (ShearX/Y, TranslateX/Y, Rotate)
+ *   2 brightness  p0 = ratio, p1 = 1 - ratio: trunc(clamp(ratio * x + (1 - ratio) * 0))
+ *   3 color       blend with the grey image trunc(0.2989 r + 0.587 g + 0.114 b)
+ *   4 contrast    blend with the mean of the grey image
+ *   5 sharpness   blend with the 3x3 smoothed image ([1 1 1; 1 5 1; 1 1 1] / 13, rounded; border unchanged)
+ *   6 posterize   p0 = byte mask (256 - 2^(8 - bits))       7 solarize  p0 = threshold: x >= p0 ? 255 - x : x
+ *   8 autocontrast (per channel: (x - min) * ((1 / (max - min)) * 255))   9 equalize (per channel histogram)   10 invert
+ * Codes outside 0..10 act as identity.  uint8 semantics of every operation are those of torchvision's tensor kernels
+ * (bit-exact; the affine map differs from grid_sample on exact ties only).  One CTA per image with the intermediate
+ * image in shared memory: 3 S^2 + 13 KB must fit 227 KB (S <= 267).  ops / params are device pointers. */
+int nvit_augment_u8(const void* src_u8_nhwc, void* dst_u8_nhwc, const int32_t* ops, const float* params, int64_t B, int64_t S,
+                    int64_t ch, void* stream);
 
 /* ---- classifier head (model.py:455-456, 466-468): mean over T -> LayerNorm(eps) -> (GEMM) ------------------- */
 int nvit_pool_ln_fwd(const float* h, const float* gamma, const float* beta, float eps, void* y_bf16, float* xhat,

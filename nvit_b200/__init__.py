@@ -8,5 +8,7 @@ from .model import ViTConfig, ViT, Block, CrossAttentionBlock, RMSNorm, justnorm
 from .kohonen import KohonenMap  # noqa: F401
 from .train import Trainer, GradReducer, DeviceLoader  # noqa: F401
 from . import ops  # noqa: F401
+from . import augment  # noqa: F401
+from .augment import AutoAugment, get_transforms  # noqa: F401
 
-__all__ = ["ViTConfig", "ViT", "Block", "CrossAttentionBlock", "RMSNorm", "justnorm", "KohonenMap", "Trainer", "GradReducer", "DeviceLoader", "ops"]
+__all__ = ["ViTConfig", "ViT", "Block", "CrossAttentionBlock", "RMSNorm", "justnorm", "KohonenMap", "Trainer", "GradReducer", "DeviceLoader", "ops", "augment", "AutoAugment", "get_transforms"]

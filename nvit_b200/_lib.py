@@ -53,6 +53,7 @@ SIGNATURES = {
     "nvit_som_smoothness": [P, P, I64, I64, I64, P, P, P, P],
     "nvit_tanh_mse_bwd": [P, P, I64, F32, P, P, P],
     "nvit_im2col_u8": [P, P, I64, I64, I64, I64, I64, I64, F32, F32, P],
+    "nvit_augment_u8": [P, P, P, P, I64, I64, I64, P],
     "nvit_im2col_bf16": [P, P, I64, I64, I64, I64, I64, I64, P],
     "nvit_pool_ln_fwd": [P, P, P, F32, P, P, P, I64, I64, I64, P],
     "nvit_pool_ln_bwd": [P, P, P, P, P, P, P, I64, I64, I64, P],

@@ -190,6 +190,25 @@ def head_scale_bwd(dlogits, raw, sz, sz_mul, draw, dsz):
     _lib.call("nvit_head_scale_bwd", _p(dlogits), _p(raw), _p(sz), float(sz_mul), _p(draw), _p(dsz), B, N, draw.stride(0), _stream())
 
 
+def augment_u8(img_u8, out, ops_i32, params_f32):
+    """Per-image two-operation AutoAugment on a uint8 [B, S, S, 3] batch (nvit_b200/augment.py draws `ops` [B, 2] int32 and
+    `params` [B, 2, 8] float32; train.py:1081-1092).  `out` is a second uint8 tensor of the same shape."""
+    if img_u8.dim() != 4 or img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise TypeError("augment_u8: expected a contiguous uint8 [B, S, S, 3] tensor")
+    B, S, S2, ch = img_u8.shape
+    if S != S2:
+        raise ValueError("augment_u8: images must be square")
+    if out.shape != img_u8.shape or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != img_u8.device:
+        raise TypeError("augment_u8: out must be a contiguous uint8 tensor of the input's shape on the same device")
+    if out.data_ptr() == img_u8.data_ptr():
+        raise ValueError("augment_u8: out must not alias the input")
+    _chk(ops_i32, torch.int32, "augment_u8: ops")
+    _chk(params_f32, F32, "augment_u8: params")
+    if tuple(ops_i32.shape) != (B, 2) or tuple(params_f32.shape) != (B, 2, 8):
+        raise ValueError(f"augment_u8: ops must be [{B}, 2] and params [{B}, 2, 8]")
+    _lib.call("nvit_augment_u8", _p(img_u8), _p(out), _p(ops_i32), _p(params_f32), B, S, ch, _stream())
+
+
 def cross_entropy(logits, target, loss, dlogits, gscale=1.0):
     """Mean softmax cross-entropy (train.py:906).  Targets are int64 class indices; a target outside [0, N) is treated like
     F.cross_entropy's ignore_index: no loss, zero gradient row (the mean still divides by B)."""

@@ -117,7 +117,10 @@ class DeviceLoader:
     only after the step that read it has been enqueued.
     """
 
-    def __init__(self, batches, device, depth: int = 2):
+    def __init__(self, batches, device, depth: int = 2, transform=None):
+        """transform: optional callable applied ON THE DEVICE to each uint8 batch as it is handed out (nvit_b200.augment's
+        AutoAugment: the reference augments in its DataLoader workers instead, train.py:1081-1092)."""
+        self.transform = transform
         self.batches, self.device, self.depth = batches, torch.device(device), max(2, depth)
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [None] * self.depth
@@ -153,6 +156,8 @@ class DeviceLoader:
 
     def _hand_out(self, slot):
         torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        if self.transform is not None:
+            return self.transform(slot["dx"]), slot["dy"]      # a new tensor on the compute stream; the slot is reusable as before
         return slot["dx"], slot["dy"]
 
     def _release(self, slot):

