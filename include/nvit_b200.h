@@ -174,7 +174,7 @@ int nvit_im2col_u8(const void* img_u8_nhwc, void* out_bf16, int64_t B, int64_t c
  *   2 brightness  p0 = ratio, p1 = 1 - ratio: trunc(clamp(ratio * x + (1 - ratio) * 0))
  *   3 color       blend with the grey image trunc(0.2989 r + 0.587 g + 0.114 b)
  *   4 contrast    blend with the mean of the grey image
- *   5 sharpness   blend with the 3x3 smoothed image ([1 1 1; 1 5 1; 1 1 1] / 13, rounded; border unchanged)
+ *   5 sharpness   blend with the 3x3 smoothed image ([1 1 1; 1 5 1; 1 1 1] / 13, rounded; on the border the image itself)
  *   6 posterize   p0 = byte mask (256 - 2^(8 - bits))       7 solarize  p0 = threshold: x >= p0 ? 255 - x : x
  *   8 autocontrast (per channel: (x - min) * ((1 / (max - min)) * 255))   9 equalize (per channel histogram)   10 invert
  * Codes outside 0..10 act as identity.  uint8 semantics of every operation are those of torchvision's tensor kernels

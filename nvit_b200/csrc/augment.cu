@@ -191,20 +191,20 @@ __device__ void aug_stage(const uint8_t* src, uint8_t* dst, int S, int op, const
       break;
     }
     case AUG_SHARPNESS: {
-      // blend with the 3 x 3 smoothed image ([1 1 1; 1 5 1; 1 1 1] / 13, rounded); the one-pixel border keeps its values.
+      // blend with the 3 x 3 smoothed image ([1 1 1; 1 5 1; 1 1 1] / 13, rounded); on the one-pixel border the smoothed image IS the image.
       // images with a side <= 2 are returned unchanged
       const float r = p[0], r1 = p[1];
       for (int j = tid; j < nbytes; j += AUG_THREADS) {
         const int i = j / 3, y = i / S, x = i - y * S;
         const int v = src[j];
-        int o = v;
-        if (S > 2 && x > 0 && x < S - 1 && y > 0 && y < S - 1) {
+        float deg = (float)v;      // the border blends with itself: r v + (1 - r) v, which truncates below v for some ratios
+        if (x > 0 && x < S - 1 && y > 0 && y < S - 1) {
           const int row = 3 * S;
           const int sum = src[j - row - 3] + src[j - row] + src[j - row + 3] + src[j - 3] + 5 * v + src[j + 3] +
                           src[j + row - 3] + src[j + row] + src[j + row + 3];
-          const float deg = rintf(__fdiv_rn((float)sum, 13.f));
-          o = blend_u8((float)v, deg, r, r1);
+          deg = rintf(__fdiv_rn((float)sum, 13.f));
         }
+        const int o = S > 2 ? blend_u8((float)v, deg, r, r1) : v;
         dst[j] = (uint8_t)o;
       }
       break;
