@@ -73,6 +73,24 @@ def test_every_ordered_pair_of_operations_is_bit_exact():
             assert np.array_equal(got[j], want[j]), (singles[a], singles[b], int((got[j] != want[j]).sum()))
 
 
+@pytest.mark.parametrize("S", [256, 258])
+def test_large_images_run_sharpness_in_many_row_bands(S):
+    """At 256 / 258 px the image leaves room for ~20 scratch rows only: the in-place sharpness walks many bands (word path at
+    256, byte path at 258, where 3 S is not a multiple of four) and must still read ORIGINAL neighbour rows."""
+    X = images(S, 1, seed=S)
+    names = [("Sharpness", 0.9), ("Sharpness", -0.9), ("Rotate", 11.0), ("Equalize", 0.0), ("Color", 0.6), ("Identity", 0.0)]
+    enc = [A.encode_op(op, mag, S) for op, mag in names]
+    pairs = [(a, b) for a in range(len(enc)) for b in range(len(enc)) if 0 in (a, b) or 1 in (a, b)]
+    for i in range(len(X)):
+        batch = np.repeat(X[i:i + 1], len(pairs), axis=0)
+        ops_h = np.array([[enc[a][0], enc[b][0]] for a, b in pairs], np.int32)
+        params_h = np.array([[enc[a][1], enc[b][1]] for a, b in pairs], np.float32)
+        got = run(batch, ops_h, params_h)
+        want = AO.apply_plan(batch, ops_h, params_h)
+        for j, (a, b) in enumerate(pairs):
+            assert np.array_equal(got[j], want[j]), (S, names[a], names[b], int((got[j] != want[j]).sum()))
+
+
 @pytest.mark.parametrize("dataset,S,B", [("cifar10", 32, 256), ("svhn", 32, 64), ("imagenet", 224, 48)])
 def test_sampled_batches_are_bit_exact(dataset, S, B):
     base = images(S, 7, seed=5)
@@ -127,7 +145,7 @@ def test_full_size_batch_properties_and_argument_checks():
         ops.augment_u8(x.float(), out, z_ops, z_par)
     with pytest.raises(ValueError):
         ops.augment_u8(x, out, z_ops[:5], z_par)
-    big = torch.zeros(1, 300, 300, 3, dtype=torch.uint8, device=DEV)
+    big = torch.zeros(1, 304, 304, 3, dtype=torch.uint8, device=DEV)
     with pytest.raises(RuntimeError, match="shared memory"):
         ops.augment_u8(big, torch.empty_like(big), z_ops[:1], z_par[:1])
     rgba = torch.zeros(1, 8, 8, 4, dtype=torch.uint8, device=DEV)
