@@ -264,7 +264,7 @@ __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, 
             const int sum = win_byte(u0, u1, u2, t + 1) + win_byte(u0, u1, u2, t + 4) + win_byte(u0, u1, u2, t + 7) +
                             win_byte(m0, m1, m2, t + 1) + 5 * v + win_byte(m0, m1, m2, t + 7) +
                             win_byte(d0, d1, d2, t + 1) + win_byte(d0, d1, d2, t + 4) + win_byte(d0, d1, d2, t + 7);
-            deg = rintf(__fdiv_rn((float)sum, 13.f));
+            deg = (float)((2 * sum + 13) / 26);      // = rint(sum / 13) for every sum in [0, 3315]: no tie, since 13 is odd
           }
           out |= (uint32_t)blend_u8((float)v, deg, r, r1) << (8 * t);
         }
@@ -279,7 +279,7 @@ __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, 
         float deg = (float)v;
         if (x > 0 && x < S - 1 && y > 0 && y < S - 1) {
           const int sum = q[-row - 3] + q[-row] + q[-row + 3] + q[-3] + 5 * v + q[3] + q[row - 3] + q[row] + q[row + 3];
-          deg = rintf(__fdiv_rn((float)sum, 13.f));
+          deg = (float)((2 * sum + 13) / 26);      // = rint(sum / 13) for every sum in [0, 3315]: no tie, since 13 is odd
         }
         img[y * row + xb] = (uint8_t)blend_u8((float)v, deg, r, r1);
       }

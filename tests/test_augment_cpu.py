@@ -159,3 +159,10 @@ def test_oracle_plan_composes_two_operations_and_identity_is_a_copy():
     assert np.array_equal(AO.apply_plan(X, z, np.zeros_like(params)), X)
     train_tf, val_tf = A.get_transforms("cifar10", seed=0)
     assert isinstance(train_tf, A.AutoAugment) and val_tf(X) is X
+
+
+def test_integer_form_of_the_smoothing_division_used_by_the_kernel():
+    """augment.cu rounds the 3 x 3 sum as (2 sum + 13) / 26 in integers; the oracle (and torchvision) round the float32 quotient
+    sum / 13 half-to-even.  Identical for every reachable sum."""
+    s = np.arange(0, 13 * 255 + 1)
+    assert np.array_equal(np.rint((s.astype(np.float32) / np.float32(13)).astype(np.float32)).astype(np.int64), (2 * s + 13) // 26)
