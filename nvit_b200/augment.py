@@ -172,39 +172,58 @@ class AutoAugment:
         self.dataset = dataset
         self.policies = policies(dataset)
         self.rng = np.random.Generator(np.random.PCG64([int(seed), int(rank)]))
-        self._table_cache: dict[int, dict] = {}
+        self._table_cache: dict = {}
+        self._rings: dict = {}
         self.last_plan = None
 
-    def _encoded(self, S: int) -> dict:
-        """(sub-policy, stage, sign) -> (code, params) for image side S; built once per S."""
+    def _encoded(self, S: int):
+        """codes int32 [25, 2, 2] and params float32 [25, 2, 2, 8] indexed (sub-policy, slot, sign bit) for image side S."""
         t = self._table_cache.get(S)
         if t is None:
-            t = {}
+            n = len(self.policies)
+            codes = np.zeros((n, 2, 2), np.int32)
+            params = np.zeros((n, 2, 2, NPARAM), np.float32)
             for i, sub in enumerate(self.policies):
                 for j, (name, _, bin_id) in enumerate(sub):
                     m = magnitude(name, bin_id, S) if bin_id is not None else 0.0
                     for sign in (0, 1):
-                        t[(i, j, sign)] = encode_op(name, -m if (name in _SIGNED and sign == 0) else m, S)
+                        codes[i, j, sign], params[i, j, sign] = encode_op(name, -m if (name in _SIGNED and sign == 0) else m, S)
+            t = (codes, params, np.array([[sub[0][1], sub[1][1]] for sub in self.policies], np.float64))
             self._table_cache[S] = t
         return t
 
     def plan(self, B: int, S: int) -> tuple[np.ndarray, np.ndarray]:
-        """Draw the operations of one batch: ops int32 [B, 2], params float32 [B, 2, 8]."""
-        table = self._encoded(S)
+        """Draw the operations of one batch: ops int32 [B, 2], params float32 [B, 2, 8] (identity where an operation's
+        probability did not fire)."""
+        codes, table, prob = self._encoded(S)
         sub = self.rng.integers(0, len(self.policies), size=B)
         probs = self.rng.random((B, 2))
         signs = self.rng.integers(0, 2, size=(B, 2))
-        ops = np.zeros((B, 2), np.int32)
-        params = np.zeros((B, 2, NPARAM), np.float32)
-        for b in range(B):
-            for j in range(2):
-                if probs[b, j] <= self.policies[sub[b]][j][1]:
-                    code, p = table[(int(sub[b]), j, int(signs[b, j]))]
-                    ops[b, j] = code
-                    params[b, j] = p
-        return ops, params
+        fire = probs <= prob[sub]                                   # [B, 2]
+        slot = np.arange(2)[None, :]
+        ops = np.where(fire, codes[sub[:, None], slot, signs], 0).astype(np.int32)
+        params = np.where(fire[..., None], table[sub[:, None], slot, signs], np.float32(0)).astype(np.float32)
+        return np.ascontiguousarray(ops), np.ascontiguousarray(params)
 
-    def __call__(self, x_u8):
+    def _staging(self, B: int, device):
+        """A small ring of pinned host buffers for the plans, so that the copy to the device is asynchronous; a slot is reused
+        only after the copy out of it has completed."""
+        import torch
+        key = (B, str(device))
+        ring = self._rings.get(key)
+        if ring is None:
+            ring = {"i": 0, "slots": [{"ops": torch.empty(B, 2, dtype=torch.int32).pin_memory(),
+                                       "params": torch.empty(B, 2, NPARAM, dtype=torch.float32).pin_memory(),
+                                       "done": None} for _ in range(4)]}
+            self._rings[key] = ring
+        slot = ring["slots"][ring["i"] % len(ring["slots"])]
+        ring["i"] += 1
+        if slot["done"] is not None:
+            slot["done"].synchronize()
+        return slot
+
+    def __call__(self, x_u8, out=None):
+        """out: optional uint8 tensor of the same shape to write into (e.g. Trainer.input_buffers, which a captured step reads)."""
         import torch
         from . import ops as _ops
         if x_u8.dim() != 4 or x_u8.dtype != torch.uint8 or x_u8.shape[1] != x_u8.shape[2] or x_u8.shape[3] != 3:
@@ -212,9 +231,15 @@ class AutoAugment:
         B, S = int(x_u8.shape[0]), int(x_u8.shape[1])
         ops_h, params_h = self.plan(B, S)
         self.last_plan = (ops_h, params_h)
-        ops_d = torch.from_numpy(ops_h).to(x_u8.device, non_blocking=True)
-        params_d = torch.from_numpy(params_h).to(x_u8.device, non_blocking=True)
-        out = torch.empty_like(x_u8)
+        slot = self._staging(B, x_u8.device)
+        slot["ops"].copy_(torch.from_numpy(ops_h))
+        slot["params"].copy_(torch.from_numpy(params_h))
+        ops_d = slot["ops"].to(x_u8.device, non_blocking=True)
+        params_d = slot["params"].to(x_u8.device, non_blocking=True)
+        slot["done"] = torch.cuda.Event()
+        slot["done"].record(torch.cuda.current_stream(x_u8.device))
+        if out is None:
+            out = torch.empty_like(x_u8)
         _ops.augment_u8(x_u8, out, ops_d, params_d)
         return out
 
