@@ -30,7 +30,7 @@ enum AugOp : int {
   AUG_IDENTITY = 0, AUG_AFFINE = 1, AUG_BRIGHTNESS = 2, AUG_COLOR = 3, AUG_CONTRAST = 4, AUG_SHARPNESS = 5,
   AUG_POSTERIZE = 6, AUG_SOLARIZE = 7, AUG_AUTOCONTRAST = 8, AUG_EQUALIZE = 9, AUG_INVERT = 10, AUG_NOPS = 11
 };
-constexpr int AUG_THREADS = 512;
+constexpr int AUG_THREADS = 1024;   // upper bound; the host picks 256 / 512 / 1024 by image size
 constexpr int AUG_NPARAM = 8;      // floats per (image, stage)
 constexpr int AUG_NHIST = 4;       // privatised histogram copies (one per lane & 3)
 
@@ -72,19 +72,19 @@ constexpr uint32_t AUG_BULK_CHUNK = 32768;
 
 // Statistics (from the image in shared memory) and the 3 x 256 table of a table operation.  Ends with a CTA barrier.
 __device__ void aug_build_lut(const uint8_t* img, int S, int op, const float* __restrict__ p, AugScratch& sc) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int npix = S * S;
   if (needs_hist(op)) {
-    for (int i = tid; i < AUG_NHIST * 3 * 256; i += AUG_THREADS) (&sc.hist[0][0][0])[i] = 0u;
+    for (int i = tid; i < AUG_NHIST * 3 * 256; i += nthr) (&sc.hist[0][0][0])[i] = 0u;
     __syncthreads();
     unsigned(*h)[256] = sc.hist[tid & (AUG_NHIST - 1)];     // neighbouring pixels (similar values) hit different copies
-    for (int i = tid; i < npix; i += AUG_THREADS) {
+    for (int i = tid; i < npix; i += nthr) {
       atomicAdd(&h[0][img[3 * i]], 1u);
       atomicAdd(&h[1][img[3 * i + 1]], 1u);
       atomicAdd(&h[2][img[3 * i + 2]], 1u);
     }
     __syncthreads();
-    for (int i = tid; i < 3 * 256; i += AUG_THREADS) {
+    for (int i = tid; i < 3 * 256; i += nthr) {
       unsigned s = 0;
 #pragma unroll
       for (int k = 0; k < AUG_NHIST; ++k) s += (&sc.hist[k][0][0])[i];
@@ -95,13 +95,13 @@ __device__ void aug_build_lut(const uint8_t* img, int S, int op, const float* __
     if (tid == 0) sc.graysum = 0ull;
     __syncthreads();
     unsigned long long s = 0;
-    for (int i = tid; i < npix; i += AUG_THREADS) s += (unsigned)gray_u8(img[3 * i], img[3 * i + 1], img[3 * i + 2]);
+    for (int i = tid; i < npix; i += nthr) s += (unsigned)gray_u8(img[3 * i], img[3 * i + 1], img[3 * i + 2]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((tid & 31) == 0) atomicAdd(&sc.graysum, s);
     __syncthreads();
   }
-  for (int i = tid; i < 3 * 256; i += AUG_THREADS) {
+  for (int i = tid; i < 3 * 256; i += nthr) {
     const int c = i >> 8, v = i & 255;
     int o = v;
     switch (op) {
@@ -150,11 +150,11 @@ __device__ void aug_build_lut(const uint8_t* img, int S, int op, const float* __
 
 // A point operation on the image where it lies in shared memory (each output pixel depends on its own input pixel only).
 __device__ void aug_point_inplace(uint8_t* img, int S, int op, const float* __restrict__ p, AugScratch& sc) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int npix = S * S, nbytes = 3 * npix;
   if (op == AUG_COLOR) {
     const float r = p[0], r1 = p[1];
-    for (int i = tid; i < npix; i += AUG_THREADS) {
+    for (int i = tid; i < npix; i += nthr) {
       const int a = img[3 * i], b = img[3 * i + 1], c = img[3 * i + 2];
       const float g = (float)gray_u8(a, b, c);
       img[3 * i] = (uint8_t)blend_u8((float)a, g, r, r1);
@@ -166,7 +166,7 @@ __device__ void aug_point_inplace(uint8_t* img, int S, int op, const float* __re
   aug_build_lut(img, S, op, p, sc);
   const uint8_t* lut = &sc.lut[0][0];
   uint32_t* w4 = reinterpret_cast<uint32_t*>(img);          // the buffer is 16-byte aligned; channel of byte j is j mod 3
-  for (int w = tid; w < nbytes / 4; w += AUG_THREADS) {
+  for (int w = tid; w < nbytes / 4; w += nthr) {
     const uint32_t x = w4[w];
     int c = (4 * w) % 3;
     uint32_t y = 0;
@@ -177,22 +177,22 @@ __device__ void aug_point_inplace(uint8_t* img, int S, int op, const float* __re
     }
     w4[w] = y;
   }
-  for (int j = (nbytes & ~3) + tid; j < nbytes; j += AUG_THREADS) img[j] = lut[(j % 3) * 256 + img[j]];
+  for (int j = (nbytes & ~3) + tid; j < nbytes; j += nthr) img[j] = lut[(j % 3) * 256 + img[j]];
 }
 
 // Affine gather: the image in shared memory -> the output image in global memory.  Four independent pixels per thread and
 // trip.  Source position = M (x - c, y - c) + o with c = (S - 1) / 2 folded into o by the host; nearest (ties to even), fill 0.
 __device__ void aug_affine(const uint8_t* img, uint8_t* __restrict__ dst, int S, const float* __restrict__ p) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int npix = S * S;
   constexpr int U = 4;
   const float m00 = p[0], m01 = p[1], ox = p[2], m10 = p[3], m11 = p[4], oy = p[5];
   const float c = 0.5f * (float)(S - 1);
-  for (int i0 = tid; i0 < npix; i0 += U * AUG_THREADS) {
+  for (int i0 = tid; i0 < npix; i0 += U * nthr) {
     uint8_t r[U], g[U], b[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * AUG_THREADS;
+      const int i = i0 + u * nthr;
       r[u] = g[u] = b[u] = 0;
       if (i < npix) {
         const int y = i / S, x = i - y * S;
@@ -208,7 +208,7 @@ __device__ void aug_affine(const uint8_t* img, uint8_t* __restrict__ dst, int S,
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * AUG_THREADS;
+      const int i = i0 + u * nthr;
       if (i < npix) { dst[3 * i] = r[u]; dst[3 * i + 1] = g[u]; dst[3 * i + 2] = b[u]; }
     }
   }
@@ -224,7 +224,7 @@ __device__ __forceinline__ int win_byte(uint32_t a, uint32_t b, uint32_t c, int 
 // below it are copied to `scratch` (rows x 3S bytes, 16 bytes of slack on either side), then the band is rewritten from there.
 __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, int S, const float* __restrict__ p) {
   if (S <= 2) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const float r = p[0], r1 = p[1];
   const int row = 3 * S, band = rows - 2;
   for (int y0 = 0; y0 < S; y0 += band) {
@@ -237,15 +237,15 @@ __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, 
       uint8_t* to = scratch + row;
       const int n = (yb - y0 + 1) * row;
       if ((row & 3) == 0) {
-        for (int w = tid; w < n / 4; w += AUG_THREADS) reinterpret_cast<uint32_t*>(to)[w] = reinterpret_cast<const uint32_t*>(from)[w];
+        for (int w = tid; w < n / 4; w += nthr) reinterpret_cast<uint32_t*>(to)[w] = reinterpret_cast<const uint32_t*>(from)[w];
       } else {
-        for (int j = tid; j < n; j += AUG_THREADS) to[j] = from[j];
+        for (int j = tid; j < n; j += nthr) to[j] = from[j];
       }
     }
     __syncthreads();
     if ((row & 3) == 0) {
       const int wrow = row / 4;
-      for (int w = tid; w < nb * wrow; w += AUG_THREADS) {
+      for (int w = tid; w < nb * wrow; w += nthr) {
         const int yl = w / wrow, xw = w - yl * wrow;
         const int y = y0 + yl;
         const uint32_t* mid = reinterpret_cast<const uint32_t*>(scratch + (yl + 1) * row) + xw;
@@ -271,7 +271,7 @@ __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, 
         reinterpret_cast<uint32_t*>(img + y * row)[xw] = out;
       }
     } else {
-      for (int j = tid; j < nb * row; j += AUG_THREADS) {
+      for (int j = tid; j < nb * row; j += nthr) {
         const int yl = j / row, xb = j - yl * row;
         const int y = y0 + yl, x = xb / 3;
         const uint8_t* q = scratch + (yl + 1) * row + xb;
@@ -286,7 +286,7 @@ __device__ void aug_sharpness_inplace(uint8_t* img, uint8_t* scratch, int rows, 
     }
     __syncthreads();
     if (y0 + band < S) {       // the original of the band's last row becomes "the row above" of the next band
-      for (int j = tid; j < row; j += AUG_THREADS) scratch[j] = scratch[band * row + j];
+      for (int j = tid; j < row; j += nthr) scratch[j] = scratch[band * row + j];
       __syncthreads();
     }
   }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(AUG_THREADS) augment_u8_kernel(const uint8_t* 
   extern __shared__ __align__(128) uint8_t aug_img[];
   __shared__ AugScratch sc;
   __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t nbytes = 3u * (uint32_t)S * (uint32_t)S;
   uint8_t* scratch = aug_img + ((nbytes + 15u) & ~15u) + 16;
   if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(AUG_THREADS) augment_u8_kernel(const uint8_t* 
       mbar_wait(&bar, phase);
       phase ^= 1u;
     } else {
-      for (uint32_t j = tid; j < nbytes; j += AUG_THREADS) aug_img[j] = from[j];
+      for (uint32_t j = tid; j < nbytes; j += nthr) aug_img[j] = from[j];
       __syncthreads();
     }
   };
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(AUG_THREADS) augment_u8_kernel(const uint8_t* 
     }
   } else {
     __syncthreads();
-    for (uint32_t j = tid; j < nbytes; j += AUG_THREADS) dst[img + j] = aug_img[j];
+    for (uint32_t j = tid; j < nbytes; j += nthr) dst[img + j] = aug_img[j];
   }
 }
 
@@ -388,7 +388,9 @@ extern "C" int nvit_augment_u8(const void* src_u8_nhwc, void* dst_u8_nhwc, const
     NVIT_CUDA_CHECK(cudaFuncSetAttribute(augment_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     once.mark(dev);
   }
-  launch(augment_u8_kernel, (unsigned)B, AUG_THREADS, smem, ST(stream), static_cast<const uint8_t*>(src_u8_nhwc),
+  // one image per SM once it exceeds ~100 KB: all 32 warps of the SM work on it; small images share an SM between many CTAs
+  const int threads = img_bytes >= 96 * 1024 ? 1024 : img_bytes >= 24 * 1024 ? 512 : 256;
+  launch(augment_u8_kernel, (unsigned)B, threads, smem, ST(stream), static_cast<const uint8_t*>(src_u8_nhwc),
          static_cast<uint8_t*>(dst_u8_nhwc), reinterpret_cast<const int*>(ops), params, (int)S, (int)scratch_rows);
   NVIT_CUDA_CHECK(cudaGetLastError());
   return NVIT_OK;
