@@ -228,6 +228,9 @@ class AutoAugment:
         from . import ops as _ops
         if x_u8.dim() != 4 or x_u8.dtype != torch.uint8 or x_u8.shape[1] != x_u8.shape[2] or x_u8.shape[3] != 3:
             raise ValueError(f"AutoAugment expects a uint8 [B, S, S, 3] (HWC) batch, got {tuple(x_u8.shape)} {x_u8.dtype}")
+        if not x_u8.is_cuda:
+            raise RuntimeError("nvit_b200.AutoAugment runs on the device only (there is no CPU path): move the batch to the GPU, "
+                               "e.g. through DeviceLoader(..., transform=aug)")
         B, S = int(x_u8.shape[0]), int(x_u8.shape[1])
         ops_h, params_h = self.plan(B, S)
         self.last_plan = (ops_h, params_h)

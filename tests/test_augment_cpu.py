@@ -166,3 +166,12 @@ def test_integer_form_of_the_smoothing_division_used_by_the_kernel():
     sum / 13 half-to-even.  Identical for every reachable sum."""
     s = np.arange(0, 13 * 255 + 1)
     assert np.array_equal(np.rint((s.astype(np.float32) / np.float32(13)).astype(np.float32)).astype(np.int64), (2 * s + 13) // 26)
+
+
+def test_the_public_call_refuses_host_tensors():
+    import torch
+    aug = A.AutoAugment("cifar10")
+    with pytest.raises(RuntimeError, match="device only"):
+        aug(torch.zeros(2, 8, 8, 3, dtype=torch.uint8))
+    with pytest.raises(ValueError, match="HWC"):
+        aug(torch.zeros(2, 3, 8, 8))

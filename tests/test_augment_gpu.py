@@ -73,6 +73,29 @@ def test_every_ordered_pair_of_operations_is_bit_exact():
             assert np.array_equal(got[j], want[j]), (singles[a], singles[b], int((got[j] != want[j]).sum()))
 
 
+@pytest.mark.parametrize("S", [1, 2, 3, 5])
+def test_degenerate_image_sizes(S):
+    """1 x 1 ... 5 x 5 images: sharpness leaves sides <= 2 alone, a 3 x 3 image has one interior pixel, statistics of a
+    single pixel are degenerate (autocontrast / equalize return the image), gathers mostly fall outside."""
+    rng = np.random.default_rng(S)
+    X = rng.integers(0, 256, (6, S, S, 3), dtype=np.uint8)
+    names = [("Identity", 0.0), ("Rotate", 30.0), ("ShearY", 0.3), ("TranslateX", 1.0), ("Brightness", -0.4), ("Color", 0.9), ("Contrast", -0.9),
+             ("Sharpness", 0.9), ("Posterize", 5.0), ("Solarize", 28.3), ("AutoContrast", 0.0), ("Equalize", 0.0), ("Invert", 0.0)]
+    enc = [A.encode_op(op, mag, S) for op, mag in names]
+    pairs = [(a, b) for a in range(len(enc)) for b in range(len(enc))]
+    for i in range(len(X)):
+        batch = np.repeat(X[i:i + 1], len(pairs), axis=0)
+        ops_h = np.array([[enc[a][0], enc[b][0]] for a, b in pairs], np.int32)
+        params_h = np.array([[enc[a][1], enc[b][1]] for a, b in pairs], np.float32)
+        got = run(batch, ops_h, params_h)
+        want = AO.apply_plan(batch, ops_h, params_h)
+        for j, (a, b) in enumerate(pairs):
+            assert np.array_equal(got[j], want[j]), (S, names[a], names[b], got[j].tolist(), want[j].tolist())
+    # out-of-range operation codes act as identity (the entry point's contract)
+    bad = np.array([[99, -3]] * len(X), np.int32)
+    assert np.array_equal(run(X, bad, np.zeros((len(X), 2, 8), np.float32)), X)
+
+
 @pytest.mark.parametrize("S", [256, 258])
 def test_large_images_run_sharpness_in_many_row_bands(S):
     """At 256 / 258 px the image leaves room for ~20 scratch rows only: the in-place sharpness walks many bands (word path at
