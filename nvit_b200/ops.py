@@ -204,6 +204,8 @@ def augment_u8(img_u8, out, ops_i32, params_f32):
         raise ValueError("augment_u8: out must not alias the input")
     _chk(ops_i32, torch.int32, "augment_u8: ops")
     _chk(params_f32, F32, "augment_u8: params")
+    if ops_i32.device != img_u8.device or params_f32.device != img_u8.device:
+        raise ValueError("augment_u8: ops and params must live on the batch's device")
     if tuple(ops_i32.shape) != (B, 2) or tuple(params_f32.shape) != (B, 2, 8):
         raise ValueError(f"augment_u8: ops must be [{B}, 2] and params [{B}, 2, 8]")
     _lib.call("nvit_augment_u8", _p(img_u8), _p(out), _p(ops_i32), _p(params_f32), B, S, ch, _stream())
