@@ -175,3 +175,99 @@ def test_the_public_call_refuses_host_tensors():
         aug(torch.zeros(2, 8, 8, 3, dtype=torch.uint8))
     with pytest.raises(ValueError, match="HWC"):
         aug(torch.zeros(2, 3, 8, 8))
+
+
+def test_operation_codes_agree_between_kernel_host_oracle_and_header():
+    """One numbering in four places: the enum of csrc/augment.cu, nvit_b200/augment.py, oracle/augment_oracle.py and the text of
+    include/nvit_b200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cu = open(os.path.join(root, "nvit_b200", "csrc", "augment.cu")).read()
+    enum = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"AUG_([A-Z]+) = (\d+)", cu))
+    names = ["IDENTITY", "AFFINE", "BRIGHTNESS", "COLOR", "CONTRAST", "SHARPNESS", "POSTERIZE", "SOLARIZE", "AUTOCONTRAST", "EQUALIZE", "INVERT"]
+    for n in names:
+        assert enum[n] == getattr(A, n) == getattr(AO, n), n
+    assert enum["NOPS"] == len(names) and int(re.search(r"AUG_NPARAM = (\d+)", cu).group(1)) == A.NPARAM
+    header = open(os.path.join(root, "include", "nvit_b200.h")).read()
+    doc = header[header.index("AutoAugment on the device"):header.index("int nvit_augment_u8")]
+    for n in names:
+        assert re.search(rf"\b{getattr(A, n)} {n.lower()}\b", doc), f"header does not document code {getattr(A, n)} as {n.lower()}"
+
+
+def test_oracle_properties():
+    """Size-independent properties of the operations (the GPU suite checks the same ones on the full-size batch)."""
+    X = images(48, 3, seed=4)
+    z = np.zeros(8, np.float32)
+    for img in X:
+        inv = AO.apply_op(img, AO.INVERT, z)
+        assert np.array_equal(AO.apply_op(inv, AO.INVERT, z), img)
+        for bits in range(0, 9):
+            c, p = A.encode_op("Posterize", float(bits), 48)
+            once = AO.apply_op(img, c, p)
+            assert np.array_equal(AO.apply_op(once, c, p), once)                      # idempotent
+            assert np.array_equal(once, img & np.uint8(256 - (1 << (8 - bits)) & 255))
+        c, p = A.encode_op("Solarize", 0.0, 48)
+        assert np.array_equal(AO.apply_op(img, c, p), inv)                            # threshold 0 inverts everything
+        c, p = A.encode_op("Solarize", 255.5, 48)
+        assert np.array_equal(AO.apply_op(img, c, p), img)
+        for op in ("Brightness", "Color", "Contrast", "Sharpness"):                   # magnitude 0 = ratio 1 = identity
+            c, p = A.encode_op(op, 0.0, 48)
+            assert np.array_equal(AO.apply_op(img, c, p), img), op
+        ac = AO.apply_op(img, AO.AUTOCONTRAST, z)
+        for ch in range(3):
+            if img[..., ch].max() > img[..., ch].min():
+                assert ac[..., ch].min() == 0 and ac[..., ch].max() == 255
+            else:
+                assert np.array_equal(ac[..., ch], img[..., ch])
+        eq = AO.apply_op(img, AO.EQUALIZE, z)
+        for ch in range(3):                                                           # monotone per channel
+            order = np.argsort(img[..., ch].reshape(-1), kind="stable")
+            assert (np.diff(eq[..., ch].reshape(-1)[order].astype(int)) >= 0).all()
+        c, p = A.encode_op("Rotate", 0.0, 48)
+        assert np.array_equal(AO.apply_op(img, c, p), img)
+        c, p = A.encode_op("Rotate", 180.0, 48)
+        assert np.array_equal(AO.apply_op(img, c, p), img[::-1, ::-1])
+        c, p = A.encode_op("Rotate", 90.0, 48)                                        # counter-clockwise
+        assert np.array_equal(AO.apply_op(img, c, p), np.rot90(img, 1))
+        c, p = A.encode_op("TranslateX", 5.0, 48)
+        t = AO.apply_op(img, c, p)
+        assert np.array_equal(t[:, 5:], img[:, :-5]) and not t[:, :5].any()
+        c, p = A.encode_op("TranslateY", -7.9, 48)                                    # int() truncates toward zero
+        t = AO.apply_op(img, c, p)
+        assert np.array_equal(t[:-7], img[7:]) and not t[-7:].any()
+
+
+def _plan_worker(rank, world, port, out):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    aug = A.AutoAugment("imagenet", seed=99, rank=dist.get_rank())
+    ops, params = aug.plan(64, 224)
+    import torch
+    gathered = [torch.zeros(64, 2, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(ops))
+    if rank == 0:
+        out.put([g.numpy().tolist() for g in gathered])
+    dist.destroy_process_group()
+
+
+def test_data_parallel_ranks_draw_different_plans_from_one_seed():
+    """N > 1 (gloo, two processes): replicas share the seed and differ by rank, so that they do not augment alike; a rank's plan
+    is reproducible."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b = np.array(got[0]), np.array(got[1])
+    assert not np.array_equal(a, b)
+    assert np.array_equal(a, A.AutoAugment("imagenet", seed=99, rank=0).plan(64, 224)[0])
+    assert np.array_equal(b, A.AutoAugment("imagenet", seed=99, rank=1).plan(64, 224)[0])
