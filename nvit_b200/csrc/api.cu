@@ -39,7 +39,7 @@ extern "C" int nvit_set_pdl(int on) {
 }
 
 extern "C" const char* nvit_last_error(void) { return g_err; }
-extern "C" int nvit_version(void) { return 100; }
+extern "C" int nvit_version(void) { return 101; }   // 101: + nvit_augment_u8, nvit_tmap_cache_stats
 extern "C" int nvit_sm_count(void) { return nvit_num_sms(); }
 extern "C" int nvit_set_sm_budget(int n) {
   if (n < 0) {
